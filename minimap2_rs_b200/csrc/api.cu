@@ -1,0 +1,597 @@
+// api.cu — C ABI of libmm2b200.so: context, sketch / seeds / chain stage entry points, and the batched mapping
+// pipeline that `mm2rs align` drives (main.rs:193-219 for every read of a batch).  Host code here only moves data,
+// sequences kernels and finishes the handful of scalar float operations that must match glibc (powf for dv).
+#include "mm2_internal.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+#include "stages.cuh"
+
+// ---- errors ----------------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+void mm2_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* mm2_last_error(void) { return g_err; }
+extern "C" void mm2_free(void* p) { free(p); }
+extern "C" void* mm2_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { mm2_set_error("cudaMallocHost(%zu) failed", bytes); return nullptr; }
+  return p;
+}
+extern "C" void mm2_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// ---- context ---------------------------------------------------------------------------------------------------------
+extern "C" int mm2_ctx_create(int device, mm2_ctx_t** out) {
+  if (!out) { mm2_set_error("mm2_ctx_create: NULL out"); return MM2_E_ARG; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    mm2_set_error("no CUDA device available (%s); libmm2b200 has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "count=0");
+    return MM2_E_CUDA;
+  }
+  if (device < 0 || device >= ndev) { mm2_set_error("device %d out of range (%d devices)", device, ndev); return MM2_E_ARG; }
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) { mm2_set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return MM2_E_CUDA; }
+  mm2_ctx* c = new mm2_ctx();
+  c->device = device;
+  e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete c; mm2_set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); return MM2_E_CUDA; }
+  c->own_stream = true;
+  *out = c;
+  return MM2_OK;
+}
+
+extern "C" void mm2_ctx_destroy(mm2_ctx_t* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  DevBuf* bufs[] = {&c->seq, &c->seq_off, &c->tile_seq, &c->tile_first, &c->tile_status, &c->misc, &c->mkey, &c->mval,
+                    &c->mini_off, &c->keep, &c->occ_cnt, &c->occ_loc, &c->anchor_off_m, &c->scan_status, &c->anchors,
+                    &c->read_aoff, &c->read_class, &c->dpA, &c->dpB, &c->dpT, &c->hits, &c->chain_idx, &c->lut, &c->sort_tmp,
+                    &c->sort_tmp2, &c->sort_keys2, &c->sort_vals2, &c->runidx, &c->run_start, &c->run_gp};
+  for (DevBuf* b : bufs) b->release();
+  c->pin_in.release(); c->pin_out.release(); c->pin_small.release();
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" int mm2_ctx_set_stream(mm2_ctx_t* c, void* cuda_stream) {
+  if (!c) { mm2_set_error("NULL ctx"); return MM2_E_ARG; }
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (cuda_stream) {
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    c->stream = (cudaStream_t)cuda_stream; c->own_stream = false;
+  } else if (!c->own_stream) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+  }
+  return MM2_OK;
+}
+extern "C" int mm2_ctx_synchronize(mm2_ctx_t* c) {
+  if (!c) { mm2_set_error("NULL ctx"); return MM2_E_ARG; }
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return MM2_OK;
+}
+extern "C" uint64_t mm2_ctx_launch_count(const mm2_ctx_t* c) { return c ? c->launches : 0; }
+extern "C" int mm2_ctx_last_timings(const mm2_ctx_t* c, const char** names, const float** ms, int* n) {
+  if (!c || !names || !ms || !n) { mm2_set_error("NULL argument"); return MM2_E_ARG; }
+  *names = c->timer.names_blob.c_str(); *ms = c->timer.ms.data(); *n = (int)c->timer.ms.size();
+  return MM2_OK;
+}
+
+// ---- small kernels of the API layer --------------------------------------------------------------------------------------
+namespace {
+__global__ void interleave_kernel(const u64* __restrict__ a, const u64* __restrict__ b, ulonglong2* __restrict__ out, u64 n) {
+  for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) out[i] = make_ulonglong2(a[i], b[i]);
+}
+__global__ void deinterleave_kernel(const ulonglong2* __restrict__ in, u64* __restrict__ a, u64* __restrict__ b, u64 n) {
+  for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) { const ulonglong2 v = in[i]; a[i] = v.x; b[i] = v.y; }
+}
+__global__ void dp_unpack_kernel(const int4* __restrict__ A, int* __restrict__ f, int* __restrict__ v, int* __restrict__ pprev, u64 n) {
+  for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) { const int4 a = A[i]; f[i] = a.x; pprev[i] = a.y; v[i] = a.z; }
+}
+inline int grid_for(u64 n, int block = 256) { return (int)std::max<u64>(1, std::min<u64>((n + block - 1) / block, 148ull * 32)); }
+
+template <class T>
+T* xmalloc(size_t n) { return (T*)malloc(std::max<size_t>(1, n) * sizeof(T)); }
+}  // namespace
+
+// ---- sketch ------------------------------------------------------------------------------------------------------------
+extern "C" int mm2_sketch_batch(mm2_ctx_t* ctx, const uint8_t* cat, const uint64_t* offs, size_t nseq, int w, int k, uint32_t rid_base,
+                                uint32_t rid_step, int is_hpc, mm2_mini_t** out, uint64_t** out_offs) {
+  if (!ctx || !offs || !out || !out_offs || (!cat && nseq && offs[nseq] > offs[0])) { mm2_set_error("mm2_sketch_batch: NULL argument"); return MM2_E_ARG; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  *out = nullptr; *out_offs = nullptr;
+  const u64 base = nseq ? offs[0] : 0, total = nseq ? offs[nseq] - base : 0;
+  std::vector<u64> off0(nseq + 1, 0);
+  for (size_t i = 0; i <= nseq && nseq; ++i) off0[i] = offs[i] - base;
+  MM2_TRY(ctx->seq.ensure(total + 64));
+  MM2_TRY(ctx->seq_off.ensure((nseq + 1) * 8));
+  if (total) CUDA_TRY(cudaMemcpyAsync(ctx->seq.p, cat + base, total, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(ctx->seq_off.p, off0.data(), (nseq + 1) * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  SketchOut so;
+  MM2_TRY(sketch_device(ctx, ctx->seq.as<u8>(), ctx->seq_off.as<u64>(), off0.data(), nseq, w, k, rid_base, rid_step, is_hpc, &so));
+  mm2_mini_t* h = xmalloc<mm2_mini_t>(so.total);
+  u64* ho = xmalloc<u64>(nseq + 1);
+  if (!h || !ho) { free(h); free(ho); mm2_set_error("out of host memory"); return MM2_E_OOM; }
+  ho[0] = 0;
+  if (nseq) {
+    MM2_TRY(ctx->anchors.ensure(std::max<u64>(1, so.total) * 16));
+    if (so.total) MM2_LAUNCH(ctx, interleave_kernel, grid_for(so.total), 256, 0, so.key, so.val, ctx->anchors.as<ulonglong2>(), so.total);
+    if (so.total) CUDA_TRY(cudaMemcpyAsync(h, ctx->anchors.p, so.total * 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(ho, so.seq_off, (nseq + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  *out = h; *out_offs = ho;
+  return MM2_OK;
+}
+
+extern "C" int mm2_sketch(mm2_ctx_t* ctx, const uint8_t* seq, size_t len, int w, int k, uint32_t rid, int is_hpc, mm2_mini_t** out, size_t* n) {
+  if (!n || !out) { mm2_set_error("mm2_sketch: NULL argument"); return MM2_E_ARG; }
+  if (len == 0) { mm2_set_error("mm2_sketch: empty sequence (sketch.rs:30 asserts !seq.is_empty())"); return MM2_E_ARG; }
+  const u64 offs[2] = {0, (u64)len};
+  u64* oo = nullptr;
+  MM2_TRY(mm2_sketch_batch(ctx, seq, offs, 1, w, k, rid, 0, is_hpc, out, &oo));
+  *n = (size_t)oo[1];
+  free(oo);
+  return MM2_OK;
+}
+
+// ---- index build entry points (device work in index.cu; FASTA parsing in index_io.cu) ----------------------------------
+extern "C" int mm2_index_build_seqs(mm2_ctx_t* ctx, const uint8_t* cat, const uint64_t* offs, const char* const* names, size_t nseq,
+                                    int w, int k, int b, int flag, mm2_index_t** out) {
+  if (!ctx || !out || (nseq && (!cat || !offs))) { mm2_set_error("mm2_index_build_seqs: NULL argument"); return MM2_E_ARG; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  static const u64 zero_off[1] = {0};
+  return index_build_device(ctx, cat, nseq ? offs : zero_off, names, nseq, w, k, b, flag, out);
+}
+
+// ---- seeds stage entry points ---------------------------------------------------------------------------------------------
+static int upload_minis(mm2_ctx* ctx, const mm2_mini_t* mv, size_t n) {
+  MM2_TRY(ctx->mkey.ensure(std::max<size_t>(1, n) * 8));
+  MM2_TRY(ctx->mval.ensure(std::max<size_t>(1, n) * 8));
+  MM2_TRY(ctx->anchors.ensure(std::max<size_t>(1, n) * 16));
+  if (n) {
+    CUDA_TRY(cudaMemcpyAsync(ctx->anchors.p, mv, n * 16, cudaMemcpyHostToDevice, ctx->stream));
+    MM2_LAUNCH(ctx, deinterleave_kernel, grid_for(n), 256, 0, ctx->anchors.as<ulonglong2>(), ctx->mkey.as<u64>(), ctx->mval.as<u64>(), (u64)n);
+  }
+  return MM2_OK;
+}
+
+extern "C" int mm2_filter_query_minimizers(mm2_ctx_t* ctx, mm2_mini_t* mv, size_t* n, int32_t q_occ_max, float q_occ_frac) {
+  if (!ctx || !n || (*n && !mv)) { mm2_set_error("mm2_filter_query_minimizers: NULL argument"); return MM2_E_ARG; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const size_t cnt = *n;
+  if (cnt == 0) return MM2_OK;
+  MM2_TRY(upload_minis(ctx, mv, cnt));
+  MM2_TRY(ctx->mini_off.ensure(16));
+  MM2_TRY(ctx->keep.ensure(cnt + 16));
+  MM2_TRY(ctx->misc.ensure(64));
+  const u64 mo[2] = {0, (u64)cnt};
+  CUDA_TRY(cudaMemcpyAsync(ctx->mini_off.p, mo, 16, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  MM2_TRY(seeds_filter(ctx, ctx->mkey.as<u64>(), ctx->mini_off.as<u64>(), 1, cnt, q_occ_max, q_occ_frac, ctx->keep.as<u8>(), ctx->misc.as<u32>()));
+  std::vector<u8> keep(cnt);
+  CUDA_TRY(cudaMemcpyAsync(keep.data(), ctx->keep.p, cnt, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  size_t j = 0;
+  for (size_t i = 0; i < cnt; ++i) if (keep[i]) mv[j++] = mv[i];  // seeds.rs:33-35: survivors keep their order
+  *n = j;
+  return MM2_OK;
+}
+
+extern "C" int mm2_build_anchors_filtered(mm2_ctx_t* ctx, const mm2_index_t* idx, const mm2_mini_t* mv, size_t n, int32_t qlen,
+                                          int32_t mid_occ, mm2_anchor_t** out, size_t* n_out) {
+  if (!ctx || !idx || !out || !n_out || (n && !mv)) { mm2_set_error("mm2_build_anchors_filtered: NULL argument"); return MM2_E_ARG; }
+  if (idx->device != ctx->device) { mm2_set_error("index lives on device %d, context on %d", idx->device, ctx->device); return MM2_E_ARG; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  *out = nullptr; *n_out = 0;
+  MM2_TRY(upload_minis(ctx, mv, n));
+  MM2_TRY(ctx->mini_off.ensure(16));
+  MM2_TRY(ctx->seq_off.ensure(16));
+  MM2_TRY(ctx->keep.ensure(n + 16));
+  MM2_TRY(ctx->occ_cnt.ensure((n + 16) * 4));
+  MM2_TRY(ctx->occ_loc.ensure((n + 16) * 8));
+  MM2_TRY(ctx->anchor_off_m.ensure((n + 2) * 8));
+  MM2_TRY(ctx->read_aoff.ensure(16));
+  const u64 mo[2] = {0, (u64)n}, ro[2] = {0, (u64)(u32)qlen};
+  CUDA_TRY(cudaMemcpyAsync(ctx->mini_off.p, mo, 16, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(ctx->seq_off.p, ro, 16, cudaMemcpyHostToDevice, st));
+  if (n) CUDA_TRY(cudaMemsetAsync(ctx->keep.p, 1, n, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  const IndexView V = idx->view();
+  MM2_TRY(seeds_lookup_count(ctx, V, ctx->mkey.as<u64>(), ctx->keep.as<u8>(), n, mid_occ, ctx->occ_cnt.as<u32>(), ctx->occ_loc.as<u64>()));
+  MM2_TRY(scan_u32_to_u64(ctx, ctx->occ_cnt.as<u32>(), ctx->anchor_off_m.as<u64>(), n));
+  u64 na = 0;
+  CUDA_TRY(cudaMemcpyAsync(&na, ctx->anchor_off_m.as<u64>() + n, 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  MM2_TRY(ctx->anchors.ensure(std::max<u64>(1, na) * 16));
+  // the deinterleave above used ctx->anchors as staging; it has completed (stream order), safe to reuse/grow
+  MM2_TRY(seeds_fill_and_sort(ctx, V, ctx->mkey.as<u64>(), ctx->mval.as<u64>(), ctx->mini_off.as<u64>(), ctx->seq_off.as<u64>(), 1,
+                              ctx->occ_cnt.as<u32>(), ctx->occ_loc.as<u64>(), ctx->anchor_off_m.as<u64>(),
+                              ctx->anchors.as<ulonglong2>(), ctx->read_aoff.as<u64>()));
+  mm2_anchor_t* h = xmalloc<mm2_anchor_t>(na);
+  if (!h) { mm2_set_error("out of host memory"); return MM2_E_OOM; }
+  if (na) CUDA_TRY(cudaMemcpyAsync(h, ctx->anchors.p, na * 16, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  *out = h; *n_out = (size_t)na;
+  return MM2_OK;
+}
+
+// ---- chaining stage entry point ---------------------------------------------------------------------------------------------
+extern "C" void mm2_default_chain_params(int32_t k, mm2_chain_params_t* p) {  // main.rs:105-123
+  const float chain_gap_scale = 0.8f;
+  volatile float t = 0.01f * chain_gap_scale;
+  volatile float g = t * (float)k;
+  p->max_dist_x = 5000; p->max_dist_y = 5000; p->bw = 500; p->max_chain_iter = 5000; p->min_chain_score = 40; p->min_cnt = 3;
+  p->chn_pen_gap = g; p->chn_pen_skip = 0.0f; p->max_chain_skip = 25; p->max_drop = 500; p->bw_long = 20000;
+  p->rmq_rescue_size = 1000; p->rmq_rescue_ratio = 0.1f;
+}
+
+namespace {
+inline i32 a_qpos(const mm2_anchor_t& a) { return (i32)(u32)a.y; }
+inline i32 a_qspan(const mm2_anchor_t& a) { return (i32)((a.y >> 32) & 0xff); }
+inline i32 a_rpos(const mm2_anchor_t& a) { return (i32)(u32)a.x; }
+struct HostChain { std::vector<u64> idx; i32 score; i32 qstart, tstart; };
+// start coordinates used as tie-breakers by sort_chains_stable (lchain.rs:179-200; an empty chain gives i32::MAX)
+void chain_starts(const mm2_anchor_t* a, HostChain& c) {
+  i32 qs = INT32_MAX, ts = INT32_MAX;
+  for (u64 i : c.idx) {
+    qs = std::min(qs, (i32)((u32)a_qpos(a[i]) - (u32)(a_qspan(a[i]) - 1)));
+    ts = std::min(ts, (i32)((u32)a_rpos(a[i]) - (u32)(a_qspan(a[i]) - 1)));
+  }
+  c.qstart = std::max(qs, 0); c.tstart = std::max(ts, 0);
+}
+}  // namespace
+
+extern "C" int mm2_chain_dp_all(mm2_ctx_t* ctx, const mm2_anchor_t* a, size_t n, const mm2_chain_params_t* p, mm2_chains_t* out) {
+  if (!ctx || !p || !out || (n && !a)) { mm2_set_error("mm2_chain_dp_all: NULL argument"); return MM2_E_ARG; }
+  memset(out, 0, sizeof *out);
+  out->chain_offs = xmalloc<u64>(1); out->chain_offs[0] = 0;
+  if (n == 0) return MM2_OK;  // lchain.rs:61
+  if (n > 0x7fffffffull) { mm2_set_error("too many anchors"); return MM2_E_ARG; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  MM2_TRY(ctx->anchors.ensure(n * 16));
+  MM2_TRY(ctx->dpA.ensure(n * 16)); MM2_TRY(ctx->dpB.ensure(n * 16)); MM2_TRY(ctx->dpT.ensure(n * 4));
+  MM2_TRY(ctx->chain_idx.ensure(n * 4 * 4));
+  MM2_TRY(ctx->read_aoff.ensure(16)); MM2_TRY(ctx->seq_off.ensure(16)); MM2_TRY(ctx->mini_off.ensure(16));
+  MM2_TRY(ctx->hits.ensure(sizeof(ReadHit) + 16)); MM2_TRY(ctx->misc.ensure(64)); MM2_TRY(ctx->mval.ensure(16));
+  const u64 ao[2] = {0, (u64)n}, zo[2] = {0, 0};
+  CUDA_TRY(cudaMemcpyAsync(ctx->anchors.p, a, n * 16, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(ctx->read_aoff.p, ao, 16, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(ctx->seq_off.p, zo, 16, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(ctx->mini_off.p, zo, 16, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(ctx->misc.p, 0, 64, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  MM2_TRY(chain_batch(ctx, ctx->anchors.as<ulonglong2>(), ctx->read_aoff.as<u64>(), ctx->seq_off.as<u64>(), ctx->mini_off.as<u64>(),
+                      ctx->mval.as<u64>(), ctx->misc.as<u32>(), 1, *p, 0, ctx->dpA.as<int4>(), ctx->dpB.as<int4>(), ctx->dpT.as<int>(),
+                      nullptr, ctx->hits.as<ReadHit>(), nullptr));
+  int* d_f = ctx->chain_idx.as<int>();
+  MM2_LAUNCH(ctx, dp_unpack_kernel, grid_for(n), 256, 0, ctx->dpA.as<int4>(), d_f, d_f + n, d_f + 2 * n, (u64)n);
+  std::vector<i32> f(n), v(n), pp(n);
+  CUDA_TRY(cudaMemcpyAsync(f.data(), d_f, n * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(v.data(), d_f + n, n * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(pp.data(), d_f + 2 * n, n * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  out->f = xmalloc<i32>(n); out->v = xmalloc<i32>(n); out->pprev = xmalloc<i64>(n);
+  for (size_t i = 0; i < n; ++i) { out->f[i] = f[i]; out->v[i] = v[i]; out->pprev[i] = pp[i]; }
+  // Backtracking (lchain.rs:93-160).  The helper that walks back from a chain end sets t[i] = 2 and then tests
+  // t[i] == 0 on the same i, so it never takes a second step: every candidate chain is {i0} with score
+  // f[i0] - f[pprev[i0]] (or is empty when that difference is <= 0), visited in order of (f desc, index desc).
+  std::vector<u64> order;
+  for (size_t i = 0; i < n; ++i) if (f[i] > 0) order.push_back(i);
+  std::vector<HostChain> chains;
+  if (!order.empty()) {
+    std::stable_sort(order.begin(), order.end(), [&](u64 x, u64 y) { return f[x] < f[y]; });  // F10: ties keep index order
+    for (size_t q = order.size(); q-- > 0;) {
+      const u64 i0 = order[q];
+      const i32 prev = pp[i0];
+      const i32 s = prev < 0 ? f[i0] : (i32)((u32)f[i0] - (u32)f[prev]);
+      HostChain c;
+      if (s > 0) { c.idx.push_back(i0); c.score = s; } else c.score = 0;
+      if (c.score >= p->min_chain_score && (i32)c.idx.size() >= p->min_cnt) chains.push_back(std::move(c));
+    }
+    if (chains.empty()) {  // lchain.rs:162-173 fallback: last maximum of f, full walk, score v[best]
+      size_t best = 0;
+      for (size_t i = 1; i < n; ++i) if (f[i] >= f[best]) best = i;
+      HostChain c;
+      for (i64 i = (i64)best; i >= 0; i = pp[(size_t)i]) c.idx.push_back((u64)i);
+      std::reverse(c.idx.begin(), c.idx.end());
+      c.score = v[best];
+      chains.push_back(std::move(c));
+    }
+    for (auto& c : chains) chain_starts(a, c);
+    std::stable_sort(chains.begin(), chains.end(), [](const HostChain& x, const HostChain& y) {  // lchain.rs:202-218
+      if (x.score != y.score) return y.score < x.score;
+      if (x.qstart != y.qstart) return x.qstart < y.qstart;
+      return x.tstart < y.tstart;
+    });
+  }
+  size_t tot = 0;
+  for (auto& c : chains) tot += c.idx.size();
+  free(out->chain_offs);
+  out->n_chains = chains.size();
+  out->chain_offs = xmalloc<u64>(chains.size() + 1);
+  out->chain_idx = xmalloc<u64>(tot);
+  out->scores = xmalloc<i32>(chains.size());
+  size_t o = 0;
+  for (size_t i = 0; i < chains.size(); ++i) {
+    out->chain_offs[i] = o;
+    for (u64 x : chains[i].idx) out->chain_idx[o++] = x;
+    out->scores[i] = chains[i].score;
+  }
+  out->chain_offs[chains.size()] = o;
+  return MM2_OK;
+}
+
+extern "C" void mm2_chains_free(mm2_chains_t* c) {
+  if (!c) return;
+  free(c->chain_offs); free(c->chain_idx); free(c->scores); free(c->f); free(c->v); free(c->pprev);
+  memset(c, 0, sizeof *c);
+}
+
+// ---- batched mapping ------------------------------------------------------------------------------------------------------
+extern "C" void mm2_default_map_opts(mm2_map_opts_t* o) {  // main.rs:55-89 defaults
+  o->w = 10; o->k = 15; o->frac_top_repetitive = 2e-4f; o->max_gap = 5000; o->bw = -1; o->bw_long = -1; o->min_cnt = 3;
+  o->min_chain_score = 40; o->mask_level = 0.5f; o->pri_ratio = 0.8f; o->best_n = 5; o->q_occ_max = 10; o->q_occ_frac = 0.01f;
+  o->mid_occ_floor = 10; o->want_stage_dump = 0;
+}
+
+static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, const u64* d_off, const u64* h_off, size_t nreads,
+                           const mm2_map_opts_t* o, mm2_map_result_t* out, bool timer_started) {
+  cudaStream_t st = ctx->stream;
+  if (nreads > 0xFFFFFFF0ull) { mm2_set_error("too many reads in one batch"); return MM2_E_ARG; }
+  if (o->w != idx->w || o->k != idx->k) {
+    // paf.rs:156 re-sketches the query with the index's w/k for dv while everything else uses the CLI's (F8)
+    mm2_set_error("mm2_map_batch: opts w/k (%d/%d) differ from the index (%d/%d): not supported yet", o->w, o->k, idx->w, idx->k);
+    return MM2_E_UNSUPPORTED;
+  }
+  if (o->min_cnt < 2) {
+    mm2_set_error("mm2_map_batch: -n < 2 (single-anchor chains of lchain.rs:127-160) is not supported on the batched path yet");
+    return MM2_E_UNSUPPORTED;
+  }
+  i32 mid_occ = 0;
+  MM2_TRY(mm2_index_calc_mid_occ(idx, o->frac_top_repetitive, &mid_occ));  // main.rs:196-197
+  if (mid_occ < o->mid_occ_floor) mid_occ = o->mid_occ_floor;
+  mm2_chain_params_t p;
+  mm2_default_chain_params(o->k, &p);  // main.rs:199-208
+  p.max_dist_x = o->max_gap; p.max_dist_y = o->max_gap; p.min_cnt = o->min_cnt; p.min_chain_score = o->min_chain_score;
+  if (o->bw >= 0) p.bw = o->bw;
+  if (o->bw_long >= 0) p.bw_long = o->bw_long;
+
+  if (!timer_started) ctx->timer.reset();
+  ctx->timer.mark(st, "sketch");
+  SketchOut so;
+  MM2_TRY(sketch_device(ctx, d_cat, d_off, h_off, nreads, o->w, o->k, 0, 0, 0, &so));  // seeds.rs:7-11: rid 0, no HPC
+  const u64 nm = so.total;
+  ctx->timer.mark(st, "filter");
+  MM2_TRY(ctx->keep.ensure(nm + 16));
+  MM2_TRY(ctx->misc.ensure((nreads + 16) * 4 + 64));
+  u32* d_sum_span = ctx->misc.as<u32>() + 16;
+  unsigned long long* d_cells = ctx->misc.as<unsigned long long>();
+  CUDA_TRY(cudaMemsetAsync(ctx->misc.p, 0, 64, st));
+  MM2_TRY(seeds_filter(ctx, so.key, so.seq_off, (u32)nreads, nm, o->q_occ_max, o->q_occ_frac, ctx->keep.as<u8>(), d_sum_span));
+  ctx->timer.mark(st, "lookup");
+  MM2_TRY(ctx->occ_cnt.ensure((nm + 16) * 4));
+  MM2_TRY(ctx->occ_loc.ensure((nm + 16) * 8));
+  MM2_TRY(ctx->anchor_off_m.ensure((nm + 2) * 8));
+  const IndexView V = idx->view();
+  MM2_TRY(seeds_lookup_count(ctx, V, so.key, ctx->keep.as<u8>(), nm, mid_occ, ctx->occ_cnt.as<u32>(), ctx->occ_loc.as<u64>()));
+  MM2_TRY(scan_u32_to_u64(ctx, ctx->occ_cnt.as<u32>(), ctx->anchor_off_m.as<u64>(), nm));
+  u64 na = 0;
+  CUDA_TRY(cudaMemcpyAsync(&na, ctx->anchor_off_m.as<u64>() + nm, 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  ctx->timer.mark(st, "anchor_fill");
+  MM2_TRY(ctx->anchors.ensure(std::max<u64>(1, na) * 16));
+  MM2_TRY(ctx->read_aoff.ensure((nreads + 2) * 8));
+  MM2_TRY(seeds_fill_and_sort(ctx, V, so.key, so.val, so.seq_off, d_off, (u32)nreads, ctx->occ_cnt.as<u32>(), ctx->occ_loc.as<u64>(),
+                              ctx->anchor_off_m.as<u64>(), ctx->anchors.as<ulonglong2>(), ctx->read_aoff.as<u64>()));
+  ctx->timer.mark(st, "chain");
+  MM2_TRY(ctx->dpA.ensure(std::max<u64>(1, na) * 16));
+  MM2_TRY(ctx->dpB.ensure(std::max<u64>(1, na) * 16));
+  MM2_TRY(ctx->dpT.ensure(std::max<u64>(1, na) * 4));
+  MM2_TRY(ctx->hits.ensure((nreads + 1) * sizeof(ReadHit)));
+  MM2_TRY(chain_batch(ctx, ctx->anchors.as<ulonglong2>(), ctx->read_aoff.as<u64>(), d_off, so.seq_off, so.val, d_sum_span, (u32)nreads,
+                      p, 1, ctx->dpA.as<int4>(), ctx->dpB.as<int4>(), ctx->dpT.as<int>(), nullptr, ctx->hits.as<ReadHit>(), d_cells));
+  ctx->timer.mark(st, "d2h");
+  MM2_TRY(ctx->pin_out.ensure((nreads + 1) * sizeof(ReadHit) + 64));
+  ReadHit* hits = ctx->pin_out.as<ReadHit>();
+  u64* h_cells = (u64*)(hits + nreads);
+  if (nreads) CUDA_TRY(cudaMemcpyAsync(hits, ctx->hits.p, nreads * sizeof(ReadHit), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(h_cells, d_cells, 8, cudaMemcpyDeviceToHost, st));
+  ctx->timer.mark(st, "end");
+  CUDA_TRY(cudaStreamSynchronize(st));
+  ctx->timer.finish();
+
+  // ---- records (paf.rs:130-222) ---------------------------------------------------------------------------------------------
+  memset(out, 0, sizeof *out);
+  out->n_reads = nreads; out->n_bases = nreads ? h_off[nreads] - h_off[0] : 0; out->n_minimizers = nm; out->n_anchors = na;
+  out->recs = xmalloc<mm2_paf_rec_t>(nreads);
+  std::vector<u32> panics;
+  size_t nr = 0;
+  for (size_t r = 0; r < nreads; ++r) {
+    const ReadHit& h = hits[r];
+    if (h.flags & 1u) out->n_rescued += 1;
+    if (h.rid_rev == 0xFFFFFFFFu) continue;  // no anchors: nothing is printed (main.rs:211-213)
+    const u32 rid0 = h.rid_rev & 0x7fffffffu;
+    if (rid0 >= idx->n_seq) { panics.push_back((u32)r); continue; }  // idx.seq[rid0] panics in the reference (F5)
+    const i32 qlen = (i32)(h_off[r + 1] - h_off[r]);
+    const bool rev = (h.rid_rev >> 31) != 0;
+    mm2_paf_rec_t& rec = out->recs[nr++];
+    rec.read_id = (u32)r; rec.rid = rid0; rec.qlen = (u32)qlen; rec.qstart = (u32)h.qs; rec.qend = (u32)h.qe;
+    rec.tlen = idx->lens[rid0]; rec.tstart = (u32)h.ts; rec.tend = (u32)h.te;
+    rec.nm = (u32)std::max((i32)((u32)h.qe - (u32)h.qs), 0); rec.blen = (u32)std::max((i32)((u32)h.te - (u32)h.ts), 0);
+    rec.cm = h.cm; rec.s1 = (u32)std::max(h.score, 0); rec.s2 = 0; rec.rl = 0;
+    rec.strand = rev ? '-' : '+'; rec.mapq = 60; rec.tp = 'P'; rec.flags = (u8)(h.flags & 1u);
+    // dv (paf.rs:156-200).  With the index's w/k equal to the query's, every chain position is one of the read's
+    // minimizer positions, so n_match = cm and n_tot spans the ranks of the chain's two end positions.
+    float dv = 0.0f;
+    if (h.n_mini > 0 && h.st_rank >= 0) {
+      const float avg_k = (float)h.sum_span / (float)h.n_mini;
+      i32 n_match = (i32)h.cm;
+      i32 en = h.en_rank >= 0 ? h.en_rank : h.st_rank;
+      if (h.en_rank < 0) n_match = 1;
+      i32 n_tot = en - h.st_rank + 1;
+      const i32 r_qs = rev ? qlen - h.qe : h.qs, r_qe = rev ? qlen - h.qs : h.qe;
+      const float fk = avg_k;
+      const i32 avg_k_i = fk != fk ? 0 : (fk >= 2147483648.0f ? INT32_MAX : (fk <= -2147483648.0f ? INT32_MIN : (i32)fk));
+      if (r_qs > avg_k_i && h.ts > avg_k_i) n_tot += 1;
+      if ((qlen - r_qe) > avg_k_i && ((i32)rec.tlen - h.te) > avg_k_i) n_tot += 1;
+      volatile float frac = (float)n_match / (float)n_tot;
+      if (frac >= 1.0f) dv = 0.0f;
+      else { volatile float ex = 1.0f / std::max(avg_k, 1.0f); volatile float pw = powf(frac, ex); dv = 1.0f - pw; }
+    }
+    rec.dv = dv;
+  }
+  out->n_recs = nr;
+  out->n_panic = panics.size();
+  out->panic_reads = xmalloc<u32>(panics.size());
+  if (!panics.empty()) memcpy(out->panic_reads, panics.data(), panics.size() * 4);
+  out->n_minimizers_kept = 0;
+  (void)h_cells;
+
+  if (o->want_stage_dump) {
+    out->mini_offs = xmalloc<u64>(nreads + 1); out->minis = xmalloc<mm2_mini_t>(nm); out->mini_keep = xmalloc<u8>(nm);
+    out->anchor_offs = xmalloc<u64>(nreads + 1); out->anchors = xmalloc<mm2_anchor_t>(na);
+    out->f = xmalloc<i32>(na); out->v = xmalloc<i32>(na); out->pprev = xmalloc<i32>(na);
+    out->mini_offs[0] = 0; out->anchor_offs[0] = 0;
+    if (nreads) {
+      CUDA_TRY(cudaMemcpyAsync(out->mini_offs, so.seq_off, (nreads + 1) * 8, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaMemcpyAsync(out->anchor_offs, ctx->read_aoff.p, (nreads + 1) * 8, cudaMemcpyDeviceToHost, st));
+    }
+    if (nm) {
+      CUDA_TRY(cudaMemcpyAsync(out->mini_keep, ctx->keep.p, nm, cudaMemcpyDeviceToHost, st));
+      MM2_TRY(ctx->sort_tmp.ensure(nm * 16));
+      MM2_LAUNCH(ctx, interleave_kernel, grid_for(nm), 256, 0, so.key, so.val, ctx->sort_tmp.as<ulonglong2>(), nm);
+      CUDA_TRY(cudaMemcpyAsync(out->minis, ctx->sort_tmp.p, nm * 16, cudaMemcpyDeviceToHost, st));
+    }
+    if (na) {
+      CUDA_TRY(cudaMemcpyAsync(out->anchors, ctx->anchors.p, na * 16, cudaMemcpyDeviceToHost, st));
+      MM2_TRY(ctx->chain_idx.ensure(na * 12));
+      int* d_f = ctx->chain_idx.as<int>();
+      MM2_LAUNCH(ctx, dp_unpack_kernel, grid_for(na), 256, 0, ctx->dpA.as<int4>(), d_f, d_f + na, d_f + 2 * na, na);
+      CUDA_TRY(cudaMemcpyAsync(out->f, d_f, na * 4, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaMemcpyAsync(out->v, d_f + na, na * 4, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaMemcpyAsync(out->pprev, d_f + 2 * na, na * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (nm) { u64 kept = 0; for (u64 i = 0; i < nm; ++i) kept += out->mini_keep[i]; out->n_minimizers_kept = kept; }
+  }
+  return MM2_OK;
+}
+
+extern "C" int mm2_map_batch_device(mm2_ctx_t* ctx, const mm2_index_t* idx, const void* d_cat, const void* d_offs, const uint64_t* h_offs,
+                                    size_t nreads, const mm2_map_opts_t* opts, mm2_map_result_t* out) {
+  if (!ctx || !idx || !h_offs || !opts || !out || (nreads && (!d_cat || !d_offs))) { mm2_set_error("mm2_map_batch_device: NULL argument"); return MM2_E_ARG; }
+  if (idx->device != ctx->device) { mm2_set_error("index lives on device %d, context on %d", idx->device, ctx->device); return MM2_E_ARG; }
+  if (nreads && h_offs[0] != 0) { mm2_set_error("mm2_map_batch_device: offsets must start at 0"); return MM2_E_ARG; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  return map_device_impl(ctx, idx, (const u8*)d_cat, (const u64*)d_offs, h_offs, nreads, opts, out, false);
+}
+
+extern "C" int mm2_map_batch(mm2_ctx_t* ctx, const mm2_index_t* idx, const uint8_t* cat, const uint64_t* offs, size_t nreads,
+                             const mm2_map_opts_t* opts, mm2_map_result_t* out) {
+  if (!ctx || !idx || !offs || !opts || !out || (nreads && !cat)) { mm2_set_error("mm2_map_batch: NULL argument"); return MM2_E_ARG; }
+  if (idx->device != ctx->device) { mm2_set_error("index lives on device %d, context on %d", idx->device, ctx->device); return MM2_E_ARG; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const u64 base = nreads ? offs[0] : 0, total = nreads ? offs[nreads] - base : 0;
+  std::vector<u64> off0(nreads + 1, 0);
+  for (size_t i = 0; i <= nreads && nreads; ++i) off0[i] = offs[i] - base;
+  ctx->timer.reset();
+  ctx->timer.mark(st, "h2d");
+  MM2_TRY(ctx->seq.ensure(total + 64));
+  MM2_TRY(ctx->seq_off.ensure((nreads + 1) * 8));
+  if (total) CUDA_TRY(cudaMemcpyAsync(ctx->seq.p, cat + base, total, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(ctx->seq_off.p, off0.data(), (nreads + 1) * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return map_device_impl(ctx, idx, ctx->seq.as<u8>(), ctx->seq_off.as<u64>(), off0.data(), nreads, opts, out, true);
+}
+
+extern "C" void mm2_map_result_free(mm2_map_result_t* r) {
+  if (!r) return;
+  free(r->recs); free(r->panic_reads); free(r->mini_offs); free(r->minis); free(r->mini_keep); free(r->anchor_offs); free(r->anchors);
+  free(r->f); free(r->v); free(r->pprev);
+  memset(r, 0, sizeof *r);
+}
+
+// ---- PAF text (paf.rs:224-236) ---------------------------------------------------------------------------------------------
+namespace {
+inline char* put_u32(char* p, u32 v) {
+  char tmp[10]; int n = 0;
+  do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+  while (n) *p++ = tmp[--n];
+  return p;
+}
+inline char* put_str(char* p, const char* s, size_t n) { memcpy(p, s, n); return p + n; }
+// upper bound of one formatted line excluding the two names
+constexpr size_t PAF_FIXED = 200;
+size_t paf_line(const mm2_paf_rec_t& rec, const char* qname, size_t qn, const char* tname, size_t tn, char* p0) {
+  char* p = p0;
+  u32 qs, qe;
+  if (rec.strand == '-') { qs = rec.qlen - rec.qend; qe = rec.qlen - rec.qstart; } else { qs = rec.qstart; qe = rec.qend; }
+  p = put_str(p, qname, qn); *p++ = '\t';
+  p = put_u32(p, rec.qlen); *p++ = '\t'; p = put_u32(p, qs); *p++ = '\t'; p = put_u32(p, qe); *p++ = '\t';
+  *p++ = (char)rec.strand; *p++ = '\t';
+  p = put_str(p, tname, tn); *p++ = '\t';
+  p = put_u32(p, rec.tlen); *p++ = '\t'; p = put_u32(p, rec.tstart); *p++ = '\t'; p = put_u32(p, rec.tend); *p++ = '\t';
+  p = put_u32(p, rec.nm); *p++ = '\t'; p = put_u32(p, rec.blen); *p++ = '\t'; p = put_u32(p, rec.mapq);
+  p = put_str(p, "\ttp:A:", 6); *p++ = (char)rec.tp;
+  p = put_str(p, "\tcm:i:", 6); p = put_u32(p, rec.cm);
+  p = put_str(p, "\ts1:i:", 6); p = put_u32(p, rec.s1);
+  p = put_str(p, "\ts2:i:", 6); p = put_u32(p, rec.s2);
+  p = put_str(p, "\tdv:f:", 6);
+  p += snprintf(p, 48, "%.4f", (double)rec.dv);  // `{:.4}` of an f32: correctly rounded decimal of the exact value
+  p = put_str(p, "\trl:i:", 6); p = put_u32(p, rec.rl);
+  return (size_t)(p - p0);
+}
+}  // namespace
+
+extern "C" int mm2_paf_format(const mm2_paf_rec_t* rec, const char* qname, const char* tname, char* buf, size_t cap) {
+  if (!rec || !buf) { mm2_set_error("mm2_paf_format: NULL argument"); return MM2_E_ARG; }
+  if (!qname) qname = "*";
+  if (!tname) tname = "*";
+  const size_t qn = strlen(qname), tn = strlen(tname);
+  if (cap < qn + tn + PAF_FIXED) { mm2_set_error("mm2_paf_format: buffer too small"); return MM2_E_ARG; }
+  const size_t n = paf_line(*rec, qname, qn, tname, tn, buf);
+  buf[n] = 0;
+  return (int)n;
+}
+
+extern "C" int mm2_paf_format_batch(const mm2_index_t* idx, const mm2_map_result_t* res, const char* const* qnames, char** out, size_t* out_len) {
+  if (!idx || !res || !out || !out_len) { mm2_set_error("mm2_paf_format_batch: NULL argument"); return MM2_E_ARG; }
+  size_t cap = 1;
+  for (size_t i = 0; i < res->n_recs; ++i) {
+    const mm2_paf_rec_t& r = res->recs[i];
+    const char* qn = qnames && qnames[r.read_id] ? qnames[r.read_id] : "*";
+    cap += strlen(qn) + (idx->has_name[r.rid] ? idx->names[r.rid].size() : 1) + PAF_FIXED;
+  }
+  char* buf = (char*)malloc(cap);
+  if (!buf) { mm2_set_error("out of host memory"); return MM2_E_OOM; }
+  char* p = buf;
+  for (size_t i = 0; i < res->n_recs; ++i) {
+    const mm2_paf_rec_t& r = res->recs[i];
+    const char* qn = qnames && qnames[r.read_id] ? qnames[r.read_id] : "*";
+    const bool hn = idx->has_name[r.rid] != 0;
+    const char* tn = hn ? idx->names[r.rid].c_str() : "*";
+    p += paf_line(r, qn, strlen(qn), tn, hn ? idx->names[r.rid].size() : 1, p);
+    *p++ = '\n';
+  }
+  *p = 0;
+  *out = buf; *out_len = (size_t)(p - buf);
+  return MM2_OK;
+}

@@ -1,0 +1,417 @@
+// index.cu — minimizer index construction, persistence and lookup tables on sm_100a.
+// Replaces index.rs:427-475 (build_index_from_fasta), :69-109 (add_minimizers + post_process), :111-154 (stats,
+// calc_mid_occ, get), :156-424 (native + MMI save/load).
+//
+// HBM layout of a built index (all buckets flattened; bucket = low b bits of the minimizer hash):
+//   hkeys[n_keys]    (minier>>b)<<1 | is_single, ascending inside each bucket   (index.rs:92-95)
+//   hvals[n_keys]    y for a singleton, start_in_bucket_p<<32 | n otherwise     (index.rs:95,100)
+//   bkt_koff[2^b+1]  first key of each bucket;  bkt_poff[2^b+1] first p entry of each bucket
+//   p[n_p]           positions of multi-occurrence keys, per bucket in ascending key order, each run ascending
+//   S[...]           4-bit packed sequence (index.rs:11-19), only needed for .mmi / get_ref_subseq
+//   tab[...]         open-addressing table {minier<<1|is_single, val} over all keys for O(1) seed lookup
+// The per-bucket Vec<Minimizer> + stable sort + HashMap of the reference become ONE device radix sort on the
+// re-keyed minimizers (bucket in the high bits, minier>>b below; stable, so equal keys keep ascending y) followed
+// by run-length grouping with exclusive scans.
+#include "mm2_internal.cuh"
+
+#include <algorithm>
+#include <cub/device/device_radix_sort.cuh>
+
+namespace {
+
+__global__ void pack_seq4_kernel(const u8* __restrict__ seq, u64 total, u32* __restrict__ S, u64 nwords) {
+  // index.rs:11-19 mm_seq4_set: base o -> bits 4*(o&7) of word o>>3 ; nt4.rs codes, 4 = other
+  for (u64 wi = blockIdx.x * (u64)blockDim.x + threadIdx.x; wi < nwords; wi += (u64)gridDim.x * blockDim.x) {
+    const u64 o = wi * 8;
+    u32 out = 0;
+    if (o < total) {
+      u32 lo = 0, hi = 0;
+      if (o + 8 <= total) {
+        const uint2 v = *reinterpret_cast<const uint2*>(seq + o);
+        lo = v.x; hi = v.y;
+      } else {
+        for (int j = 0; j < 8 && o + j < total; ++j) {
+          const u32 b = seq[o + j];
+          if (j < 4) lo |= b << (8 * j); else hi |= b << (8 * (j - 4));
+        }
+      }
+      const u32 wd[2] = {lo, hi};
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const u32 u = wd[h] & 0xDFDFDFDFu;
+        const u32 vm = __vcmpeq4(u, 0x41414141u) | __vcmpeq4(u, 0x43434343u) | __vcmpeq4(u, 0x47474747u) | __vcmpeq4(u, 0x54545454u);
+        u32 x = (wd[h] >> 1) & 0x03030303u;
+        x = x ^ ((x >> 1) & 0x01010101u);
+        x = (x & vm) | (0x04040404u & ~vm);
+        // bytes past the end of the genome stay 0 (the reference zero-fills S)
+        u32 nib = (x & 0xFu) | ((x >> 4) & 0xF0u) | ((x >> 8) & 0xF00u) | ((x >> 12) & 0xF000u);
+        if (o + 4 * h + 4 > total) {
+          const int valid = (int)((i64)total - (i64)(o + 4 * h));
+          nib = valid <= 0 ? 0u : (nib & ((1u << (4 * valid)) - 1u));
+        }
+        out |= nib << (16 * h);
+      }
+    }
+    S[wi] = out;
+  }
+}
+
+// bucket-major sort key: (minier & (2^b-1)) << R | minier >> b   (index.rs:70-71 bucket id, :92 key_top)
+__global__ void rekey_kernel(const u64* __restrict__ key_span, u64* __restrict__ ckey, u64 n, int b, int R) {
+  const u64 bmask = (1ULL << b) - 1;
+  for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    const u64 m = key_span[i] >> 8;
+    ckey[i] = ((m & bmask) << R) | (m >> b);
+  }
+}
+
+__global__ void head_flag_kernel(const u64* __restrict__ ckey, u32* __restrict__ flag, u64 n) {
+  for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+    flag[i] = (i == 0 || ckey[i] != ckey[i - 1]) ? 1u : 0u;
+}
+
+__global__ void run_start_kernel(const u32* __restrict__ flag, const u64* __restrict__ excl, u64* __restrict__ run_start, u64 n) {
+  for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i <= n; i += (u64)gridDim.x * blockDim.x) {
+    if (i == n) run_start[excl[n]] = n;
+    else if (flag[i]) run_start[excl[i]] = i;
+  }
+}
+
+__global__ void run_pcount_kernel(const u64* __restrict__ run_start, u32* __restrict__ pc, u64 n_keys) {
+  for (u64 r = blockIdx.x * (u64)blockDim.x + threadIdx.x; r < n_keys; r += (u64)gridDim.x * blockDim.x) {
+    const u64 n = run_start[r + 1] - run_start[r];
+    pc[r] = n > 1 ? (u32)n : 0u;
+  }
+}
+
+__global__ void bucket_off_kernel(const u64* __restrict__ ckey, const u64* __restrict__ run_start, const u64* __restrict__ gp,
+                                  u64 n_keys, int b, int R, u64* __restrict__ bkt_koff, u64* __restrict__ bkt_poff) {
+  const u64 nb = 1ULL << b;
+  for (u64 bi = blockIdx.x * (u64)blockDim.x + threadIdx.x; bi <= nb; bi += (u64)gridDim.x * blockDim.x) {
+    u64 lo = 0, hi = n_keys;  // first run whose bucket >= bi
+    while (lo < hi) {
+      const u64 mid = (lo + hi) >> 1;
+      if ((ckey[run_start[mid]] >> R) < bi) lo = mid + 1; else hi = mid;
+    }
+    bkt_koff[bi] = lo;
+    bkt_poff[bi] = gp[lo];
+  }
+}
+
+__global__ void run_fill_kernel(const u64* __restrict__ ckey, const u64* __restrict__ y, const u64* __restrict__ run_start,
+                                const u64* __restrict__ gp, const u64* __restrict__ bkt_poff, u64 n_keys, int R,
+                                u64* __restrict__ hkeys, u64* __restrict__ hvals, unsigned long long* __restrict__ hist,
+                                u32* __restrict__ big, u32* __restrict__ n_big, u32 big_cap) {
+  const u64 rmask = R >= 64 ? ~0ULL : ((1ULL << R) - 1);
+  for (u64 r = blockIdx.x * (u64)blockDim.x + threadIdx.x; r < n_keys; r += (u64)gridDim.x * blockDim.x) {
+    const u64 first = run_start[r];
+    const u64 n = run_start[r + 1] - first;
+    const u64 ck = ckey[first];
+    const u64 key_top = (ck & rmask) << 1;
+    if (n == 1) {
+      hkeys[r] = key_top | 1;
+      hvals[r] = y[first];
+    } else {
+      hkeys[r] = key_top;
+      hvals[r] = ((gp[r] - bkt_poff[ck >> R]) << 32) | n;
+    }
+    if (n < 65536) atomicAdd(&hist[n], 1ULL);
+    else { const u32 s = atomicAdd(n_big, 1u); if (s < big_cap) big[s] = (u32)std::min<u64>(n, 0xFFFFFFFFull); }
+  }
+}
+
+__global__ void p_fill_kernel(const u64* __restrict__ y, const u32* __restrict__ flag, const u64* __restrict__ excl,
+                              const u64* __restrict__ run_start, const u64* __restrict__ gp, u64 n, u64* __restrict__ p,
+                              u32* __restrict__ unsorted) {
+  for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    const u64 r = excl[i] + flag[i] - 1;
+    const u64 first = run_start[r];
+    const u64 cnt = run_start[r + 1] - first;
+    if (cnt > 1) {
+      p[gp[r] + (i - first)] = y[i];
+      if (i > first && y[i] < y[i - 1]) *unsorted = 1u;
+    }
+  }
+}
+
+// rare repair path: positions inside a run were not ascending (only possible when the sketch emitted out of
+// position order); index.rs:98 sorts each run, so do the same with one thread per run
+__global__ void p_sort_runs_kernel(const u64* __restrict__ run_start, const u64* __restrict__ gp, u64 n_keys, u64* __restrict__ p) {
+  for (u64 r = blockIdx.x * (u64)blockDim.x + threadIdx.x; r < n_keys; r += (u64)gridDim.x * blockDim.x) {
+    const u64 n = run_start[r + 1] - run_start[r];
+    if (n < 2) continue;
+    u64* a = p + gp[r];
+    for (u64 i = 1; i < n; ++i) {
+      const u64 v = a[i];
+      u64 j = i;
+      while (j > 0 && a[j - 1] > v) { a[j] = a[j - 1]; --j; }
+      a[j] = v;
+    }
+  }
+}
+
+// ---- open-addressing lookup table over all keys ---------------------------------------------------------------------
+__device__ __forceinline__ u64 tab_hash(u64 minier) {
+  u64 x = minier * 0x9E3779B97F4A7C15ULL;
+  return x ^ (x >> 29);
+}
+__global__ void tab_build_kernel(const u64* __restrict__ hkeys, const u64* __restrict__ hvals, const u64* __restrict__ bkt_koff,
+                                 u64 n_keys, int b, ulonglong2* __restrict__ tab, u64 tab_mask) {
+  const u64 nb = 1ULL << b;
+  for (u64 r = blockIdx.x * (u64)blockDim.x + threadIdx.x; r < n_keys; r += (u64)gridDim.x * blockDim.x) {
+    // bucket of key r: last bucket whose koff <= r
+    u64 lo = 0, hi = nb;
+    while (lo < hi) {
+      const u64 mid = (lo + hi + 1) >> 1;
+      if (bkt_koff[mid] <= r) lo = mid; else hi = mid - 1;
+    }
+    const u64 hk = hkeys[r];
+    const u64 minier = ((hk >> 1) << b) | lo;
+    const u64 tag = (minier << 1) | (hk & 1);
+    u64 slot = tab_hash(minier) & tab_mask;
+    for (;;) {
+      const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&tab[slot].x), ~0ULL, (unsigned long long)tag);
+      if (old == ~0ULL) { tab[slot].y = hvals[r]; break; }
+      slot = (slot + 1) & tab_mask;
+    }
+  }
+}
+
+__global__ void index_get_kernel(IndexView V, u64 minier, u64* out3) {
+  // out3 = {kind, val_or_count, p offset}
+  const u64 bmask = (1ULL << V.b) - 1;
+  const u64 bi = minier & bmask;
+  const u64 want = (minier >> V.b);
+  u64 lo = V.bkt_koff[bi], hi = V.bkt_koff[bi + 1];
+  out3[0] = 0; out3[1] = 0; out3[2] = 0;
+  while (lo < hi) {
+    const u64 mid = (lo + hi) >> 1;
+    const u64 kk = V.hkeys[mid] >> 1;
+    if (kk < want) lo = mid + 1; else if (kk > want) hi = mid;
+    else {
+      const u64 v = V.hvals[mid];
+      if (V.hkeys[mid] & 1) { out3[0] = 1; out3[1] = v; }
+      else { out3[0] = 2; out3[1] = v & 0xffffffffULL; out3[2] = V.bkt_poff[bi] + (v >> 32); }
+      return;
+    }
+  }
+}
+
+inline size_t kroundup64(size_t x) {  // index.rs:10
+  x -= 1; x |= x >> 1; x |= x >> 2; x |= x >> 4; x |= x >> 8; x |= x >> 16; x |= x >> 32;
+  return x + 1;
+}
+
+inline int grid_for(u64 n, int block = 256) { return (int)std::min<u64>((n + block - 1) / block, 148ull * 32); }
+
+}  // namespace
+
+IndexView mm2_index::view() const {
+  IndexView v;
+  v.w = w; v.k = k; v.b = b; v.flag = flag; v.n_seq = n_seq; v.n_keys = n_keys; v.n_p = n_p;
+  v.hkeys = hkeys.as<u64>(); v.hvals = hvals.as<u64>(); v.bkt_koff = bkt_koff.as<u64>(); v.bkt_poff = bkt_poff.as<u64>();
+  v.p = p.as<u64>(); v.seq_len = seq_len.as<u32>();
+  v.tab = tab.as<ulonglong2>(); v.tab_mask = tab_mask;
+  return v;
+}
+
+// Build the O(1) lookup table from the flat key arrays (also used after loading an index from disk).
+int index_build_table(mm2_ctx* ctx, mm2_index* idx) {
+  u64 slots = 1024;
+  while (slots < idx->n_keys * 2) slots <<= 1;
+  MM2_TRY(idx->tab.ensure(slots * 16));
+  idx->tab_mask = slots - 1;
+  CUDA_TRY(cudaMemsetAsync(idx->tab.p, 0xFF, slots * 16, ctx->stream));
+  if (idx->n_keys) {
+    MM2_LAUNCH(ctx, tab_build_kernel, grid_for(idx->n_keys), 256, 0, idx->hkeys.as<u64>(), idx->hvals.as<u64>(),
+               idx->bkt_koff.as<u64>(), idx->n_keys, idx->b, idx->tab.as<ulonglong2>(), idx->tab_mask);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return MM2_OK;
+}
+
+// device-side part of the build once the minimizers (ctx->mkey/mval, n of them) are resident
+static int index_finish_from_minimizers(mm2_ctx* ctx, mm2_index* idx, u64 n) {
+  cudaStream_t st = ctx->stream;
+  const int b = idx->b, k = idx->k;
+  const int R = std::max(2 * k - b, 0);
+  const int end_bit = std::max(1, std::min(64, b + R));
+  const u64 nb = 1ULL << b;
+  idx->n_minimizers = n;
+  MM2_TRY(idx->bkt_koff.ensure((nb + 1) * 8));
+  MM2_TRY(idx->bkt_poff.ensure((nb + 1) * 8));
+  idx->occ_hist.assign(65536, 0);
+  idx->occ_big.clear();
+  if (n == 0) {
+    CUDA_TRY(cudaMemsetAsync(idx->bkt_koff.p, 0, (nb + 1) * 8, st));
+    CUDA_TRY(cudaMemsetAsync(idx->bkt_poff.p, 0, (nb + 1) * 8, st));
+    idx->n_keys = 0; idx->n_p = 0;
+    return index_build_table(ctx, idx);
+  }
+  // ---- radix sort of (ckey, y) --------------------------------------------------------------------------------------
+  MM2_TRY(ctx->sort_keys2.ensure(n * 8));
+  MM2_TRY(ctx->sort_vals2.ensure(n * 8));
+  MM2_TRY(ctx->sort_tmp2.ensure(n * 8));
+  u64* ckey_in = ctx->sort_tmp2.as<u64>();
+  MM2_LAUNCH(ctx, rekey_kernel, grid_for(n), 256, 0, ctx->mkey.as<u64>(), ckey_in, n, b, R);
+  size_t tmp_bytes = 0;
+  CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ckey_in, ctx->sort_keys2.as<u64>(), ctx->mval.as<u64>(),
+                                           ctx->sort_vals2.as<u64>(), n, 0, end_bit, st));
+  MM2_TRY(ctx->sort_tmp.ensure(tmp_bytes));
+  CUDA_TRY(cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp_bytes, ckey_in, ctx->sort_keys2.as<u64>(), ctx->mval.as<u64>(),
+                                           ctx->sort_vals2.as<u64>(), n, 0, end_bit, st));
+  ctx->launches += 8;  // CUB's histogram + onesweep passes (library kernels, not ours)
+  ctx->timer.mark(st, "bucket_build");
+  const u64* ckey = ctx->sort_keys2.as<u64>();
+  const u64* y = ctx->sort_vals2.as<u64>();
+  // ---- run-length grouping --------------------------------------------------------------------------------------------
+  MM2_TRY(ctx->runidx.ensure(n * 4 + (n + 1) * 8 + 64));
+  u32* flag = ctx->runidx.as<u32>();
+  u64* excl = (u64*)((u8*)ctx->runidx.p + ((n * 4 + 15) / 16) * 16);
+  MM2_LAUNCH(ctx, head_flag_kernel, grid_for(n), 256, 0, ckey, flag, n);
+  MM2_TRY(scan_u32_to_u64(ctx, flag, excl, n));
+  u64 n_keys = 0;
+  CUDA_TRY(cudaMemcpyAsync(&n_keys, excl + n, 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  idx->n_keys = n_keys;
+  MM2_TRY(ctx->run_start.ensure((n_keys + 1) * 8));
+  MM2_TRY(ctx->run_gp.ensure(((n_keys * 4 + 15) / 16) * 16 + (n_keys + 1) * 8 + 64));
+  u64* run_start = ctx->run_start.as<u64>();
+  u32* pc = ctx->run_gp.as<u32>();
+  u64* gp = (u64*)((u8*)ctx->run_gp.p + ((n_keys * 4 + 15) / 16) * 16);
+  MM2_LAUNCH(ctx, run_start_kernel, grid_for(n + 1), 256, 0, flag, excl, run_start, n);
+  MM2_LAUNCH(ctx, run_pcount_kernel, grid_for(n_keys), 256, 0, run_start, pc, n_keys);
+  MM2_TRY(scan_u32_to_u64(ctx, pc, gp, n_keys));
+  u64 n_p = 0;
+  CUDA_TRY(cudaMemcpyAsync(&n_p, gp + n_keys, 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  idx->n_p = n_p;
+  MM2_TRY(idx->hkeys.ensure(std::max<u64>(1, n_keys) * 8));
+  MM2_TRY(idx->hvals.ensure(std::max<u64>(1, n_keys) * 8));
+  MM2_TRY(idx->p.ensure(std::max<u64>(1, n_p) * 8));
+  MM2_LAUNCH(ctx, bucket_off_kernel, grid_for(nb + 1), 256, 0, ckey, run_start, gp, n_keys, b, R, idx->bkt_koff.as<u64>(),
+             idx->bkt_poff.as<u64>());
+  // histogram of occurrence counts (calc_mid_occ / stats)
+  const u32 big_cap = (u32)(n / 65536 + 16);
+  MM2_TRY(ctx->misc.ensure(65536 * 8 + 16 + (size_t)big_cap * 4));
+  unsigned long long* d_hist = ctx->misc.as<unsigned long long>();
+  u32* d_nbig = (u32*)(d_hist + 65536);
+  u32* d_unsorted = d_nbig + 1;
+  u32* d_big = d_nbig + 4;
+  CUDA_TRY(cudaMemsetAsync(ctx->misc.p, 0, 65536 * 8 + 16, st));
+  MM2_LAUNCH(ctx, run_fill_kernel, grid_for(n_keys), 256, 0, ckey, y, run_start, gp, idx->bkt_poff.as<u64>(), n_keys, R,
+             idx->hkeys.as<u64>(), idx->hvals.as<u64>(), d_hist, d_big, d_nbig, big_cap);
+  MM2_LAUNCH(ctx, p_fill_kernel, grid_for(n), 256, 0, y, flag, excl, run_start, gp, n, idx->p.as<u64>(), d_unsorted);
+  CUDA_TRY(cudaGetLastError());
+  u32 h_small[2] = {0, 0};
+  CUDA_TRY(cudaMemcpyAsync(idx->occ_hist.data(), d_hist, 65536 * 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(h_small, d_nbig, 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (h_small[0]) {
+    idx->occ_big.resize(std::min(h_small[0], big_cap));
+    CUDA_TRY(cudaMemcpyAsync(idx->occ_big.data(), d_big, idx->occ_big.size() * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    std::sort(idx->occ_big.begin(), idx->occ_big.end());
+  }
+  if (h_small[1]) {
+    MM2_LAUNCH(ctx, p_sort_runs_kernel, grid_for(n_keys), 256, 0, run_start, gp, n_keys, idx->p.as<u64>());
+    CUDA_TRY(cudaGetLastError());
+  }
+  ctx->timer.mark(st, "lookup_table");
+  return index_build_table(ctx, idx);
+}
+
+int index_build_device(mm2_ctx* ctx, const u8* h_cat, const u64* h_off, const char* const* names, size_t nseq, int w, int k,
+                       int b, int flag, mm2_index** out) {
+  if (!(w > 0 && w < 256) || !(k > 0 && k <= 28)) { mm2_set_error("index: need 0<w<256 and 0<k<=28 (sketch.rs:31-32)"); return MM2_E_ARG; }
+  if (b < 0 || b > 28) { mm2_set_error("index: bucket bits out of range"); return MM2_E_ARG; }
+  if (nseq > 0x7fffffffull) { mm2_set_error("index: too many sequences"); return MM2_E_ARG; }
+  const u64 total = nseq ? h_off[nseq] - h_off[0] : 0;
+  for (size_t i = 0; i < nseq; ++i)
+    if (h_off[i + 1] - h_off[i] >= (1ull << 31)) { mm2_set_error("index: sequence %zu is >= 2^31 bp (sketch.rs:72 packs pos<<1 in 32 bits)", i); return MM2_E_ARG; }
+  cudaStream_t st = ctx->stream;
+  mm2_index* idx = new mm2_index();
+  idx->device = ctx->device; idx->w = w; idx->k = k; idx->b = b; idx->flag = flag; idx->n_seq = (u32)nseq;
+  u64 sum = 0;
+  for (size_t i = 0; i < nseq; ++i) {
+    const bool hn = names && names[i];
+    idx->has_name.push_back(1);  // build_index_from_fasta always stores Some(name) (index.rs:435)
+    idx->names.push_back(hn ? std::string(names[i]) : std::string());
+    idx->lens.push_back((u32)(h_off[i + 1] - h_off[i]));
+    idx->seq_offset.push_back(sum);
+    idx->is_alt.push_back(0);
+    sum += h_off[i + 1] - h_off[i];
+  }
+  idx->total_len = total;
+  auto fail = [&](int rc) { mm2_index_free(idx); return rc; };
+#define IB_TRY(x) do { int r_ = (x); if (r_ != MM2_OK) return fail(r_); } while (0)
+#define IB_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { mm2_set_error("%s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); return fail(MM2_E_CUDA); } } while (0)
+  ctx->timer.reset();
+  ctx->timer.mark(st, "h2d");
+  // offsets rebased to 0 so that they double as IndexSeq.offset
+  std::vector<u64> off0(nseq + 1, 0);
+  for (size_t i = 0; i <= nseq && nseq; ++i) off0[i] = h_off[i] - h_off[0];
+  IB_TRY(ctx->seq.ensure(total + 64));
+  IB_TRY(ctx->seq_off.ensure((nseq + 1) * 8));
+  if (total) IB_CUDA(cudaMemcpyAsync(ctx->seq.p, h_cat + (nseq ? h_off[0] : 0), total, cudaMemcpyHostToDevice, st));
+  IB_CUDA(cudaMemcpyAsync(ctx->seq_off.p, off0.data(), (nseq + 1) * 8, cudaMemcpyHostToDevice, st));
+  IB_CUDA(cudaStreamSynchronize(st));  // off0 is a stack vector
+  IB_TRY(idx->seq_len.ensure(std::max<size_t>(1, nseq) * 4));
+  if (nseq) IB_CUDA(cudaMemcpyAsync(idx->seq_len.p, idx->lens.data(), nseq * 4, cudaMemcpyHostToDevice, st));
+  ctx->timer.mark(st, "pack");
+  const u64 words_used = (total + 7) / 8;
+  idx->S_words_alloc = total ? kroundup64((size_t)words_used) : 0;
+  IB_TRY(idx->S.ensure(std::max<u64>(1, idx->S_words_alloc) * 4));
+  if (idx->S_words_alloc) {
+    MM2_LAUNCH(ctx, pack_seq4_kernel, grid_for(idx->S_words_alloc), 256, 0, ctx->seq.as<u8>(), total, idx->S.as<u32>(), idx->S_words_alloc);
+    IB_CUDA(cudaGetLastError());
+  }
+  ctx->timer.mark(st, "sketch");
+  SketchOut so;
+  IB_TRY(sketch_device(ctx, ctx->seq.as<u8>(), ctx->seq_off.as<u64>(), off0.data(), nseq, w, k, 0, 1, flag & 1, &so));
+  ctx->timer.mark(st, "sort");
+  IB_TRY(index_finish_from_minimizers(ctx, idx, so.total));
+  ctx->timer.mark(st, "end");
+  IB_CUDA(cudaStreamSynchronize(st));
+  ctx->timer.finish();
+  // h2d, pack, sketch, sort, bucket_build, lookup_table
+  float tot = 0;
+  for (size_t i = 0; i < ctx->timer.ms.size(); ++i) {
+    const std::string& nm = ctx->timer.names[i];
+    const float t = ctx->timer.ms[i];
+    if (nm == "sketch") idx->build_ms[0] = t;
+    else if (nm == "sort") idx->build_ms[1] = t;
+    else if (nm == "bucket_build" || nm == "lookup_table") idx->build_ms[2] += t;
+    else if (nm == "pack") idx->build_ms[3] = t;
+    tot += t;
+  }
+  idx->build_ms[4] = tot;
+#undef IB_TRY
+#undef IB_CUDA
+  *out = idx;
+  return MM2_OK;
+}
+
+// ---- public index entry points that need kernels ------------------------------------------------------------------
+extern "C" int mm2_index_get(const mm2_index_t* idx, uint64_t minier, uint64_t** occ, size_t* n, int* kind) {
+  if (!idx || !occ || !n || !kind) { mm2_set_error("mm2_index_get: NULL argument"); return MM2_E_ARG; }
+  CUDA_TRY(cudaSetDevice(idx->device));
+  u64* d3 = nullptr;
+  CUDA_TRY(cudaMalloc(&d3, 24));
+  index_get_kernel<<<1, 1>>>(idx->view(), minier, d3);
+  u64 h3[3] = {0, 0, 0};
+  cudaError_t e = cudaMemcpy(h3, d3, 24, cudaMemcpyDeviceToHost);
+  cudaFree(d3);
+  CUDA_TRY(e);
+  *kind = (int)h3[0];
+  *n = 0; *occ = nullptr;
+  if (h3[0] == 1) {
+    *occ = (u64*)malloc(8); if (!*occ) return MM2_E_OOM;
+    (*occ)[0] = h3[1]; *n = 1;
+  } else if (h3[0] == 2) {
+    *occ = (u64*)malloc(h3[1] * 8); if (!*occ) return MM2_E_OOM;
+    CUDA_TRY(cudaMemcpy(*occ, idx->p.as<u64>() + h3[2], h3[1] * 8, cudaMemcpyDeviceToHost));
+    *n = (size_t)h3[1];
+  }
+  return MM2_OK;
+}

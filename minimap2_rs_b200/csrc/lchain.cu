@@ -1,0 +1,300 @@
+// lchain.cu — minimap2-style chaining DP on sm_100a, one warp per read.
+// Replaces lchain.rs:59-92 (forward DP with max_dist/bw/max_chain_iter/max_chain_skip), :162-173 (the fallback chain,
+// which under `-n >= 2` is the only chain chain_dp_all ever returns — SURVEY.md F3), :316-330 (rescue_long_join's
+// rerun with bw_long) and the per-chain reductions of paf.rs:133-147.
+//
+// The j-loop of lchain.rs:80-88 is executed 32 predecessors at a time, highest j in lane 0:
+//  * every lane evaluates comput_sc (lchain.rs:17-34) for its j;
+//  * all lanes with a score publish their mark t[pprev[j]] = i first (marks are only ever compared with the current i
+//    and pprev[j] < j, so marks by lanes past the break point are unobservable), then read t[j];
+//  * "sc > max_f" in sequence order is "sc > exclusive prefix max" (warp max-scan);
+//  * n_skip evolves by x -> max(x-1,0) on a new maximum and x -> x+1 on a marked non-maximum; both are maps
+//    x -> max(x+a, b), closed under composition, so a 5-step warp scan gives every lane its n_skip; the first lane
+//    whose n_skip exceeds max_chain_skip is the `break`.
+// tests/models.py:chain_fwd_model is the CPU model of this restatement (checked against the oracle).
+// The gap penalty (lchain.rs:28-32) is computed with explicitly rounded f32 ops (no FMA contraction) and a host-built
+// table of 0.5*log2(dd+1) (glibc logf, as Rust's f32::ln), so scores are bit-identical to the CPU.
+#include "mm2_internal.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+#include "stages.cuh"
+
+namespace {
+
+struct ChainArgs {
+  const ulonglong2* anchors;
+  const u64* read_aoff;
+  const u64* read_off;   // read offsets in bases (qlen)
+  const u64* mini_off;   // unfiltered minimizer offsets
+  const u64* mval;       // rid_pos_strand of the minimizers
+  const u32* sum_span;
+  u32 nreads;
+  mm2_chain_params_t p;
+  int do_rescue;
+  const float* half_log;  // 0.5 * mg_log2(dd + 1), dd = 0 .. max(bw, bw_long)
+  int4* A; int4* B; int* T; int* chain;
+  ReadHit* hits;
+  unsigned long long* cells;
+};
+
+constexpr int CH_WARPS = 4;
+constexpr int NEG_INF = -(1 << 28);
+
+__device__ __forceinline__ int wadd(int a, int b) { return (int)((u32)a + (u32)b); }
+__device__ __forceinline__ int wsub(int a, int b) { return (int)((u32)a - (u32)b); }
+
+__global__ void __launch_bounds__(CH_WARPS * 32) chain_kernel(ChainArgs G) {
+  const u32 r = blockIdx.x * CH_WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= G.nreads) return;
+  const u64 a0 = G.read_aoff[r];
+  const i64 n64 = (i64)(G.read_aoff[r + 1] - a0);
+  const i32 qlen = (i32)(G.read_off[r + 1] - G.read_off[r]);
+  const u64 m0 = G.mini_off[r], m1 = G.mini_off[r + 1];
+  ReadHit hit;
+  hit.rid_rev = 0xFFFFFFFFu; hit.qs = hit.qe = hit.ts = hit.te = 0; hit.cm = 0; hit.score = 0;
+  hit.n_anchors = (u32)n64; hit.n_mini = (u32)(m1 - m0); hit.sum_span = G.sum_span[r];
+  hit.st_rank = hit.en_rank = -1; hit.flags = 0; hit.best = -1; hit.pad0 = hit.pad1 = 0;
+  if (n64 <= 0 || n64 > 0x7fffffff) {
+    if (lane == 0) G.hits[r] = hit;
+    return;
+  }
+  const int n = (int)n64;
+  const ulonglong2* an = G.anchors + a0;
+  int4* A = G.A + a0;
+  int4* B = G.B + a0;
+  int* T = G.T + a0;
+  const mm2_chain_params_t& p = G.p;
+  unsigned long long cells = 0;
+  int best = 0;
+  int4 bestA = make_int4(0, -1, 0, 0), bestB = make_int4(0, 0, 0, 0);
+
+  for (int pass = 0; pass < 2; ++pass) {
+    const int bw = pass == 0 ? p.bw : p.bw_long;                 // lchain.rs:327-328
+    const int mdx = max(p.max_dist_x, bw), mdy = max(p.max_dist_y, bw);  // lchain.rs:63-66
+    const int mark_base = pass * n;                              // marks of the two passes never collide
+    if (pass == 0) for (int j = lane; j < n; j += 32) T[j] = -1;
+    __syncwarp();
+    int st = 0;
+    for (int i = 0; i < n; ++i) {
+      const ulonglong2 ai = an[i];
+      const u32 hi_i = (u32)(ai.x >> 32);
+      const int ri = (int)(u32)ai.x, qi = (int)(u32)ai.y, spi = (int)((ai.y >> 32) & 0xff);
+      // lchain.rs:75: st only ever advances
+      for (;;) {
+        const int idx = st + lane;
+        bool adv = false;
+        if (idx < i) {
+          const u64 xj = an[idx].x;
+          adv = ((u32)(xj >> 32) != hi_i) || (ri > wadd((int)(u32)xj, mdx));
+        }
+        const u32 m = __ballot_sync(0xFFFFFFFFu, adv);
+        const int lead = (m == 0xFFFFFFFFu) ? 32 : (__ffs(~m) - 1);
+        st += lead;
+        if (lead < 32) break;
+      }
+      const int start_j = (wsub(i, p.max_chain_iter) > st) ? wsub(i, p.max_chain_iter) : st;  // lchain.rs:78
+      int max_f = spi, max_j = -1, n_skip = 0;
+      int mv = 0, mcnt = 0, mqs = 0, mts = 0, mfirst = 0;  // v/cnt/qs_min/ts_min/first of max_j
+      const int mark = mark_base + i;
+      for (int jb = i - 1; jb >= start_j; jb -= 32) {
+        const int j = jb - lane;
+        const bool act = j >= start_j;
+        bool valid = false;
+        int sc = NEG_INF;
+        int4 aj = make_int4(0, -1, 0, 0), bj = make_int4(0, 0, 0, 0);
+        if (act) {
+          const ulonglong2 v = an[j];
+          aj = A[j]; bj = B[j];
+          if ((u32)(v.x >> 32) == hi_i) {                         // lchain.rs:81
+            const int dq = wsub(qi, (int)(u32)v.y);               // lchain.rs:18
+            if (!(dq <= 0 || dq > mdx)) {
+              const int dr = wsub(ri, (int)(u32)v.x);
+              if (!(dr == 0 || dq > mdy)) {
+                int dd = wsub(dr, dq); if (dd < 0) dd = wsub(0, dd);   // i32::abs wraps on MIN in release
+                if (!(dd > bw || dd < 0)) {
+                  const int dg = min(dr, dq);
+                  const int q_span = (int)((v.y >> 32) & 0xff);
+                  int s0 = min(q_span, dg);
+                  if (dd != 0 || dg > q_span) {
+                    const float lin = __fadd_rn(__fmul_rn(p.chn_pen_gap, (float)dd), __fmul_rn(p.chn_pen_skip, (float)dg));
+                    s0 = wsub(s0, __float2int_rz(__fadd_rn(lin, G.half_log[dd])));
+                  }
+                  sc = wadd(s0, aj.x);
+                  valid = true;
+                }
+              }
+            }
+          }
+        }
+        if (valid && aj.y >= 0) T[aj.y] = mark;                   // lchain.rs:86 (all lanes first, see header)
+        __syncwarp();
+        const int tj = valid ? T[j] : -1;
+        // exclusive prefix max of the scores, seeded with the running max_f
+        int incl = valid ? sc : NEG_INF * 4;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+          if (lane >= d) incl = max(incl, t);
+        }
+        int excl = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+        if (lane == 0) excl = NEG_INF * 4;
+        excl = max(excl, max_f);
+        const bool rec = valid && sc > excl;                      // lchain.rs:84
+        const bool marked = valid && !rec && tj == mark;          // lchain.rs:85
+        // n_skip as a composition of x -> max(x + a, b)
+        int fa = rec ? -1 : (marked ? 1 : 0), fb = rec ? 0 : NEG_INF;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int ta = __shfl_up_sync(0xFFFFFFFFu, fa, d), tb = __shfl_up_sync(0xFFFFFFFFu, fb, d);
+          if (lane >= d) { fb = max(tb + fa, fb); fa = ta + fa; }
+        }
+        const int x_after = max(n_skip + fa, fb);
+        const u32 bmask = __ballot_sync(0xFFFFFFFFu, marked && x_after > p.max_chain_skip);
+        const int first_brk = bmask ? (__ffs(bmask) - 1) : 32;
+        const u32 amask = __ballot_sync(0xFFFFFFFFu, act);
+        u32 rmask = __ballot_sync(0xFFFFFFFFu, rec);
+        if (first_brk < 32) rmask &= (1u << first_brk) - 1u;
+        if (rmask) {
+          const int last = 31 - __clz(rmask);
+          max_f = __shfl_sync(0xFFFFFFFFu, sc, last);
+          max_j = jb - last;
+          mv = __shfl_sync(0xFFFFFFFFu, aj.z, last);
+          mcnt = __shfl_sync(0xFFFFFFFFu, aj.w, last);
+          mqs = __shfl_sync(0xFFFFFFFFu, bj.x, last);
+          mts = __shfl_sync(0xFFFFFFFFu, bj.y, last);
+          mfirst = __shfl_sync(0xFFFFFFFFu, bj.z, last);
+        }
+        if (first_brk < 32) { cells += (unsigned)(first_brk + 1); break; }
+        cells += (unsigned)__popc(amask);
+        n_skip = __shfl_sync(0xFFFFFFFFu, x_after, 31);
+      }
+      // lchain.rs:89-90 (+ the chain reductions of paf.rs:136-147 carried along the best-predecessor links)
+      if (lane == 0) {
+        const int own_qs = wsub(qi, spi - 1), own_ts = wsub(ri, spi - 1);
+        int4 oa, ob;
+        oa.x = max_f; oa.y = max_j;
+        oa.z = (max_j >= 0 && mv > max_f) ? mv : max_f;
+        oa.w = max_j >= 0 ? mcnt + 1 : 1;
+        ob.x = max_j >= 0 ? min(mqs, own_qs) : own_qs;
+        ob.y = max_j >= 0 ? min(mts, own_ts) : own_ts;
+        ob.z = max_j >= 0 ? mfirst : i;
+        ob.w = 0;
+        A[i] = oa; B[i] = ob;
+      }
+      __syncwarp();
+    }
+    // lchain.rs:163: Iterator::max_by_key returns the LAST maximum of f
+    int bf = NEG_INF * 4, bi = -1;
+    for (int j = lane; j < n; j += 32) {
+      const int f = A[j].x;
+      if (f >= bf) { bf = f; bi = j; }   // j ascending per lane
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const int of = __shfl_xor_sync(0xFFFFFFFFu, bf, d), oi = __shfl_xor_sync(0xFFFFFFFFu, bi, d);
+      if (of > bf || (of == bf && oi > bi)) { bf = of; bi = oi; }
+    }
+    best = bi;
+    bestA = A[best]; bestB = B[best];
+    if (pass == 1 || !G.do_rescue) break;
+    // lchain.rs:321-330 rescue_long_join on the single (fallback) chain
+    const ulonglong2 ab = an[best];
+    const int qe = wadd((int)(u32)ab.y, 1);
+    const int qs = max(bestB.x, 0);
+    const int best_cov = max(wsub(qe, qs), 0);
+    const int uncovered = max(wsub(qlen, best_cov), 0);
+    const bool rescue = uncovered > p.rmq_rescue_size ||
+                        (float)best_cov < __fmul_rn((float)qlen, __fsub_rn(1.0f, p.rmq_rescue_ratio));
+    if (!rescue) break;
+    hit.flags |= 1u;
+    __syncwarp();
+  }
+
+  // ---- the reported chain: fallback chain ending at `best` (lchain.rs:164-172), score v[best] -----------------------------
+  const ulonglong2 ab = an[best];
+  const ulonglong2 af = an[bestB.z];
+  hit.rid_rev = (u32)(af.x >> 32);  // paf.rs:132,148 use the chain's FIRST anchor
+  hit.qs = max(bestB.x, 0); hit.qe = wadd((int)(u32)ab.y, 1);
+  hit.ts = max(bestB.y, 0); hit.te = wadd((int)(u32)ab.x, 1);
+  hit.cm = (u32)bestA.w; hit.score = bestA.z; hit.best = best;
+  if (G.chain) {  // stage dump: walk the links (serial; parity harness only)
+    if (lane == 0) {
+      int* ch = G.chain + a0;
+      int i = best, c = 0;
+      while (i >= 0) { ch[c++] = i; i = A[i].y; }
+    }
+  }
+  // ---- dv inputs (paf.rs:174-191): ranks of the chain's first/last forward query positions among the read's minimizers ----
+  {
+    const bool rev = (af.x >> 63) != 0;
+    auto qpos_fwd = [&](const ulonglong2& a) -> int {
+      const int qp = (int)(u32)a.y, qsp = (int)((a.y >> 32) & 0xff);
+      return rev ? wsub(wsub(qlen, 1), wsub(wadd(qp, 1), qsp)) : qp;
+    };
+    // '+': chain order; '-': reversed chain order (paf.rs:170-173)
+    const int first_q = rev ? qpos_fwd(ab) : qpos_fwd(af);
+    const int last_q = rev ? qpos_fwd(af) : qpos_fwd(ab);
+    const int want = lane == 0 ? first_q : last_q;
+    if (lane < 2) {
+      // first index whose position == want (positions ascend for odd k, see sketch.cu)
+      u64 lo = m0, hi = m1;
+      while (lo < hi) {
+        const u64 mid = (lo + hi) >> 1;
+        const int pos = (int)(u32)((G.mval[mid] >> 1) & 0xffffffffULL);
+        if (pos < want) lo = mid + 1; else hi = mid;
+      }
+      int rank = -1;
+      if (lo < m1 && (int)(u32)((G.mval[lo] >> 1) & 0xffffffffULL) == want) rank = (int)(lo - m0);
+      if (lane == 0) hit.st_rank = rank; else hit.en_rank = rank;
+    }
+    hit.en_rank = __shfl_sync(0xFFFFFFFFu, hit.en_rank, 1);
+  }
+  if (lane == 0) {  // `cells` is warp-uniform
+    G.hits[r] = hit;
+    if (G.cells) atomicAdd(G.cells, cells);
+  }
+}
+
+}  // namespace
+
+// host-built table of 0.5 * mg_log2(dd + 1) (lchain.rs:15,30-31): glibc logf, division by f32 LN_2, exact halving
+static std::vector<float> build_half_log(int n) {
+  std::vector<float> t((size_t)n);
+  for (int dd = 0; dd < n; ++dd) {
+    float log_pen = 0.0f;
+    if (dd >= 1) {
+      const int x = dd + 1;
+      volatile float lx = logf((float)x);
+      volatile float q = lx / 0.6931472f;
+      log_pen = x <= 1 ? 0.0f : q;
+    }
+    volatile float h = 0.5f * log_pen;
+    t[(size_t)dd] = h;
+  }
+  return t;
+}
+
+int chain_batch(mm2_ctx* ctx, const ulonglong2* d_anchors, const u64* d_read_aoff, const u64* d_read_off, const u64* d_mini_off,
+                const u64* d_mval, const u32* d_sum_span, u32 nreads, const mm2_chain_params_t& p, int do_rescue, int4* d_A,
+                int4* d_B, int* d_T, int* d_chain, ReadHit* d_hits, unsigned long long* d_cells) {
+  if (!nreads) return MM2_OK;
+  const int max_bw = std::max(p.bw, do_rescue ? p.bw_long : p.bw);
+  if (max_bw < 0 || max_bw > (1 << 26)) { mm2_set_error("chain: bandwidth out of range"); return MM2_E_ARG; }
+  const int nl = max_bw + 2;
+  std::vector<float> hl = build_half_log(nl);
+  MM2_TRY(ctx->lut.ensure((size_t)nl * 4));
+  MM2_TRY(ctx->pin_small.ensure((size_t)nl * 4));
+  memcpy(ctx->pin_small.p, hl.data(), (size_t)nl * 4);
+  CUDA_TRY(cudaMemcpyAsync(ctx->lut.p, ctx->pin_small.p, (size_t)nl * 4, cudaMemcpyHostToDevice, ctx->stream));
+  ChainArgs G;
+  G.anchors = d_anchors; G.read_aoff = d_read_aoff; G.read_off = d_read_off; G.mini_off = d_mini_off; G.mval = d_mval;
+  G.sum_span = d_sum_span; G.nreads = nreads; G.p = p; G.do_rescue = do_rescue; G.half_log = ctx->lut.as<float>();
+  G.A = d_A; G.B = d_B; G.T = d_T; G.chain = d_chain; G.hits = d_hits; G.cells = d_cells;
+  const int grid = (int)((nreads + CH_WARPS - 1) / CH_WARPS);
+  MM2_LAUNCH(ctx, chain_kernel, grid, CH_WARPS * 32, 0, G);
+  CUDA_TRY(cudaGetLastError());
+  return MM2_OK;
+}

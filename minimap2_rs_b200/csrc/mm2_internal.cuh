@@ -1,0 +1,173 @@
+// mm2_internal.cuh — shared host/device declarations of libmm2b200.so (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mm2b200.h"
+
+typedef uint64_t u64;
+typedef uint32_t u32;
+typedef uint16_t u16;
+typedef uint8_t u8;
+typedef int32_t i32;
+typedef int64_t i64;
+
+void mm2_set_error(const char* fmt, ...);
+
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      mm2_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__));     \
+      return e__ == cudaErrorMemoryAllocation ? MM2_E_OOM : MM2_E_CUDA;                         \
+    }                                                                                           \
+  } while (0)
+#define MM2_TRY(expr)            \
+  do {                           \
+    int r__ = (expr);            \
+    if (r__ != MM2_OK) return r__; \
+  } while (0)
+
+// growable device buffer (cudaMalloc is slow; buffers persist in the context and only ever grow)
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return MM2_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { mm2_set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); p = nullptr; return MM2_E_OOM; }
+    cap = want;
+    return MM2_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return (T*)p; }
+};
+
+struct PinBuf {  // growable page-locked host staging buffer
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return MM2_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e != cudaSuccess) { mm2_set_error("cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e)); p = nullptr; return MM2_E_OOM; }
+    cap = want;
+    return MM2_OK;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return (T*)p; }
+};
+
+struct StageTimer {  // CUDA-event stopwatch on the context stream
+  std::vector<std::string> names;
+  std::vector<cudaEvent_t> ev;
+  std::vector<float> ms;
+  std::string names_blob;
+  void reset() { names.clear(); n_used = 0; }
+  size_t n_used = 0;
+  void mark(cudaStream_t s, const char* name) {  // marks the START of stage `name` (and the end of the previous one)
+    if (n_used == ev.size()) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); }
+    cudaEventRecord(ev[n_used++], s);
+    names.push_back(name);
+  }
+  void finish() {  // call after a stream sync; the last mark is a terminator
+    ms.clear(); names_blob.clear();
+    for (size_t i = 0; i + 1 < n_used; ++i) {
+      float t = 0; cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
+      ms.push_back(t);
+      names_blob += names[i]; names_blob.push_back('\0');
+    }
+    names_blob.push_back('\0');
+  }
+  ~StageTimer() { for (auto e : ev) cudaEventDestroy(e); }
+};
+
+struct mm2_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  u64 launches = 0;
+  StageTimer timer;
+  // scratch arenas (named by first use; all only ever grow)
+  DevBuf seq, seq_off, tile_seq, tile_first, tile_status, misc;      // sketch inputs / bookkeeping
+  DevBuf mkey, mval, mini_off;                                       // minimizers (SoA) + per-sequence offsets
+  DevBuf keep, occ_cnt, occ_loc, anchor_off_m, scan_status;          // filter / lookup
+  DevBuf anchors, read_aoff, read_class;                             // anchors
+  DevBuf dpA, dpB, dpT, hits, chain_idx, lut;                        // chaining
+  DevBuf sort_tmp, sort_tmp2, sort_keys2, sort_vals2, runidx, run_start, run_gp;  // index build
+  PinBuf pin_in, pin_out, pin_small;
+};
+
+#define MM2_LAUNCH(ctx, kern, grid, block, smem, ...)                         \
+  do {                                                                         \
+    kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);             \
+    (ctx)->launches += 1;                                                      \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
+// device-side index view (see index.cu for the layout)
+struct IndexView {
+  int w, k, b, flag;
+  u32 n_seq;
+  u64 n_keys, n_p;
+  const u64* hkeys;      // n_keys: (minier>>b)<<1 | is_single, ascending inside each bucket
+  const u64* hvals;      // n_keys: y (single) or start_in_bucket_p<<32 | n
+  const u64* bkt_koff;   // (1<<b)+1
+  const u64* bkt_poff;   // (1<<b)+1
+  const u64* p;          // n_p
+  const u32* seq_len;    // n_seq
+  // open-addressing table over all keys: slot = {tag = minier<<1|is_single (0 = empty slot marker ~0), val}
+  const ulonglong2* tab;
+  u64 tab_mask;
+};
+
+struct mm2_index {
+  int device = 0;
+  int w = 0, k = 0, b = 0, flag = 0;
+  u32 n_seq = 0;
+  std::vector<std::string> names;
+  std::vector<u8> has_name;
+  std::vector<u32> lens;
+  std::vector<u64> seq_offset;  // index.rs:29 IndexSeq.offset
+  std::vector<u8> is_alt;
+  u64 total_len = 0;
+  u64 S_words_alloc = 0;       // kroundup64((total+7)/8) as allocated by build (native format writes all of it)
+  u64 n_keys = 0, n_p = 0, n_minimizers = 0;
+  DevBuf S, hkeys, hvals, bkt_koff, bkt_poff, p, seq_len, tab;
+  u64 tab_mask = 0;
+  // occurrence histogram for calc_mid_occ/stats (index.rs:111-141): hist[c] = #keys with count c (c < 65536)
+  std::vector<u64> occ_hist;
+  std::vector<u32> occ_big;     // counts >= 65536
+  float build_ms[5] = {0, 0, 0, 0, 0};
+  IndexView view() const;
+};
+
+// ---- stage entry points shared between translation units (all asynchronous on ctx->stream unless noted) ----
+struct SketchOut {  // device SoA minimizers of a batch
+  u64* key = nullptr;   // key_span
+  u64* val = nullptr;   // rid_pos_strand
+  u64* seq_off = nullptr;  // nseq+1 (device)
+  u64 total = 0;           // host copy of seq_off[nseq] (valid after sketch_device returns; it synchronises)
+};
+// Sketch nseq sequences resident on the device (d_cat/d_off) into ctx->mkey/mval/mini_off.  h_off is the host copy
+// of the offsets.  Synchronises the stream once (to learn the total / handle capacity overflow).
+int sketch_device(mm2_ctx* ctx, const u8* d_cat, const u64* d_off, const u64* h_off, size_t nseq, int w, int k,
+                  u32 rid_base, u32 rid_step, int is_hpc, SketchOut* out);
+
+int index_build_device(mm2_ctx* ctx, const u8* h_cat, const u64* h_off, const char* const* names, size_t nseq, int w,
+                       int k, int b, int flag, mm2_index** out);
+
+// generic single-pass exclusive scan of u32 counts into u64 offsets (n+1 outputs; out[n] = total)
+int scan_u32_to_u64(mm2_ctx* ctx, const u32* d_in, u64* d_out, size_t n);

@@ -1,0 +1,186 @@
+"""Pure-numpy/Python models of the data-parallel reformulations used by the CUDA kernels.
+
+They exist so that the *algorithmic* restatement (position-parallel sketch emission, warp-tiled chaining DP)
+can be checked against the oracle on CPU, where no GPU is available; the kernels transcribe these models.
+"""
+import numpy as np
+
+U64MAX = np.uint64(0xFFFFFFFFFFFFFFFF)
+_NT4 = np.full(256, 4, dtype=np.uint8)
+for _i, _c in enumerate("ACGT"):
+    _NT4[ord(_c)] = _i
+    _NT4[ord(_c.lower())] = _i
+
+
+def hash64(key, mask):
+    key = key.astype(np.uint64)
+    m = np.uint64(mask)
+    with np.errstate(over="ignore"):
+        key = (~key + (key << np.uint64(21))) & m
+        key ^= key >> np.uint64(24)
+        key = (key + (key << np.uint64(3)) + (key << np.uint64(8))) & m
+        key ^= key >> np.uint64(14)
+        key = (key + (key << np.uint64(2)) + (key << np.uint64(4))) & m
+        key ^= key >> np.uint64(28)
+        key = (key + (key << np.uint64(31))) & m
+    return key
+
+
+def sketch_model(seq, w, k, rid=0):
+    """position-parallel formulation of sketch.rs:29-100 (non-HPC, odd k: no palindromic k-mers)."""
+    assert k % 2 == 1
+    c = _NT4[np.frombuffer(bytes(seq), dtype=np.uint8)].astype(np.int64)
+    L = c.size
+    valid = c < 4
+    # l[i]: consecutive valid bases ending at i
+    idx = np.arange(L)
+    lastN = np.maximum.accumulate(np.where(valid, -1, idx))
+    l = idx - lastN
+    c2 = (c & 3).astype(np.uint64)
+    fwd = np.zeros(L, dtype=np.uint64)
+    rev = np.zeros(L, dtype=np.uint64)
+    for t in range(k):  # base at position i-t contributes to digit t (fwd) / digit k-1-t (rev, complemented)
+        if t >= L:
+            break
+        sh = np.zeros(L, dtype=np.uint64)
+        sh[t:] = c2[:L - t]
+        fwd |= sh << np.uint64(2 * t)
+        shc = np.zeros(L, dtype=np.uint64)
+        shc[t:] = np.uint64(3) - c2[:L - t]
+        rev |= shc << np.uint64(2 * (k - 1 - t))
+    mask = (1 << (2 * k)) - 1
+    z = (fwd >= rev).astype(np.uint64)  # 0 if fwd<rev else 1 (equal impossible for odd k)
+    km = np.where(z == 0, fwd, rev)
+    ok = l >= k
+    key = np.where(ok, (hash64(km, mask) << np.uint64(8)) | np.uint64(k), U64MAX)
+    val = (np.uint64(rid) << np.uint64(32)) | (idx.astype(np.uint64) << np.uint64(1)) | z
+    # windowed newest-argmin with multiplicity of the minimum
+    m_cur = np.zeros(L, dtype=np.int64)
+    cnt = np.zeros(L, dtype=np.int64)
+    for i in range(L):
+        lo = max(0, i - w + 1)
+        win = key[lo:i + 1]
+        mk = win.min()
+        eq = np.nonzero(win == mk)[0]
+        m_cur[i] = lo + eq[-1]
+        cnt[i] = eq.size
+    out = []
+    for i in range(L):
+        li = l[i] if valid[i] else 0
+        prev = m_cur[i - 1] if i > 0 else -1
+        kp = key[prev] if prev >= 0 else U64MAX
+        if li == w + k - 1 and kp != U64MAX:
+            for j in range(max(0, i - w + 1), i):
+                if key[j] == kp and j != prev:
+                    out.append((key[j], val[j]))
+        if key[i] <= kp:
+            if li >= w + k and kp != U64MAX:
+                out.append((key[prev], val[prev]))
+        elif prev == i - w:
+            if li >= w + k - 1 and kp != U64MAX:
+                out.append((key[prev], val[prev]))
+            cur = m_cur[i]
+            if li >= w + k - 1 and key[cur] != U64MAX and cnt[i] > 1:
+                for j in range(max(0, i - w + 1), i + 1):
+                    if key[j] == key[cur] and j != cur:
+                        out.append((key[j], val[j]))
+    cur = m_cur[L - 1]
+    if key[cur] != U64MAX:
+        out.append((key[cur], val[cur]))
+    res = np.zeros(len(out), dtype=[("key_span", "<u8"), ("rid_pos_strand", "<u8")])
+    if out:
+        res["key_span"] = [o[0] for o in out]
+        res["rid_pos_strand"] = [o[1] for o in out]
+    return res
+
+
+def chain_fwd_model(anchors, p, half_log_lut=None):
+    """warp-tiled (32 predecessors per step) forward DP of lchain.rs:59-92; returns f, pprev, v, cells_tiles."""
+    import math
+    x = anchors["x"].astype(np.uint64)
+    y = anchors["y"].astype(np.uint64)
+    n = x.size
+    rpos = (x & np.uint64(0xffffffff)).astype(np.uint32).view(np.int32).astype(np.int64)
+    hi = (x >> np.uint64(32)).astype(np.int64)  # rev | rid
+    qpos = (y & np.uint64(0xffffffff)).astype(np.uint32).view(np.int32).astype(np.int64)
+    qspan = ((y >> np.uint64(32)) & np.uint64(0xff)).astype(np.int64)
+    max_dist_x = max(p.max_dist_x, p.bw)
+    max_dist_y = max(p.max_dist_y, p.bw)
+    f = np.zeros(n, dtype=np.int64)
+    v = np.zeros(n, dtype=np.int64)
+    t = np.zeros(n, dtype=np.int64)
+    pprev = np.full(n, -1, dtype=np.int64)
+    f32 = np.float32
+
+    def pen(dd, dg):
+        lin = f32(f32(p.chn_pen_gap) * f32(dd)) + f32(f32(p.chn_pen_skip) * f32(dg))
+        lg = f32(0.0) if dd < 1 else f32(f32(math.log(f32(dd + 1))) if False else np.log(f32(dd + 1), dtype=np.float32)) / f32(0.6931472)
+        return int(f32(lin) + f32(0.5) * lg)
+
+    st = 0
+    for i in range(n):
+        while st < i and (hi[st] != hi[i] or rpos[i] > rpos[st] + max_dist_x):
+            st += 1
+        max_f = int(qspan[i])
+        max_j = -1
+        n_skip = 0
+        start_j = max(st, i - p.max_chain_iter)
+        jb = i - 1
+        done = False
+        while jb >= start_j and not done:
+            lanes = [jb - ln for ln in range(32) if jb - ln >= start_j]
+            sc = [None] * len(lanes)
+            for q, j in enumerate(lanes):
+                if hi[j] != hi[i]:
+                    continue
+                dq = qpos[i] - qpos[j]
+                if dq <= 0 or dq > max_dist_x:
+                    continue
+                dr = rpos[i] - rpos[j]
+                if dr == 0 or dq > max_dist_y:
+                    continue
+                dd = abs(dr - dq)
+                if dd > p.bw:
+                    continue
+                dg = min(dr, dq)
+                s = min(int(qspan[j]), dg)
+                if dd != 0 or dg > qspan[j]:
+                    s -= pen(int(dd), int(dg))
+                sc[q] = int(s + f[j])
+            # phase 1: all valid lanes mark (marks past the break point are harmless)
+            for q, j in enumerate(lanes):
+                if sc[q] is not None and pprev[j] >= 0:
+                    t[pprev[j]] = i
+            # phase 2: records via exclusive prefix max; n_skip via composition of x -> max(x+a, b)
+            run_max = max_f
+            rec = [False] * len(lanes)
+            for q in range(len(lanes)):
+                if sc[q] is not None and sc[q] > run_max:
+                    rec[q] = True
+                    run_max = sc[q]
+            # maps (a, b): x -> max(x + a, b)
+            xs = n_skip
+            brk = -1
+            for q, j in enumerate(lanes):
+                if sc[q] is None:
+                    continue
+                if rec[q]:
+                    xs = max(xs - 1, 0)
+                elif t[j] == i:
+                    xs = xs + 1
+                    if xs > p.max_chain_skip:
+                        brk = q
+                        break
+            upto = len(lanes) if brk < 0 else brk
+            for q in range(upto):
+                if rec[q]:
+                    max_f = sc[q]
+                    max_j = lanes[q]
+            n_skip = xs
+            if brk >= 0:
+                done = True
+            jb -= 32
+        f[i] = max_f
+        pprev[i] = max_j
+        v[i] = v[max_j] if (max_j >= 0 and v[max_j] > max_f) else max_f
+    return f, pprev, v

@@ -1,0 +1,296 @@
+"""GPU parity suite (-m gpu): every stage of the CUDA path, called through the C ABI, against the CPU oracle — bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _eq(a, b, what):
+    assert a.size == b.size, "%s: size %d vs %d" % (what, a.size, b.size)
+    if a.size:
+        bad = np.nonzero(a != b)[0]
+        assert bad.size == 0, "%s: first mismatch at %d: %s vs %s" % (what, bad[0], a[bad[0]], b[bad[0]])
+
+
+# ---- sketch ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("w,k", cases.WK)
+def test_sketch_tile_kernel(ctx, orc, w, k):
+    for name, s in cases.sketch_cases(big=(w, k) in ((10, 15), (10, 19))):
+        _eq(ctx.sketch_sequence(s, w, k, rid=3), orc.sketch(s, w, k, rid=3), "sketch %s w=%d k=%d" % (name, w, k))
+
+
+@pytest.mark.parametrize("w,k,hpc", [(10, 14, False), (10, 16, False), (5, 4, False), (10, 28, False), (10, 15, True), (10, 14, True)])
+def test_sketch_literal_kernel(ctx, orc, w, k, hpc):
+    rng = np.random.default_rng(4)
+    seqs = [s for _, s in cases.sketch_cases()] + [b"AT" * 400 + cases.rnd_seq(rng, 300) + b"ACGT" * 100]
+    for i, s in enumerate(seqs):
+        _eq(ctx.sketch_sequence(s, w, k, rid=1, is_hpc=hpc), orc.sketch(s, w, k, rid=1, is_hpc=hpc), "literal %d" % i)
+
+
+def test_sketch_batch_many_sequences(ctx, orc):
+    rng = np.random.default_rng(8)
+    seqs = [cases.rnd_seq(rng, int(n)) for n in rng.integers(1, 9000, 300)] + [b"N" * 100, b"A"]
+    cat, offs = cases.cat_offs(seqs)
+    mv, mo = ctx.sketch_batch(cat, offs, 10, 15, rid_base=0, rid_step=1)
+    for i, s in enumerate(seqs):
+        _eq(mv[int(mo[i]):int(mo[i + 1])], orc.sketch(s, 10, 15, rid=i), "seq %d" % i)
+    mv0, _ = ctx.sketch_batch(cat, offs, 10, 19)
+    want = np.concatenate([orc.sketch(s, 10, 19, rid=0) for s in seqs])
+    _eq(mv0, want, "rid 0 batch")
+
+
+def test_sketch_rejects_what_the_reference_asserts_on(ctx, mm2):
+    for args in ((b"", 10, 15), (b"ACGT", 0, 15), (b"ACGT", 256, 15), (b"ACGT", 10, 0), (b"ACGT", 10, 29)):
+        with pytest.raises(mm2.Mm2Error) as e:
+            ctx.sketch_sequence(*args)
+        assert e.value.code == mm2.MM2_E_ARG
+
+
+# ---- index ----------------------------------------------------------------------------------------------------
+def _genome_records(gen, seed, total, with_n=True):
+    g = gen.repeat_genome(seed, total, 0.3, 0.2) if seed % 2 else gen.genome(seed, total, 1e-3 if with_n else 0.0, 30.0)
+    cut1, cut2 = total // 2, total // 2 + total // 3
+    seqs = [bytes(g[:cut1]), b"N", bytes(g[cut1:cut2]), b"NNNNNNNN", bytes(g[cut2:])]
+    return seqs, ["chrA", "dummy1", "chrB extra words", "d2", "chrC"]
+
+
+@pytest.mark.parametrize("w,k,b,seed", [(10, 15, 14, 1), (10, 19, 14, 2), (10, 15, 8, 3), (5, 5, 14, 4), (11, 21, 12, 5), (10, 14, 10, 6)])
+def test_index_build_mmi_bytes(ctx, mm2, orc, gen, tmp_path, w, k, b, seed):
+    seqs, names = _genome_records(gen, seed, 400_000)
+    cat, offs = cases.cat_offs(seqs)
+    gi = mm2.Index.build(ctx, cat, offs, [n.split()[0] for n in names], w=w, k=k, b=b)
+    oi = orc.Index.build(cat, offs, [n.split()[0] for n in names], w=w, k=k, b=b, threads=4)
+    assert gi.stats() == oi.stats()
+    for frac in (2e-4, 1e-2, 0.5, 0.0, 1.0):
+        assert gi.calc_mid_occ(frac) == oi.calc_mid_occ(frac)
+    pg, po = str(tmp_path / "g.mmi"), str(tmp_path / "o.mmi")
+    gi.save_to_mmi(pg)
+    oi.save_mmi(po)
+    bg, bo = open(pg, "rb").read(), open(po, "rb").read()
+    assert len(bg) == len(bo)
+    assert bg == bo, "first differing byte %d" % next(i for i in range(len(bg)) if bg[i] != bo[i])
+    # lookups
+    mv = orc.sketch(seqs[0][:20000], w, k)
+    for m in mv[::37]:
+        minier = int(m["key_span"]) >> 8
+        kg, og = gi.get(minier)
+        ko, oo = oi.get(minier)
+        assert kg == ko and (og == oo).all()
+    assert gi.get((1 << (2 * k)) - 1 if k < 28 else 12345)[0] == oi.get((1 << (2 * k)) - 1 if k < 28 else 12345)[0]
+    assert gi.get_ref_subseq(0, 100, 180) == bytes(seqs[0][100:180]).upper().replace(b"R", b"N")
+    assert gi.seq(2) == ("chrB", len(seqs[2]))
+
+
+def test_index_load_roundtrips(ctx, mm2, orc, gen, tmp_path):
+    seqs, names = _genome_records(gen, 7, 300_000)
+    cat, offs = cases.cat_offs(seqs)
+    oi = orc.Index.build(cat, offs, names, threads=4)
+    po, pn = str(tmp_path / "o.mmi"), str(tmp_path / "o.idx")
+    oi.save_mmi(po)
+    oi.save_native(pn)
+    g1 = mm2.Index.load_from_mmi(ctx, po)
+    g2 = mm2.Index.load_from_file(ctx, pn)
+    g3 = mm2.Index.load_auto(ctx, po)
+    for g in (g1, g2, g3):
+        assert g.stats() == oi.stats() and g.calc_mid_occ() == oi.calc_mid_occ()
+        assert (g.w, g.k, g.b, g.n_seq) == (10, 15, 14, 5)
+    p1, p2 = str(tmp_path / "g1.mmi"), str(tmp_path / "g2.idx")
+    g1.save_to_mmi(p1)
+    g2.save_to_file(p2)
+    assert open(p1, "rb").read() == open(po, "rb").read()
+    assert open(p2, "rb").read() == open(pn, "rb").read()
+    with pytest.raises(mm2.Mm2Error) as e:
+        mm2.Index.load_from_mmi(ctx, pn)
+    assert e.value.code == mm2.MM2_E_FORMAT
+    # FASTA ingest + load_auto fallback (main.rs:135-145)
+    fa = str(tmp_path / "ref.fa")
+    with open(fa, "wb") as f:
+        for n, s in zip(names, seqs):
+            f.write(b">" + n.encode() + b"\n")
+            for i in range(0, len(s), 70):
+                f.write(s[i:i + 70] + b"\n")
+    g4 = mm2.Index.load_auto(ctx, fa)
+    o4 = orc.Index.build_fasta(fa)
+    p4, q4 = str(tmp_path / "g4.mmi"), str(tmp_path / "o4.mmi")
+    g4.save_to_mmi(p4)
+    o4.save_mmi(q4)
+    assert open(p4, "rb").read() == open(q4, "rb").read()
+
+
+# ---- seeds / chain stage entry points ------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def small_world(ctx, mm2, orc, gen):
+    g = gen.repeat_genome(77, 300_000, 0.4, 0.2)
+    offs = np.array([0, g.size], dtype=np.uint64)
+    gi = mm2.Index.build(ctx, g, offs, ["c"])
+    oi = orc.Index.build(g, offs, ["c"], threads=4)
+    cat, roffs = gen.reads(5, g, offs, 12, 3000, 0.02, 0.02, 0.02)
+    return g, gi, oi, cat, roffs
+
+
+def test_filter_and_anchors(ctx, orc, small_world):
+    g, gi, oi, cat, roffs = small_world
+    mid = max(10, oi.calc_mid_occ())
+    assert max(10, gi.calc_mid_occ()) == mid
+    for r in range(12):
+        q = cat[int(roffs[r]):int(roffs[r + 1])]
+        mv = orc.sketch(q, 10, 15)
+        for qmax, frac in ((10, 0.01), (2, 0.001), (10, 0.0)):
+            _eq(ctx.filter_query_minimizers(mv, qmax, frac), orc.filter_query_minimizers(mv, qmax, frac), "filter r%d" % r)
+        mvf = orc.filter_query_minimizers(mv)
+        for mo in (mid, 200, 0x7fffffff):
+            _eq(ctx.build_anchors_filtered(gi, mvf, q.size, mo), oi.anchors(mvf, q.size, mo), "anchors r%d mid_occ %d" % (r, mo))
+    # a read made of one repeated unit: the query-side filter must drop its over-represented minimizers
+    unit = bytes(g[1000:1180])
+    q = np.frombuffer(unit * 30, dtype=np.uint8)
+    mv = orc.sketch(q, 10, 15)
+    a, b = ctx.filter_query_minimizers(mv), orc.filter_query_minimizers(mv)
+    assert b.size < mv.size
+    _eq(a, b, "repeat read filter")
+
+
+def test_chain_dp_all(ctx, orc, small_world):
+    g, gi, oi, cat, roffs = small_world
+    for r in range(12):
+        q = cat[int(roffs[r]):int(roffs[r + 1])]
+        a = oi.anchors(orc.filter_query_minimizers(orc.sketch(q, 10, 15)), q.size, 200 if r % 2 else 60)
+        if a.size > 30000:
+            a = a[:30000]
+        for variant in range(4):
+            p = orc.default_chain_params(15)
+            if variant == 1:
+                p.bw = 20000
+            if variant == 2:
+                p.max_chain_skip, p.max_chain_iter = 3, 50
+            if variant == 3:
+                p.min_cnt, p.min_chain_score = 1, 10
+            o = orc.chain_dp_all(a, p)
+            import ctypes as C
+            import minimap2_rs_b200 as m
+            gp = m.ChainParams.from_buffer_copy(bytes(p))
+            gres = ctx.chain_dp_all(a, gp)
+            _eq(gres["f"], o["f"], "f r%d v%d" % (r, variant))
+            _eq(gres["pprev"], o["pprev"], "pprev r%d v%d" % (r, variant))
+            _eq(gres["v"], o["v"], "v r%d v%d" % (r, variant))
+            assert len(gres["chains"]) == len(o["chains"])
+            _eq(gres["scores"], o["scores"], "scores")
+            for cg, co in zip(gres["chains"], o["chains"]):
+                _eq(cg, co, "chain")
+
+
+# ---- the batched mapping path: PAF lines ---------------------------------------------------------------------------
+def _map_compare(ctx, mm2, orc, gi, oi, cat, roffs, names, opts_w_k=(10, 15), dump=True):
+    w, k = opts_w_k
+    o = mm2.default_map_opts(w, k)
+    o.want_stage_dump = 1 if dump else 0
+    res = ctx.map_batch(gi, cat, roffs, o)
+    oo = orc.AlignOpts.default(w, k)
+    want, st = oi.align_batch(cat, roffs, names, oo, threads=8)
+    if dump:
+        sd = res.stage
+        mid = max(10, oi.calc_mid_occ())
+        for r in range(len(names)):
+            q = cat[int(roffs[r]):int(roffs[r + 1])]
+            mv = orc.sketch(q, w, k)
+            gm = sd["minis"][int(sd["mini_offs"][r]):int(sd["mini_offs"][r + 1])]
+            _eq(gm, mv, "minimizers of read %d" % r)
+            keep = sd["mini_keep"][int(sd["mini_offs"][r]):int(sd["mini_offs"][r + 1])].astype(bool)
+            mvf = orc.filter_query_minimizers(mv)
+            _eq(gm[keep], mvf, "kept minimizers of read %d" % r)
+            a = oi.anchors(mvf, q.size, mid)
+            ga = sd["anchors"][int(sd["anchor_offs"][r]):int(sd["anchor_offs"][r + 1])]
+            _eq(ga, a, "anchors of read %d" % r)
+        assert res.stats["n_minimizers"] == st.n_minimizers and res.stats["n_anchors"] == st.n_anchors
+        assert res.stats["n_minimizers_kept"] == st.n_minimizers_kept
+    got = res.paf_lines(names)
+    assert res.stats["n_rescued"] == st.n_rescued
+    assert len(got) == len(want)
+    for i, (x, y) in enumerate(zip(got, want)):
+        assert x == y, "PAF line %d:\n%s\n%s" % (i, x, y)
+    return res, st
+
+
+def test_map_batch_random_genome(ctx, mm2, orc, gen):
+    g = gen.genome(0xB2000001, 3_000_000)
+    offs = np.array([0, g.size], dtype=np.uint64)
+    gi = mm2.Index.build(ctx, g, offs, ["chr8"])
+    oi = orc.Index.build(g, offs, ["chr8"], threads=8)
+    for seed, n, ln, e in ((1, 200, 10000, 0.0333), (2, 300, 600, 0.002), (3, 50, 15000, 0.0017), (4, 40, 30000, 0.05)):
+        cat, roffs = gen.reads(seed, g, offs, n, ln, e, e, e)
+        names = ["r%06d" % i for i in range(n)]
+        _map_compare(ctx, mm2, orc, gi, oi, cat, roffs, names)
+
+
+def test_map_batch_ragged_and_empty_reads(ctx, mm2, orc, gen):
+    g = gen.genome(5, 1_000_000, 1e-3, 40.0)
+    offs = np.array([0, g.size], dtype=np.uint64)
+    gi = mm2.Index.build(ctx, g, offs, ["ref"])
+    oi = orc.Index.build(g, offs, ["ref"], threads=8)
+    rng = np.random.default_rng(12)
+    reads = []
+    for i in range(120):
+        ln = int(rng.choice([1, 10, 24, 25, 30, 100, 500, 2037, 2038, 2039, 5000, 12000]))
+        p = int(rng.integers(0, g.size - ln))
+        s = bytearray(g[p:p + ln].tobytes())
+        if i % 7 == 0:
+            s = bytearray(cases.rnd_seq(rng, ln))          # unrelated read: usually no anchors -> no PAF line
+        if i % 5 == 0 and ln > 50:
+            s = bytearray(bytes(s).translate(bytes.maketrans(b"ACGT", b"TGCA"))[::-1])
+        reads.append(bytes(s))
+    cat, roffs = cases.cat_offs(reads)
+    _map_compare(ctx, mm2, orc, gi, oi, cat, roffs, ["q%d" % i for i in range(len(reads))])
+    # an empty batch is fine
+    res = ctx.map_batch(gi, np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.uint64))
+    assert res.recs.size == 0
+
+
+def test_map_batch_repeats_rescue_and_hifi_preset(ctx, mm2, orc, gen):
+    g = gen.repeat_genome(77, 2_000_000, 0.4, 0.2)
+    offs = np.array([0, g.size], dtype=np.uint64)
+    w, k = mm2.apply_preset("map-hifi", 10, 15)
+    gi = mm2.Index.build(ctx, g, offs, ["rep"], w=w, k=k)
+    oi = orc.Index.build(g, offs, ["rep"], w=w, k=k, threads=8)
+    cat, roffs = gen.reads(21, g, offs, 60, 8000, 0.002, 0.0015, 0.0015)
+    # chimeric reads (two distant pieces) force rescue_long_join's rerun
+    chim = []
+    rng = np.random.default_rng(1)
+    for i in range(20):
+        a, b = int(rng.integers(0, g.size - 5000)), int(rng.integers(0, g.size - 5000))
+        chim.append(g[a:a + 4000].tobytes() + g[b:b + 3000].tobytes())
+    cat2, roffs2 = cases.cat_offs([cat[int(roffs[i]):int(roffs[i + 1])].tobytes() for i in range(60)] + chim)
+    res, st = _map_compare(ctx, mm2, orc, gi, oi, cat2, roffs2, ["h%d" % i for i in range(80)], (w, k))
+    assert st.n_rescued > 0
+
+
+def test_map_batch_multi_sequence_even_rids_and_panic(ctx, mm2, orc, gen):
+    g = gen.genome(9, 1_200_000)
+    seqs = [g[:500_000].tobytes(), b"N", g[500_000:900_000].tobytes(), g[900_000:].tobytes()]
+    cat, offs = cases.cat_offs(seqs)
+    names = ["c0", "n1", "c2", "c3odd"]
+    gi = mm2.Index.build(ctx, cat, offs, names)
+    oi = orc.Index.build(cat, offs, names, threads=8)
+    reads = [seqs[0][1000:4000], seqs[2][5000:9000], seqs[3][100:3100], seqs[2][100_000:101_000]]
+    rc, ro = cases.cat_offs(reads)
+    res, st = _map_compare(ctx, mm2, orc, gi, oi, rc, ro, ["a", "b", "c", "d"], dump=False)
+    assert st.n_panic == 1 and res.panic_reads.tolist() == [2]     # odd rid -> the reference panics (F5)
+
+
+def test_map_batch_device_resident_and_stream(ctx, mm2, orc, gen):
+    import torch
+    g = gen.genome(31, 1_000_000)
+    offs = np.array([0, g.size], dtype=np.uint64)
+    gi = mm2.Index.build(ctx, g, offs, ["t"])
+    oi = orc.Index.build(g, offs, ["t"], threads=8)
+    cat, roffs = gen.reads(3, g, offs, 100, 5000, 0.02, 0.02, 0.02)
+    d_cat = torch.from_numpy(cat.copy()).cuda()
+    d_off = torch.from_numpy(roffs.astype(np.int64)).cuda()
+    c2 = mm2.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    res = c2.map_batch(gi, None, roffs, device_ptrs=(d_cat.data_ptr(), d_off.data_ptr()))
+    want, _ = oi.align_batch(cat, roffs, ["x%d" % i for i in range(100)], threads=8)
+    assert res.paf_lines(["x%d" % i for i in range(100)]) == want
+    assert c2.launch_count > 0 and "chain" in c2.last_timings()
+    c2.close()
