@@ -426,7 +426,7 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
   for (size_t r = 0; r < nreads; ++r) {
     const ReadHit& h = hits[r];
     if (h.flags & 1u) out->n_rescued += 1;
-    if (h.rid_rev == 0xFFFFFFFFu) continue;  // no anchors: nothing is printed (main.rs:211-213)
+    if (h.n_anchors == 0) continue;  // no anchors: nothing is printed (main.rs:211-213)
     const u32 rid0 = h.rid_rev & 0x7fffffffu;
     if (rid0 >= idx->n_seq) { panics.push_back((u32)r); continue; }  // idx.seq[rid0] panics in the reference (F5)
     const i32 qlen = (i32)(h_off[r + 1] - h_off[r]);

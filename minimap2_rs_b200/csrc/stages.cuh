@@ -4,7 +4,7 @@
 
 // per-read result of the chaining stage (device -> host), 64 bytes
 struct ReadHit {
-  u32 rid_rev;      // (x >> 32) of the chain's first anchor: rev<<31 | rid ; 0xFFFFFFFF when the read has no anchors
+  u32 rid_rev;      // (x >> 32) of the chain's first anchor: rev<<31 | rid (an odd-rid anchor reads 0xFFFFFFFF, F5); n_anchors == 0 means no hit
   i32 qs, qe, ts, te;  // paf.rs:136-147 (qs/ts already clamped at 0)
   u32 cm;           // chain length
   i32 score;        // v[best] (lchain.rs:170)

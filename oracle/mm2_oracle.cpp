@@ -907,12 +907,14 @@ i32 chain_query_coverage(const std::vector<Anchor>& a, const std::vector<size_t>
 
 // ---- lchain.rs:321-330 --------------------------------------------------------------------
 void rescue_long_join(const std::vector<Anchor>& a, const Chains& chains, const std::vector<i32>& scores, const ChainParams& p,
-                      i32 qlen, Chains& out_chains, std::vector<i32>& out_scores, u64* cells) {
+                      i32 qlen, Chains& out_chains, std::vector<i32>& out_scores, u64* cells, bool* reran) {
+  if (reran) *reran = false;
   if (chains.empty()) { out_chains = chains; out_scores = scores; return; }
   i32 best_cov = chain_query_coverage(a, chains[0]);
   i32 uncovered = std::max(qlen - best_cov, 0);
   bool rescue = uncovered > p.rmq_rescue_size || (float)best_cov < (float)qlen * (1.0f - p.rmq_rescue_ratio);
   if (!rescue) { out_chains = chains; out_scores = scores; return; }
+  if (reran) *reran = true;
   ChainParams p2 = p;
   p2.bw = p.bw_long;
   DpTrace tr;
@@ -1106,8 +1108,9 @@ std::vector<std::string> align_read(const Index& idx, i32 mid_occ, const AlignOp
   } else {
     Chains chains_rescued; std::vector<i32> scores_rescued;
     u64 cells2 = 0;
-    rescue_long_join(anchors, chains_all, scores_all, p, (i32)qlen, chains_rescued, scores_rescued, st ? &cells2 : nullptr);
-    if (st) { st->cells += cells2; if (cells2) st->rescued = true; }
+    bool reran = false;
+    rescue_long_join(anchors, chains_all, scores_all, p, (i32)qlen, chains_rescued, scores_rescued, st ? &cells2 : nullptr, &reran);
+    if (st) { st->cells += cells2; st->rescued = reran; }
     Chains chains_merged = merge_adjacent_chains_with_gap(anchors, chains_rescued, p.max_dist_y, p.max_dist_y);
     Chains chains; std::vector<i32> scores; std::vector<bool> is_pri; i32 s1, s2;
     select_and_filter_chains(anchors, chains_merged, scores_rescued, o.mask_level, o.pri_ratio, o.best_n, chains, scores, is_pri, &s1, &s2);

@@ -143,7 +143,7 @@ Chains merge_adjacent_chains_with_gap(const std::vector<Anchor>& a, const Chains
 i32 chain_query_coverage(const std::vector<Anchor>& a, const std::vector<size_t>& chain);             // :316-319
 void rescue_long_join(const std::vector<Anchor>& a, const Chains& chains, const std::vector<i32>& scores,
                       const ChainParams& p, i32 qlen, Chains& out_chains, std::vector<i32>& out_scores,
-                      u64* cells = nullptr);                                                          // :321-330
+                      u64* cells = nullptr, bool* reran = nullptr);                                   // :321-330
 
 // ---- paf (src/paf.rs) ---------------------------------------------------------------------
 struct PafRecord {
