@@ -115,8 +115,12 @@ __global__ void run_fill_kernel(const u64* __restrict__ ckey, const u64* __restr
       hkeys[r] = key_top;
       hvals[r] = ((gp[r] - bkt_poff[ck >> R]) << 32) | n;
     }
-    if (n < 65536) atomicAdd(&hist[n], 1ULL);
-    else { const u32 s = atomicAdd(n_big, 1u); if (s < big_cap) big[s] = (u32)std::min<u64>(n, 0xFFFFFFFFull); }
+    // occurrence histogram; singletons (the vast majority) are counted per warp to avoid hammering one address
+    const unsigned act = __activemask();
+    const unsigned ones = __ballot_sync(act, n == 1);
+    if (n == 1) { if ((threadIdx.x & 31) == (unsigned)(__ffs(ones) - 1)) atomicAdd(&hist[1], (unsigned long long)__popc(ones)); }
+    else if (n < 65536) atomicAdd(&hist[n], 1ULL);
+    else { const u32 s = atomicAdd(n_big, 1u); if (s < big_cap) big[s] = (u32)(n > 0xFFFFFFFFull ? 0xFFFFFFFFull : n); }
   }
 }
 
