@@ -361,6 +361,306 @@ __global__ void __launch_bounds__(SK_NT) sketch_tile_kernel(SketchParams P) {
 #undef KIDX
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Version 2 of the tile kernel (used for w >= 9): same phases 1-2, but the window argmin is computed per thread with
+// prefix/suffix minima over its 8 consecutive positions (3 merges per position instead of w compares), the emission
+// decisions are taken in registers, and the minimizers are written by the thread that decided them.
+// A candidate is (key, meta) ordered by key, then meta; meta = (2047 - u) << 1 | dup, so among equal keys the NEWEST
+// position wins (sketch.rs:84,90-91) and `dup` says whether the minimum occurs at least twice in the merged range.
+template <class KT> struct Cand;
+template <> struct Cand<u32> {
+  u64 v;
+  static __device__ __forceinline__ Cand make(u32 key, int u) { Cand c; c.v = ((u64)key << 12) | (u64)((2047 - u) << 1); return c; }
+  static __device__ __forceinline__ Cand inf() { Cand c; c.v = ~0ULL; return c; }
+  __device__ __forceinline__ u32 key() const { return (u32)(v >> 12); }
+  __device__ __forceinline__ int pos() const { return 2047 - (int)((v >> 1) & 2047u); }
+  __device__ __forceinline__ bool dup() const { return (v & 1ULL) != 0; }
+  static __device__ __forceinline__ Cand merge(Cand a, Cand b) {
+    Cand r; r.v = min(a.v, b.v) | (u64)(((a.v ^ b.v) >> 12) == 0);
+    return r;
+  }
+};
+template <> struct Cand<u64> {
+  u64 k; u32 m;
+  static __device__ __forceinline__ Cand make(u64 key, int u) { Cand c; c.k = key; c.m = (u32)((2047 - u) << 1); return c; }
+  static __device__ __forceinline__ Cand inf() { Cand c; c.k = ~0ULL; c.m = ~0u; return c; }
+  __device__ __forceinline__ u64 key() const { return k; }
+  __device__ __forceinline__ int pos() const { return 2047 - (int)((m >> 1) & 2047u); }
+  __device__ __forceinline__ bool dup() const { return (m & 1u) != 0; }
+  static __device__ __forceinline__ Cand merge(Cand a, Cand b) {
+    const bool tb = (b.k < a.k) || (b.k == a.k && b.m < a.m);
+    Cand r = tb ? b : a;
+    r.m |= (a.k == b.k) ? 1u : 0u;
+    return r;
+  }
+};
+
+// rare paths of version 2 (a window holding the same key twice), kept out of line so they cost no registers in the hot loop
+template <class KT, int PAD>
+__device__ __noinline__ u32 sk_count_dups(const KT* s_key, int lo, int hi, KT kv, int excl) {
+  u32 n = 0;
+  for (int x = lo; x <= hi; ++x) n += (s_key[x + (x >> PAD)] == kv && x != excl) ? 1u : 0u;
+  return n;
+}
+template <class KT, int PAD>
+__device__ __noinline__ u64 sk_emit_dups(const KT* s_key, const u8* s_z, int lo, int hi, int excl, u64 o, u64 cap, u64* out_key,
+                                         u64* out_val, u64 rid_hi, i64 P0, int k) {
+  const KT kv = s_key[excl + (excl >> PAD)];
+  for (int x = lo; x <= hi; ++x)
+    if (s_key[x + (x >> PAD)] == kv && x != excl) {
+      if (o < cap) {
+        out_key[o] = ((u64)kv << 8) | (u64)k;
+        out_val[o] = rid_hi | ((u64)(P0 + x) << 1) | (u64)((s_z[x >> 3] >> (x & 7)) & 1u);
+      }
+      ++o;
+    }
+  return o;
+}
+
+template <class KT>
+__global__ void __launch_bounds__(SK_NT, 4) sketch_tile_kernel_v2(SketchParams P) {
+  constexpr int PAD = KeyTraits<KT>::PAD;
+  constexpr KT KMAX = (KT)~(KT)0;
+  typedef Cand<KT> C;
+#define KIDX(u) ((u) + ((u) >> PAD))
+  __shared__ __align__(16) KT s_key[SK_REGION + (SK_REGION >> PAD) + 8];
+  __shared__ __align__(16) u32 s_pack[SK_MAXCHUNK + 4];
+  __shared__ __align__(16) u32 s_nm[SK_MAXCHUNK / 2 + 4];
+  __shared__ u8 s_z[SK_NT];
+  __shared__ u32 s_wsum[SK_NT / 32];
+  __shared__ u32 s_tile;
+  __shared__ u64 s_base;
+
+  const int tid = threadIdx.x;
+  const int w = P.w, k = P.k;
+  const int cap = w + k;
+  const int T = SK_REGION - w;
+  const KT mask = (KT)((((u64)1) << (2 * k)) - 1);
+  const int shift1 = 2 * (k - 1);
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_tile = atomicAdd(P.ticket, 1u);
+    __syncthreads();
+    const u32 tile = s_tile;
+    if (tile >= P.ntiles) break;
+    const u32 q = P.tile_seq[tile];
+    const u64 soff = P.seq_off[q];
+    const i64 len = (i64)(P.seq_off[q + 1] - soff);
+    const i64 s = (i64)(tile - P.tile_first[q]) * T;
+    const i64 e = min(len, s + (i64)T);
+    const int nsteps = (int)(e - s);
+    const i64 P0 = s - w;
+    const i64 a = P0 - cap;
+    const i64 gidx = (i64)soff + a;
+    const i64 g0 = (gidx >> 4) << 4;
+    const int delta = (int)(gidx - g0);
+    const int nchunks = (delta + SK_REGION + cap + 15) >> 4;
+
+    // ---- phase 1: 128-bit loads -> 2-bit packed codes + N mask (as in version 1) ---------------------------------
+    for (int c = tid; c < SK_MAXCHUNK + 4; c += SK_NT) {
+      u32 packed = 0, nmask = 0xFFFFu;
+      if (c < nchunks) {
+        const i64 gi = g0 + 16 * (i64)c;
+        u32 wd[4] = {0, 0, 0, 0};
+        if (P.vec_ok && gi >= 0 && gi + 16 <= (i64)P.buf_len) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(P.seq + gi));
+          wd[0] = v.x; wd[1] = v.y; wd[2] = v.z; wd[3] = v.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const i64 g = gi + j;
+            u32 b = (g >= 0 && g < (i64)P.buf_len) ? (u32)P.seq[g] : 0u;
+            wd[j >> 2] |= b << (8 * (j & 3));
+          }
+        }
+        nmask = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          u32 c4, vm;
+          nt4x4(wd[j], c4, vm);
+          packed |= pack4(c4) << (8 * j);
+          nmask |= nbits4(vm) << (4 * j);
+        }
+        const i64 pstart = a + 16 * (i64)c - delta;
+        const i64 lo = max((i64)0, -pstart), hi = min((i64)16, len - pstart);
+        u32 inseq = 0;
+        if (hi > lo) inseq = ((hi >= 16 ? 0x10000u : (1u << hi)) - 1u) & ~((1u << lo) - 1u);
+        nmask = (nmask | ~inseq) & 0xFFFFu;
+      }
+      s_pack[c] = packed;
+      reinterpret_cast<u16*>(s_nm)[c] = (u16)nmask;
+    }
+    __syncthreads();
+
+    // ---- phase 2: 8 consecutive k-mers per thread -> keys (registers + shared), strand bits, l gates -----------------
+    KT K[SK_CH];
+    u32 ge_cap = 0, eq_capm1 = 0;
+    {
+      const int r0 = cap + SK_CH * tid + delta;
+      int l = run_len_at(s_nm, r0 - 1, cap);
+      const int rs = r0 - k;
+      const int wi = rs >> 4, sh = 2 * (rs & 15);
+      const u32 w0 = s_pack[wi], w1 = s_pack[wi + 1], w2 = s_pack[wi + 2];
+      const u32 flo = __funnelshift_r(w0, w1, sh), fhi = __funnelshift_r(w1, w2, sh);
+      const u64 field = (((u64)fhi << 32) | flo) & (u64)mask;
+      KT rev = (KT)((~field) & (u64)mask);
+      u64 br = __brevll(field);
+      br = ((br & 0x5555555555555555ULL) << 1) | ((br >> 1) & 0x5555555555555555ULL);
+      KT fwd = (KT)(br >> (64 - 2 * k));
+      const u32 cw = __funnelshift_r(s_pack[r0 >> 4], s_pack[(r0 >> 4) + 1], 2 * (r0 & 15));
+      const u32 nb = __funnelshift_r(s_nm[r0 >> 5], s_nm[(r0 >> 5) + 1], r0 & 31);
+      u32 zbits = 0;
+#pragma unroll
+      for (int j = 0; j < SK_CH; ++j) {
+        const u32 c = (cw >> (2 * j)) & 3u;
+        l = ((nb >> j) & 1u) ? 0 : min(l + 1, cap);
+        fwd = (KT)(((fwd << 2) | (KT)c) & mask);
+        rev = (KT)((rev >> 2) | ((KT)(3u ^ c) << shift1));
+        const bool z = !(fwd < rev);
+        KT key = KMAX;
+        if (l >= k) key = hash_mix<KT>(z ? rev : fwd, mask);
+        K[j] = key;
+        s_key[KIDX(SK_CH * tid + j)] = key;
+        zbits |= (u32)z << j;
+        ge_cap |= (u32)(l >= cap) << j;
+        eq_capm1 |= (u32)(l == cap - 1) << j;
+      }
+      s_z[tid] = (u8)zbits;
+    }
+    __syncthreads();
+
+    // ---- phase 3: window minima of this thread's 8 positions + emission decisions (sketch.rs:80-96) -----------------
+    const int c0 = SK_CH * tid;
+    const int u_last = w + nsteps - 1;
+    const bool last_tile = (e == len);
+    auto keyat = [&](int t) -> KT { return t >= 0 ? s_key[KIDX(t)] : KMAX; };
+    u32 tot = 0, eflags = 0;  // bits 0-7: emit prev; 8-15: first-window duplicates; 16-23: rescan duplicates; 24: end emit
+    u32 pp[4] = {0, 0, 0, 0};  // position of the previous minimum for each of the 8 steps (u16 x 8)
+    int cur7 = 0;              // position of the window minimum at this thread's last position
+    if (c0 + SK_CH > w && c0 < w + nsteps) {
+      C R = C::inf();
+      int t = c0 - 1;
+      for (; t > c0 - (w - 1) + 7; --t) R = C::merge(R, C::make(keyat(t), t));
+      C S[SK_CH];
+#pragma unroll
+      for (int jj = SK_CH - 1; jj >= 0; --jj) { R = C::merge(R, C::make(keyat(t), t)); S[jj] = R; --t; }
+      C prev = C::merge(R, C::make(keyat(t), t));  // window [c0-w, c0-1]
+      C Pm = C::inf();
+#pragma unroll
+      for (int j = 0; j < SK_CH; ++j) {
+        const int u = c0 + j;
+        Pm = C::merge(Pm, C::make(K[j], u));
+        const C cur = C::merge(S[j], Pm);            // window [u-w+1, u]
+        const int ppos = prev.pos();
+        pp[j >> 1] |= (u32)ppos << (16 * (j & 1));
+        if (u >= w && u <= u_last) {
+          const KT kp = prev.key(), ki = K[j];
+          const bool gc = (ge_cap >> j) & 1u, ec1 = (eq_capm1 >> j) & 1u;
+          if (kp != KMAX) {
+            if (ec1 && prev.dup()) {
+              const u32 c1 = sk_count_dups<KT, PAD>(s_key, u - w + 1, u - 1, kp, ppos);
+              if (c1) { tot += c1; eflags |= 1u << (8 + j); }
+            }
+            if (ki <= kp) {
+              if (gc) { tot += 1; eflags |= 1u << j; }
+            } else if (ppos == u - w) {
+              if (gc || ec1) {
+                tot += 1; eflags |= 1u << j;
+                if (cur.key() != KMAX && cur.dup()) {
+                  const u32 c3 = sk_count_dups<KT, PAD>(s_key, u - w + 1, u, cur.key(), cur.pos());
+                  if (c3) { tot += c3; eflags |= 1u << (16 + j); }
+                }
+              }
+            }
+          }
+          if (last_tile && u == u_last && cur.key() != KMAX) { tot += 1; eflags |= 1u << 24; }
+        }
+        if (u == min(c0 + SK_CH - 1, u_last)) cur7 = cur.pos();
+        prev = cur;
+      }
+    }
+
+    // ---- exclusive scan of the per-thread counts, then decoupled look-back for the tile's global base --------------------
+    u32 inc = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u32 tt = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+      if ((tid & 31) >= d) inc += tt;
+    }
+    if ((tid & 31) == 31) s_wsum[tid >> 5] = inc;
+    __syncthreads();
+    u32 wbase = 0, tile_count = 0;
+#pragma unroll
+    for (int x = 0; x < SK_NT / 32; ++x) {
+      const u32 ws = s_wsum[x];
+      if (x < (tid >> 5)) wbase += ws;
+      tile_count += ws;
+    }
+    const u32 my_off = wbase + inc - tot;
+    if (tid < 32) {
+      volatile u64* st = P.tile_status;
+      u64 excl = 0;
+      if (tile == 0) {
+        if (tid == 0) st[0] = (2ULL << 62) | (u64)tile_count;
+      } else {
+        if (tid == 0) st[tile] = (1ULL << 62) | (u64)tile_count;
+        i64 look = (i64)tile - 1;
+        for (;;) {
+          const i64 idx = look - tid;
+          u64 v;
+          if (idx >= 0) { do { v = st[idx]; } while ((v >> 62) == 0); } else v = (2ULL << 62);
+          const u32 incl_mask = __ballot_sync(0xFFFFFFFFu, (v >> 62) == 2);
+          const int first_incl = incl_mask ? (__ffs(incl_mask) - 1) : 32;
+          u64 contrib = (tid <= first_incl) ? (v & ((1ULL << 62) - 1)) : 0;
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xFFFFFFFFu, contrib, d);
+          excl += contrib;
+          if (incl_mask) break;
+          look -= 32;
+        }
+        if (tid == 0) st[tile] = (2ULL << 62) | (excl + (u64)tile_count);
+      }
+      if (tid == 0) {
+        s_base = excl;
+        if (tile == P.tile_first[q]) P.seq_out_off[q] = excl;
+        if (tile == P.ntiles - 1) P.seq_out_off[P.nseq] = excl + (u64)tile_count;
+      }
+    }
+    __syncthreads();
+
+    // ---- write this thread's minimizers in step order ------------------------------------------------------------------
+    if (tot) {
+      u64 o = s_base + my_off;
+      const u64 rid_hi = (u64)(P.rid_base + q * P.rid_step) << 32;
+      auto emit = [&](int x) {
+        if (o < P.out_cap) {
+          const u64 pos = (u64)(P0 + x);
+          const u32 z = (s_z[x >> 3] >> (x & 7)) & 1u;
+          P.out_key[o] = ((u64)s_key[KIDX(x)] << 8) | (u64)k;
+          P.out_val[o] = rid_hi | (pos << 1) | (u64)z;
+        }
+        ++o;
+      };
+#pragma unroll
+      for (int j = 0; j < SK_CH; ++j) {
+        const int u = c0 + j;
+        const int ppos = (int)((pp[j >> 1] >> (16 * (j & 1))) & 0xFFFFu);
+        if (eflags & (1u << (8 + j)))
+          o = sk_emit_dups<KT, PAD>(s_key, s_z, u - w + 1, u - 1, ppos, o, P.out_cap, P.out_key, P.out_val, rid_hi, P0, k);
+        if (eflags & (1u << j)) emit(ppos);
+        if (eflags & (1u << (16 + j))) {
+          const int cpos = (j == SK_CH - 1) ? cur7 : (int)((pp[(j + 1) >> 1] >> (16 * ((j + 1) & 1))) & 0xFFFFu);
+          o = sk_emit_dups<KT, PAD>(s_key, s_z, u - w + 1, u, cpos, o, P.out_cap, P.out_key, P.out_val, rid_hi, P0, k);
+        }
+      }
+      if (eflags & (1u << 24)) emit(cur7);
+    }
+  }
+#undef KIDX
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Literal state machine (sketch.rs:29-100), one thread per sequence.  MODE 0: count only; MODE 1: write.
 __device__ __forceinline__ u32 nt4_dev(u8 b) {
@@ -531,8 +831,13 @@ int sketch_device(mm2_ctx* ctx, const u8* d_cat, const u64* d_off, const u64* h_
       P.tile_status = ctx->tile_status.as<u64>();
       P.ticket = (u32*)((u8*)ctx->tile_status.p + (size_t)ntiles * 8);
       const int grid = (int)std::min<u64>(ntiles, (u64)num_sms(ctx->device) * 5);
-      if (k <= 15) MM2_LAUNCH(ctx, sketch_tile_kernel<u32>, grid, SK_NT, 0, P);
-      else MM2_LAUNCH(ctx, sketch_tile_kernel<u64>, grid, SK_NT, 0, P);
+      if (w >= 9) {  // version 2: per-thread prefix/suffix window minima
+        if (k <= 15) MM2_LAUNCH(ctx, sketch_tile_kernel_v2<u32>, grid, SK_NT, 0, P);
+        else MM2_LAUNCH(ctx, sketch_tile_kernel_v2<u64>, grid, SK_NT, 0, P);
+      } else {
+        if (k <= 15) MM2_LAUNCH(ctx, sketch_tile_kernel<u32>, grid, SK_NT, 0, P);
+        else MM2_LAUNCH(ctx, sketch_tile_kernel<u64>, grid, SK_NT, 0, P);
+      }
       CUDA_TRY(cudaGetLastError());
       u64 total = 0;
       CUDA_TRY(cudaMemcpyAsync(&total, ctx->mini_off.as<u64>() + nseq, 8, cudaMemcpyDeviceToHost, st));
