@@ -294,3 +294,29 @@ def test_map_batch_device_resident_and_stream(ctx, mm2, orc, gen):
     assert res.paf_lines(["x%d" % i for i in range(100)]) == want
     assert c2.launch_count > 0 and "chain" in c2.last_timings()
     c2.close()
+
+
+def test_gpu_matches_golden_fixtures(ctx, mm2, gen, tmp_path):
+    """the committed vectors (tests/golden), without recomputing the oracle"""
+    import hashlib
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    d = np.load(os.path.join(gold, "sketch.npz"))
+    for i in range(int(d["n"])):
+        mv = ctx.sketch_sequence(d["seq%d" % i].tobytes(), int(d["w"][i]), int(d["k"][i]), rid=1)
+        assert (mv["key_span"] == d["key%d" % i]).all() and (mv["rid_pos_strand"] == d["val%d" % i]).all(), i
+    g = gen.genome(0xB2000001, 200_000)
+    offs = np.array([0, g.size], dtype=np.uint64)
+    gi = mm2.Index.build(ctx, g, offs, ["chr8"])
+    p = str(tmp_path / "g.mmi")
+    gi.save_to_mmi(p)
+    sha, size = open(os.path.join(gold, "index_200k.sha256")).read().split()
+    assert hashlib.sha256(open(p, "rb").read()).hexdigest() == sha and os.path.getsize(p) == int(size)
+    cat, roffs = gen.reads(0xB2001001, g, offs, 24, 3000, 0.02, 0.02, 0.02)
+    res = ctx.map_batch(gi, cat, roffs)
+    assert res.paf_lines(["r%02d" % i for i in range(24)]) == open(os.path.join(gold, "align_24reads.paf")).read().split("\n")[:-1]
+    s = np.load(os.path.join(gold, "read0_stages.npz"))
+    a = np.zeros(s["ax"].size, dtype=mm2.ANCHOR_DT)
+    a["x"], a["y"] = s["ax"], s["ay"]
+    r = ctx.chain_dp_all(a, mm2.default_chain_params(15))
+    assert (r["f"] == s["f"]).all() and (r["pprev"] == s["pprev"]).all() and (r["chains"][0] == s["chain0"]).all()
+    assert r["scores"][0] == int(s["score0"])

@@ -151,3 +151,32 @@ def test_paf_line_shape(orc, gen):
     assert f[0] == "read1" and f[1] == "600" and f[4] == "+" and f[5] == "chr8" and f[6] == "400000" and f[11] == "60"
     assert f[12] == "tp:A:P" and f[15] == "s2:i:0" and f[17] == "rl:i:0" and len(f[16].split(":")[2].split(".")[1]) == 4
     assert abs(int(f[7]) - 59_340) < 30 and abs(int(f[8]) - 59_940) < 30
+
+
+# ---- committed golden fixtures (tests/golden/make_golden.py) -----------------------------------------------------
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_oracle_matches_golden_fixtures(orc, gen):
+    import hashlib
+    d = np.load(os.path.join(GOLD, "sketch.npz"))
+    for i in range(int(d["n"])):
+        mv = orc.sketch(d["seq%d" % i].tobytes(), int(d["w"][i]), int(d["k"][i]), rid=1)
+        assert (mv["key_span"] == d["key%d" % i]).all() and (mv["rid_pos_strand"] == d["val%d" % i]).all(), i
+    g = gen.genome(0xB2000001, 200_000)
+    offs = np.array([0, g.size], dtype=np.uint64)
+    idx = orc.Index.build(g, offs, ["chr8"], threads=4)
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "x.mmi")
+        idx.save_mmi(p)
+        sha, size = open(os.path.join(GOLD, "index_200k.sha256")).read().split()
+        assert hashlib.sha256(open(p, "rb").read()).hexdigest() == sha and os.path.getsize(p) == int(size)
+    cat, roffs = gen.reads(0xB2001001, g, offs, 24, 3000, 0.02, 0.02, 0.02)
+    lines, _ = idx.align_batch(cat, roffs, ["r%02d" % i for i in range(24)])
+    assert lines == open(os.path.join(GOLD, "align_24reads.paf")).read().split("\n")[:-1]
+    s = np.load(os.path.join(GOLD, "read0_stages.npz"))
+    a = idx.anchors(orc.filter_query_minimizers(orc.sketch(cat[:3000], 10, 15)), 3000, max(10, idx.calc_mid_occ()))
+    assert (a["x"] == s["ax"]).all() and (a["y"] == s["ay"]).all()
+    o = orc.chain_dp_all(a, orc.default_chain_params(15))
+    assert (o["f"] == s["f"]).all() and (o["pprev"] == s["pprev"]).all() and (o["chains"][0] == s["chain0"]).all()

@@ -1,0 +1,69 @@
+"""CPU suite: the N>1 host logic (read sharding + ordered gather) with gloo, world_size 2."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_reads_partitions_exactly():
+    sys.path.insert(0, ROOT)
+    from minimap2_rs_b200 import shard
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 2, 7, 1000):
+        lens = rng.integers(1, 20000, n)
+        offs = np.zeros(n + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum(lens)
+        for world in (1, 2, 3, 8):
+            cover = []
+            for r in range(world):
+                lo, hi = shard.shard_reads(offs, world, r)
+                assert 0 <= lo <= hi <= n
+                cover.extend(range(lo, hi))
+                if n >= 1000:
+                    assert abs(int(offs[hi] - offs[lo]) - int(offs[-1]) / world) < 25000   # balanced by bases
+            assert cover == list(range(n))
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from minimap2_rs_b200 import shard
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(1)
+    lens = rng.integers(5, 50, 101)
+    offs = np.zeros(102, dtype=np.uint64)
+    offs[1:] = np.cumsum(lens)
+    cat = rng.integers(65, 70, int(offs[-1])).astype(np.uint8)
+    names = ["q%d" % i for i in range(101)]
+
+    def fake_map(c, o, nm):  # stands in for Context.map_batch(...).paf_lines(...): one line per read
+        return ["%s\t%d\t%d" % (nm[i], int(o[i + 1] - o[i]), int(c[int(o[i]):int(o[i + 1])].sum())) for i in range(len(nm))]
+
+    mine, (lo, hi) = shard.map_sharded(fake_map, cat, offs, names, world, rank)
+    allv = shard.gather_lines(mine, dst=0)
+    if rank == 0:
+        q.put(allv == fake_map(cat, offs, names))
+    else:
+        assert allv is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_gather_in_input_order():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    ok = q.get(timeout=120)
+    for p in ps:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert ok
