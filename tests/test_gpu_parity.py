@@ -320,3 +320,57 @@ def test_gpu_matches_golden_fixtures(ctx, mm2, gen, tmp_path):
     r = ctx.chain_dp_all(a, mm2.default_chain_params(15))
     assert (r["f"] == s["f"]).all() and (r["pprev"] == s["pprev"]).all() and (r["chains"][0] == s["chain0"]).all()
     assert r["scores"][0] == int(s["score0"])
+
+
+def test_cli_index_align_anchors_chain(ctx, mm2, orc, gen, tmp_path):
+    """the `mm2rs` binary: same subcommands / flags / stdout as src/main.rs (Appendix D of SURVEY.md)"""
+    import subprocess
+    exe = os.path.join(os.path.dirname(mm2.LIB_PATH), "mm2rs")
+    g = gen.genome(41, 600_000)
+    seqs = [g[:350_000].tobytes(), b"N", g[350_000:].tobytes()]
+    fa, qa = str(tmp_path / "ref.fa"), str(tmp_path / "q.fa")
+    with open(fa, "wb") as f:
+        for n, s in zip(["chrA desc", "gap", "chrB"], seqs):
+            f.write(b">" + n.encode() + b"\n")
+            for i in range(0, len(s), 60):
+                f.write(s[i:i + 60] + b"\n")
+    cat, offs = cases.cat_offs(seqs)
+    goffs = np.array([0, g.size], dtype=np.uint64)
+    rc, ro = gen.reads(4, g[:350_000], np.array([0, 350_000], dtype=np.uint64), 3, 4000, 0.03, 0.03, 0.03)
+    with open(qa, "wb") as f:
+        for i in range(3):
+            f.write(b">read%d some comment\n" % i + rc[int(ro[i]):int(ro[i + 1])].tobytes() + b"\n")
+    oi = orc.Index.build(cat, offs, ["chrA", "gap", "chrB"], threads=4)
+    mmi = str(tmp_path / "ref.mmi")
+    out = subprocess.run([exe, "index", "-d", mmi, fa], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    nk, ao, sp, tl = oi.stats()
+    assert out.stdout == "kmer size: 15; skip: 10; is_hpc: 0; #seq: 3\ndistinct minimizers: %d (avg occ %.2f) avg spacing %.3f total length %d\n" % (nk, ao, sp, tl)
+    po = str(tmp_path / "o.mmi")
+    oi.save_mmi(po)
+    assert open(mmi, "rb").read() == open(po, "rb").read()
+    names = ["read%d" % i for i in range(3)]
+    want, _ = oi.align_batch(rc, ro, names)
+    # strict drop-in: first record only (main.rs:92-103)
+    out = subprocess.run([exe, "align", mmi, qa], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout == want[0] + "\n", (out.stdout, out.stderr)
+    # all reads, from the FASTA reference directly (load_index_auto fallback), into a file
+    pf = str(tmp_path / "o.paf")
+    out = subprocess.run([exe, "align", fa, qa, "--all-reads", "-o", pf, "-x", "map-ont"], capture_output=True, text=True)
+    assert out.returncode == 0 and open(pf).read() == "\n".join(want) + "\n", out.stderr
+    # anchors / chain debug subcommands
+    q0 = rc[int(ro[0]):int(ro[1])]
+    a = oi.anchors(orc.filter_query_minimizers(orc.sketch(q0, 10, 15)), q0.size, max(10, oi.calc_mid_occ()))
+    exp = "anchors: %d\n" % a.size + "".join("x=0x%016x y=0x%016x\n" % (int(v["x"]), int(v["y"])) for v in a[:10])
+    out = subprocess.run([exe, "anchors", mmi, qa], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout == exp
+    p = orc.default_chain_params(15)
+    p.bw = 300
+    ch = orc.chain_dp_all(a, p)["chains"][0]
+    exp = "best_chain_len: %d\nstart: x=0x%016x y=0x%016x\nend:   x=0x%016x y=0x%016x\n" % (
+        ch.size, int(a[ch[0]]["x"]), int(a[ch[0]]["y"]), int(a[ch[-1]]["x"]), int(a[ch[-1]]["y"]))
+    out = subprocess.run([exe, "chain", mmi, qa, "-r", "300"], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout == exp, (out.stdout, exp)
+    # errors: missing file -> "Error: ..." exit 1
+    out = subprocess.run([exe, "align", str(tmp_path / "missing.mmi"), qa], capture_output=True, text=True)
+    assert out.returncode == 1 and out.stderr.startswith("Error:")
