@@ -97,6 +97,34 @@ int mm2_index_get_ref_subseq(const mm2_index_t* idx, uint32_t rid, int32_t st, i
 /* device-time breakdown of the build that produced idx (ms): sketch, sort, bucket build, pack, total; genome bases */
 int mm2_index_build_timings(const mm2_index_t* idx, float* ms5, uint64_t* n_bases, uint64_t* n_minimizers);
 
+/* ---- multi-GPU index build building blocks (index.rs:427-475 split over ranks) --------------------------
+ * One process per GPU.  Rank r sketches a contiguous range of sequences, sorts its minimizers bucket-major, sends each
+ * bucket owner its slice (all-to-all), builds the buckets it owns, and the finished ranges are replicated to every GPU.
+ * The exchange itself is done by the caller (minimap2_rs_b200/multi_gpu.py over torch.distributed / NCCL). */
+typedef struct {
+  uint64_t n_keys, n_p, n_minimizers, S_words;
+  const void *hkeys, *hvals, *p, *bkt_koff, *bkt_poff, *S;  /* device pointers, valid until mm2_index_free */
+  const uint64_t* occ_hist;                                  /* host, 65536 entries */
+  size_t n_occ_big; const uint32_t* occ_big;                 /* host */
+} mm2_index_raw_t;
+/* sketch sequences [seq_lo, seq_hi) (rid = global sequence number), sort by (bucket, key); counts[r] = records owned by rank r */
+int mm2_mg_sketch_sort(mm2_ctx_t* ctx, const uint8_t* cat, const uint64_t* offs, size_t nseq, size_t seq_lo, size_t seq_hi, int w,
+                       int k, int b, int flag, int nranks, uint64_t* counts);
+/* copy the n sorted (key, position) records of the last mm2_mg_sketch_sort into caller-owned device buffers */
+int mm2_mg_export_sorted(mm2_ctx_t* ctx, void* d_ckey, void* d_y, size_t n);
+/* received records (device, source-rank order) -> the buckets this rank owns (index.rs:74-109), no lookup table */
+int mm2_mg_build_partial(mm2_ctx_t* ctx, const void* d_ckey, const void* d_y, size_t n, int w, int k, int b, int flag,
+                         mm2_index_t** out);
+/* 4-bit pack (index.rs:11-19) words [word_lo, word_hi) of the genome into d_S (a device array of all S words) */
+int mm2_mg_pack_seq(mm2_ctx_t* ctx, const uint8_t* cat, uint64_t total_len, uint64_t word_lo, uint64_t word_hi, void* d_S);
+int mm2_device_copy(mm2_ctx_t* ctx, void* dst, const void* src, size_t nbytes);
+int mm2_index_raw(const mm2_index_t* idx, mm2_index_raw_t* out);
+/* build the replicated index object from fully gathered device arrays (+ summed occurrence histogram) */
+int mm2_index_assemble(mm2_ctx_t* ctx, const uint64_t* offs, const char* const* names, size_t nseq, int w, int k, int b, int flag,
+                       uint64_t n_keys, uint64_t n_p, const void* d_hkeys, const void* d_hvals, const void* d_p, const void* d_koff,
+                       const void* d_poff, const void* d_S, uint64_t S_words, const uint64_t* occ_hist, const uint32_t* occ_big,
+                       size_t n_occ_big, mm2_index_t** out);
+
 /* ---- seeds (seeds.rs) -------------------------------------------------------------------------------------- */
 /* seeds.rs:13 filter_query_minimizers: in place, *n updated */
 int mm2_filter_query_minimizers(mm2_ctx_t* ctx, mm2_mini_t* mv, size_t* n, int32_t q_occ_max, float q_occ_frac);

@@ -49,6 +49,13 @@ class _Chains(C.Structure):
                 ("f", C.c_void_p), ("v", C.c_void_p), ("pprev", C.c_void_p)]
 
 
+class IndexRaw(C.Structure):  # mm2_index_raw_t
+    _fields_ = [("n_keys", C.c_uint64), ("n_p", C.c_uint64), ("n_minimizers", C.c_uint64), ("S_words", C.c_uint64),
+                ("hkeys", C.c_void_p), ("hvals", C.c_void_p), ("p", C.c_void_p), ("bkt_koff", C.c_void_p),
+                ("bkt_poff", C.c_void_p), ("S", C.c_void_p), ("occ_hist", C.c_void_p), ("n_occ_big", C.c_size_t),
+                ("occ_big", C.c_void_p)]
+
+
 class _MapResult(C.Structure):
     _fields_ = [("n_recs", C.c_size_t), ("recs", C.c_void_p), ("n_panic", C.c_size_t), ("panic_reads", C.c_void_p),
                 ("n_reads", C.c_uint64), ("n_bases", C.c_uint64), ("n_minimizers", C.c_uint64),
@@ -66,7 +73,8 @@ ABI_SYMBOLS = [
     "mm2_index_calc_mid_occ", "mm2_index_params", "mm2_index_seq", "mm2_index_get_ref_subseq", "mm2_index_build_timings",
     "mm2_filter_query_minimizers", "mm2_build_anchors_filtered", "mm2_chain_dp_all", "mm2_chains_free",
     "mm2_default_chain_params", "mm2_default_map_opts", "mm2_map_batch", "mm2_map_batch_device", "mm2_map_result_free",
-    "mm2_paf_format", "mm2_paf_format_batch",
+    "mm2_paf_format", "mm2_paf_format_batch", "mm2_mg_sketch_sort", "mm2_mg_export_sorted", "mm2_mg_build_partial",
+    "mm2_mg_pack_seq", "mm2_device_copy", "mm2_index_raw", "mm2_index_assemble",
 ]
 
 _LIB = None
@@ -124,6 +132,14 @@ def lib():
     L.mm2_map_result_free.argtypes = [C.POINTER(_MapResult)]
     L.mm2_paf_format.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p, sz]
     L.mm2_paf_format_batch.argtypes = [vp, C.POINTER(_MapResult), vp, C.POINTER(vp), C.POINTER(sz)]
+    L.mm2_mg_sketch_sort.argtypes = [vp, vp, vp, sz, sz, sz, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    L.mm2_mg_export_sorted.argtypes = [vp, vp, vp, sz]
+    L.mm2_mg_build_partial.argtypes = [vp, vp, vp, sz, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.mm2_mg_pack_seq.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, vp]
+    L.mm2_device_copy.argtypes = [vp, vp, vp, sz]
+    L.mm2_index_raw.argtypes = [vp, C.POINTER(IndexRaw)]
+    L.mm2_index_assemble.argtypes = [vp, vp, vp, sz, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp,
+                                     vp, C.c_uint64, vp, vp, sz, C.POINTER(vp)]
     _LIB = L
     return L
 
@@ -314,6 +330,43 @@ class Context:
                                               offs.ctypes.data, offs.size - 1, C.byref(opts), C.byref(res)))
         return MapResult(idx, res, offs.size - 1)
 
+    # ---- multi-GPU index build building blocks (orchestrated by minimap2_rs_b200.multi_gpu) ----------------------
+    def mg_sketch_sort(self, cat, offs, seq_lo, seq_hi, w, k, b, flag, nranks):
+        cat = cat if isinstance(cat, np.ndarray) and cat.dtype == np.uint8 else as_u8(cat)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        counts = np.zeros(nranks, dtype=np.uint64)
+        _check(lib().mm2_mg_sketch_sort(self.h, cat.ctypes.data, offs.ctypes.data, offs.size - 1, seq_lo, seq_hi, w, k, b, flag,
+                                        nranks, counts.ctypes.data))
+        return counts
+
+    def mg_export_sorted(self, d_ckey, d_y, n):
+        _check(lib().mm2_mg_export_sorted(self.h, C.c_void_p(d_ckey), C.c_void_p(d_y), n))
+
+    def mg_build_partial(self, d_ckey, d_y, n, w, k, b, flag):
+        h = C.c_void_p()
+        _check(lib().mm2_mg_build_partial(self.h, C.c_void_p(d_ckey), C.c_void_p(d_y), n, w, k, b, flag, C.byref(h)))
+        return Index(h)
+
+    def mg_pack_seq(self, cat, total_len, word_lo, word_hi, d_S):
+        cat = cat if isinstance(cat, np.ndarray) and cat.dtype == np.uint8 else as_u8(cat)
+        _check(lib().mm2_mg_pack_seq(self.h, cat.ctypes.data, total_len, word_lo, word_hi, C.c_void_p(d_S)))
+
+    def device_copy(self, dst, src, nbytes):
+        _check(lib().mm2_device_copy(self.h, C.c_void_p(dst), C.c_void_p(src), nbytes))
+
+    def index_assemble(self, offs, names, w, k, b, flag, n_keys, n_p, d_hkeys, d_hvals, d_p, d_koff, d_poff, d_S, S_words, occ_hist,
+                       occ_big):
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        enc = [n.encode() if isinstance(n, str) else bytes(n) for n in names]
+        arr = (C.c_char_p * len(enc))(*enc)
+        occ_hist = np.ascontiguousarray(occ_hist, dtype=np.uint64)
+        occ_big = np.ascontiguousarray(occ_big, dtype=np.uint32)
+        h = C.c_void_p()
+        _check(lib().mm2_index_assemble(self.h, offs.ctypes.data, arr, len(enc), w, k, b, flag, n_keys, n_p, C.c_void_p(d_hkeys),
+                                        C.c_void_p(d_hvals), C.c_void_p(d_p), C.c_void_p(d_koff), C.c_void_p(d_poff),
+                                        C.c_void_p(d_S), S_words, occ_hist.ctypes.data, occ_big.ctypes.data, occ_big.size, C.byref(h)))
+        return Index(h)
+
     def close(self):
         if getattr(self, "h", None):
             lib().mm2_ctx_destroy(self.h)
@@ -447,6 +500,15 @@ class Index:
         out, n = C.c_void_p(), C.c_size_t()
         _check(lib().mm2_index_get_ref_subseq(self.h, rid, st, en, C.byref(out), C.byref(n)))
         return _copy_out(out.value, n.value, np.uint8).tobytes()
+
+    def raw(self):
+        """device pointers and counts of the flat arrays (mm2_index_raw_t) + host copies of the occurrence histogram"""
+        r = IndexRaw()
+        _check(lib().mm2_index_raw(self.h, C.byref(r)))
+        hist = np.frombuffer((C.c_char * (65536 * 8)).from_address(r.occ_hist), dtype=np.uint64, count=65536).copy()
+        big = (np.frombuffer((C.c_char * (r.n_occ_big * 4)).from_address(r.occ_big), dtype=np.uint32, count=r.n_occ_big).copy()
+               if r.n_occ_big else np.zeros(0, dtype=np.uint32))
+        return r, hist, big
 
     def build_timings(self):
         ms = (C.c_float * 5)()

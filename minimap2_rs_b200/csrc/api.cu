@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <numeric>
+#include <thread>
 
 #include "stages.cuh"
 
@@ -45,6 +46,8 @@ extern "C" int mm2_ctx_create(int device, mm2_ctx_t** out) {
   e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete c; mm2_set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); return MM2_E_CUDA; }
   c->own_stream = true;
+  { const char* e = getenv("MM2_PIPELINE"); if (e && atoi(e) == 0) c->pipeline = false; }
+  { const char* e = getenv("MM2_SUBBATCH_MB"); if (e && atoi(e) > 0) c->subbatch_bytes = (u64)atoi(e) << 20; }
   *out = c;
   return MM2_OK;
 }
@@ -60,6 +63,7 @@ extern "C" void mm2_ctx_destroy(mm2_ctx_t* c) {
   for (DevBuf* b : bufs) b->release();
   c->pin_in.release(); c->pin_out.release(); c->pin_small.release();
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  for (int w = 0; w < 2; ++w) if (c->worker[w]) mm2_ctx_destroy(c->worker[w]);
   delete c;
 }
 
@@ -503,10 +507,9 @@ extern "C" int mm2_map_batch_device(mm2_ctx_t* ctx, const mm2_index_t* idx, cons
   return map_device_impl(ctx, idx, (const u8*)d_cat, (const u64*)d_offs, h_offs, nreads, opts, out, false);
 }
 
-extern "C" int mm2_map_batch(mm2_ctx_t* ctx, const mm2_index_t* idx, const uint8_t* cat, const uint64_t* offs, size_t nreads,
-                             const mm2_map_opts_t* opts, mm2_map_result_t* out) {
-  if (!ctx || !idx || !offs || !opts || !out || (nreads && !cat)) { mm2_set_error("mm2_map_batch: NULL argument"); return MM2_E_ARG; }
-  if (idx->device != ctx->device) { mm2_set_error("index lives on device %d, context on %d", idx->device, ctx->device); return MM2_E_ARG; }
+// one sub-batch from host memory on `ctx`: H2D of the reads, the device pipeline, D2H of the hits
+static int map_host_single(mm2_ctx* ctx, const mm2_index* idx, const u8* cat, const u64* offs, size_t nreads, const mm2_map_opts_t* opts,
+                           mm2_map_result_t* out) {
   CUDA_TRY(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const u64 base = nreads ? offs[0] : 0, total = nreads ? offs[nreads] - base : 0;
@@ -520,6 +523,84 @@ extern "C" int mm2_map_batch(mm2_ctx_t* ctx, const mm2_index_t* idx, const uint8
   CUDA_TRY(cudaMemcpyAsync(ctx->seq_off.p, off0.data(), (nreads + 1) * 8, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   return map_device_impl(ctx, idx, ctx->seq.as<u8>(), ctx->seq_off.as<u64>(), off0.data(), nreads, opts, out, true);
+}
+
+// Large host batches are cut into sub-batches that alternate between two worker contexts (own stream, own arenas, own
+// host thread), so the H2D copy and the host-side record assembly of one sub-batch overlap the kernels of the other.
+// Reads are independent (main.rs:193-219), so the records are simply concatenated in input order.
+static int map_host_pipelined(mm2_ctx* ctx, const mm2_index* idx, const u8* cat, const u64* offs, size_t nreads,
+                              const mm2_map_opts_t* opts, mm2_map_result_t* out, size_t nsub) {
+  for (int w = 0; w < 2; ++w)
+    if (!ctx->worker[w]) MM2_TRY(mm2_ctx_create(ctx->device, &ctx->worker[w]));
+  // sub-batch boundaries balanced by bases
+  std::vector<size_t> cut(nsub + 1, nreads);
+  cut[0] = 0;
+  const u64 base = offs[0], total = offs[nreads] - base;
+  for (size_t sidx = 1; sidx < nsub; ++sidx) {
+    const u64 target = base + total * sidx / nsub;
+    cut[sidx] = (size_t)(std::lower_bound(offs, offs + nreads + 1, target) - offs);
+    if (cut[sidx] < cut[sidx - 1]) cut[sidx] = cut[sidx - 1];
+  }
+  std::vector<mm2_map_result_t> part(nsub);
+  for (auto& p : part) memset(&p, 0, sizeof p);
+  int rc[2] = {MM2_OK, MM2_OK};
+  std::string err[2];
+  std::vector<std::vector<float>> ms_sum(2);
+  auto work = [&](int w) {
+    mm2_ctx* c = ctx->worker[w];
+    for (size_t sidx = (size_t)w; sidx < nsub; sidx += 2) {
+      const size_t lo = cut[sidx], hi = cut[sidx + 1];
+      const int r = map_host_single(c, idx, cat, offs + lo, hi - lo, opts, &part[sidx]);
+      if (r != MM2_OK) { rc[w] = r; err[w] = mm2_last_error(); return; }
+      if (ms_sum[w].size() < c->timer.ms.size()) ms_sum[w].resize(c->timer.ms.size(), 0.f);
+      for (size_t i = 0; i < c->timer.ms.size(); ++i) ms_sum[w][i] += c->timer.ms[i];
+    }
+  };
+  const u64 l0 = ctx->worker[0]->launches + ctx->worker[1]->launches;
+  std::thread t1(work, 1);
+  work(0);
+  t1.join();
+  ctx->launches += ctx->worker[0]->launches + ctx->worker[1]->launches - l0;
+  for (int w = 0; w < 2; ++w)
+    if (rc[w] != MM2_OK) {
+      for (auto& p : part) mm2_map_result_free(&p);
+      mm2_set_error("%s", err[w].c_str());
+      return rc[w];
+    }
+  // stage times: sum over both workers (device time spent per stage, not wall time)
+  ctx->timer.names = ctx->worker[0]->timer.names;
+  ctx->timer.ms.assign(ms_sum[0].size(), 0.f);
+  for (int w = 0; w < 2; ++w) for (size_t i = 0; i < ms_sum[w].size() && i < ctx->timer.ms.size(); ++i) ctx->timer.ms[i] += ms_sum[w][i];
+  ctx->timer.names_blob.clear();
+  for (size_t i = 0; i < ctx->timer.ms.size() && i < ctx->timer.names.size(); ++i) { ctx->timer.names_blob += ctx->timer.names[i]; ctx->timer.names_blob.push_back('\0'); }
+  ctx->timer.names_blob.push_back('\0');
+  // merge
+  memset(out, 0, sizeof *out);
+  size_t nrec = 0, npan = 0;
+  for (auto& p : part) { nrec += p.n_recs; npan += p.n_panic; }
+  out->recs = xmalloc<mm2_paf_rec_t>(nrec);
+  out->panic_reads = xmalloc<u32>(npan);
+  for (size_t sidx = 0; sidx < nsub; ++sidx) {
+    mm2_map_result_t& p = part[sidx];
+    for (size_t i = 0; i < p.n_recs; ++i) { mm2_paf_rec_t r = p.recs[i]; r.read_id += (u32)cut[sidx]; out->recs[out->n_recs++] = r; }
+    for (size_t i = 0; i < p.n_panic; ++i) out->panic_reads[out->n_panic++] = p.panic_reads[i] + (u32)cut[sidx];
+    out->n_reads += p.n_reads; out->n_bases += p.n_bases; out->n_minimizers += p.n_minimizers;
+    out->n_minimizers_kept += p.n_minimizers_kept; out->n_anchors += p.n_anchors; out->n_rescued += p.n_rescued;
+    mm2_map_result_free(&p);
+  }
+  return MM2_OK;
+}
+
+extern "C" int mm2_map_batch(mm2_ctx_t* ctx, const mm2_index_t* idx, const uint8_t* cat, const uint64_t* offs, size_t nreads,
+                             const mm2_map_opts_t* opts, mm2_map_result_t* out) {
+  if (!ctx || !idx || !offs || !opts || !out || (nreads && !cat)) { mm2_set_error("mm2_map_batch: NULL argument"); return MM2_E_ARG; }
+  if (idx->device != ctx->device) { mm2_set_error("index lives on device %d, context on %d", idx->device, ctx->device); return MM2_E_ARG; }
+  const u64 total = nreads ? offs[nreads] - offs[0] : 0;
+  // sub-batches of ~96 Mbase (MM2_SUBBATCH_MB); small batches and stage dumps take the single-context path
+  size_t nsub = (size_t)std::min<u64>(64, total / ctx->subbatch_bytes);
+  if (nsub > nreads) nsub = nreads;
+  if (nsub >= 2 && !opts->want_stage_dump && ctx->pipeline) return map_host_pipelined(ctx, idx, cat, offs, nreads, opts, out, nsub);
+  return map_host_single(ctx, idx, cat, offs, nreads, opts, out);
 }
 
 extern "C" void mm2_map_result_free(mm2_map_result_t* r) {

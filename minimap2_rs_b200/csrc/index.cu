@@ -234,12 +234,42 @@ int index_build_table(mm2_ctx* ctx, mm2_index* idx) {
   return MM2_OK;
 }
 
+// (ckey, y) pairs -> ctx->sort_keys2 / ctx->sort_vals2, sorted by ckey (stable: equal keys keep their input order)
+static int index_sort_pairs(mm2_ctx* ctx, const u64* ckey_in, const u64* y_in, u64 n, int end_bit) {
+  cudaStream_t st = ctx->stream;
+  MM2_TRY(ctx->sort_keys2.ensure(std::max<u64>(1, n) * 8));
+  MM2_TRY(ctx->sort_vals2.ensure(std::max<u64>(1, n) * 8));
+  if (n == 0) return MM2_OK;
+  size_t tmp_bytes = 0;
+  CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ckey_in, ctx->sort_keys2.as<u64>(), y_in, ctx->sort_vals2.as<u64>(), n, 0,
+                                           end_bit, st));
+  MM2_TRY(ctx->sort_tmp.ensure(tmp_bytes));
+  CUDA_TRY(cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp_bytes, ckey_in, ctx->sort_keys2.as<u64>(), y_in, ctx->sort_vals2.as<u64>(),
+                                           n, 0, end_bit, st));
+  ctx->launches += 2 + (u64)((end_bit + 7) / 8);  // CUB's histogram + onesweep passes (library kernels, not ours)
+  return MM2_OK;
+}
+
+static int index_finish_from_sorted(mm2_ctx* ctx, mm2_index* idx, const u64* ckey, const u64* y, u64 n, bool build_table);
+
 // device-side part of the build once the minimizers (ctx->mkey/mval, n of them) are resident
 static int index_finish_from_minimizers(mm2_ctx* ctx, mm2_index* idx, u64 n) {
-  cudaStream_t st = ctx->stream;
   const int b = idx->b, k = idx->k;
   const int R = std::max(2 * k - b, 0);
   const int end_bit = std::max(1, std::min(64, b + R));
+  if (n) {
+    MM2_TRY(ctx->sort_tmp2.ensure(n * 8));
+    MM2_LAUNCH(ctx, rekey_kernel, grid_for(n), 256, 0, ctx->mkey.as<u64>(), ctx->sort_tmp2.as<u64>(), n, b, R);
+  }
+  MM2_TRY(index_sort_pairs(ctx, ctx->sort_tmp2.as<u64>(), ctx->mval.as<u64>(), n, end_bit));
+  return index_finish_from_sorted(ctx, idx, ctx->sort_keys2.as<u64>(), ctx->sort_vals2.as<u64>(), n, true);
+}
+
+// run-length grouping of the sorted pairs into the flat index arrays (+ occurrence histogram, + lookup table)
+static int index_finish_from_sorted(mm2_ctx* ctx, mm2_index* idx, const u64* ckey, const u64* y, u64 n, bool build_table) {
+  cudaStream_t st = ctx->stream;
+  const int b = idx->b, k = idx->k;
+  const int R = std::max(2 * k - b, 0);
   const u64 nb = 1ULL << b;
   idx->n_minimizers = n;
   MM2_TRY(idx->bkt_koff.ensure((nb + 1) * 8));
@@ -250,24 +280,10 @@ static int index_finish_from_minimizers(mm2_ctx* ctx, mm2_index* idx, u64 n) {
     CUDA_TRY(cudaMemsetAsync(idx->bkt_koff.p, 0, (nb + 1) * 8, st));
     CUDA_TRY(cudaMemsetAsync(idx->bkt_poff.p, 0, (nb + 1) * 8, st));
     idx->n_keys = 0; idx->n_p = 0;
-    return index_build_table(ctx, idx);
+    MM2_TRY(idx->hkeys.ensure(8)); MM2_TRY(idx->hvals.ensure(8)); MM2_TRY(idx->p.ensure(8));
+    return build_table ? index_build_table(ctx, idx) : MM2_OK;
   }
-  // ---- radix sort of (ckey, y) --------------------------------------------------------------------------------------
-  MM2_TRY(ctx->sort_keys2.ensure(n * 8));
-  MM2_TRY(ctx->sort_vals2.ensure(n * 8));
-  MM2_TRY(ctx->sort_tmp2.ensure(n * 8));
-  u64* ckey_in = ctx->sort_tmp2.as<u64>();
-  MM2_LAUNCH(ctx, rekey_kernel, grid_for(n), 256, 0, ctx->mkey.as<u64>(), ckey_in, n, b, R);
-  size_t tmp_bytes = 0;
-  CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ckey_in, ctx->sort_keys2.as<u64>(), ctx->mval.as<u64>(),
-                                           ctx->sort_vals2.as<u64>(), n, 0, end_bit, st));
-  MM2_TRY(ctx->sort_tmp.ensure(tmp_bytes));
-  CUDA_TRY(cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp_bytes, ckey_in, ctx->sort_keys2.as<u64>(), ctx->mval.as<u64>(),
-                                           ctx->sort_vals2.as<u64>(), n, 0, end_bit, st));
-  ctx->launches += 8;  // CUB's histogram + onesweep passes (library kernels, not ours)
   ctx->timer.mark(st, "bucket_build");
-  const u64* ckey = ctx->sort_keys2.as<u64>();
-  const u64* y = ctx->sort_vals2.as<u64>();
   // ---- run-length grouping --------------------------------------------------------------------------------------------
   MM2_TRY(ctx->runidx.ensure(n * 4 + (n + 1) * 8 + 64));
   u32* flag = ctx->runidx.as<u32>();
@@ -322,7 +338,7 @@ static int index_finish_from_minimizers(mm2_ctx* ctx, mm2_index* idx, u64 n) {
     CUDA_TRY(cudaGetLastError());
   }
   ctx->timer.mark(st, "lookup_table");
-  return index_build_table(ctx, idx);
+  return build_table ? index_build_table(ctx, idx) : MM2_OK;
 }
 
 int index_build_device(mm2_ctx* ctx, const u8* h_cat, const u64* h_off, const char* const* names, size_t nseq, int w, int k,
@@ -417,5 +433,169 @@ extern "C" int mm2_index_get(const mm2_index_t* idx, uint64_t minier, uint64_t**
     CUDA_TRY(cudaMemcpy(*occ, idx->p.as<u64>() + h3[2], h3[1] * 8, cudaMemcpyDeviceToHost));
     *n = (size_t)h3[1];
   }
+  return MM2_OK;
+}
+
+// =====================================================================================================================
+// Multi-GPU index build building blocks.  One process per GPU; the orchestration and the two exchange
+// steps (all-to-all of minimizers by bucket owner, replication of the finished bucket ranges) live in
+// minimap2_rs_b200/multi_gpu.py on top of torch.distributed/NCCL.  Rank r owns the contiguous bucket range
+// [ceil(r*2^b/R), ceil((r+1)*2^b/R)); because the sort key is bucket-major, each destination's records are one contiguous
+// slice of the locally sorted array, and because every rank sketches a contiguous range of sequences (ascending rid) and
+// the receive buffer is laid out in source-rank order, the receiver's stable re-sort keeps positions ascending.
+namespace {
+__global__ void owner_bounds_kernel(const u64* __restrict__ ckey, u64 n, int b, int R, int nranks, u64* __restrict__ bounds) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > nranks) return;
+  const u64 nb = 1ULL << b;
+  const u64 first_bucket = ((u64)r * nb + (u64)nranks - 1) / (u64)nranks;  // ceil(r * 2^b / nranks)
+  u64 lo = 0, hi = n;
+  while (lo < hi) {
+    const u64 mid = (lo + hi) >> 1;
+    if ((ckey[mid] >> R) < first_bucket) lo = mid + 1; else hi = mid;
+  }
+  bounds[r] = lo;
+}
+}  // namespace
+
+extern "C" int mm2_mg_sketch_sort(mm2_ctx_t* ctx, const uint8_t* cat, const uint64_t* offs, size_t nseq, size_t seq_lo, size_t seq_hi, int w,
+                                  int k, int b, int flag, int nranks, uint64_t* counts) {
+  if (!ctx || !offs || !counts || nranks < 1 || seq_lo > seq_hi || seq_hi > nseq) { mm2_set_error("mm2_mg_sketch_sort: bad argument"); return MM2_E_ARG; }
+  if (b < 0 || b > 28 || nranks > 1024) { mm2_set_error("mm2_mg_sketch_sort: b / nranks out of range"); return MM2_E_ARG; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t ns = seq_hi - seq_lo;
+  const u64 base = offs[seq_lo], total = offs[seq_hi] - base;
+  std::vector<u64> off0(ns + 1, 0);
+  for (size_t i = 0; i <= ns; ++i) off0[i] = offs[seq_lo + i] - base;
+  MM2_TRY(ctx->seq.ensure(total + 64));
+  MM2_TRY(ctx->seq_off.ensure((ns + 1) * 8));
+  if (total) CUDA_TRY(cudaMemcpyAsync(ctx->seq.p, cat + base, total, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(ctx->seq_off.p, off0.data(), (ns + 1) * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  SketchOut so;
+  so.total = 0;
+  if (ns) MM2_TRY(sketch_device(ctx, ctx->seq.as<u8>(), ctx->seq_off.as<u64>(), off0.data(), ns, w, k, (u32)seq_lo, 1, flag & 1, &so));
+  const u64 n = so.total;
+  const int R = std::max(2 * k - b, 0);
+  const int end_bit = std::max(1, std::min(64, b + R));
+  if (n) {
+    MM2_TRY(ctx->sort_tmp2.ensure(n * 8));
+    MM2_LAUNCH(ctx, rekey_kernel, grid_for(n), 256, 0, ctx->mkey.as<u64>(), ctx->sort_tmp2.as<u64>(), n, b, R);
+  }
+  MM2_TRY(index_sort_pairs(ctx, ctx->sort_tmp2.as<u64>(), ctx->mval.as<u64>(), n, end_bit));
+  MM2_TRY(ctx->misc.ensure(((size_t)nranks + 2) * 8));
+  MM2_LAUNCH(ctx, owner_bounds_kernel, (nranks + 1 + 63) / 64, 64, 0, ctx->sort_keys2.as<u64>(), n, b, R, nranks, ctx->misc.as<u64>());
+  std::vector<u64> bounds((size_t)nranks + 1);
+  CUDA_TRY(cudaMemcpyAsync(bounds.data(), ctx->misc.p, ((size_t)nranks + 1) * 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  for (int r = 0; r < nranks; ++r) counts[r] = bounds[(size_t)r + 1] - bounds[(size_t)r];
+  ctx->mg_sorted_n = n;
+  return MM2_OK;
+}
+
+extern "C" int mm2_mg_export_sorted(mm2_ctx_t* ctx, void* d_ckey, void* d_y, size_t n) {
+  if (!ctx || (n && (!d_ckey || !d_y)) || n != ctx->mg_sorted_n) { mm2_set_error("mm2_mg_export_sorted: bad argument"); return MM2_E_ARG; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (n) {
+    CUDA_TRY(cudaMemcpyAsync(d_ckey, ctx->sort_keys2.p, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_y, ctx->sort_vals2.p, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return MM2_OK;
+}
+
+extern "C" int mm2_mg_build_partial(mm2_ctx_t* ctx, const void* d_ckey, const void* d_y, size_t n, int w, int k, int b, int flag,
+                                    mm2_index_t** out) {
+  if (!ctx || !out || (n && (!d_ckey || !d_y))) { mm2_set_error("mm2_mg_build_partial: bad argument"); return MM2_E_ARG; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  mm2_index* idx = new mm2_index();
+  idx->device = ctx->device; idx->w = w; idx->k = k; idx->b = b; idx->flag = flag;
+  const int R = std::max(2 * k - b, 0);
+  const int end_bit = std::max(1, std::min(64, b + R));
+  ctx->timer.reset();
+  ctx->timer.mark(ctx->stream, "sort");
+  int rc = index_sort_pairs(ctx, (const u64*)d_ckey, (const u64*)d_y, n, end_bit);
+  if (rc == MM2_OK) rc = index_finish_from_sorted(ctx, idx, ctx->sort_keys2.as<u64>(), ctx->sort_vals2.as<u64>(), n, false);
+  if (rc == MM2_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) { mm2_set_error("stream sync failed"); rc = MM2_E_CUDA; }
+  if (rc != MM2_OK) { mm2_index_free(idx); return rc; }
+  *out = idx;
+  return MM2_OK;
+}
+
+extern "C" int mm2_mg_pack_seq(mm2_ctx_t* ctx, const uint8_t* cat, uint64_t total_len, uint64_t word_lo, uint64_t word_hi, void* d_S) {
+  if (!ctx || !d_S || word_lo > word_hi) { mm2_set_error("mm2_mg_pack_seq: bad argument"); return MM2_E_ARG; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const u64 nwords = word_hi - word_lo;
+  if (!nwords) return MM2_OK;
+  const u64 b0 = std::min<u64>(total_len, word_lo * 8), b1 = std::min<u64>(total_len, word_hi * 8);
+  MM2_TRY(ctx->seq.ensure((b1 - b0) + 64));
+  if (b1 > b0) CUDA_TRY(cudaMemcpyAsync(ctx->seq.p, cat + b0, b1 - b0, cudaMemcpyHostToDevice, ctx->stream));
+  MM2_LAUNCH(ctx, pack_seq4_kernel, grid_for(nwords), 256, 0, ctx->seq.as<u8>(), b1 - b0, (u32*)d_S + word_lo, nwords);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return MM2_OK;
+}
+
+extern "C" int mm2_device_copy(mm2_ctx_t* ctx, void* dst, const void* src, size_t nbytes) {
+  if (!ctx || (nbytes && (!dst || !src))) { mm2_set_error("mm2_device_copy: bad argument"); return MM2_E_ARG; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (nbytes) CUDA_TRY(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return MM2_OK;
+}
+
+extern "C" int mm2_index_raw(const mm2_index_t* idx, mm2_index_raw_t* out) {
+  if (!idx || !out) { mm2_set_error("mm2_index_raw: NULL argument"); return MM2_E_ARG; }
+  out->n_keys = idx->n_keys; out->n_p = idx->n_p; out->n_minimizers = idx->n_minimizers; out->S_words = idx->S_words_alloc;
+  out->hkeys = idx->hkeys.p; out->hvals = idx->hvals.p; out->p = idx->p.p; out->bkt_koff = idx->bkt_koff.p; out->bkt_poff = idx->bkt_poff.p;
+  out->S = idx->S.p; out->occ_hist = idx->occ_hist.data(); out->n_occ_big = idx->occ_big.size(); out->occ_big = idx->occ_big.data();
+  return MM2_OK;
+}
+
+extern "C" int mm2_index_assemble(mm2_ctx_t* ctx, const uint64_t* offs, const char* const* names, size_t nseq, int w, int k, int b, int flag,
+                                  uint64_t n_keys, uint64_t n_p, const void* d_hkeys, const void* d_hvals, const void* d_p,
+                                  const void* d_koff, const void* d_poff, const void* d_S, uint64_t S_words, const uint64_t* occ_hist,
+                                  const uint32_t* occ_big, size_t n_occ_big, mm2_index_t** out) {
+  if (!ctx || !out || !d_koff || !d_poff || !occ_hist || (nseq && !offs)) { mm2_set_error("mm2_index_assemble: NULL argument"); return MM2_E_ARG; }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  mm2_index* idx = new mm2_index();
+  idx->device = ctx->device; idx->w = w; idx->k = k; idx->b = b; idx->flag = flag; idx->n_seq = (u32)nseq;
+  u64 sum = 0;
+  for (size_t i = 0; i < nseq; ++i) {
+    idx->has_name.push_back(1);
+    idx->names.push_back(names && names[i] ? std::string(names[i]) : std::string());
+    idx->lens.push_back((u32)(offs[i + 1] - offs[i]));
+    idx->seq_offset.push_back(sum);
+    idx->is_alt.push_back(0);
+    sum += offs[i + 1] - offs[i];
+  }
+  idx->total_len = sum;
+  idx->n_keys = n_keys; idx->n_p = n_p; idx->S_words_alloc = S_words;
+  const size_t nb = (size_t)1 << b;
+  auto fail = [&](int rc) { mm2_index_free(idx); return rc; };
+#define AS_TRY(x) do { int r_ = (x); if (r_ != MM2_OK) return fail(r_); } while (0)
+#define AS_CUDA(x) do { if ((x) != cudaSuccess) { mm2_set_error("%s:%d: CUDA error", __FILE__, __LINE__); return fail(MM2_E_CUDA); } } while (0)
+  AS_TRY(idx->hkeys.ensure(std::max<u64>(1, n_keys) * 8)); AS_TRY(idx->hvals.ensure(std::max<u64>(1, n_keys) * 8));
+  AS_TRY(idx->p.ensure(std::max<u64>(1, n_p) * 8)); AS_TRY(idx->bkt_koff.ensure((nb + 1) * 8)); AS_TRY(idx->bkt_poff.ensure((nb + 1) * 8));
+  AS_TRY(idx->S.ensure(std::max<u64>(1, S_words) * 4)); AS_TRY(idx->seq_len.ensure(std::max<size_t>(1, nseq) * 4));
+  if (n_keys) { AS_CUDA(cudaMemcpyAsync(idx->hkeys.p, d_hkeys, n_keys * 8, cudaMemcpyDeviceToDevice, st)); AS_CUDA(cudaMemcpyAsync(idx->hvals.p, d_hvals, n_keys * 8, cudaMemcpyDeviceToDevice, st)); }
+  if (n_p) AS_CUDA(cudaMemcpyAsync(idx->p.p, d_p, n_p * 8, cudaMemcpyDeviceToDevice, st));
+  AS_CUDA(cudaMemcpyAsync(idx->bkt_koff.p, d_koff, (nb + 1) * 8, cudaMemcpyDeviceToDevice, st));
+  AS_CUDA(cudaMemcpyAsync(idx->bkt_poff.p, d_poff, (nb + 1) * 8, cudaMemcpyDeviceToDevice, st));
+  if (S_words && d_S) AS_CUDA(cudaMemcpyAsync(idx->S.p, d_S, S_words * 4, cudaMemcpyDeviceToDevice, st));
+  if (nseq) AS_CUDA(cudaMemcpyAsync(idx->seq_len.p, idx->lens.data(), nseq * 4, cudaMemcpyHostToDevice, st));
+  idx->occ_hist.assign(occ_hist, occ_hist + 65536);
+  if (n_occ_big && occ_big) { idx->occ_big.assign(occ_big, occ_big + n_occ_big); std::sort(idx->occ_big.begin(), idx->occ_big.end()); }
+  u64 so = 0;
+  for (size_t c = 0; c < 65536; ++c) so += idx->occ_hist[c] * c;
+  for (u32 c : idx->occ_big) so += c;
+  idx->n_minimizers = so;
+  AS_TRY(index_build_table(ctx, idx));
+  AS_CUDA(cudaStreamSynchronize(st));
+#undef AS_TRY
+#undef AS_CUDA
+  *out = idx;
   return MM2_OK;
 }

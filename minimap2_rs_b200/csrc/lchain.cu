@@ -82,8 +82,13 @@ __global__ void __launch_bounds__(CH_WARPS * 32) chain_kernel(ChainArgs G) {
       const ulonglong2 ai = an[i];
       const u32 hi_i = (u32)(ai.x >> 32);
       const int ri = (int)(u32)ai.x, qi = (int)(u32)ai.y, spi = (int)((ai.y >> 32) & 0xff);
-      // lchain.rs:75: st only ever advances
-      for (;;) {
+      // lchain.rs:75: st only ever advances.  Fast path: one warp-uniform load tells whether it moves at all.
+      bool st_moves = false;
+      if (st < i) {
+        const u64 xs = an[st].x;
+        st_moves = ((u32)(xs >> 32) != hi_i) || (ri > wadd((int)(u32)xs, mdx));
+      }
+      while (st_moves) {
         const int idx = st + lane;
         bool adv = false;
         if (idx < i) {

@@ -108,6 +108,10 @@ struct mm2_ctx {
   DevBuf dpA, dpB, dpT, hits, chain_idx, lut;                        // chaining
   DevBuf sort_tmp, sort_tmp2, sort_keys2, sort_vals2, runidx, run_start, run_gp;  // index build
   PinBuf pin_in, pin_out, pin_small;
+  mm2_ctx* worker[2] = {nullptr, nullptr};  // sub-batch pipeline of mm2_map_batch (host buffers)
+  bool pipeline = true;
+  u64 subbatch_bytes = 96ull << 20;
+  u64 mg_sorted_n = 0;  // records left in sort_keys2/sort_vals2 by mm2_mg_sketch_sort
 };
 
 #define MM2_LAUNCH(ctx, kern, grid, block, smem, ...)                         \

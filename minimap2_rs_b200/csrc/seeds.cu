@@ -26,9 +26,18 @@ __global__ void __launch_bounds__(FL_NT) filter_kernel(const u64* __restrict__ m
   const u64 m0 = mini_off[r], m1 = mini_off[r + 1];
   const u64 n = m1 - m0;
   const int tid = threadIdx.x;
-  // sum of spans (paf.rs:160 sum_k) while the keys stream by
+  // One streaming pass: sum of spans (paf.rs:160 sum_k) and a 2048-bin count sketch of the keys.  A key can only be
+  // dropped if it occurs > thr times, and then its bin holds > thr as well, so when no bin exceeds thr (the normal
+  // case: ~1 key per bin) the exact hash-table passes below are skipped.
+  u32* bins = reinterpret_cast<u32*>(fl_smem);
+  for (int s = tid; s < 2048; s += FL_NT) bins[s] = 0;
+  __syncthreads();
   u32 ss = 0;
-  for (u64 i = m0 + tid; i < m1; i += FL_NT) ss += (u32)(mkey[i] & 0xff);
+  for (u64 i = m0 + tid; i < m1; i += FL_NT) {
+    const u64 ks = mkey[i];
+    ss += (u32)(ks & 0xff);
+    atomicAdd(&bins[(u32)(((ks >> 8) * 0x9E3779B97F4A7C15ULL) >> 53)], 1u);
+  }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, d);
   if ((tid & 31) == 0) s_red[tid >> 5] = ss;
@@ -39,6 +48,11 @@ __global__ void __launch_bounds__(FL_NT) filter_kernel(const u64* __restrict__ m
   const float cf = __fmul_rn((float)n, q_occ_frac);                     // seeds.rs:23
   const u64 cutoff = cf <= 0.0f ? 0ull : (cf >= 18446744073709551616.0f ? ~0ull : (u64)cf);
   const u64 thr = max((u64)q_occ_max, cutoff);                          // cnt > q_occ_max && cnt > cutoff
+  {
+    int over = 0;
+    for (int s = tid; s < 2048; s += FL_NT) over |= (u64)bins[s] > thr;
+    if (!__syncthreads_or(over)) return;
+  }
   const u32 npass = (u32)((n + FL_PER_PASS - 1) / FL_PER_PASS);
   for (u32 pass = 0; pass < npass; ++pass) {
     __syncthreads();

@@ -374,3 +374,48 @@ def test_cli_index_align_anchors_chain(ctx, mm2, orc, gen, tmp_path):
     # errors: missing file -> "Error: ..." exit 1
     out = subprocess.run([exe, "align", str(tmp_path / "missing.mmi"), qa], capture_output=True, text=True)
     assert out.returncode == 1 and out.stderr.startswith("Error:")
+
+
+def test_map_batch_pipelined_equals_single(mm2, orc, gen):
+    """large host batches are split into sub-batches over two worker contexts; records must not change"""
+    g = gen.genome(51, 2_000_000)
+    offs = np.array([0, g.size], dtype=np.uint64)
+    os.environ["MM2_SUBBATCH_MB"] = "2"
+    c = mm2.Context(0)
+    del os.environ["MM2_SUBBATCH_MB"]
+    gi = mm2.Index.build(c, g, offs, ["p"])
+    cat, roffs = gen.reads(8, g, offs, 3000, 4000, 0.03, 0.03, 0.03)   # 12 MB -> 6 sub-batches
+    r1 = c.map_batch(gi, cat, roffs)
+    o = mm2.default_map_opts()
+    o.want_stage_dump = 1                                              # forces the single-context path
+    r2 = c.map_batch(gi, cat, roffs, o)
+    assert r1.recs.size == r2.recs.size == 3000 and (r1.recs == r2.recs).all()
+    assert r1.stats["n_anchors"] == r2.stats["n_anchors"] and r1.stats["n_minimizers"] == r2.stats["n_minimizers"]
+    oi = orc.Index.build(g, offs, ["p"], threads=8)
+    names = ["n%d" % i for i in range(3000)]
+    want, _ = oi.align_batch(cat, roffs, names, threads=8)
+    assert r1.paf_lines(names) == want
+    c.close()
+
+
+@pytest.mark.parametrize("world,k,b", [(2, 15, 14), (3, 19, 10), (8, 15, 14)])
+def test_multi_gpu_index_build_emulated_ranks(ctx, mm2, orc, gen, tmp_path, world, k, b):
+    """bucket-partitioned build with R virtual ranks on one GPU: byte-identical .mmi"""
+    from minimap2_rs_b200 import multi_gpu
+    g = gen.repeat_genome(61, 900_000, 0.3, 0.2)
+    cuts = [0, 200_003, 200_004, 450_000, 450_017, 700_001, 900_000]
+    seqs = [g[cuts[i]:cuts[i + 1]].tobytes() for i in range(len(cuts) - 1)]
+    names = ["s%d" % i for i in range(len(seqs))]
+    cat, offs = cases.cat_offs(seqs)
+    gi = multi_gpu.build_index_sharded_emulated(ctx, cat, offs, names, w=10, k=k, b=b, world=world)
+    oi = orc.Index.build(cat, offs, names, w=10, k=k, b=b, threads=8)
+    assert gi.stats() == oi.stats() and gi.calc_mid_occ() == oi.calc_mid_occ()
+    pg, po = str(tmp_path / "g.mmi"), str(tmp_path / "o.mmi")
+    gi.save_to_mmi(pg)
+    oi.save_mmi(po)
+    assert open(pg, "rb").read() == open(po, "rb").read()
+    # and it maps like the single-GPU index
+    rc, ro = gen.reads(2, g[:200_000], np.array([0, 200_000], dtype=np.uint64), 20, 3000, 0.02, 0.02, 0.02)
+    res = ctx.map_batch(gi, rc, ro, mm2.default_map_opts(10, k))
+    want, _ = oi.align_batch(rc, ro, ["m%d" % i for i in range(20)], orc.AlignOpts.default(10, k), threads=4)
+    assert res.paf_lines(["m%d" % i for i in range(20)]) == want
