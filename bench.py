@@ -22,6 +22,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints a banner)
 
 GENOME_SEED, READS_SEED = 0xB2000002, 0xB2001002
 W, K = 10, 15

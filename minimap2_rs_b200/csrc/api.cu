@@ -58,7 +58,7 @@ extern "C" void mm2_ctx_destroy(mm2_ctx_t* c) {
   cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->seq, &c->seq_off, &c->tile_seq, &c->tile_first, &c->tile_status, &c->misc, &c->mkey, &c->mval,
                     &c->mini_off, &c->keep, &c->occ_cnt, &c->occ_loc, &c->anchor_off_m, &c->scan_status, &c->anchors,
-                    &c->read_aoff, &c->read_class, &c->dpA, &c->dpB, &c->dpT, &c->hits, &c->chain_idx, &c->lut, &c->sort_tmp,
+                    &c->read_aoff, &c->read_class, &c->dpA, &c->dpB, &c->dpT, &c->dpW, &c->hits, &c->chain_idx, &c->lut, &c->sort_tmp,
                     &c->sort_tmp2, &c->sort_keys2, &c->sort_vals2, &c->runidx, &c->run_start, &c->run_gp};
   for (DevBuf* b : bufs) b->release();
   c->pin_in.release(); c->pin_out.release(); c->pin_small.release();
@@ -270,7 +270,7 @@ extern "C" int mm2_chain_dp_all(mm2_ctx_t* ctx, const mm2_anchor_t* a, size_t n,
   CUDA_TRY(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   MM2_TRY(ctx->anchors.ensure(n * 16));
-  MM2_TRY(ctx->dpA.ensure(n * 16)); MM2_TRY(ctx->dpB.ensure(n * 16)); MM2_TRY(ctx->dpT.ensure(n * 4));
+  MM2_TRY(ctx->dpA.ensure(n * 16)); MM2_TRY(ctx->dpB.ensure(n * 16)); MM2_TRY(ctx->dpT.ensure(n * 4)); MM2_TRY(ctx->dpW.ensure(n * 4));
   MM2_TRY(ctx->chain_idx.ensure(n * 4 * 4));
   MM2_TRY(ctx->read_aoff.ensure(16)); MM2_TRY(ctx->seq_off.ensure(16)); MM2_TRY(ctx->mini_off.ensure(16));
   MM2_TRY(ctx->hits.ensure(sizeof(ReadHit) + 16)); MM2_TRY(ctx->misc.ensure(64)); MM2_TRY(ctx->mval.ensure(16));
@@ -283,7 +283,7 @@ extern "C" int mm2_chain_dp_all(mm2_ctx_t* ctx, const mm2_anchor_t* a, size_t n,
   CUDA_TRY(cudaStreamSynchronize(st));
   MM2_TRY(chain_batch(ctx, ctx->anchors.as<ulonglong2>(), ctx->read_aoff.as<u64>(), ctx->seq_off.as<u64>(), ctx->mini_off.as<u64>(),
                       ctx->mval.as<u64>(), ctx->misc.as<u32>(), 1, *p, 0, ctx->dpA.as<int4>(), ctx->dpB.as<int4>(), ctx->dpT.as<int>(),
-                      nullptr, ctx->hits.as<ReadHit>(), nullptr));
+                      ctx->dpW.as<int>(), nullptr, ctx->hits.as<ReadHit>(), nullptr));
   int* d_f = ctx->chain_idx.as<int>();
   MM2_LAUNCH(ctx, dp_unpack_kernel, grid_for(n), 256, 0, ctx->dpA.as<int4>(), d_f, d_f + n, d_f + 2 * n, (u64)n);
   std::vector<i32> f(n), v(n), pp(n);
@@ -408,9 +408,10 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
   MM2_TRY(ctx->dpA.ensure(std::max<u64>(1, na) * 16));
   MM2_TRY(ctx->dpB.ensure(std::max<u64>(1, na) * 16));
   MM2_TRY(ctx->dpT.ensure(std::max<u64>(1, na) * 4));
+  MM2_TRY(ctx->dpW.ensure(std::max<u64>(1, na) * 4));
   MM2_TRY(ctx->hits.ensure((nreads + 1) * sizeof(ReadHit)));
   MM2_TRY(chain_batch(ctx, ctx->anchors.as<ulonglong2>(), ctx->read_aoff.as<u64>(), d_off, so.seq_off, so.val, d_sum_span, (u32)nreads,
-                      p, 1, ctx->dpA.as<int4>(), ctx->dpB.as<int4>(), ctx->dpT.as<int>(), nullptr, ctx->hits.as<ReadHit>(), d_cells));
+                      p, 1, ctx->dpA.as<int4>(), ctx->dpB.as<int4>(), ctx->dpT.as<int>(), ctx->dpW.as<int>(), nullptr, ctx->hits.as<ReadHit>(), d_cells));
   ctx->timer.mark(st, "d2h");
   MM2_TRY(ctx->pin_out.ensure((nreads + 1) * sizeof(ReadHit) + 64));
   ReadHit* hits = ctx->pin_out.as<ReadHit>();

@@ -34,7 +34,7 @@ struct ChainArgs {
   mm2_chain_params_t p;
   int do_rescue;
   const float* half_log;  // 0.5 * mg_log2(dd + 1), dd = 0 .. max(bw, bw_long)
-  int4* A; int4* B; int* T; int* chain;
+  int4* A; int4* B; int* T; int* W; int* chain;
   ReadHit* hits;
   unsigned long long* cells;
 };
@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(CH_WARPS * 32) chain_kernel(ChainArgs G) {
   int4* A = G.A + a0;
   int4* B = G.B + a0;
   int* T = G.T + a0;
+  int* W = G.W + a0;
   const mm2_chain_params_t& p = G.p;
   unsigned long long cells = 0;
   int best = 0;
@@ -75,32 +76,47 @@ __global__ void __launch_bounds__(CH_WARPS * 32) chain_kernel(ChainArgs G) {
     const int bw = pass == 0 ? p.bw : p.bw_long;                 // lchain.rs:327-328
     const int mdx = max(p.max_dist_x, bw), mdy = max(p.max_dist_y, bw);  // lchain.rs:63-66
     const int mark_base = pass * n;                              // marks of the two passes never collide
-    if (pass == 0) for (int j = lane; j < n; j += 32) T[j] = -1;
+    // ---- parallel pre-pass ---------------------------------------------------------------------------------------
+    // The window start of lchain.rs:75-78 depends on the anchors only: they are sorted by x = (rev|rid, rpos), so
+    // "rid/strand differ or rpos(i) > rpos(st) + max_dist_x" is true on a prefix of [0, i) and `st` (which only ever
+    // advances) is the first index where it is false.  Every lane finds it for its own anchors by binary search.
+    // Anchors with an empty window (about half of them on ONT-like reads: random hits far from everything else) get
+    // their final DP state here (f = v = q_span, no predecessor, lchain.rs:77,89-90); the others go to a work list
+    // that the sequential DP below walks in index order.
+    int nwork = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      const int i = i0 + lane;
+      bool work = false;
+      if (i < n) {
+        if (pass == 0) T[i] = -1;
+        const ulonglong2 ai = an[i];
+        const u32 hi_i = (u32)(ai.x >> 32);
+        const int ri = (int)(u32)ai.x, qi = (int)(u32)ai.y, spi = (int)((ai.y >> 32) & 0xff);
+        int lo = 0, hi = i;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          const u64 xm = an[mid].x;
+          const bool adv = ((u32)(xm >> 32) != hi_i) || (ri > wadd((int)(u32)xm, mdx));
+          if (adv) lo = mid + 1; else hi = mid;
+        }
+        const int start_j = (wsub(i, p.max_chain_iter) > lo) ? wsub(i, p.max_chain_iter) : lo;  // lchain.rs:78
+        work = start_j < i;
+        int4 ob;
+        ob.x = wsub(qi, spi - 1); ob.y = wsub(ri, spi - 1); ob.z = i; ob.w = start_j;
+        B[i] = ob;
+        if (!work) A[i] = make_int4(spi, -1, spi, 1);
+      }
+      const u32 wm = __ballot_sync(0xFFFFFFFFu, work);
+      if (work) W[nwork + __popc(wm & ((1u << lane) - 1u))] = i;
+      nwork += __popc(wm);
+    }
     __syncwarp();
-    int st = 0;
-    for (int i = 0; i < n; ++i) {
+    for (int t = 0; t < nwork; ++t) {
+      const int i = W[t];
       const ulonglong2 ai = an[i];
       const u32 hi_i = (u32)(ai.x >> 32);
       const int ri = (int)(u32)ai.x, qi = (int)(u32)ai.y, spi = (int)((ai.y >> 32) & 0xff);
-      // lchain.rs:75: st only ever advances.  Fast path: one warp-uniform load tells whether it moves at all.
-      bool st_moves = false;
-      if (st < i) {
-        const u64 xs = an[st].x;
-        st_moves = ((u32)(xs >> 32) != hi_i) || (ri > wadd((int)(u32)xs, mdx));
-      }
-      while (st_moves) {
-        const int idx = st + lane;
-        bool adv = false;
-        if (idx < i) {
-          const u64 xj = an[idx].x;
-          adv = ((u32)(xj >> 32) != hi_i) || (ri > wadd((int)(u32)xj, mdx));
-        }
-        const u32 m = __ballot_sync(0xFFFFFFFFu, adv);
-        const int lead = (m == 0xFFFFFFFFu) ? 32 : (__ffs(~m) - 1);
-        st += lead;
-        if (lead < 32) break;
-      }
-      const int start_j = (wsub(i, p.max_chain_iter) > st) ? wsub(i, p.max_chain_iter) : st;  // lchain.rs:78
+      const int start_j = B[i].w;
       int max_f = spi, max_j = -1, n_skip = 0;
       int mv = 0, mcnt = 0, mqs = 0, mts = 0, mfirst = 0;  // v/cnt/qs_min/ts_min/first of max_j
       const int mark = mark_base + i;
@@ -186,7 +202,7 @@ __global__ void __launch_bounds__(CH_WARPS * 32) chain_kernel(ChainArgs G) {
         ob.x = max_j >= 0 ? min(mqs, own_qs) : own_qs;
         ob.y = max_j >= 0 ? min(mts, own_ts) : own_ts;
         ob.z = max_j >= 0 ? mfirst : i;
-        ob.w = 0;
+        ob.w = start_j;
         A[i] = oa; B[i] = ob;
       }
       __syncwarp();
@@ -284,7 +300,7 @@ static std::vector<float> build_half_log(int n) {
 
 int chain_batch(mm2_ctx* ctx, const ulonglong2* d_anchors, const u64* d_read_aoff, const u64* d_read_off, const u64* d_mini_off,
                 const u64* d_mval, const u32* d_sum_span, u32 nreads, const mm2_chain_params_t& p, int do_rescue, int4* d_A,
-                int4* d_B, int* d_T, int* d_chain, ReadHit* d_hits, unsigned long long* d_cells) {
+                int4* d_B, int* d_T, int* d_W, int* d_chain, ReadHit* d_hits, unsigned long long* d_cells) {
   if (!nreads) return MM2_OK;
   const int max_bw = std::max(p.bw, do_rescue ? p.bw_long : p.bw);
   if (max_bw < 0 || max_bw > (1 << 26)) { mm2_set_error("chain: bandwidth out of range"); return MM2_E_ARG; }
@@ -297,7 +313,7 @@ int chain_batch(mm2_ctx* ctx, const ulonglong2* d_anchors, const u64* d_read_aof
   ChainArgs G;
   G.anchors = d_anchors; G.read_aoff = d_read_aoff; G.read_off = d_read_off; G.mini_off = d_mini_off; G.mval = d_mval;
   G.sum_span = d_sum_span; G.nreads = nreads; G.p = p; G.do_rescue = do_rescue; G.half_log = ctx->lut.as<float>();
-  G.A = d_A; G.B = d_B; G.T = d_T; G.chain = d_chain; G.hits = d_hits; G.cells = d_cells;
+  G.A = d_A; G.B = d_B; G.T = d_T; G.W = d_W; G.chain = d_chain; G.hits = d_hits; G.cells = d_cells;
   const int grid = (int)((nreads + CH_WARPS - 1) / CH_WARPS);
   MM2_LAUNCH(ctx, chain_kernel, grid, CH_WARPS * 32, 0, G);
   CUDA_TRY(cudaGetLastError());

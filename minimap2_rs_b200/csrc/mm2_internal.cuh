@@ -105,7 +105,7 @@ struct mm2_ctx {
   DevBuf mkey, mval, mini_off;                                       // minimizers (SoA) + per-sequence offsets
   DevBuf keep, occ_cnt, occ_loc, anchor_off_m, scan_status;          // filter / lookup
   DevBuf anchors, read_aoff, read_class;                             // anchors
-  DevBuf dpA, dpB, dpT, hits, chain_idx, lut;                        // chaining
+  DevBuf dpA, dpB, dpT, dpW, hits, chain_idx, lut;                        // chaining
   DevBuf sort_tmp, sort_tmp2, sort_keys2, sort_vals2, runidx, run_start, run_gp;  // index build
   PinBuf pin_in, pin_out, pin_small;
   mm2_ctx* worker[2] = {nullptr, nullptr};  // sub-batch pipeline of mm2_map_batch (host buffers)

@@ -27,9 +27,10 @@ int seeds_fill_and_sort(mm2_ctx* ctx, const IndexView& V, const u64* d_mkey, con
                         ulonglong2* d_anchors, u64* d_read_aoff);
 
 // lchain.rs:59-176 forward DP + fallback chain (+ rescue rerun, lchain.rs:321-330) for every read; one warp per read.
-// d_A/d_B: int4 per anchor ({f, pprev, v, cnt}, {qs_min, ts_min, first, -}); d_T: int per anchor.
+// d_A/d_B: int4 per anchor ({f, pprev, v, cnt}, {qs_min, ts_min, first, window start}); d_T, d_W: int per anchor
+// (skip marks of lchain.rs:85-86; work list of the anchors that have a non-empty predecessor window).
 // d_chain (optional, n_anchors ints): the reported chain of each read, last anchor first, at the read's anchor offset.
 int chain_batch(mm2_ctx* ctx, const ulonglong2* d_anchors, const u64* d_read_aoff, const u64* d_read_off, const u64* d_mini_off,
                 const u64* d_mval, const u32* d_sum_span, u32 nreads, const mm2_chain_params_t& p, int do_rescue,
-                int4* d_A, int4* d_B, int* d_T, int* d_chain, ReadHit* d_hits, unsigned long long* d_cells);
+                int4* d_A, int4* d_B, int* d_T, int* d_W, int* d_chain, ReadHit* d_hits, unsigned long long* d_cells);
 int index_build_table(mm2_ctx* ctx, mm2_index* idx);
