@@ -366,35 +366,8 @@ __global__ void __launch_bounds__(SK_NT) sketch_tile_kernel(SketchParams P) {
 // Version 2 of the tile kernel (used for w >= 9): same phases 1-2, but the window argmin is computed per thread with
 // prefix/suffix minima over its 8 consecutive positions (3 merges per position instead of w compares), the emission
 // decisions are taken in registers, and the minimizers are written by the thread that decided them.
-// A candidate is (key, meta) ordered by key, then meta; meta = (2047 - u) << 1 | dup, so among equal keys the NEWEST
-// position wins (sketch.rs:84,90-91) and `dup` says whether the minimum occurs at least twice in the merged range.
-template <class KT> struct Cand;
-template <> struct Cand<u32> {
-  u64 v;
-  static __device__ __forceinline__ Cand make(u32 key, int u) { Cand c; c.v = ((u64)key << 12) | (u64)((2047 - u) << 1); return c; }
-  static __device__ __forceinline__ Cand inf() { Cand c; c.v = ~0ULL; return c; }
-  __device__ __forceinline__ u32 key() const { return (u32)(v >> 12); }
-  __device__ __forceinline__ int pos() const { return 2047 - (int)((v >> 1) & 2047u); }
-  __device__ __forceinline__ bool dup() const { return (v & 1ULL) != 0; }
-  static __device__ __forceinline__ Cand merge(Cand a, Cand b) {
-    Cand r; r.v = min(a.v, b.v) | (u64)(((a.v ^ b.v) >> 12) == 0);
-    return r;
-  }
-};
-template <> struct Cand<u64> {
-  u64 k; u32 m;
-  static __device__ __forceinline__ Cand make(u64 key, int u) { Cand c; c.k = key; c.m = (u32)((2047 - u) << 1); return c; }
-  static __device__ __forceinline__ Cand inf() { Cand c; c.k = ~0ULL; c.m = ~0u; return c; }
-  __device__ __forceinline__ u64 key() const { return k; }
-  __device__ __forceinline__ int pos() const { return 2047 - (int)((m >> 1) & 2047u); }
-  __device__ __forceinline__ bool dup() const { return (m & 1u) != 0; }
-  static __device__ __forceinline__ Cand merge(Cand a, Cand b) {
-    const bool tb = (b.k < a.k) || (b.k == a.k && b.m < a.m);
-    Cand r = tb ? b : a;
-    r.m |= (a.k == b.k) ? 1u : 0u;
-    return r;
-  }
-};
+// Window minima are kept as (key, pos << 1 | dup): among equal keys the NEWEST position wins (sketch.rs:84,90-91) and
+// `dup` says whether the minimum occurs at least twice in the range.
 
 // rare paths of version 2 (a window holding the same key twice), kept out of line so they cost no registers in the hot loop
 template <class KT, int PAD>
@@ -422,7 +395,6 @@ template <class KT>
 __global__ void __launch_bounds__(SK_NT, 4) sketch_tile_kernel_v2(SketchParams P) {
   constexpr int PAD = KeyTraits<KT>::PAD;
   constexpr KT KMAX = (KT)~(KT)0;
-  typedef Cand<KT> C;
 #define KIDX(u) ((u) + ((u) >> PAD))
   __shared__ __align__(16) KT s_key[SK_REGION + (SK_REGION >> PAD) + 8];
   __shared__ __align__(16) u32 s_pack[SK_MAXCHUNK + 4];
@@ -540,26 +512,44 @@ __global__ void __launch_bounds__(SK_NT, 4) sketch_tile_kernel_v2(SketchParams P
     u32 pp[4] = {0, 0, 0, 0};  // position of the previous minimum for each of the 8 steps (u16 x 8)
     int cur7 = 0;              // position of the window minimum at this thread's last position
     if (c0 + SK_CH > w && c0 < w + nsteps) {
-      C R = C::inf();
+      // suffix minima over the w keys before this thread's chunk, newest position winning ties (sketch.rs:84,90-91).
+      // A range is (key, pd) with pd = pos << 1 | dup, dup = "the minimum occurs at least twice in the range".
+      KT rk = KMAX; int rpd = 0;
       int t = c0 - 1;
-      for (; t > c0 - (w - 1) + 7; --t) R = C::merge(R, C::make(keyat(t), t));
-      C S[SK_CH];
+      for (; t > c0 - (w - 1) + 7; --t) {
+        const KT kx = keyat(t);
+        if (kx < rk) { rk = kx; rpd = t << 1; } else if (kx == rk) rpd |= 1;
+      }
+      KT Sk[SK_CH]; int Spd[SK_CH];
 #pragma unroll
-      for (int jj = SK_CH - 1; jj >= 0; --jj) { R = C::merge(R, C::make(keyat(t), t)); S[jj] = R; --t; }
-      C prev = C::merge(R, C::make(keyat(t), t));  // window [c0-w, c0-1]
-      C Pm = C::inf();
+      for (int jj = SK_CH - 1; jj >= 0; --jj) {
+        const KT kx = keyat(t);
+        if (kx < rk) { rk = kx; rpd = t << 1; } else if (kx == rk) rpd |= 1;
+        Sk[jj] = rk; Spd[jj] = rpd;
+        --t;
+      }
+      KT pk_prev; int ppd_prev;  // window [c0-w, c0-1]
+      {
+        const KT kx = keyat(t);
+        pk_prev = rk; ppd_prev = rpd;
+        if (kx < rk) { pk_prev = kx; ppd_prev = t << 1; } else if (kx == rk) ppd_prev |= 1;
+      }
+      KT fk = KMAX; int fpd = 0;  // prefix minima inside the chunk (newer element wins ties)
 #pragma unroll
       for (int j = 0; j < SK_CH; ++j) {
         const int u = c0 + j;
-        Pm = C::merge(Pm, C::make(K[j], u));
-        const C cur = C::merge(S[j], Pm);            // window [u-w+1, u]
-        const int ppos = prev.pos();
+        const KT ki = K[j];
+        if (ki <= fk) { fpd = (u << 1) | (ki == fk ? 1 : 0); fk = ki; }
+        // window [u-w+1, u] = older part (suffix) + newer part (prefix); the newer part wins ties
+        KT ck; int cpd;
+        if (fk <= Sk[j]) { ck = fk; cpd = fpd | (fk == Sk[j] ? 1 : 0); } else { ck = Sk[j]; cpd = Spd[j]; }
+        const int ppos = ppd_prev >> 1;
         pp[j >> 1] |= (u32)ppos << (16 * (j & 1));
         if (u >= w && u <= u_last) {
-          const KT kp = prev.key(), ki = K[j];
+          const KT kp = pk_prev;
           const bool gc = (ge_cap >> j) & 1u, ec1 = (eq_capm1 >> j) & 1u;
           if (kp != KMAX) {
-            if (ec1 && prev.dup()) {
+            if (ec1 && (ppd_prev & 1)) {
               const u32 c1 = sk_count_dups<KT, PAD>(s_key, u - w + 1, u - 1, kp, ppos);
               if (c1) { tot += c1; eflags |= 1u << (8 + j); }
             }
@@ -568,17 +558,17 @@ __global__ void __launch_bounds__(SK_NT, 4) sketch_tile_kernel_v2(SketchParams P
             } else if (ppos == u - w) {
               if (gc || ec1) {
                 tot += 1; eflags |= 1u << j;
-                if (cur.key() != KMAX && cur.dup()) {
-                  const u32 c3 = sk_count_dups<KT, PAD>(s_key, u - w + 1, u, cur.key(), cur.pos());
+                if (ck != KMAX && (cpd & 1)) {
+                  const u32 c3 = sk_count_dups<KT, PAD>(s_key, u - w + 1, u, ck, cpd >> 1);
                   if (c3) { tot += c3; eflags |= 1u << (16 + j); }
                 }
               }
             }
           }
-          if (last_tile && u == u_last && cur.key() != KMAX) { tot += 1; eflags |= 1u << 24; }
+          if (last_tile && u == u_last && ck != KMAX) { tot += 1; eflags |= 1u << 24; }
         }
-        if (u == min(c0 + SK_CH - 1, u_last)) cur7 = cur.pos();
-        prev = cur;
+        if (u == min(c0 + SK_CH - 1, u_last)) cur7 = cpd >> 1;
+        pk_prev = ck; ppd_prev = cpd;
       }
     }
 
@@ -643,15 +633,20 @@ __global__ void __launch_bounds__(SK_NT, 4) sketch_tile_kernel_v2(SketchParams P
         }
         ++o;
       };
-#pragma unroll
-      for (int j = 0; j < SK_CH; ++j) {
+      u32 jm = (eflags | (eflags >> 8) | (eflags >> 16)) & 0xFFu;  // steps of this thread that emit anything
+      while (jm) {
+        const int j = __ffs(jm) - 1;
+        jm &= jm - 1;
         const int u = c0 + j;
-        const int ppos = (int)((pp[j >> 1] >> (16 * (j & 1))) & 0xFFFFu);
+        const u32 pw = (j >> 1) == 0 ? pp[0] : (j >> 1) == 1 ? pp[1] : (j >> 1) == 2 ? pp[2] : pp[3];
+        const int ppos = (int)((pw >> (16 * (j & 1))) & 0xFFFFu);
         if (eflags & (1u << (8 + j)))
           o = sk_emit_dups<KT, PAD>(s_key, s_z, u - w + 1, u - 1, ppos, o, P.out_cap, P.out_key, P.out_val, rid_hi, P0, k);
         if (eflags & (1u << j)) emit(ppos);
         if (eflags & (1u << (16 + j))) {
-          const int cpos = (j == SK_CH - 1) ? cur7 : (int)((pp[(j + 1) >> 1] >> (16 * ((j + 1) & 1))) & 0xFFFFu);
+          const int j1 = j + 1;
+          const u32 pw1 = (j1 >> 1) == 0 ? pp[0] : (j1 >> 1) == 1 ? pp[1] : (j1 >> 1) == 2 ? pp[2] : pp[3];
+          const int cpos = (j == SK_CH - 1) ? cur7 : (int)((pw1 >> (16 * (j1 & 1))) & 0xFFFFu);
           o = sk_emit_dups<KT, PAD>(s_key, s_z, u - w + 1, u, cpos, o, P.out_cap, P.out_key, P.out_val, rid_hi, P0, k);
         }
       }
