@@ -47,6 +47,7 @@ extern "C" int mm2_ctx_create(int device, mm2_ctx_t** out) {
   if (e != cudaSuccess) { delete c; mm2_set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); return MM2_E_CUDA; }
   c->own_stream = true;
   { const char* e = getenv("MM2_PIPELINE"); if (e && atoi(e) == 0) c->pipeline = false; }
+  { const char* e = getenv("MM2_WORKERS"); if (e && atoi(e) >= 2 && atoi(e) <= 4) c->n_workers = atoi(e); }
   { const char* e = getenv("MM2_SUBBATCH_MB"); if (e && atoi(e) > 0) c->subbatch_bytes = (u64)atoi(e) << 20; }
   *out = c;
   return MM2_OK;
@@ -63,7 +64,7 @@ extern "C" void mm2_ctx_destroy(mm2_ctx_t* c) {
   for (DevBuf* b : bufs) b->release();
   c->pin_in.release(); c->pin_out.release(); c->pin_small.release();
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
-  for (int w = 0; w < 2; ++w) if (c->worker[w]) mm2_ctx_destroy(c->worker[w]);
+  for (int w = 0; w < 4; ++w) if (c->worker[w]) mm2_ctx_destroy(c->worker[w]);
   delete c;
 }
 
@@ -526,12 +527,13 @@ static int map_host_single(mm2_ctx* ctx, const mm2_index* idx, const u8* cat, co
   return map_device_impl(ctx, idx, ctx->seq.as<u8>(), ctx->seq_off.as<u64>(), off0.data(), nreads, opts, out, true);
 }
 
-// Large host batches are cut into sub-batches that alternate between two worker contexts (own stream, own arenas, own
+// Large host batches are cut into sub-batches that rotate over a few worker contexts (own stream, own arenas, own
 // host thread), so the H2D copy and the host-side record assembly of one sub-batch overlap the kernels of the other.
 // Reads are independent (main.rs:193-219), so the records are simply concatenated in input order.
 static int map_host_pipelined(mm2_ctx* ctx, const mm2_index* idx, const u8* cat, const u64* offs, size_t nreads,
                               const mm2_map_opts_t* opts, mm2_map_result_t* out, size_t nsub) {
-  for (int w = 0; w < 2; ++w)
+  const int NW = ctx->n_workers;
+  for (int w = 0; w < NW; ++w)
     if (!ctx->worker[w]) MM2_TRY(mm2_ctx_create(ctx->device, &ctx->worker[w]));
   // sub-batch boundaries balanced by bases
   std::vector<size_t> cut(nsub + 1, nreads);
@@ -544,12 +546,12 @@ static int map_host_pipelined(mm2_ctx* ctx, const mm2_index* idx, const u8* cat,
   }
   std::vector<mm2_map_result_t> part(nsub);
   for (auto& p : part) memset(&p, 0, sizeof p);
-  int rc[2] = {MM2_OK, MM2_OK};
-  std::string err[2];
-  std::vector<std::vector<float>> ms_sum(2);
+  int rc[4] = {MM2_OK, MM2_OK, MM2_OK, MM2_OK};
+  std::string err[4];
+  std::vector<std::vector<float>> ms_sum(4);
   auto work = [&](int w) {
     mm2_ctx* c = ctx->worker[w];
-    for (size_t sidx = (size_t)w; sidx < nsub; sidx += 2) {
+    for (size_t sidx = (size_t)w; sidx < nsub; sidx += (size_t)NW) {
       const size_t lo = cut[sidx], hi = cut[sidx + 1];
       const int r = map_host_single(c, idx, cat, offs + lo, hi - lo, opts, &part[sidx]);
       if (r != MM2_OK) { rc[w] = r; err[w] = mm2_last_error(); return; }
@@ -557,12 +559,15 @@ static int map_host_pipelined(mm2_ctx* ctx, const mm2_index* idx, const u8* cat,
       for (size_t i = 0; i < c->timer.ms.size(); ++i) ms_sum[w][i] += c->timer.ms[i];
     }
   };
-  const u64 l0 = ctx->worker[0]->launches + ctx->worker[1]->launches;
-  std::thread t1(work, 1);
+  u64 l0 = 0, l1 = 0;
+  for (int w = 0; w < NW; ++w) l0 += ctx->worker[w]->launches;
+  std::vector<std::thread> th;
+  for (int w = 1; w < NW; ++w) th.emplace_back(work, w);
   work(0);
-  t1.join();
-  ctx->launches += ctx->worker[0]->launches + ctx->worker[1]->launches - l0;
-  for (int w = 0; w < 2; ++w)
+  for (auto& t : th) t.join();
+  for (int w = 0; w < NW; ++w) l1 += ctx->worker[w]->launches;
+  ctx->launches += l1 - l0;
+  for (int w = 0; w < NW; ++w)
     if (rc[w] != MM2_OK) {
       for (auto& p : part) mm2_map_result_free(&p);
       mm2_set_error("%s", err[w].c_str());
@@ -571,7 +576,9 @@ static int map_host_pipelined(mm2_ctx* ctx, const mm2_index* idx, const u8* cat,
   // stage times: sum over both workers (device time spent per stage, not wall time)
   ctx->timer.names = ctx->worker[0]->timer.names;
   ctx->timer.ms.assign(ms_sum[0].size(), 0.f);
-  for (int w = 0; w < 2; ++w) for (size_t i = 0; i < ms_sum[w].size() && i < ctx->timer.ms.size(); ++i) ctx->timer.ms[i] += ms_sum[w][i];
+  for (int w = 1; w < NW; ++w) if (ms_sum[w].size() > ms_sum[0].size()) ms_sum[0].resize(ms_sum[w].size(), 0.f);
+  ctx->timer.ms.assign(ms_sum[0].size(), 0.f);
+  for (int w = 0; w < NW; ++w) for (size_t i = 0; i < ms_sum[w].size() && i < ctx->timer.ms.size(); ++i) ctx->timer.ms[i] += ms_sum[w][i];
   ctx->timer.names_blob.clear();
   for (size_t i = 0; i < ctx->timer.ms.size() && i < ctx->timer.names.size(); ++i) { ctx->timer.names_blob += ctx->timer.names[i]; ctx->timer.names_blob.push_back('\0'); }
   ctx->timer.names_blob.push_back('\0');
@@ -597,7 +604,7 @@ extern "C" int mm2_map_batch(mm2_ctx_t* ctx, const mm2_index_t* idx, const uint8
   if (!ctx || !idx || !offs || !opts || !out || (nreads && !cat)) { mm2_set_error("mm2_map_batch: NULL argument"); return MM2_E_ARG; }
   if (idx->device != ctx->device) { mm2_set_error("index lives on device %d, context on %d", idx->device, ctx->device); return MM2_E_ARG; }
   const u64 total = nreads ? offs[nreads] - offs[0] : 0;
-  // sub-batches of ~96 Mbase (MM2_SUBBATCH_MB); small batches and stage dumps take the single-context path
+  // sub-batches of ~64 Mbase (MM2_SUBBATCH_MB) over 4 worker contexts (MM2_WORKERS): measured best on configs[1]; small batches and stage dumps take the single-context path
   size_t nsub = (size_t)std::min<u64>(64, total / ctx->subbatch_bytes);
   if (nsub > nreads) nsub = nreads;
   if (nsub >= 2 && !opts->want_stage_dump && ctx->pipeline) return map_host_pipelined(ctx, idx, cat, offs, nreads, opts, out, nsub);

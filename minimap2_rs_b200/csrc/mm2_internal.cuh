@@ -108,9 +108,10 @@ struct mm2_ctx {
   DevBuf dpA, dpB, dpT, dpW, hits, chain_idx, lut;                        // chaining
   DevBuf sort_tmp, sort_tmp2, sort_keys2, sort_vals2, runidx, run_start, run_gp;  // index build
   PinBuf pin_in, pin_out, pin_small;
-  mm2_ctx* worker[2] = {nullptr, nullptr};  // sub-batch pipeline of mm2_map_batch (host buffers)
+  mm2_ctx* worker[4] = {nullptr, nullptr, nullptr, nullptr};  // sub-batch pipeline of mm2_map_batch (host buffers)
+  int n_workers = 4;
   bool pipeline = true;
-  u64 subbatch_bytes = 96ull << 20;
+  u64 subbatch_bytes = 64ull << 20;
   u64 mg_sorted_n = 0;  // records left in sort_keys2/sort_vals2 by mm2_mg_sketch_sort
 };
 
