@@ -356,6 +356,39 @@ extern "C" void mm2_default_map_opts(mm2_map_opts_t* o) {  // main.rs:55-89 defa
   o->mid_occ_floor = 10; o->want_stage_dump = 0;
 }
 
+// paf.rs:130-222 for the single reported chain of a read: 0 = no record (no anchors, main.rs:211-213), 1 = record,
+// 2 = the reference panics on this read (idx.seq[rid0] out of bounds after the odd-rid sign extension, F5)
+static int build_record(const mm2_index* idx, const ReadHit& h, u32 r, i32 qlen, mm2_paf_rec_t& rec) {
+  if (h.n_anchors == 0) return 0;
+  const u32 rid0 = h.rid_rev & 0x7fffffffu;
+  if (rid0 >= idx->n_seq) return 2;
+  const bool rev = (h.rid_rev >> 31) != 0;
+  rec.read_id = r; rec.rid = rid0; rec.qlen = (u32)qlen; rec.qstart = (u32)h.qs; rec.qend = (u32)h.qe;
+  rec.tlen = idx->lens[rid0]; rec.tstart = (u32)h.ts; rec.tend = (u32)h.te;
+  rec.nm = (u32)std::max((i32)((u32)h.qe - (u32)h.qs), 0); rec.blen = (u32)std::max((i32)((u32)h.te - (u32)h.ts), 0);
+  rec.cm = h.cm; rec.s1 = (u32)std::max(h.score, 0); rec.s2 = 0; rec.rl = 0;
+  rec.strand = rev ? '-' : '+'; rec.mapq = 60; rec.tp = 'P'; rec.flags = (u8)(h.flags & 1u);
+  // dv (paf.rs:156-200).  With the index's w/k equal to the query's, every chain position is one of the read's
+  // minimizer positions, so n_match = cm and n_tot spans the ranks of the chain's two end positions.
+  float dv = 0.0f;
+  if (h.n_mini > 0 && h.st_rank >= 0) {
+    const float avg_k = (float)h.sum_span / (float)h.n_mini;
+    i32 n_match = (i32)h.cm;
+    const i32 en = h.en_rank >= 0 ? h.en_rank : h.st_rank;
+    if (h.en_rank < 0) n_match = 1;
+    i32 n_tot = en - h.st_rank + 1;
+    const i32 r_qs = rev ? qlen - h.qe : h.qs, r_qe = rev ? qlen - h.qs : h.qe;
+    const i32 avg_k_i = avg_k != avg_k ? 0 : (avg_k >= 2147483648.0f ? INT32_MAX : (avg_k <= -2147483648.0f ? INT32_MIN : (i32)avg_k));
+    if (r_qs > avg_k_i && h.ts > avg_k_i) n_tot += 1;
+    if ((qlen - r_qe) > avg_k_i && ((i32)rec.tlen - h.te) > avg_k_i) n_tot += 1;
+    const float frac = (float)n_match / (float)n_tot;
+    if (frac >= 1.0f) dv = 0.0f;
+    else dv = 1.0f - powf(frac, 1.0f / std::max(avg_k, 1.0f));
+  }
+  rec.dv = dv;
+  return 1;
+}
+
 static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, const u64* d_off, const u64* h_off, size_t nreads,
                            const mm2_map_opts_t* o, mm2_map_result_t* out, bool timer_started) {
   cudaStream_t st = ctx->stream;
@@ -363,10 +396,6 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
   if (o->w != idx->w || o->k != idx->k) {
     // paf.rs:156 re-sketches the query with the index's w/k for dv while everything else uses the CLI's (F8)
     mm2_set_error("mm2_map_batch: opts w/k (%d/%d) differ from the index (%d/%d): not supported yet", o->w, o->k, idx->w, idx->k);
-    return MM2_E_UNSUPPORTED;
-  }
-  if (o->min_cnt < 2) {
-    mm2_set_error("mm2_map_batch: -n < 2 (single-anchor chains of lchain.rs:127-160) is not supported on the batched path yet");
     return MM2_E_UNSUPPORTED;
   }
   i32 mid_occ = 0;
@@ -405,12 +434,14 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
   MM2_TRY(ctx->read_aoff.ensure((nreads + 2) * 8));
   MM2_TRY(seeds_fill_and_sort(ctx, V, so.key, so.val, so.seq_off, d_off, (u32)nreads, ctx->occ_cnt.as<u32>(), ctx->occ_loc.as<u64>(),
                               ctx->anchor_off_m.as<u64>(), ctx->anchors.as<ulonglong2>(), ctx->read_aoff.as<u64>()));
-  ctx->timer.mark(st, "chain");
   MM2_TRY(ctx->dpA.ensure(std::max<u64>(1, na) * 16));
   MM2_TRY(ctx->dpB.ensure(std::max<u64>(1, na) * 16));
   MM2_TRY(ctx->dpT.ensure(std::max<u64>(1, na) * 4));
   MM2_TRY(ctx->dpW.ensure(std::max<u64>(1, na) * 4));
   MM2_TRY(ctx->hits.ensure((nreads + 1) * sizeof(ReadHit)));
+  if (o->min_cnt < 2)  // chain_dp_all really returns many (single-anchor) chains: general tail of main.rs:209-218
+    return map_general_finish(ctx, idx, d_off, h_off, nreads, o, p, so, d_sum_span, nm, na, out);
+  ctx->timer.mark(st, "chain");
   MM2_TRY(chain_batch(ctx, ctx->anchors.as<ulonglong2>(), ctx->read_aoff.as<u64>(), d_off, so.seq_off, so.val, d_sum_span, (u32)nreads,
                       p, 1, ctx->dpA.as<int4>(), ctx->dpB.as<int4>(), ctx->dpT.as<int>(), ctx->dpW.as<int>(), nullptr, ctx->hits.as<ReadHit>(), d_cells));
   ctx->timer.mark(st, "d2h");
@@ -429,39 +460,34 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
   out->recs = xmalloc<mm2_paf_rec_t>(nreads);
   std::vector<u32> panics;
   size_t nr = 0;
-  for (size_t r = 0; r < nreads; ++r) {
-    const ReadHit& h = hits[r];
-    if (h.flags & 1u) out->n_rescued += 1;
-    if (h.n_anchors == 0) continue;  // no anchors: nothing is printed (main.rs:211-213)
-    const u32 rid0 = h.rid_rev & 0x7fffffffu;
-    if (rid0 >= idx->n_seq) { panics.push_back((u32)r); continue; }  // idx.seq[rid0] panics in the reference (F5)
-    const i32 qlen = (i32)(h_off[r + 1] - h_off[r]);
-    const bool rev = (h.rid_rev >> 31) != 0;
-    mm2_paf_rec_t& rec = out->recs[nr++];
-    rec.read_id = (u32)r; rec.rid = rid0; rec.qlen = (u32)qlen; rec.qstart = (u32)h.qs; rec.qend = (u32)h.qe;
-    rec.tlen = idx->lens[rid0]; rec.tstart = (u32)h.ts; rec.tend = (u32)h.te;
-    rec.nm = (u32)std::max((i32)((u32)h.qe - (u32)h.qs), 0); rec.blen = (u32)std::max((i32)((u32)h.te - (u32)h.ts), 0);
-    rec.cm = h.cm; rec.s1 = (u32)std::max(h.score, 0); rec.s2 = 0; rec.rl = 0;
-    rec.strand = rev ? '-' : '+'; rec.mapq = 60; rec.tp = 'P'; rec.flags = (u8)(h.flags & 1u);
-    // dv (paf.rs:156-200).  With the index's w/k equal to the query's, every chain position is one of the read's
-    // minimizer positions, so n_match = cm and n_tot spans the ranks of the chain's two end positions.
-    float dv = 0.0f;
-    if (h.n_mini > 0 && h.st_rank >= 0) {
-      const float avg_k = (float)h.sum_span / (float)h.n_mini;
-      i32 n_match = (i32)h.cm;
-      i32 en = h.en_rank >= 0 ? h.en_rank : h.st_rank;
-      if (h.en_rank < 0) n_match = 1;
-      i32 n_tot = en - h.st_rank + 1;
-      const i32 r_qs = rev ? qlen - h.qe : h.qs, r_qe = rev ? qlen - h.qs : h.qe;
-      const float fk = avg_k;
-      const i32 avg_k_i = fk != fk ? 0 : (fk >= 2147483648.0f ? INT32_MAX : (fk <= -2147483648.0f ? INT32_MIN : (i32)fk));
-      if (r_qs > avg_k_i && h.ts > avg_k_i) n_tot += 1;
-      if ((qlen - r_qe) > avg_k_i && ((i32)rec.tlen - h.te) > avg_k_i) n_tot += 1;
-      volatile float frac = (float)n_match / (float)n_tot;
-      if (frac >= 1.0f) dv = 0.0f;
-      else { volatile float ex = 1.0f / std::max(avg_k, 1.0f); volatile float pw = powf(frac, ex); dv = 1.0f - pw; }
+  {
+    // host threads over contiguous read ranges; results are concatenated in read order
+    const int nth = nreads >= 16384 ? 8 : 1;
+    std::vector<std::vector<mm2_paf_rec_t>> part((size_t)nth);
+    std::vector<std::vector<u32>> ppan((size_t)nth);
+    std::vector<u64> presc((size_t)nth, 0);
+    auto work = [&](int t) {
+      const size_t lo = nreads * (size_t)t / (size_t)nth, hi = nreads * (size_t)(t + 1) / (size_t)nth;
+      part[(size_t)t].reserve(hi - lo);
+      for (size_t r = lo; r < hi; ++r) {
+        const ReadHit& h = hits[r];
+        if (h.flags & 1u) presc[(size_t)t] += 1;
+        mm2_paf_rec_t rec;
+        const int kind = build_record(idx, h, (u32)r, (i32)(h_off[r + 1] - h_off[r]), rec);
+        if (kind == 1) part[(size_t)t].push_back(rec);
+        else if (kind == 2) ppan[(size_t)t].push_back((u32)r);
+      }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nth; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& t : th) t.join();
+    for (int t = 0; t < nth; ++t) {
+      if (!part[(size_t)t].empty()) memcpy(out->recs + nr, part[(size_t)t].data(), part[(size_t)t].size() * sizeof(mm2_paf_rec_t));
+      nr += part[(size_t)t].size();
+      panics.insert(panics.end(), ppan[(size_t)t].begin(), ppan[(size_t)t].end());
+      out->n_rescued += presc[(size_t)t];
     }
-    rec.dv = dv;
   }
   out->n_recs = nr;
   out->n_panic = panics.size();

@@ -34,3 +34,8 @@ int chain_batch(mm2_ctx* ctx, const ulonglong2* d_anchors, const u64* d_read_aof
                 const u64* d_mval, const u32* d_sum_span, u32 nreads, const mm2_chain_params_t& p, int do_rescue,
                 int4* d_A, int4* d_B, int* d_T, int* d_W, int* d_chain, ReadHit* d_hits, unsigned long long* d_cells);
 int index_build_table(mm2_ctx* ctx, mm2_index* idx);
+
+// general.cu: the multi-chain tail of main.rs:209-218 (only reachable with -n < 2)
+int map_general_finish(mm2_ctx* ctx, const mm2_index* idx, const u64* d_read_off, const u64* h_off, size_t nreads,
+                       const mm2_map_opts_t* o, const mm2_chain_params_t& p, const SketchOut& so, const u32* d_sum_span, u64 nm, u64 na,
+                       mm2_map_result_t* out);

@@ -419,3 +419,28 @@ def test_multi_gpu_index_build_emulated_ranks(ctx, mm2, orc, gen, tmp_path, worl
     res = ctx.map_batch(gi, rc, ro, mm2.default_map_opts(10, k))
     want, _ = oi.align_batch(rc, ro, ["m%d" % i for i in range(20)], orc.AlignOpts.default(10, k), threads=4)
     assert res.paf_lines(["m%d" % i for i in range(20)]) == want
+
+
+@pytest.mark.parametrize("min_cnt,min_score,extra", [(1, 10, {}), (1, 40, {}), (1, 5, dict(best_n=2, pri_ratio=0.5, mask_level=0.9)), (1, 10, dict(bw=100, bw_long=3000))])
+def test_map_batch_general_path_single_anchor_chains(ctx, mm2, orc, gen, min_cnt, min_score, extra):
+    """-n 1: chain_dp_all returns many single-anchor chains (F3) -> rescue / merge / select / several PAF lines per read"""
+    g = gen.repeat_genome(91, 800_000, 0.3, 0.2)
+    offs = np.array([0, g.size], dtype=np.uint64)
+    gi = mm2.Index.build(ctx, g, offs, ["gp"])
+    oi = orc.Index.build(g, offs, ["gp"], threads=8)
+    cat, roffs = gen.reads(6, g, offs, 40, 2500, 0.03, 0.03, 0.03)
+    names = ["g%d" % i for i in range(40)]
+    o = mm2.default_map_opts()
+    oo = orc.AlignOpts.default()
+    o.min_cnt = oo.min_cnt = min_cnt
+    o.min_chain_score = oo.min_chain_score = min_score
+    for kk, vv in extra.items():
+        setattr(o, kk, vv)
+        setattr(oo, kk, vv)
+    res = ctx.map_batch(gi, cat, roffs, o)
+    want, st = oi.align_batch(cat, roffs, names, oo, threads=8)
+    got = res.paf_lines(names)
+    if min_score <= 15:
+        assert len(want) > 40                  # really several lines per read
+    assert got == want
+    assert res.stats["n_rescued"] == st.n_rescued
