@@ -393,11 +393,8 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
                            const mm2_map_opts_t* o, mm2_map_result_t* out, bool timer_started) {
   cudaStream_t st = ctx->stream;
   if (nreads > 0xFFFFFFF0ull) { mm2_set_error("too many reads in one batch"); return MM2_E_ARG; }
-  if (o->w != idx->w || o->k != idx->k) {
-    // paf.rs:156 re-sketches the query with the index's w/k for dv while everything else uses the CLI's (F8)
-    mm2_set_error("mm2_map_batch: opts w/k (%d/%d) differ from the index (%d/%d): not supported yet", o->w, o->k, idx->w, idx->k);
-    return MM2_E_UNSUPPORTED;
-  }
+  // paf.rs:156 re-sketches the query with the INDEX's w/k for dv while everything else uses the CLI's
+  const bool wk_mismatch = (o->w != idx->w || o->k != idx->k);
   i32 mid_occ = 0;
   MM2_TRY(mm2_index_calc_mid_occ(idx, o->frac_top_repetitive, &mid_occ));  // main.rs:196-197
   if (mid_occ < o->mid_occ_floor) mid_occ = o->mid_occ_floor;
@@ -439,8 +436,21 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
   MM2_TRY(ctx->dpT.ensure(std::max<u64>(1, na) * 4));
   MM2_TRY(ctx->dpW.ensure(std::max<u64>(1, na) * 4));
   MM2_TRY(ctx->hits.ensure((nreads + 1) * sizeof(ReadHit)));
-  if (o->min_cnt < 2)  // chain_dp_all really returns many (single-anchor) chains: general tail of main.rs:209-218
-    return map_general_finish(ctx, idx, d_off, h_off, nreads, o, p, so, d_sum_span, nm, na, out);
+  if (o->min_cnt < 2 || wk_mismatch) {
+    // general tail of main.rs:209-218: chain_dp_all may return many (single-anchor) chains, and/or dv needs the
+    // minimizers of the query under the index's own w/k
+    SketchOut dvs = so;
+    u64 nm_dv = nm;
+    if (wk_mismatch) {
+      MM2_TRY(sketch_device(ctx, d_cat, d_off, h_off, nreads, idx->w, idx->k, 0, 0, 0, &dvs));
+      nm_dv = dvs.total;
+      MM2_TRY(ctx->keep.ensure(nm_dv + 16));
+      MM2_TRY(seeds_filter(ctx, dvs.key, dvs.seq_off, (u32)nreads, nm_dv, 0, 0.0f, ctx->keep.as<u8>(), d_sum_span));  // sum of spans only
+    }
+    const int rc = map_general_finish(ctx, idx, d_off, h_off, nreads, o, p, dvs, d_sum_span, nm_dv, na, out);
+    if (rc == MM2_OK) out->n_minimizers = nm;
+    return rc;
+  }
   ctx->timer.mark(st, "chain");
   MM2_TRY(chain_batch(ctx, ctx->anchors.as<ulonglong2>(), ctx->read_aoff.as<u64>(), d_off, so.seq_off, so.val, d_sum_span, (u32)nreads,
                       p, 1, ctx->dpA.as<int4>(), ctx->dpB.as<int4>(), ctx->dpT.as<int>(), ctx->dpW.as<int>(), nullptr, ctx->hits.as<ReadHit>(), d_cells));

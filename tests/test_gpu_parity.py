@@ -444,3 +444,17 @@ def test_map_batch_general_path_single_anchor_chains(ctx, mm2, orc, gen, min_cnt
         assert len(want) > 40                  # really several lines per read
     assert got == want
     assert res.stats["n_rescued"] == st.n_rescued
+
+
+def test_map_batch_query_wk_differs_from_index(ctx, mm2, orc, gen):
+    """align sketches the query with the CLI's w/k, dv uses the index's (paf.rs:156)"""
+    g = gen.genome(93, 600_000)
+    offs = np.array([0, g.size], dtype=np.uint64)
+    gi = mm2.Index.build(ctx, g, offs, ["wk"], w=10, k=15)
+    oi = orc.Index.build(g, offs, ["wk"], w=10, k=15, threads=8)
+    cat, roffs = gen.reads(7, g, offs, 30, 3000, 0.01, 0.01, 0.01)
+    names = ["k%d" % i for i in range(30)]
+    for w, k in ((5, 15), (10, 14), (12, 15)):
+        res = ctx.map_batch(gi, cat, roffs, mm2.default_map_opts(w, k))
+        want, _ = oi.align_batch(cat, roffs, names, orc.AlignOpts.default(w, k), threads=8)
+        assert res.paf_lines(names) == want, (w, k)
