@@ -180,11 +180,15 @@ def main():
     t0 = time.perf_counter()
     gi = mm2.Index.build(ctx, pg, goffs, ["chr8"], w=W, k=K, b=14)
     t_build = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    gi2 = mm2.Index.build(ctx, pg, goffs, ["chr8"], w=W, k=K, b=14)   # warm: allocations and kernels already loaded
-    t_build_warm = time.perf_counter() - t0
-    bt = gi2.build_timings()
-    gi2.close()
+    mm2.Index.build(ctx, pg, goffs, ["chr8"], w=W, k=K, b=14).close()   # warm-up: kernels loaded, arenas and the index pool grown
+    t_build_warm = 1e9
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        gi2 = mm2.Index.build(ctx, pg, goffs, ["chr8"], w=W, k=K, b=14)   # from pinned host ASCII to an index resident in HBM
+        t_build_warm = min(t_build_warm, time.perf_counter() - t0)
+        bt = gi2.build_timings()
+        gi2.close()
     n_keys = gi.stats()[0]
 
     # ---- reads: pinned host copy (e2e) and HBM-resident copy (value) ---------------------------------------------------------

@@ -41,6 +41,13 @@ extern "C" int mm2_ctx_create(int device, mm2_ctx_t** out) {
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 10) { mm2_set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return MM2_E_CUDA; }
+  {  // keep freed index pages in the default memory pool (see DevBuf::pooled)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long thr = ~0ULL;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  }
   mm2_ctx* c = new mm2_ctx();
   c->device = device;
   e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);

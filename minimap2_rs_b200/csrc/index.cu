@@ -102,6 +102,10 @@ __global__ void run_fill_kernel(const u64* __restrict__ ckey, const u64* __restr
                                 const u64* __restrict__ gp, const u64* __restrict__ bkt_poff, u64 n_keys, int R,
                                 u64* __restrict__ hkeys, u64* __restrict__ hvals, unsigned long long* __restrict__ hist,
                                 u32* __restrict__ big, u32* __restrict__ n_big, u32 big_cap) {
+  // occurrence histogram (index.rs:124-141): counts < 64 (virtually all keys) are accumulated per block in shared memory
+  __shared__ u32 s_hist[64];
+  if (threadIdx.x < 64) s_hist[threadIdx.x] = 0;
+  __syncthreads();
   const u64 rmask = R >= 64 ? ~0ULL : ((1ULL << R) - 1);
   for (u64 r = blockIdx.x * (u64)blockDim.x + threadIdx.x; r < n_keys; r += (u64)gridDim.x * blockDim.x) {
     const u64 first = run_start[r];
@@ -115,13 +119,12 @@ __global__ void run_fill_kernel(const u64* __restrict__ ckey, const u64* __restr
       hkeys[r] = key_top;
       hvals[r] = ((gp[r] - bkt_poff[ck >> R]) << 32) | n;
     }
-    // occurrence histogram; singletons (the vast majority) are counted per warp to avoid hammering one address
-    const unsigned act = __activemask();
-    const unsigned ones = __ballot_sync(act, n == 1);
-    if (n == 1) { if ((threadIdx.x & 31) == (unsigned)(__ffs(ones) - 1)) atomicAdd(&hist[1], (unsigned long long)__popc(ones)); }
+    if (n < 64) atomicAdd(&s_hist[n], 1u);
     else if (n < 65536) atomicAdd(&hist[n], 1ULL);
     else { const u32 s = atomicAdd(n_big, 1u); if (s < big_cap) big[s] = (u32)(n > 0xFFFFFFFFull ? 0xFFFFFFFFull : n); }
   }
+  __syncthreads();
+  if (threadIdx.x < 64 && s_hist[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)s_hist[threadIdx.x]);
 }
 
 __global__ void p_fill_kernel(const u64* __restrict__ y, const u32* __restrict__ flag, const u64* __restrict__ excl,
@@ -181,6 +184,34 @@ __global__ void tab_build_kernel(const u64* __restrict__ hkeys, const u64* __res
   }
 }
 
+__device__ __forceinline__ void bloom_bits(u64 minier, u64 mask, u64& blk, uint4& bits) {
+  const u64 h = minier * 0xD6E8FEB86659FD93ULL;
+  blk = (h >> 40) & mask;
+  u32 w[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const u32 b = (u32)(h >> (7 * i)) & 127u; w[b >> 5] |= 1u << (b & 31); }
+  bits = make_uint4(w[0], w[1], w[2], w[3]);
+}
+__global__ void bloom_build_kernel(const u64* __restrict__ hkeys, const u64* __restrict__ bkt_koff, u64 n_keys, int b, u32* __restrict__ bloom,
+                                   u64 bloom_mask) {
+  const u64 nb = 1ULL << b;
+  for (u64 r = blockIdx.x * (u64)blockDim.x + threadIdx.x; r < n_keys; r += (u64)gridDim.x * blockDim.x) {
+    u64 lo = 0, hi = nb;
+    while (lo < hi) {
+      const u64 mid = (lo + hi + 1) >> 1;
+      if (bkt_koff[mid] <= r) lo = mid; else hi = mid - 1;
+    }
+    const u64 minier = ((hkeys[r] >> 1) << b) | lo;
+    u64 blk; uint4 bits;
+    bloom_bits(minier, bloom_mask, blk, bits);
+    u32* w = bloom + blk * 4;
+    if (bits.x) atomicOr(w + 0, bits.x);
+    if (bits.y) atomicOr(w + 1, bits.y);
+    if (bits.z) atomicOr(w + 2, bits.z);
+    if (bits.w) atomicOr(w + 3, bits.w);
+  }
+}
+
 __global__ void index_get_kernel(IndexView V, u64 minier, u64* out3) {
   // out3 = {kind, val_or_count, p offset}
   const u64 bmask = (1ULL << V.b) - 1;
@@ -216,6 +247,7 @@ IndexView mm2_index::view() const {
   v.hkeys = hkeys.as<u64>(); v.hvals = hvals.as<u64>(); v.bkt_koff = bkt_koff.as<u64>(); v.bkt_poff = bkt_poff.as<u64>();
   v.p = p.as<u64>(); v.seq_len = seq_len.as<u32>();
   v.tab = tab.as<ulonglong2>(); v.tab_mask = tab_mask;
+  v.bloom = has_bloom ? bloom.as<uint4>() : nullptr; v.bloom_mask = bloom_mask;
   return v;
 }
 
@@ -230,6 +262,19 @@ int index_build_table(mm2_ctx* ctx, mm2_index* idx) {
     MM2_LAUNCH(ctx, tab_build_kernel, grid_for(idx->n_keys), 256, 0, idx->hkeys.as<u64>(), idx->hvals.as<u64>(),
                idx->bkt_koff.as<u64>(), idx->n_keys, idx->b, idx->tab.as<ulonglong2>(), idx->tab_mask);
     CUDA_TRY(cudaGetLastError());
+  }
+  // Bloom filter in front of the table, only while it fits comfortably in the 126 MB L2
+  idx->has_bloom = false;
+  u64 nblk = 1024;
+  while (nblk < idx->n_keys / 8) nblk <<= 1;
+  if (idx->n_keys && nblk * 16 <= (96ull << 20) && !getenv("MM2_NO_BLOOM")) {
+    MM2_TRY(idx->bloom.ensure(nblk * 16));
+    idx->bloom_mask = nblk - 1;
+    CUDA_TRY(cudaMemsetAsync(idx->bloom.p, 0, nblk * 16, ctx->stream));
+    MM2_LAUNCH(ctx, bloom_build_kernel, grid_for(idx->n_keys), 256, 0, idx->hkeys.as<u64>(), idx->bkt_koff.as<u64>(), idx->n_keys, idx->b,
+               idx->bloom.as<u32>(), idx->bloom_mask);
+    CUDA_TRY(cudaGetLastError());
+    idx->has_bloom = true;
   }
   return MM2_OK;
 }

@@ -149,7 +149,7 @@ extern "C" void mm2_index_free(mm2_index_t* idx) {
   if (!idx) return;
   cudaSetDevice(idx->device);
   idx->S.release(); idx->hkeys.release(); idx->hvals.release(); idx->bkt_koff.release(); idx->bkt_poff.release();
-  idx->p.release(); idx->seq_len.release(); idx->tab.release();
+  idx->p.release(); idx->seq_len.release(); idx->tab.release(); idx->bloom.release();
   delete idx;
 }
 

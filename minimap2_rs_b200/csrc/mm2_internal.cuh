@@ -35,21 +35,33 @@ void mm2_set_error(const char* fmt, ...);
     if (r__ != MM2_OK) return r__; \
   } while (0)
 
-// growable device buffer (cudaMalloc is slow; buffers persist in the context and only ever grow)
+// growable device buffer (cudaMalloc is slow; buffers persist in the context and only ever grow).
+// `pooled` buffers (the arrays of an index object, which come and go with every build/load) use the stream-ordered
+// allocator on the legacy default stream with an unlimited release threshold, so a rebuilt index reuses the pages of the
+// freed one instead of paying cudaMalloc/cudaFree again.
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
+  bool pooled = false;
   int ensure(size_t bytes) {
     if (bytes <= cap) return MM2_OK;
-    if (p) cudaFree(p);
-    p = nullptr; cap = 0;
+    release();
     size_t want = bytes + bytes / 8 + 256;
-    cudaError_t e = cudaMalloc(&p, want);
-    if (e != cudaSuccess) { mm2_set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); p = nullptr; return MM2_E_OOM; }
+    cudaError_t e;
+    if (pooled) {
+      e = cudaMallocAsync(&p, want, (cudaStream_t)0);
+      if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)0);
+    } else e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { mm2_set_error("device allocation of %zu bytes failed: %s", want, cudaGetErrorString(e)); p = nullptr; cudaGetLastError(); return MM2_E_OOM; }
     cap = want;
     return MM2_OK;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  void release() {
+    if (p) {
+      if (pooled) { cudaDeviceSynchronize(); cudaFreeAsync(p, (cudaStream_t)0); } else cudaFree(p);
+    }
+    p = nullptr; cap = 0;
+  }
   template <class T> T* as() const { return (T*)p; }
 };
 
@@ -136,6 +148,10 @@ struct IndexView {
   // open-addressing table over all keys: slot = {tag = minier<<1|is_single (0 = empty slot marker ~0), val}
   const ulonglong2* tab;
   u64 tab_mask;
+  // blocked Bloom filter over the keys (one 16-byte block per key, 4 bits), small enough to live in L2: answers most
+  // of the ~80 % of query minimizers that are absent from the index without touching the table in HBM.  NULL = disabled.
+  const uint4* bloom;
+  u64 bloom_mask;
 };
 
 struct mm2_index {
@@ -150,12 +166,14 @@ struct mm2_index {
   u64 total_len = 0;
   u64 S_words_alloc = 0;       // kroundup64((total+7)/8) as allocated by build (native format writes all of it)
   u64 n_keys = 0, n_p = 0, n_minimizers = 0;
-  DevBuf S, hkeys, hvals, bkt_koff, bkt_poff, p, seq_len, tab;
-  u64 tab_mask = 0;
+  DevBuf S, hkeys, hvals, bkt_koff, bkt_poff, p, seq_len, tab, bloom;
+  u64 tab_mask = 0, bloom_mask = 0;
+  bool has_bloom = false;
   // occurrence histogram for calc_mid_occ/stats (index.rs:111-141): hist[c] = #keys with count c (c < 65536)
   std::vector<u64> occ_hist;
   std::vector<u32> occ_big;     // counts >= 65536
   float build_ms[5] = {0, 0, 0, 0, 0};
+  mm2_index() { S.pooled = hkeys.pooled = hvals.pooled = bkt_koff.pooled = bkt_poff.pooled = p.pooled = seq_len.pooled = tab.pooled = bloom.pooled = true; }
   IndexView view() const;
 };
 

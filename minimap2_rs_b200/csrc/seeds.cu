@@ -94,8 +94,16 @@ __global__ void lookup_count_kernel(IndexView V, const u64* __restrict__ mkey, c
     u32 cnt = 0; u64 loc = 0;
     if (keep[i]) {
       const u64 minier = mkey[i] >> 8;
+      bool maybe = true;
+      if (V.bloom) {  // L2-resident pre-filter: a cleared bit proves the key is not in the index
+        const u64 h = minier * 0xD6E8FEB86659FD93ULL;
+        const uint4 blk = __ldg(&V.bloom[(h >> 40) & V.bloom_mask]);
+        const u32 wd[4] = {blk.x, blk.y, blk.z, blk.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const u32 b = (u32)(h >> (7 * q)) & 127u; maybe = maybe && ((wd[b >> 5] >> (b & 31)) & 1u); }
+      }
       u64 slot = tab_hash(minier) & V.tab_mask;
-      for (;;) {
+      while (maybe) {
         const ulonglong2 e = __ldg(&V.tab[slot]);
         if (e.x == ~0ULL) break;
         if ((e.x >> 1) == minier) {
