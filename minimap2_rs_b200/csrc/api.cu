@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <numeric>
+#include <mutex>
 #include <thread>
 
 #include "stages.cuh"
@@ -69,7 +70,7 @@ extern "C" void mm2_ctx_destroy(mm2_ctx_t* c) {
                     &c->read_aoff, &c->read_class, &c->dpA, &c->dpB, &c->dpT, &c->dpW, &c->hits, &c->chain_idx, &c->lut, &c->sort_tmp,
                     &c->sort_tmp2, &c->sort_keys2, &c->sort_vals2, &c->runidx, &c->run_start, &c->run_gp};
   for (DevBuf* b : bufs) b->release();
-  c->pin_in.release(); c->pin_out.release(); c->pin_small.release();
+  c->pin_in.release(); c->pin_out.release(); c->pin_small.release(); c->pin_scalar.release();
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   for (int w = 0; w < 4; ++w) if (c->worker[w]) mm2_ctx_destroy(c->worker[w]);
   delete c;
@@ -228,8 +229,7 @@ extern "C" int mm2_build_anchors_filtered(mm2_ctx_t* ctx, const mm2_index_t* idx
   MM2_TRY(seeds_lookup_count(ctx, V, ctx->mkey.as<u64>(), ctx->keep.as<u8>(), n, mid_occ, ctx->occ_cnt.as<u32>(), ctx->occ_loc.as<u64>()));
   MM2_TRY(scan_u32_to_u64(ctx, ctx->occ_cnt.as<u32>(), ctx->anchor_off_m.as<u64>(), n));
   u64 na = 0;
-  CUDA_TRY(cudaMemcpyAsync(&na, ctx->anchor_off_m.as<u64>() + n, 8, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
+  MM2_TRY(read_scalar_u64(ctx, ctx->anchor_off_m.as<u64>() + n, &na));
   MM2_TRY(ctx->anchors.ensure(std::max<u64>(1, na) * 16));
   // the deinterleave above used ctx->anchors as staging; it has completed (stream order), safe to reuse/grow
   MM2_TRY(seeds_fill_and_sort(ctx, V, ctx->mkey.as<u64>(), ctx->mval.as<u64>(), ctx->mini_off.as<u64>(), ctx->seq_off.as<u64>(), 1,
@@ -431,8 +431,7 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
   MM2_TRY(seeds_lookup_count(ctx, V, so.key, ctx->keep.as<u8>(), nm, mid_occ, ctx->occ_cnt.as<u32>(), ctx->occ_loc.as<u64>()));
   MM2_TRY(scan_u32_to_u64(ctx, ctx->occ_cnt.as<u32>(), ctx->anchor_off_m.as<u64>(), nm));
   u64 na = 0;
-  CUDA_TRY(cudaMemcpyAsync(&na, ctx->anchor_off_m.as<u64>() + nm, 8, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
+  MM2_TRY(read_scalar_u64(ctx, ctx->anchor_off_m.as<u64>() + nm, &na));
   ctx->timer.mark(st, "anchor_fill");
   MM2_TRY(ctx->anchors.ensure(std::max<u64>(1, na) * 16));
   MM2_TRY(ctx->read_aoff.ensure((nreads + 2) * 8));
@@ -564,9 +563,17 @@ static int map_host_single(mm2_ctx* ctx, const mm2_index* idx, const u8* cat, co
   ctx->timer.mark(st, "h2d");
   MM2_TRY(ctx->seq.ensure(total + 64));
   MM2_TRY(ctx->seq_off.ensure((nreads + 1) * 8));
-  if (total) CUDA_TRY(cudaMemcpyAsync(ctx->seq.p, cat + base, total, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(ctx->seq_off.p, off0.data(), (nreads + 1) * 8, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
+  MM2_TRY(ctx->pin_in.ensure((nreads + 1) * 8));
+  {
+    // one H2D at a time: concurrent copies from several workers would share the link and all finish together, which
+    // keeps the workers in lock step (copy, copy, copy, then compute, compute, compute) instead of overlapping
+    static std::mutex h2d_mutex;
+    std::lock_guard<std::mutex> lk(h2d_mutex);
+    if (total) CUDA_TRY(cudaMemcpyAsync(ctx->seq.p, cat + base, total, cudaMemcpyHostToDevice, st));
+    memcpy(ctx->pin_in.p, off0.data(), (nreads + 1) * 8);  // pinned bounce: pageable sources serialise the streams
+    CUDA_TRY(cudaMemcpyAsync(ctx->seq_off.p, ctx->pin_in.p, (nreads + 1) * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
   return map_device_impl(ctx, idx, ctx->seq.as<u8>(), ctx->seq_off.as<u64>(), off0.data(), nreads, opts, out, true);
 }
 

@@ -336,8 +336,7 @@ static int index_finish_from_sorted(mm2_ctx* ctx, mm2_index* idx, const u64* cke
   MM2_LAUNCH(ctx, head_flag_kernel, grid_for(n), 256, 0, ckey, flag, n);
   MM2_TRY(scan_u32_to_u64(ctx, flag, excl, n));
   u64 n_keys = 0;
-  CUDA_TRY(cudaMemcpyAsync(&n_keys, excl + n, 8, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
+  MM2_TRY(read_scalar_u64(ctx, excl + n, &n_keys));
   idx->n_keys = n_keys;
   MM2_TRY(ctx->run_start.ensure((n_keys + 1) * 8));
   MM2_TRY(ctx->run_gp.ensure(((n_keys * 4 + 15) / 16) * 16 + (n_keys + 1) * 8 + 64));
@@ -348,8 +347,7 @@ static int index_finish_from_sorted(mm2_ctx* ctx, mm2_index* idx, const u64* cke
   MM2_LAUNCH(ctx, run_pcount_kernel, grid_for(n_keys), 256, 0, run_start, pc, n_keys);
   MM2_TRY(scan_u32_to_u64(ctx, pc, gp, n_keys));
   u64 n_p = 0;
-  CUDA_TRY(cudaMemcpyAsync(&n_p, gp + n_keys, 8, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
+  MM2_TRY(read_scalar_u64(ctx, gp + n_keys, &n_p));
   idx->n_p = n_p;
   MM2_TRY(idx->hkeys.ensure(std::max<u64>(1, n_keys) * 8));
   MM2_TRY(idx->hvals.ensure(std::max<u64>(1, n_keys) * 8));

@@ -305,11 +305,15 @@ int chain_batch(mm2_ctx* ctx, const ulonglong2* d_anchors, const u64* d_read_aof
   const int max_bw = std::max(p.bw, do_rescue ? p.bw_long : p.bw);
   if (max_bw < 0 || max_bw > (1 << 26)) { mm2_set_error("chain: bandwidth out of range"); return MM2_E_ARG; }
   const int nl = max_bw + 2;
-  std::vector<float> hl = build_half_log(nl);
-  MM2_TRY(ctx->lut.ensure((size_t)nl * 4));
-  MM2_TRY(ctx->pin_small.ensure((size_t)nl * 4));
-  memcpy(ctx->pin_small.p, hl.data(), (size_t)nl * 4);
-  CUDA_TRY(cudaMemcpyAsync(ctx->lut.p, ctx->pin_small.p, (size_t)nl * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (ctx->lut_n < nl) {  // the table depends on dd only: upload once per context and keep it (no per-batch H2D)
+    std::vector<float> hl = build_half_log(nl);
+    MM2_TRY(ctx->lut.ensure((size_t)nl * 4));
+    MM2_TRY(ctx->pin_small.ensure((size_t)nl * 4));
+    memcpy(ctx->pin_small.p, hl.data(), (size_t)nl * 4);
+    CUDA_TRY(cudaMemcpyAsync(ctx->lut.p, ctx->pin_small.p, (size_t)nl * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->lut_n = nl;
+  }
   ChainArgs G;
   G.anchors = d_anchors; G.read_aoff = d_read_aoff; G.read_off = d_read_off; G.mini_off = d_mini_off; G.mval = d_mval;
   G.sum_span = d_sum_span; G.nreads = nreads; G.p = p; G.do_rescue = do_rescue; G.half_log = ctx->lut.as<float>();

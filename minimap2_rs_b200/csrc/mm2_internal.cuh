@@ -119,11 +119,12 @@ struct mm2_ctx {
   DevBuf anchors, read_aoff, read_class;                             // anchors
   DevBuf dpA, dpB, dpT, dpW, hits, chain_idx, lut;                        // chaining
   DevBuf sort_tmp, sort_tmp2, sort_keys2, sort_vals2, runidx, run_start, run_gp;  // index build
-  PinBuf pin_in, pin_out, pin_small;
+  PinBuf pin_in, pin_out, pin_small, pin_scalar;  // pin_scalar: 8-byte device->host reads (pageable targets serialise streams)
   mm2_ctx* worker[4] = {nullptr, nullptr, nullptr, nullptr};  // sub-batch pipeline of mm2_map_batch (host buffers)
   int n_workers = 4;
   bool pipeline = true;
   u64 subbatch_bytes = 64ull << 20;
+  int lut_n = 0;        // entries of the chaining log table resident in `lut`
   u64 mg_sorted_n = 0;  // records left in sort_keys2/sort_vals2 by mm2_mg_sketch_sort
 };
 
@@ -176,6 +177,9 @@ struct mm2_index {
   mm2_index() { S.pooled = hkeys.pooled = hvals.pooled = bkt_koff.pooled = bkt_poff.pooled = p.pooled = seq_len.pooled = tab.pooled = bloom.pooled = true; }
   IndexView view() const;
 };
+
+// read one u64 from device memory through a pinned bounce slot and wait for it
+int read_scalar_u64(mm2_ctx* ctx, const u64* d_src, u64* out);
 
 // ---- stage entry points shared between translation units (all asynchronous on ctx->stream unless noted) ----
 struct SketchOut {  // device SoA minimizers of a batch

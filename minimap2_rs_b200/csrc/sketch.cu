@@ -28,7 +28,7 @@ struct SketchParams {
   const u64* seq_off;     // nseq+1
   u64 buf_len;            // readable bytes in seq
   const u32* tile_seq;    // ntiles: sequence of each tile
-  const u32* tile_first;  // nseq+1: first tile of each sequence
+  const u64* tile_first;  // nseq+1: first tile of each sequence
   u32 nseq, ntiles;
   int w, k;
   int vec_ok;             // seq is 16-byte aligned
@@ -764,6 +764,26 @@ __global__ void excl_scan_u64_small(const u64* in, u64* out, u32 n) {  // single
   }
 }
 
+// number of tiles of each sequence (at least one, so that empty sequences still get an output offset)
+__global__ void tile_count_kernel(const u64* __restrict__ seq_off, u32 nseq, int T, u32* __restrict__ cnt) {
+  const u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nseq) return;
+  const u64 len = seq_off[q + 1] - seq_off[q];
+  const u64 c = (len + (u64)T - 1) / (u64)T;
+  cnt[q] = (u32)(c ? c : 1);
+}
+// sequence of each tile: last q with tile_first[q] <= tile
+__global__ void tile_seq_kernel(const u64* __restrict__ tile_first, u32 nseq, u32 ntiles, u32* __restrict__ tile_seq) {
+  for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < ntiles; t += gridDim.x * blockDim.x) {
+    u32 lo = 0, hi = nseq - 1;
+    while (lo < hi) {
+      const u32 mid = (lo + hi + 1) >> 1;
+      if (tile_first[mid] <= (u64)t) lo = mid; else hi = mid - 1;
+    }
+    tile_seq[t] = lo;
+  }
+}
+
 int g_num_sms = 0;
 
 }  // namespace
@@ -790,34 +810,31 @@ int sketch_device(mm2_ctx* ctx, const u8* d_cat, const u64* d_off, const u64* h_
   u64 cap = (u64)((double)total_len * 2.0 / (double)(w + 1) * 1.25) + 2 * nseq + 1024;
   if (tile_path) {
     const int T = SK_REGION - w;
-    std::vector<u32> tile_first(nseq + 1);
     u64 nt = 0;
     for (size_t i = 0; i < nseq; ++i) {
-      tile_first[i] = (u32)nt;
       const u64 len = h_off[i + 1] - h_off[i];
       nt += std::max<u64>(1, (len + T - 1) / T);
       if (nt >= 0xFFFFFFF0ull) { mm2_set_error("sketch: too many tiles"); return MM2_E_ARG; }
     }
-    tile_first[nseq] = (u32)nt;
     const u32 ntiles = (u32)nt;
-    MM2_TRY(ctx->pin_small.ensure((nseq + 1 + (size_t)ntiles) * 4));
-    u32* h_tf = ctx->pin_small.as<u32>();
-    u32* h_ts = h_tf + nseq + 1;
-    memcpy(h_tf, tile_first.data(), (nseq + 1) * 4);
-    for (size_t i = 0; i < nseq; ++i)
-      for (u32 t = tile_first[i]; t < tile_first[i + 1]; ++t) h_ts[t] = (u32)i;
-    MM2_TRY(ctx->tile_first.ensure((nseq + 1) * 4));
+    // tile -> sequence tables are derived ON the device from the resident offsets (no small H2D copies: they would
+    // queue behind another context's bulk read upload on the copy engine and stall this stream)
+    MM2_TRY(ctx->tile_first.ensure((nseq + 4) * 8 + (nseq + 8) * 4));
     MM2_TRY(ctx->tile_seq.ensure((size_t)ntiles * 4));
     MM2_TRY(ctx->tile_status.ensure((size_t)ntiles * 8 + 16));
-    CUDA_TRY(cudaMemcpyAsync(ctx->tile_first.p, h_tf, (nseq + 1) * 4, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(ctx->tile_seq.p, h_ts, (size_t)ntiles * 4, cudaMemcpyHostToDevice, st));
+    u64* d_tf64 = ctx->tile_first.as<u64>();
+    u32* d_tcnt = (u32*)((u8*)ctx->tile_first.p + ((((nseq + 2) * 8) + 15) / 16) * 16);  // 16-byte aligned for the scan's vector loads
+    MM2_LAUNCH(ctx, tile_count_kernel, (int)((nseq + 255) / 256), 256, 0, d_off, (u32)nseq, T, d_tcnt);
+    MM2_TRY(scan_u32_to_u64(ctx, d_tcnt, d_tf64, nseq));
+    MM2_LAUNCH(ctx, tile_seq_kernel, (int)std::min<u64>(((u64)ntiles + 255) / 256, 148ull * 32), 256, 0, d_tf64, (u32)nseq, ntiles,
+               ctx->tile_seq.as<u32>());
     for (int attempt = 0; attempt < 2; ++attempt) {
       MM2_TRY(ctx->mkey.ensure(cap * 8));
       MM2_TRY(ctx->mval.ensure(cap * 8));
       CUDA_TRY(cudaMemsetAsync(ctx->tile_status.p, 0, (size_t)ntiles * 8 + 16, st));
       SketchParams P;
       P.seq = d_cat; P.seq_off = d_off; P.buf_len = h_off[nseq];
-      P.tile_seq = ctx->tile_seq.as<u32>(); P.tile_first = ctx->tile_first.as<u32>();
+      P.tile_seq = ctx->tile_seq.as<u32>(); P.tile_first = d_tf64;
       P.nseq = (u32)nseq; P.ntiles = ntiles; P.w = w; P.k = k;
       P.vec_ok = ((uintptr_t)d_cat & 15) == 0;
       P.rid_base = rid_base; P.rid_step = rid_step;
@@ -835,8 +852,7 @@ int sketch_device(mm2_ctx* ctx, const u8* d_cat, const u64* d_off, const u64* h_
       }
       CUDA_TRY(cudaGetLastError());
       u64 total = 0;
-      CUDA_TRY(cudaMemcpyAsync(&total, ctx->mini_off.as<u64>() + nseq, 8, cudaMemcpyDeviceToHost, st));
-      CUDA_TRY(cudaStreamSynchronize(st));
+      MM2_TRY(read_scalar_u64(ctx, ctx->mini_off.as<u64>() + nseq, &total));
       out->total = total;
       if (total <= cap) break;
       if (attempt == 1) { mm2_set_error("sketch: output capacity overflow after retry"); return MM2_E_CUDA; }
@@ -856,8 +872,7 @@ int sketch_device(mm2_ctx* ctx, const u8* d_cat, const u64* d_off, const u64* h_
     MM2_LAUNCH(ctx, sketch_literal_kernel<0>, nb, 64, 0, P);
     MM2_LAUNCH(ctx, excl_scan_u64_small, 1, 1, 0, d_counts, ctx->mini_off.as<u64>(), (u32)nseq);
     u64 total = 0;
-    CUDA_TRY(cudaMemcpyAsync(&total, ctx->mini_off.as<u64>() + nseq, 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    MM2_TRY(read_scalar_u64(ctx, ctx->mini_off.as<u64>() + nseq, &total));
     cap = total + 16;
     MM2_TRY(ctx->mkey.ensure(cap * 8));
     MM2_TRY(ctx->mval.ensure(cap * 8));
