@@ -186,8 +186,7 @@ template <int CAP, int NT>
 __global__ void __launch_bounds__(NT) anchor_sort_smem_kernel(ulonglong2* __restrict__ anchors, const u64* __restrict__ read_aoff,
                                                               u32 nreads, u32 lo_excl, u32 hi_incl) {
   extern __shared__ __align__(16) unsigned char as_smem[];
-  u64* sx = reinterpret_cast<u64*>(as_smem);
-  u64* sy = sx + CAP;
+  ulonglong2* sa = reinterpret_cast<ulonglong2*>(as_smem);
   const u32 r = blockIdx.x;
   if (r >= nreads) return;
   const u64 a0 = read_aoff[r];
@@ -195,29 +194,37 @@ __global__ void __launch_bounds__(NT) anchor_sort_smem_kernel(ulonglong2* __rest
   if (n64 <= lo_excl || n64 > hi_incl) return;
   const int n = (int)n64;
   ulonglong2* a = anchors + a0;
-  for (int i = threadIdx.x; i < n; i += NT) { const ulonglong2 v = a[i]; sx[i] = v.x; sy[i] = v.y; }
+  for (int i = threadIdx.x; i < n; i += NT) sa[i] = a[i];
   __syncthreads();
-  for (int k = 2; (k >> 1) < n; k <<= 1) {
-    for (int i = threadIdx.x; i < n; i += NT) {
+  int m = 2;
+  while (m < n) m <<= 1;          // network size (elements past n behave as +inf and never move)
+  const int half = m >> 1;
+  // every thread owns comparators, not elements: comparator t of a sub-step with distance j touches
+  // i = (t / j) * 2j + (t % j) and its partner, so no thread idles on the "upper" element of a pair
+  for (int k = 2; k <= m; k <<= 1) {
+    const int hk = k >> 1;
+    for (int t = threadIdx.x; t < half; t += NT) {   // first sub-step of the stage: partner = mirror inside the block of k
+      const int i = ((t & ~(hk - 1)) << 1) | (t & (hk - 1));
       const int p = i ^ (k - 1);
-      if (p > i && p < n) {
-        const u64 x1 = sx[i], y1 = sy[i], x2 = sx[p], y2 = sy[p];
-        if (a_less(x2, y2, x1, y1)) { sx[i] = x2; sy[i] = y2; sx[p] = x1; sy[p] = y1; }
+      if (p < n) {
+        const ulonglong2 v1 = sa[i], v2 = sa[p];
+        if (a_less(v2.x, v2.y, v1.x, v1.y)) { sa[i] = v2; sa[p] = v1; }
       }
     }
     __syncthreads();
     for (int j = k >> 2; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < n; i += NT) {
-        const int p = i ^ j;
-        if (p > i && p < n) {
-          const u64 x1 = sx[i], y1 = sy[i], x2 = sx[p], y2 = sy[p];
-          if (a_less(x2, y2, x1, y1)) { sx[i] = x2; sy[i] = y2; sx[p] = x1; sy[p] = y1; }
+      for (int t = threadIdx.x; t < half; t += NT) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int p = i + j;
+        if (p < n) {
+          const ulonglong2 v1 = sa[i], v2 = sa[p];
+          if (a_less(v2.x, v2.y, v1.x, v1.y)) { sa[i] = v2; sa[p] = v1; }
         }
       }
       __syncthreads();
     }
   }
-  for (int i = threadIdx.x; i < n; i += NT) a[i] = make_ulonglong2(sx[i], sy[i]);
+  for (int i = threadIdx.x; i < n; i += NT) a[i] = sa[i];
 }
 
 // reads with more anchors than fit in shared memory: same network over global memory (L2-resident), one CTA per read
