@@ -112,8 +112,9 @@ int mm2_mg_sketch_sort(mm2_ctx_t* ctx, const uint8_t* cat, const uint64_t* offs,
                        int k, int b, int flag, int nranks, uint64_t* counts);
 /* copy the n sorted (key, position) records of the last mm2_mg_sketch_sort into caller-owned device buffers */
 int mm2_mg_export_sorted(mm2_ctx_t* ctx, void* d_ckey, void* d_y, size_t n);
-/* received records (device, source-rank order) -> the buckets this rank owns (index.rs:74-109), no lookup table */
-int mm2_mg_build_partial(mm2_ctx_t* ctx, const void* d_ckey, const void* d_y, size_t n, int w, int k, int b, int flag,
+/* received records (device, source-rank order; the two buffers are used as sort scratch) -> the buckets this rank owns
+ * (index.rs:74-109), no lookup table */
+int mm2_mg_build_partial(mm2_ctx_t* ctx, void* d_ckey, void* d_y, size_t n, int w, int k, int b, int flag,
                          mm2_index_t** out);
 /* 4-bit pack (index.rs:11-19) words [word_lo, word_hi) of the genome into d_S (a device array of all S words) */
 int mm2_mg_pack_seq(mm2_ctx_t* ctx, const uint8_t* cat, uint64_t total_len, uint64_t word_lo, uint64_t word_hi, void* d_S);

@@ -279,12 +279,18 @@ int index_build_table(mm2_ctx* ctx, mm2_index* idx) {
   return MM2_OK;
 }
 
-// (ckey, y) pairs -> ctx->sort_keys2 / ctx->sort_vals2, sorted by ckey (stable: equal keys keep their input order)
-static int index_sort_pairs(mm2_ctx* ctx, const u64* ckey_in, const u64* y_in, u64 n, int end_bit) {
+// (ckey, y) pairs sorted by ckey (stable: equal keys keep their input order).  The input arrays are scratch afterwards;
+// ctx->sorted_k / ctx->sorted_v point at the result.  MM2_SORT=cub selects the CUB onesweep sort for comparison.
+int radix_sort_pairs(mm2_ctx* ctx, u64* a_keys, u64* a_vals, u64* b_keys, u64* b_vals, u64 n, int end_bit, u64** res_keys, u64** res_vals);
+static int index_sort_pairs(mm2_ctx* ctx, u64* ckey_in, u64* y_in, u64 n, int end_bit) {
   cudaStream_t st = ctx->stream;
   MM2_TRY(ctx->sort_keys2.ensure(std::max<u64>(1, n) * 8));
   MM2_TRY(ctx->sort_vals2.ensure(std::max<u64>(1, n) * 8));
+  ctx->sorted_k = ctx->sort_keys2.as<u64>(); ctx->sorted_v = ctx->sort_vals2.as<u64>();
   if (n == 0) return MM2_OK;
+  static int use_cub = -1;
+  if (use_cub < 0) { const char* e = getenv("MM2_SORT"); use_cub = (e && !strcmp(e, "cub")) ? 1 : 0; }
+  if (!use_cub) return radix_sort_pairs(ctx, ckey_in, y_in, ctx->sort_keys2.as<u64>(), ctx->sort_vals2.as<u64>(), n, end_bit, &ctx->sorted_k, &ctx->sorted_v);
   size_t tmp_bytes = 0;
   CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ckey_in, ctx->sort_keys2.as<u64>(), y_in, ctx->sort_vals2.as<u64>(), n, 0,
                                            end_bit, st));
@@ -307,7 +313,7 @@ static int index_finish_from_minimizers(mm2_ctx* ctx, mm2_index* idx, u64 n) {
     MM2_LAUNCH(ctx, rekey_kernel, grid_for(n), 256, 0, ctx->mkey.as<u64>(), ctx->sort_tmp2.as<u64>(), n, b, R);
   }
   MM2_TRY(index_sort_pairs(ctx, ctx->sort_tmp2.as<u64>(), ctx->mval.as<u64>(), n, end_bit));
-  return index_finish_from_sorted(ctx, idx, ctx->sort_keys2.as<u64>(), ctx->sort_vals2.as<u64>(), n, true);
+  return index_finish_from_sorted(ctx, idx, ctx->sorted_k, ctx->sorted_v, n, true);
 }
 
 // run-length grouping of the sorted pairs into the flat index arrays (+ occurrence histogram, + lookup table)
@@ -528,7 +534,7 @@ extern "C" int mm2_mg_sketch_sort(mm2_ctx_t* ctx, const uint8_t* cat, const uint
   }
   MM2_TRY(index_sort_pairs(ctx, ctx->sort_tmp2.as<u64>(), ctx->mval.as<u64>(), n, end_bit));
   MM2_TRY(ctx->misc.ensure(((size_t)nranks + 2) * 8));
-  MM2_LAUNCH(ctx, owner_bounds_kernel, (nranks + 1 + 63) / 64, 64, 0, ctx->sort_keys2.as<u64>(), n, b, R, nranks, ctx->misc.as<u64>());
+  MM2_LAUNCH(ctx, owner_bounds_kernel, (nranks + 1 + 63) / 64, 64, 0, ctx->sorted_k, n, b, R, nranks, ctx->misc.as<u64>());
   std::vector<u64> bounds((size_t)nranks + 1);
   CUDA_TRY(cudaMemcpyAsync(bounds.data(), ctx->misc.p, ((size_t)nranks + 1) * 8, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
@@ -541,14 +547,14 @@ extern "C" int mm2_mg_export_sorted(mm2_ctx_t* ctx, void* d_ckey, void* d_y, siz
   if (!ctx || (n && (!d_ckey || !d_y)) || n != ctx->mg_sorted_n) { mm2_set_error("mm2_mg_export_sorted: bad argument"); return MM2_E_ARG; }
   CUDA_TRY(cudaSetDevice(ctx->device));
   if (n) {
-    CUDA_TRY(cudaMemcpyAsync(d_ckey, ctx->sort_keys2.p, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(d_y, ctx->sort_vals2.p, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_ckey, ctx->sorted_k, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_y, ctx->sorted_v, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   }
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return MM2_OK;
 }
 
-extern "C" int mm2_mg_build_partial(mm2_ctx_t* ctx, const void* d_ckey, const void* d_y, size_t n, int w, int k, int b, int flag,
+extern "C" int mm2_mg_build_partial(mm2_ctx_t* ctx, void* d_ckey, void* d_y, size_t n, int w, int k, int b, int flag,
                                     mm2_index_t** out) {
   if (!ctx || !out || (n && (!d_ckey || !d_y))) { mm2_set_error("mm2_mg_build_partial: bad argument"); return MM2_E_ARG; }
   CUDA_TRY(cudaSetDevice(ctx->device));
@@ -558,8 +564,8 @@ extern "C" int mm2_mg_build_partial(mm2_ctx_t* ctx, const void* d_ckey, const vo
   const int end_bit = std::max(1, std::min(64, b + R));
   ctx->timer.reset();
   ctx->timer.mark(ctx->stream, "sort");
-  int rc = index_sort_pairs(ctx, (const u64*)d_ckey, (const u64*)d_y, n, end_bit);
-  if (rc == MM2_OK) rc = index_finish_from_sorted(ctx, idx, ctx->sort_keys2.as<u64>(), ctx->sort_vals2.as<u64>(), n, false);
+  int rc = index_sort_pairs(ctx, (u64*)d_ckey, (u64*)d_y, n, end_bit);  // the received buffers are scratch from here on
+  if (rc == MM2_OK) rc = index_finish_from_sorted(ctx, idx, ctx->sorted_k, ctx->sorted_v, n, false);
   if (rc == MM2_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) { mm2_set_error("stream sync failed"); rc = MM2_E_CUDA; }
   if (rc != MM2_OK) { mm2_index_free(idx); return rc; }
   *out = idx;

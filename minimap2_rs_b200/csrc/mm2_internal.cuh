@@ -118,7 +118,8 @@ struct mm2_ctx {
   DevBuf keep, occ_cnt, occ_loc, anchor_off_m, scan_status;          // filter / lookup
   DevBuf anchors, read_aoff, read_class;                             // anchors
   DevBuf dpA, dpB, dpT, dpW, hits, chain_idx, lut;                        // chaining
-  DevBuf sort_tmp, sort_tmp2, sort_keys2, sort_vals2, runidx, run_start, run_gp;  // index build
+  DevBuf sort_tmp, sort_tmp2, sort_keys2, sort_vals2, runidx, run_start, run_gp, rs_counts, rs_offs;  // index build
+  u64* sorted_k = nullptr; u64* sorted_v = nullptr;  // where the last index_sort_pairs left its result
   PinBuf pin_in, pin_out, pin_small, pin_scalar;  // pin_scalar: 8-byte device->host reads (pageable targets serialise streams)
   mm2_ctx* worker[4] = {nullptr, nullptr, nullptr, nullptr};  // sub-batch pipeline of mm2_map_batch (host buffers)
   int n_workers = 4;

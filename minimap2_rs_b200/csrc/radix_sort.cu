@@ -1,0 +1,160 @@
+// radix_sort.cu — stable LSD radix sort of (u64 key, u64 value) pairs, 10 bits per pass, hand-written for sm_100a.
+// Replaces the per-bucket `sort_by_key` of index.rs:79 (the bucket id is folded into the high bits of the key, so one
+// global sort yields bucket-major, key-minor order; stability keeps positions ascending inside equal keys).
+//
+// Each pass is three kernels over tiles of RS_TILE consecutive pairs:
+//   rs_hist     per-tile histogram of the current digit            (reads 8 B / pair)
+//   scan        exclusive scan of the (digit-major, tile-minor) counts  -> first output slot of every (digit, tile)
+//   rs_scatter  stable rank of every pair inside its tile + scatter     (reads 16 B, writes 16 B / pair)
+// Ranks inside a tile: every warp owns a contiguous slice of the tile and walks it 32 pairs at a time; lanes holding the
+// same digit find each other with __match_any_sync, the lowest of them bumps the warp's private counter for that digit,
+// and rank = old count + number of lower lanes with the same digit.  The per-warp counters are then prefix-summed over the
+// warps of the CTA, which makes the rank stable over the whole tile.
+#include "mm2_internal.cuh"
+
+#include <algorithm>
+
+namespace {
+
+constexpr int RS_NT = 256;             // threads per CTA
+constexpr int RS_WARPS = RS_NT / 32;
+constexpr int RS_ROWS = 16;            // 32-pair rows per warp
+constexpr int RS_TILE = RS_WARPS * RS_ROWS * 32;  // 4096 pairs per CTA
+constexpr int RS_BITS = 10;            // digit width: 30 key bits (k = 15) take 3 passes
+constexpr int RS_BINS = 1 << RS_BITS;
+constexpr int RS_DPT = RS_BINS / RS_NT;  // digits per thread in the per-digit loops
+
+__global__ void __launch_bounds__(RS_NT) rs_hist_kernel(const u64* __restrict__ keys, u64 n, int shift, u32 ntiles, u32* __restrict__ counts) {
+  __shared__ u32 s_h[RS_BINS];
+  for (u32 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+#pragma unroll
+    for (int q = 0; q < RS_DPT; ++q) s_h[q * RS_NT + threadIdx.x] = 0;
+    __syncthreads();
+    const u64 base = (u64)tile * RS_TILE;
+#pragma unroll 4
+    for (int r = 0; r < RS_TILE / RS_NT; ++r) {
+      const u64 i = base + (u64)r * RS_NT + threadIdx.x;
+      if (i < n) atomicAdd(&s_h[(u32)(keys[i] >> shift) & (RS_BINS - 1)], 1u);
+    }
+    __syncthreads();
+    // digit-major so that one scan orders digits first, tiles second
+#pragma unroll
+    for (int q = 0; q < RS_DPT; ++q) counts[(u64)(q * RS_NT + threadIdx.x) * ntiles + tile] = s_h[q * RS_NT + threadIdx.x];
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(RS_NT) rs_scatter_kernel(const u64* __restrict__ keys, const u64* __restrict__ vals, u64 n, int shift,
+                                                           u32 ntiles, const u64* __restrict__ offs, u64* __restrict__ out_keys,
+                                                           u64* __restrict__ out_vals) {
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  u64* sk = reinterpret_cast<u64*>(rs_smem);          // tile staged in (digit, rank) order: keys
+  u64* sv = sk + RS_TILE;                             //                                    values
+  __shared__ u16 s_cnt[RS_WARPS][RS_BINS];  // per-warp digit counters, then exclusive prefix over the warps
+  __shared__ u64 s_base[RS_BINS];           // first global output slot of each digit for this tile
+  __shared__ u16 s_toff[RS_BINS];           // first staged slot of each digit inside the tile
+  __shared__ u32 s_wsum[RS_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const u32 lt = (1u << lane) - 1u;
+  for (u32 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+#pragma unroll
+    for (int q = 0; q < RS_DPT; ++q) {
+      const int dg = q * RS_NT + threadIdx.x;
+#pragma unroll
+      for (int w = 0; w < RS_WARPS; ++w) s_cnt[w][dg] = 0;
+      s_base[dg] = offs[(u64)dg * ntiles + tile];
+    }
+    __syncthreads();
+    const u64 tbase = (u64)tile * RS_TILE;
+    const u64 wbase = tbase + (u64)warp * (RS_ROWS * 32);
+    const u32 tile_n = (u32)min((u64)RS_TILE, n - tbase);
+    u64 k[RS_ROWS];
+    u32 rank[RS_ROWS];   // digit << 16 | rank inside the warp's slice
+#pragma unroll
+    for (int r = 0; r < RS_ROWS; ++r) {
+      const u64 i = wbase + (u64)r * 32 + lane;
+      const bool in = i < n;
+      k[r] = in ? keys[i] : ~0ULL;
+      const u32 d = in ? ((u32)(k[r] >> shift) & (RS_BINS - 1)) : (u32)RS_BINS;   // out-of-range lanes form their own group
+      const u32 peers = __match_any_sync(0xFFFFFFFFu, d);
+      const int leader = __ffs(peers) - 1;
+      u32 old = 0;
+      if (lane == leader && in) { old = s_cnt[warp][d]; s_cnt[warp][d] = (u16)(old + __popc(peers)); }
+      old = __shfl_sync(0xFFFFFFFFu, old, leader);
+      rank[r] = (d << 16) | (old + __popc(peers & lt));
+      __syncwarp();
+    }
+    __syncthreads();
+    // exclusive prefix of the per-warp counters over the warps (each thread owns RS_DPT CONSECUTIVE digits), the digit
+    // totals of the tile, and their exclusive scan -> where each digit's run starts in the staged tile
+    u32 tot[RS_DPT], tsum = 0;
+#pragma unroll
+    for (int q = 0; q < RS_DPT; ++q) {
+      const int dg = threadIdx.x * RS_DPT + q;
+      u32 run = 0;
+#pragma unroll
+      for (int w = 0; w < RS_WARPS; ++w) { const u32 c = s_cnt[w][dg]; s_cnt[w][dg] = (u16)run; run += c; }
+      tot[q] = run; tsum += run;
+    }
+    u32 inc = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const u32 t = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += t; }
+    if (lane == 31) s_wsum[warp] = inc;
+    __syncthreads();
+    u32 wb = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) if (w < warp) wb += s_wsum[w];
+    {
+      u32 run = wb + inc - tsum;
+#pragma unroll
+      for (int q = 0; q < RS_DPT; ++q) { s_toff[threadIdx.x * RS_DPT + q] = (u16)run; run += tot[q]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ROWS; ++r) {
+      const u64 i = wbase + (u64)r * 32 + lane;
+      if (i < n) {
+        const u32 d = rank[r] >> 16;
+        const u32 lp = s_toff[d] + s_cnt[warp][d] + (rank[r] & 0xFFFFu);
+        sk[lp] = k[r];
+        sv[lp] = vals[i];
+      }
+    }
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < tile_n; i += RS_NT) {   // consecutive staged slots of a digit go to consecutive addresses
+      const u64 kk = sk[i];
+      const u32 d = (u32)(kk >> shift) & (RS_BINS - 1);
+      const u64 o = s_base[d] + (u64)(i - s_toff[d]);
+      out_keys[o] = kk;
+      out_vals[o] = sv[i];
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+// Sorts n pairs by key bits [0, end_bit).  The passes ping-pong between buffer A = (a_keys, a_vals), which holds the input
+// and is overwritten, and buffer B; *res_keys / *res_vals say which one holds the result.
+int radix_sort_pairs(mm2_ctx* ctx, u64* a_keys, u64* a_vals, u64* b_keys, u64* b_vals, u64 n, int end_bit, u64** res_keys, u64** res_vals) {
+  *res_keys = a_keys; *res_vals = a_vals;
+  if (n == 0) return MM2_OK;
+  static bool attr_done = false;
+  if (!attr_done) { cudaFuncSetAttribute(rs_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TILE * 16); attr_done = true; }
+  const int npass = std::max(1, (end_bit + RS_BITS - 1) / RS_BITS);
+  const u32 ntiles = (u32)((n + RS_TILE - 1) / RS_TILE);
+  const size_t ncnt = (size_t)ntiles * RS_BINS;
+  MM2_TRY(ctx->rs_counts.ensure(ncnt * 4 + 64));
+  MM2_TRY(ctx->rs_offs.ensure((ncnt + 1) * 8 + 64));
+  const int grid = (int)std::min<u32>(ntiles, 148u * 3u);
+  u64 *src_k = a_keys, *src_v = a_vals, *dst_k = b_keys, *dst_v = b_vals;
+  for (int pass = 0; pass < npass; ++pass) {
+    MM2_LAUNCH(ctx, rs_hist_kernel, grid, RS_NT, 0, src_k, n, pass * RS_BITS, ntiles, ctx->rs_counts.as<u32>());
+    MM2_TRY(scan_u32_to_u64(ctx, ctx->rs_counts.as<u32>(), ctx->rs_offs.as<u64>(), ncnt));
+    MM2_LAUNCH(ctx, rs_scatter_kernel, grid, RS_NT, RS_TILE * 16, src_k, src_v, n, pass * RS_BITS, ntiles, ctx->rs_offs.as<u64>(), dst_k, dst_v);
+    std::swap(src_k, dst_k); std::swap(src_v, dst_v);
+  }
+  CUDA_TRY(cudaGetLastError());
+  *res_keys = src_k; *res_vals = src_v;
+  return MM2_OK;
+}
