@@ -363,6 +363,23 @@ extern "C" void mm2_default_map_opts(mm2_map_opts_t* o) {  // main.rs:55-89 defa
   o->mid_occ_floor = 10; o->want_stage_dump = 0;
 }
 
+// concatenate the results of consecutive read ranges (first[i] = index of the first read of part i) in read order
+static void merge_map_results(mm2_map_result_t* parts, const size_t* first, size_t nparts, mm2_map_result_t* out) {
+  memset(out, 0, sizeof *out);
+  size_t nrec = 0, npan = 0;
+  for (size_t i = 0; i < nparts; ++i) { nrec += parts[i].n_recs; npan += parts[i].n_panic; }
+  out->recs = xmalloc<mm2_paf_rec_t>(nrec);
+  out->panic_reads = xmalloc<u32>(npan);
+  for (size_t i = 0; i < nparts; ++i) {
+    mm2_map_result_t& p = parts[i];
+    for (size_t j = 0; j < p.n_recs; ++j) { mm2_paf_rec_t r = p.recs[j]; r.read_id += (u32)first[i]; out->recs[out->n_recs++] = r; }
+    for (size_t j = 0; j < p.n_panic; ++j) out->panic_reads[out->n_panic++] = p.panic_reads[j] + (u32)first[i];
+    out->n_reads += p.n_reads; out->n_bases += p.n_bases; out->n_minimizers += p.n_minimizers;
+    out->n_minimizers_kept += p.n_minimizers_kept; out->n_anchors += p.n_anchors; out->n_rescued += p.n_rescued;
+    mm2_map_result_free(&p);
+  }
+}
+
 // paf.rs:130-222 for the single reported chain of a read: 0 = no record (no anchors, main.rs:211-213), 1 = record,
 // 2 = the reference panics on this read (idx.seq[rid0] out of bounds after the odd-rid sign extension, F5)
 static int build_record(const mm2_index* idx, const ReadHit& h, u32 r, i32 qlen, mm2_paf_rec_t& rec) {
@@ -432,6 +449,27 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
   MM2_TRY(scan_u32_to_u64(ctx, ctx->occ_cnt.as<u32>(), ctx->anchor_off_m.as<u64>(), nm));
   u64 na = 0;
   MM2_TRY(read_scalar_u64(ctx, ctx->anchor_off_m.as<u64>() + nm, &na));
+  {
+    // Anchors and DP state take 56 B per anchor.  If a batch of repeat-rich reads needs more than what is free, map its
+    // two halves one after the other (reads are independent; the cheap stages above are simply redone per half).
+    auto grow = [](const DevBuf& b, u64 bytes) -> u64 { return bytes > b.cap ? bytes + bytes / 8 + 256 : 0; };
+    const u64 need = grow(ctx->anchors, na * 16) + grow(ctx->dpA, na * 16) + grow(ctx->dpB, na * 16) + grow(ctx->dpT, na * 4) +
+                     grow(ctx->dpW, na * 4);
+    size_t free_b = 0, total_b = 0;
+    bool have_info = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess;
+    if (const char* e = getenv("MM2_ANCHOR_BUDGET_MB")) { free_b = (size_t)atoll(e) << 20; have_info = true; }  // test hook
+    if (need && have_info && need > (u64)(free_b * 0.9) && nreads > 1 && !o->want_stage_dump) {
+      const size_t mid = nreads / 2;
+      mm2_map_result_t part[2];
+      memset(part, 0, sizeof part);
+      int rc = map_device_impl(ctx, idx, d_cat, d_off, h_off, mid, o, &part[0], true);
+      if (rc == MM2_OK) rc = map_device_impl(ctx, idx, d_cat, d_off + mid, h_off + mid, nreads - mid, o, &part[1], true);
+      if (rc != MM2_OK) { mm2_map_result_free(&part[0]); mm2_map_result_free(&part[1]); return rc; }
+      const size_t first[2] = {0, mid};
+      merge_map_results(part, first, 2, out);
+      return MM2_OK;
+    }
+  }
   ctx->timer.mark(st, "anchor_fill");
   MM2_TRY(ctx->anchors.ensure(std::max<u64>(1, na) * 16));
   MM2_TRY(ctx->read_aoff.ensure((nreads + 2) * 8));
@@ -632,20 +670,7 @@ static int map_host_pipelined(mm2_ctx* ctx, const mm2_index* idx, const u8* cat,
   ctx->timer.names_blob.clear();
   for (size_t i = 0; i < ctx->timer.ms.size() && i < ctx->timer.names.size(); ++i) { ctx->timer.names_blob += ctx->timer.names[i]; ctx->timer.names_blob.push_back('\0'); }
   ctx->timer.names_blob.push_back('\0');
-  // merge
-  memset(out, 0, sizeof *out);
-  size_t nrec = 0, npan = 0;
-  for (auto& p : part) { nrec += p.n_recs; npan += p.n_panic; }
-  out->recs = xmalloc<mm2_paf_rec_t>(nrec);
-  out->panic_reads = xmalloc<u32>(npan);
-  for (size_t sidx = 0; sidx < nsub; ++sidx) {
-    mm2_map_result_t& p = part[sidx];
-    for (size_t i = 0; i < p.n_recs; ++i) { mm2_paf_rec_t r = p.recs[i]; r.read_id += (u32)cut[sidx]; out->recs[out->n_recs++] = r; }
-    for (size_t i = 0; i < p.n_panic; ++i) out->panic_reads[out->n_panic++] = p.panic_reads[i] + (u32)cut[sidx];
-    out->n_reads += p.n_reads; out->n_bases += p.n_bases; out->n_minimizers += p.n_minimizers;
-    out->n_minimizers_kept += p.n_minimizers_kept; out->n_anchors += p.n_anchors; out->n_rescued += p.n_rescued;
-    mm2_map_result_free(&p);
-  }
+  merge_map_results(part.data(), cut.data(), nsub, out);
   return MM2_OK;
 }
 

@@ -153,6 +153,23 @@ __global__ void __launch_bounds__(CH_WARPS * 32) chain_kernel(ChainArgs G) {
         if (valid && aj.y >= 0) T[aj.y] = mark;                   // lchain.rs:86 (all lanes first, see header)
         __syncwarp();
         const int tj = valid ? T[j] : -1;
+        // Fast path (most tiles of a long predecessor window): no lane beats the running maximum, so there is no new
+        // record in this tile and n_skip can only grow, by one per marked lane, until it crosses max_chain_skip.
+        if (__ballot_sync(0xFFFFFFFFu, valid && sc > max_f) == 0u) {
+          const u32 mm = __ballot_sync(0xFFFFFFFFu, valid && tj == mark);
+          const u32 am = __ballot_sync(0xFFFFFFFFu, act);
+          const int cnt = __popc(mm);
+          if (n_skip + cnt > p.max_chain_skip) {   // the (max_chain_skip + 1 - n_skip)-th marked lane is the `break`
+            u32 tm = mm;
+            for (int q = p.max_chain_skip - n_skip; q > 0; --q) tm &= tm - 1;   // drop the marked lanes that still fit
+            const int brk = __ffs(tm) - 1;
+            cells += (unsigned)(brk + 1);
+            break;
+          }
+          n_skip += cnt;
+          cells += (unsigned)__popc(am);
+          continue;
+        }
         // exclusive prefix max of the scores, seeded with the running max_f
         int incl = valid ? sc : NEG_INF * 4;
 #pragma unroll

@@ -458,3 +458,30 @@ def test_map_batch_query_wk_differs_from_index(ctx, mm2, orc, gen):
         res = ctx.map_batch(gi, cat, roffs, mm2.default_map_opts(w, k))
         want, _ = oi.align_batch(cat, roffs, names, orc.AlignOpts.default(w, k), threads=8)
         assert res.paf_lines(names) == want, (w, k)
+
+
+def test_map_batch_splits_when_anchors_exceed_memory(mm2, orc, gen):
+    """a batch whose anchors + DP state do not fit is mapped in halves (recursively); records must not change"""
+    g = gen.repeat_genome(97, 1_000_000, 0.4, 0.2)
+    offs = np.array([0, g.size], dtype=np.uint64)
+    c = mm2.Context(0)
+    gi = mm2.Index.build(c, g, offs, ["m"])
+    cat, roffs = gen.reads(5, g, offs, 64, 4000, 0.03, 0.03, 0.03)
+    d_cat = None
+    import torch
+    d_cat = torch.from_numpy(cat.copy()).cuda()
+    d_off = torch.from_numpy(roffs.astype(np.int64)).cuda()
+    r_full = c.map_batch(gi, None, roffs, device_ptrs=(d_cat.data_ptr(), d_off.data_ptr()))
+    os.environ["MM2_ANCHOR_BUDGET_MB"] = "1"
+    try:
+        c2 = mm2.Context(0)      # fresh arenas: everything has to "grow", and 1 MB never suffices for more than a few reads
+        r_split = c2.map_batch(gi, None, roffs, device_ptrs=(d_cat.data_ptr(), d_off.data_ptr()))
+    finally:
+        del os.environ["MM2_ANCHOR_BUDGET_MB"]
+    assert r_full.recs.size == r_split.recs.size and (r_full.recs == r_split.recs).all()
+    assert r_full.stats == r_split.stats
+    names = ["s%d" % i for i in range(64)]
+    oi = orc.Index.build(g, offs, ["m"], threads=8)
+    want, _ = oi.align_batch(cat, roffs, names, threads=8)
+    assert r_split.paf_lines(names) == want
+    c.close(); c2.close()
