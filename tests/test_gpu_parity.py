@@ -485,3 +485,54 @@ def test_map_batch_splits_when_anchors_exceed_memory(mm2, orc, gen):
     want, _ = oi.align_batch(cat, roffs, names, threads=8)
     assert r_split.paf_lines(names) == want
     c.close(); c2.close()
+
+
+def test_fuzz_sketch_parameters(ctx, orc):
+    """seeded differential fuzz of the sketch kernels over (w, k, alphabet, N density, length)"""
+    rng = np.random.default_rng(2024)
+    for it in range(120):
+        k = int(rng.integers(1, 29))
+        w = int(rng.choice([1, 2, 3, 5, 8, 9, 10, 11, 16, 19, 33, 64, 100, 255]))
+        n = int(rng.choice([1, 7, 30, 100, 500, 2030, 2050, 4100, 9000]))
+        alpha = rng.choice(["ACGT", "ACGTN", "AC", "ACGTacgtRYn", "AT"])
+        s = cases.rnd_seq(rng, n, alpha)
+        if rng.random() < 0.3 and n > 50:
+            b = bytearray(s)
+            p = int(rng.integers(0, n - 20))
+            b[p:p + 20] = b[max(0, p - 20):p][:20].ljust(20, b"A")   # local duplication -> equal keys inside a window
+            s = bytes(b)
+        hpc = bool(rng.random() < 0.15)
+        a, b_ = ctx.sketch_sequence(s, w, k, rid=int(rng.integers(0, 5)) * 2, is_hpc=hpc), None
+        b_ = orc.sketch(s, w, k, rid=int(a["rid_pos_strand"][0] >> np.uint64(32)) if a.size else 0, is_hpc=hpc)
+        _eq(a, b_, "fuzz %d: w=%d k=%d n=%d alpha=%s hpc=%s" % (it, w, k, n, alpha, hpc))
+
+
+def test_fuzz_map_options(ctx, mm2, orc, gen):
+    """seeded differential fuzz of mm2_map_batch over the align flag surface"""
+    rng = np.random.default_rng(7)
+    g = gen.repeat_genome(123, 700_000, 0.3, 0.2)
+    seqs = [g[:400_000].tobytes(), b"NN", g[400_000:].tobytes()]
+    cat, offs = cases.cat_offs(seqs)
+    names = ["a", "pad", "b"]
+    for k, w in ((15, 10), (17, 7)):
+        gi = mm2.Index.build(ctx, cat, offs, names, w=w, k=k, b=12)
+        oi = orc.Index.build(cat, offs, names, w=w, k=k, b=12, threads=8)
+        for it in range(6):
+            n = 25
+            ln = int(rng.choice([300, 1500, 4000]))
+            e = float(rng.choice([0.0, 0.01, 0.05]))
+            rc, ro = gen.reads(int(rng.integers(1, 1000)), cat, offs, n, ln, e, e, e)
+            o, oo = mm2.default_map_opts(w, k), orc.AlignOpts.default(w, k)
+            for name, val in (("max_gap", int(rng.choice([500, 5000, 20000]))), ("min_cnt", int(rng.choice([1, 2, 3, 6]))),
+                              ("min_chain_score", int(rng.choice([5, 40, 200]))), ("bw", int(rng.choice([-1, 50, 500, 3000]))),
+                              ("bw_long", int(rng.choice([-1, 1000, 20000]))), ("frac_top_repetitive", float(rng.choice([2e-4, 1e-2, 0.3]))),
+                              ("best_n", int(rng.choice([0, 1, 5]))), ("pri_ratio", float(rng.choice([0.3, 0.8]))),
+                              ("mask_level", float(rng.choice([0.1, 0.5, 0.95])))):
+                setattr(o, name, val)
+                setattr(oo, name, val)
+            if o.bw < 0:
+                o.bw_long = oo.bw_long = -1       # `-r` absent: neither value is given (main.rs:202-208)
+            qn = ["f%d" % i for i in range(n)]
+            res = ctx.map_batch(gi, rc, ro, o)
+            want, _ = oi.align_batch(rc, ro, qn, oo, threads=8)
+            assert res.paf_lines(qn) == want, "fuzz k=%d it=%d opts=%s" % (k, it, {f: getattr(o, f) for f, _ in o._fields_})
