@@ -45,6 +45,54 @@ constexpr int NEG_INF = -(1 << 28);
 __device__ __forceinline__ int wadd(int a, int b) { return (int)((u32)a + (u32)b); }
 __device__ __forceinline__ int wsub(int a, int b) { return (int)((u32)a - (u32)b); }
 
+// The reported chain (lchain.rs:162-173), its coordinates (paf.rs:133-147) and the dv inputs (paf.rs:174-191) of one read.
+__device__ __forceinline__ void chain_finish(const ChainArgs& G, u32 r, int lane, const ulonglong2* an, const int4* A, u64 a0, i32 qlen,
+                                             u64 m0, u64 m1, int best, int4 bestA, int4 bestB, ReadHit& hit, unsigned long long cells) {
+  // ---- the reported chain: fallback chain ending at `best` (lchain.rs:164-172), score v[best] -----------------------------
+  const ulonglong2 ab = an[best];
+  const ulonglong2 af = an[bestB.z];
+  hit.rid_rev = (u32)(af.x >> 32);  // paf.rs:132,148 use the chain's FIRST anchor
+  hit.qs = max(bestB.x, 0); hit.qe = wadd((int)(u32)ab.y, 1);
+  hit.ts = max(bestB.y, 0); hit.te = wadd((int)(u32)ab.x, 1);
+  hit.cm = (u32)bestA.w; hit.score = bestA.z; hit.best = best;
+  if (G.chain) {  // stage dump: walk the links (serial; parity harness only)
+    if (lane == 0) {
+      int* ch = G.chain + a0;
+      int i = best, c = 0;
+      while (i >= 0) { ch[c++] = i; i = A[i].y; }
+    }
+  }
+  // ---- dv inputs (paf.rs:174-191): ranks of the chain's first/last forward query positions among the read's minimizers ----
+  {
+    const bool rev = (af.x >> 63) != 0;
+    auto qpos_fwd = [&](const ulonglong2& a) -> int {
+      const int qp = (int)(u32)a.y, qsp = (int)((a.y >> 32) & 0xff);
+      return rev ? wsub(wsub(qlen, 1), wsub(wadd(qp, 1), qsp)) : qp;
+    };
+    // '+': chain order; '-': reversed chain order (paf.rs:170-173)
+    const int first_q = rev ? qpos_fwd(ab) : qpos_fwd(af);
+    const int last_q = rev ? qpos_fwd(af) : qpos_fwd(ab);
+    const int want = lane == 0 ? first_q : last_q;
+    if (lane < 2) {
+      // first index whose position == want (positions ascend for odd k, see sketch.cu)
+      u64 lo = m0, hi = m1;
+      while (lo < hi) {
+        const u64 mid = (lo + hi) >> 1;
+        const int pos = (int)(u32)((G.mval[mid] >> 1) & 0xffffffffULL);
+        if (pos < want) lo = mid + 1; else hi = mid;
+      }
+      int rank = -1;
+      if (lo < m1 && (int)(u32)((G.mval[lo] >> 1) & 0xffffffffULL) == want) rank = (int)(lo - m0);
+      if (lane == 0) hit.st_rank = rank; else hit.en_rank = rank;
+    }
+    hit.en_rank = __shfl_sync(0xFFFFFFFFu, hit.en_rank, 1);
+  }
+  if (lane == 0) {  // `cells` is warp-uniform
+    G.hits[r] = hit;
+    if (G.cells) atomicAdd(G.cells, cells);
+  }
+}
+
 __global__ void __launch_bounds__(CH_WARPS * 32) chain_kernel(ChainArgs G) {
   const u32 r = blockIdx.x * CH_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -251,49 +299,348 @@ __global__ void __launch_bounds__(CH_WARPS * 32) chain_kernel(ChainArgs G) {
     __syncwarp();
   }
 
-  // ---- the reported chain: fallback chain ending at `best` (lchain.rs:164-172), score v[best] -----------------------------
-  const ulonglong2 ab = an[best];
-  const ulonglong2 af = an[bestB.z];
-  hit.rid_rev = (u32)(af.x >> 32);  // paf.rs:132,148 use the chain's FIRST anchor
-  hit.qs = max(bestB.x, 0); hit.qe = wadd((int)(u32)ab.y, 1);
-  hit.ts = max(bestB.y, 0); hit.te = wadd((int)(u32)ab.x, 1);
-  hit.cm = (u32)bestA.w; hit.score = bestA.z; hit.best = best;
-  if (G.chain) {  // stage dump: walk the links (serial; parity harness only)
-    if (lane == 0) {
-      int* ch = G.chain + a0;
-      int i = best, c = 0;
-      while (i >= 0) { ch[c++] = i; i = A[i].y; }
-    }
+  chain_finish(G, r, lane, an, A, a0, qlen, m0, m1, best, bestA, bestB, hit, cells);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// chain_ring_kernel — the default.  One warp per read; the DP state of the 32 most recent anchors lives in REGISTERS:
+// lane l owns the ring slot of every anchor j with j % 32 == l (static x/y fields and f, pprev, v, cnt, qs_min, ts_min,
+// first).  Anchors are read 32 at a time with one coalesced 128-bit load per lane, so the lane that loads anchor i is
+// the one that owns its slot; the state is flushed to A/B with one coalesced store per 32 anchors.
+//  * Window membership (lchain.rs:75-78) is evaluated per lane on its own slot: the predicate "other rid/strand or
+//    rpos(i) > rpos(j) + max_dist_x" is true on a prefix of [0, i) (anchors are sorted by x), so "j >= st" is "predicate
+//    false for j", and the window of i is empty exactly when the predicate is true for i - 1.  Anchors with an empty
+//    window (about half of them on ONT-like reads) cost nothing: their state is (span, no predecessor) and is committed
+//    to the ring in bulk by the next anchor that has a window.
+//  * The ring is visited first, in the reference's order (i-1, i-2, ...).  Marks (lchain.rs:86) among ring slots are one
+//    warp OR-reduction of 1 << (pprev & 31).  When at most max_chain_skip slots are marked no `break` is possible
+//    (n_skip starts at 0 and grows only on marked slots), so max_f is the warp maximum and max_j the first slot in
+//    visiting order that reaches it (records are strict prefix maxima).  Otherwise the records are enumerated one
+//    ballot at a time and the n_skip walk of lchain.rs:84-85 is done on the ballot masks (chain_tile_walk).
+//  * Only when the ring was visited without a break AND the slot that anchor i overwrites (j = i - 32) is still inside
+//    the window does the loop continue, 32 predecessors at a time, on A/T in global memory.  On ONT-like reads the loop
+//    breaks inside the ring for nearly every anchor (about 27 visited predecessors: max_chain_skip = 25).
+// Same arithmetic and same order of decisions as chain_kernel; the tests compare both against the oracle.
+
+__device__ __forceinline__ u32 low_mask(int n) { return n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u); }
+// position of the n-th (1-based) set bit of m; popc(m) >= n
+__device__ __forceinline__ int nth_set_bit(u32 m, int n) {
+  int pos = 0;
+#pragma unroll
+  for (int s = 16; s; s >>= 1) {
+    const int c = __popc(m & (((1u << s) - 1u) << pos));
+    if (c < n) { n -= c; pos += s; }
   }
-  // ---- dv inputs (paf.rs:174-191): ranks of the chain's first/last forward query positions among the read's minimizers ----
-  {
-    const bool rev = (af.x >> 63) != 0;
-    auto qpos_fwd = [&](const ulonglong2& a) -> int {
-      const int qp = (int)(u32)a.y, qsp = (int)((a.y >> 32) & 0xff);
-      return rev ? wsub(wsub(qlen, 1), wsub(wadd(qp, 1), qsp)) : qp;
-    };
-    // '+': chain order; '-': reversed chain order (paf.rs:170-173)
-    const int first_q = rev ? qpos_fwd(ab) : qpos_fwd(af);
-    const int last_q = rev ? qpos_fwd(af) : qpos_fwd(ab);
-    const int want = lane == 0 ? first_q : last_q;
-    if (lane < 2) {
-      // first index whose position == want (positions ascend for odd k, see sketch.cu)
-      u64 lo = m0, hi = m1;
-      while (lo < hi) {
-        const u64 mid = (lo + hi) >> 1;
-        const int pos = (int)(u32)((G.mval[mid] >> 1) & 0xffffffffULL);
-        if (pos < want) lo = mid + 1; else hi = mid;
+  return pos;
+}
+
+// One tile of <= 32 predecessors, lane p = p-th visited (lchain.rs:80-88).  V/M/ACT: ballots of "has a score", "t[j] == i",
+// "inside the window".  Updates max_f / n_skip, returns the lane of the last new maximum in rec_last (-1: none) and
+// true when the reference's loop breaks inside this tile.
+__device__ __forceinline__ bool chain_tile_walk(int lane, u32 V, u32 M, u32 ACT, int sc, int max_skip, int& max_f, int& n_skip,
+                                                int& rec_last, unsigned long long& cells) {
+  const bool valid = (V >> lane) & 1u;
+  // records: strict prefix maxima of the scores, seeded with max_f (lchain.rs:84)
+  u32 R = 0;
+  int cur = max_f;
+  u32 cand = __ballot_sync(0xFFFFFFFFu, valid && sc > cur);
+  while (cand) {
+    const int l = __ffs(cand) - 1;
+    R |= 1u << l;
+    cur = __shfl_sync(0xFFFFFFFFu, sc, l);
+    cand = __ballot_sync(0xFFFFFFFFu, valid && sc > cur) & ~low_mask(l + 1);
+  }
+  // n_skip: -1 (floored at 0) on a record, +1 on a marked non-record, break when it exceeds max_skip (lchain.rs:84-85)
+  const u32 Mnr = M & V & ~R;
+  int x = n_skip, pos = 0, brk = -1;
+  u32 rem = R;
+  for (;;) {
+    const int seg_end = rem ? (__ffs(rem) - 1) : 32;
+    const u32 seg = Mnr & low_mask(seg_end) & ~low_mask(pos);
+    const int cnt = __popc(seg);
+    const int need = max(max_skip + 1 - x, 1);
+    if (cnt >= need) { brk = nth_set_bit(seg, need); break; }
+    x += cnt;
+    if (!rem) break;
+    x = max(x - 1, 0);
+    pos = seg_end + 1;
+    rem &= rem - 1;
+  }
+  if (brk >= 0) R &= low_mask(brk);
+  rec_last = R ? (31 - __clz(R)) : -1;
+  if (rec_last >= 0) {
+    const int top = __shfl_sync(0xFFFFFFFFu, sc, rec_last);   // == cur unless later records were cut off by the break
+    max_f = top;
+  }
+  if (brk >= 0) { cells += (unsigned)(brk + 1); return true; }
+  cells += (unsigned)__popc(ACT);
+  n_skip = x;
+  return false;
+}
+
+// comput_sc (lchain.rs:17-34) of anchor i = (ri, qi) against a predecessor (rj, qj, span_j) of the same rid/strand
+__device__ __forceinline__ bool chain_sc(int ri, int qi, int rj, int qj, int span_j, int mdx, int mdy, int bw, float pen_gap,
+                                         float pen_skip, const float* __restrict__ half_log, int& s0) {
+  const int dq = wsub(qi, qj);
+  if (dq <= 0 || dq > mdx) return false;
+  const int dr = wsub(ri, rj);
+  if (dr == 0 || dq > mdy) return false;
+  int dd = wsub(dr, dq); if (dd < 0) dd = wsub(0, dd);
+  if (dd > bw || dd < 0) return false;
+  const int dg = min(dr, dq);
+  s0 = min(span_j, dg);
+  if (dd != 0 || dg > span_j) {
+    const float lin = __fadd_rn(__fmul_rn(pen_gap, (float)dd), __fmul_rn(pen_skip, (float)dg));
+    s0 = wsub(s0, __float2int_rz(__fadd_rn(lin, half_log[dd])));
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(CH_WARPS * 32) chain_ring_kernel(ChainArgs G) {
+  const u32 r = blockIdx.x * CH_WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= G.nreads) return;
+  const u64 a0 = G.read_aoff[r];
+  const i64 n64 = (i64)(G.read_aoff[r + 1] - a0);
+  const i32 qlen = (i32)(G.read_off[r + 1] - G.read_off[r]);
+  const u64 m0 = G.mini_off[r], m1 = G.mini_off[r + 1];
+  ReadHit hit;
+  hit.rid_rev = 0xFFFFFFFFu; hit.qs = hit.qe = hit.ts = hit.te = 0; hit.cm = 0; hit.score = 0;
+  hit.n_anchors = (u32)n64; hit.n_mini = (u32)(m1 - m0); hit.sum_span = G.sum_span[r];
+  hit.st_rank = hit.en_rank = -1; hit.flags = 0; hit.best = -1; hit.pad0 = hit.pad1 = 0;
+  if (n64 <= 0 || n64 > 0x7fffffff) {
+    if (lane == 0) G.hits[r] = hit;
+    return;
+  }
+  const int n = (int)n64;
+  const ulonglong2* __restrict__ an = G.anchors + a0;
+  int4* A = G.A + a0;
+  int4* B = G.B + a0;
+  int* T = G.T + a0;
+  const mm2_chain_params_t& p = G.p;
+  // n_skip never exceeds the number of anchors (< 2^31) and every max_chain_skip < 0 breaks on the first marked slot
+  const int max_skip = min(max(p.max_chain_skip, -1), 0x3fffffff);
+  const int max_iter = p.max_chain_iter;
+  unsigned long long cells = 0;
+  const bool count_cells = G.cells != nullptr;   // a statistic (lchain.rs:80 iterations), not part of the result
+  int best = 0;
+  int4 bestA = make_int4(0, -1, 0, 0), bestB = make_int4(0, 0, 0, 0);
+  bool t_init = false;
+
+  for (int pass = 0; pass < 2; ++pass) {
+    const int bw = pass == 0 ? p.bw : p.bw_long;                 // lchain.rs:327-328
+    const int mdx = max(p.max_dist_x, bw), mdy = max(p.max_dist_y, bw);  // lchain.rs:63-66
+    const int mark_base = pass * n;
+    // ring slot of this lane
+    int rj = -1, rx = 0, rq = 0, rsp = 0; u32 rhi = 0;
+    int rf = 0, rpp = -1, rv = 0, rcnt = 0, rqs = 0, rts = 0, rfirst = 0;
+    int bf = NEG_INF * 4, bi = 0;
+    int st = 0;   // lower bound of the window start, used only by windows longer than the ring
+    ulonglong2 nxt = make_ulonglong2(0, 0);
+    if (lane < n) nxt = an[lane];
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      const int tile_n = min(32, n - i0);
+      const ulonglong2 cur = nxt;
+      if (i0 + 32 + lane < n) nxt = an[i0 + 32 + lane];          // next tile's anchors are in flight during this tile
+      const int cx = (int)(u32)cur.x, cq = (int)(u32)cur.y, csp = (int)((cur.y >> 32) & 0xff);
+      const u32 chi = (u32)(cur.x >> 32);
+      // state of this lane's anchor; final unless the anchor finds a predecessor (lchain.rs:77,89-90)
+      int nf = csp, npp = -1, nv = csp, ncnt = 1, nqs = wsub(cq, csp - 1), nts = wsub(cx, csp - 1), nfirst = i0 + lane;
+      // anchors whose window is not empty: the predicate of lchain.rs:75 is false for i - 1, and max_chain_iter >= 1
+      u32 workmask;
+      {
+        int px = __shfl_up_sync(0xFFFFFFFFu, cx, 1);
+        u32 phi = __shfl_up_sync(0xFFFFFFFFu, chi, 1);
+        const int rx31 = __shfl_sync(0xFFFFFFFFu, rx, 31);
+        const u32 rhi31 = __shfl_sync(0xFFFFFFFFu, rhi, 31);
+        if (lane == 0) { px = rx31; phi = rhi31; }
+        const int i = i0 + lane;
+        const bool work = lane < tile_n && i > 0 && (i - 1) >= wsub(i, max_iter) && phi == chi && !(cx > wadd(px, mdx));
+        workmask = __ballot_sync(0xFFFFFFFFu, work);
       }
-      int rank = -1;
-      if (lo < m1 && (int)(u32)((G.mval[lo] >> 1) & 0xffffffffULL) == want) rank = (int)(lo - m0);
-      if (lane == 0) hit.st_rank = rank; else hit.en_rank = rank;
+      int done = 0;   // lanes [0, done) of this tile are committed to the ring
+      while (workmask) {
+        const int c = __ffs(workmask) - 1;
+        workmask &= workmask - 1;
+        const int i = i0 + c;
+        if (lane >= done && lane < c) {                          // the anchors before i that are not in the ring yet
+          rj = i0 + lane; rx = cx; rq = cq; rsp = csp; rhi = chi;
+          rf = nf; rpp = npp; rv = nv; rcnt = ncnt; rqs = nqs; rts = nts; rfirst = nfirst;
+        }
+        done = c;
+        const int ri = __shfl_sync(0xFFFFFFFFu, cx, c), qi = __shfl_sync(0xFFFFFFFFu, cq, c), spi = __shfl_sync(0xFFFFFFFFu, csp, c);
+        const u32 hi_i = __shfl_sync(0xFFFFFFFFu, chi, c);
+        const int low_iter = wsub(i, max_iter);                  // lchain.rs:78
+        const bool inwin = rj >= 0 && rj >= low_iter && rhi == hi_i && !(ri > wadd(rx, mdx));
+        int sc = NEG_INF;
+        bool valid = false;
+        if (inwin) {
+          int s0;
+          if (chain_sc(ri, qi, rx, rq, rsp, mdx, mdy, bw, p.chn_pen_gap, p.chn_pen_skip, G.half_log, s0)) {
+            sc = wadd(s0, rf);
+            valid = true;
+          }
+        }
+        const u32 inmask = __ballot_sync(0xFFFFFFFFu, inwin);
+        const u32 vmask = __ballot_sync(0xFFFFFFFFu, valid);
+        int max_f = spi, max_j = -1, n_skip = 0;
+        bool from_ring = true;                                   // max_j's state is in the ring (else in A/B)
+        bool more = (inmask >> c) & 1u;                          // slot c holds j = i - 32: the window may go on beyond the ring
+        if (vmask) {
+          const int low_ring = max(i - 32, 0);
+          const u32 markbits = __reduce_or_sync(0xFFFFFFFFu, (valid && rpp >= low_ring) ? (1u << (rpp & 31)) : 0u) & vmask;
+          // visiting order p <-> lane (c - 1 - p) & 31, i.e. bit p of brev(rotr(mask, c))
+          const u32 Ms = __brev(__funnelshift_r(markbits, markbits, c));
+          const int m = __reduce_max_sync(0xFFFFFFFFu, sc);      // NEG_INF on the slots without a score
+          int pm = -1;                                           // first visited slot that reaches m
+          if (m > spi) {
+            const u32 eq = __ballot_sync(0xFFFFFFFFu, valid && sc == m);
+            pm = __clz(__funnelshift_r(eq, eq, c));
+          }
+          if (pm < 0 || (Ms & low_mask(pm)) == 0u) {
+            // No record at all, or nothing marked before the slot that sets the final maximum: n_skip is still 0 there
+            // (records only decrement it), that slot is the last record, and everything after it is a non-record.
+            if (pm >= 0) { max_f = m; max_j = i - 1 - pm; }
+            const u32 after = Ms & ~low_mask(pm + 1);
+            const int cnt = __popc(after), need = max(max_skip + 1, 1);
+            if (cnt >= need) {                                   // lchain.rs:85: the need-th marked slot breaks the loop
+              if (count_cells) cells += (unsigned)(nth_set_bit(after, need) + 1);
+              more = false;
+            } else {
+              n_skip = cnt;
+              if (count_cells) cells += (unsigned)__popc(inmask);
+            }
+          } else {
+            const int sc_s = __shfl_sync(0xFFFFFFFFu, sc, (c - 1 - lane) & 31);
+            const u32 Vs = __brev(__funnelshift_r(vmask, vmask, c)), As = __brev(__funnelshift_r(inmask, inmask, c));
+            int rec_last;
+            const bool brk = chain_tile_walk(lane, Vs, Ms, As, sc_s, max_skip, max_f, n_skip, rec_last, cells);
+            if (rec_last >= 0) max_j = i - 1 - rec_last;
+            if (brk) more = false;
+          }
+        } else if (count_cells) {
+          cells += (unsigned)__popc(inmask);
+        }
+        if (more) {
+          // ---- the window goes on beyond the ring: 32 predecessors at a time from global memory -------------------------
+          if (!t_init) {
+            for (int x = lane; x < n; x += 32) T[x] = -1;
+            t_init = true;
+            __syncwarp();
+          }
+          const int mark = mark_base + i;
+          const int hi_known = i - 32;                           // inside the window
+          if (valid && rpp >= 0 && rpp < hi_known) T[rpp] = mark;   // marks of the ring slots on older anchors
+          // window start: first j in [st, i - 32] for which the predicate of lchain.rs:75 is false
+          int lo = st;
+          {
+            int rounds = 0;
+            for (;;) {
+              const int j = lo + lane;
+              bool adv = false;
+              if (j < hi_known) {
+                const u64 xm = an[j].x;
+                adv = ((u32)(xm >> 32) != hi_i) || (ri > wadd((int)(u32)xm, mdx));
+              }
+              const u32 b = __ballot_sync(0xFFFFFFFFu, !adv);
+              if (b) { lo += __ffs(b) - 1; break; }
+              lo += 32;
+              if (++rounds == 2) {
+                int hi = hi_known;
+                while (lo < hi) {
+                  const int mid = (lo + hi) >> 1;
+                  const u64 xm = an[mid].x;
+                  const bool adv2 = ((u32)(xm >> 32) != hi_i) || (ri > wadd((int)(u32)xm, mdx));
+                  if (adv2) lo = mid + 1; else hi = mid;
+                }
+                break;
+              }
+            }
+          }
+          st = lo;
+          const int start_j = low_iter > lo ? low_iter : lo;
+          for (int jb = i - 33; jb >= start_j; jb -= 32) {
+            const int j = jb - lane;
+            const bool act = j >= start_j;
+            bool v2 = false;
+            int sc2 = NEG_INF, ppj = -1;
+            if (act) {
+              const ulonglong2 v = an[j];
+              if ((u32)(v.x >> 32) == hi_i) {                     // lchain.rs:81
+                int s0;
+                if (chain_sc(ri, qi, (int)(u32)v.x, (int)(u32)v.y, (int)((v.y >> 32) & 0xff), mdx, mdy, bw, p.chn_pen_gap,
+                             p.chn_pen_skip, G.half_log, s0)) {
+                  const int2 fj = *reinterpret_cast<const int2*>(A + j);
+                  sc2 = wadd(s0, fj.x);
+                  ppj = fj.y;
+                  v2 = true;
+                }
+              }
+            }
+            if (v2 && ppj >= 0) T[ppj] = mark;                    // lchain.rs:86 (all lanes first, see the header)
+            __syncwarp();
+            const bool tm = v2 ? (T[j] == mark) : false;
+            const u32 V2 = __ballot_sync(0xFFFFFFFFu, v2), M2 = __ballot_sync(0xFFFFFFFFu, tm), A2 = __ballot_sync(0xFFFFFFFFu, act);
+            int rec_last;
+            const bool brk = chain_tile_walk(lane, V2, M2, A2, sc2, max_skip, max_f, n_skip, rec_last, cells);
+            if (rec_last >= 0) { max_j = jb - rec_last; from_ring = false; }
+            if (brk) break;
+          }
+        }
+        // ---- lchain.rs:89-90 and the chain reductions of paf.rs:136-147 carried along the best-predecessor links -------
+        if (max_j >= 0) {
+          const int L = max_j & 31;
+          int mv = __shfl_sync(0xFFFFFFFFu, rv, L), mcnt = __shfl_sync(0xFFFFFFFFu, rcnt, L), mqs = __shfl_sync(0xFFFFFFFFu, rqs, L);
+          int mts = __shfl_sync(0xFFFFFFFFu, rts, L), mfirst = __shfl_sync(0xFFFFFFFFu, rfirst, L);
+          if (lane == c) {
+            if (!from_ring) {
+              const int4 aj = A[max_j], bj = B[max_j];
+              mv = aj.z; mcnt = aj.w; mqs = bj.x; mts = bj.y; mfirst = bj.z;
+            }
+            nf = max_f; npp = max_j;
+            nv = mv > max_f ? mv : max_f;
+            ncnt = mcnt + 1;
+            nqs = min(mqs, nqs);
+            nts = min(mts, nts);
+            nfirst = mfirst;
+          }
+        }
+      }
+      if (lane >= done && lane < tile_n) {
+        rj = i0 + lane; rx = cx; rq = cq; rsp = csp; rhi = chi;
+        rf = nf; rpp = npp; rv = nv; rcnt = ncnt; rqs = nqs; rts = nts; rfirst = nfirst;
+      }
+      if (lane < tile_n) {
+        A[i0 + lane] = make_int4(nf, npp, nv, ncnt);
+        B[i0 + lane] = make_int4(nqs, nts, nfirst, 0);
+      }
+      {  // lchain.rs:163: the LAST maximum of f
+        const int fl = lane < tile_n ? nf : NEG_INF * 4;
+        const int m = __reduce_max_sync(0xFFFFFFFFu, fl);
+        if (m >= bf) {
+          const u32 eq = __ballot_sync(0xFFFFFFFFu, fl == m);
+          bf = m;
+          bi = i0 + 31 - __clz(eq);
+        }
+      }
+      __syncwarp();
     }
-    hit.en_rank = __shfl_sync(0xFFFFFFFFu, hit.en_rank, 1);
+    best = bi;
+    bestA = A[best]; bestB = B[best];
+    if (pass == 1 || !G.do_rescue) break;
+    // lchain.rs:321-330 rescue_long_join on the single (fallback) chain
+    const ulonglong2 ab = an[best];
+    const int qe = wadd((int)(u32)ab.y, 1);
+    const int qs = max(bestB.x, 0);
+    const int best_cov = max(wsub(qe, qs), 0);
+    const int uncovered = max(wsub(qlen, best_cov), 0);
+    const bool rescue = uncovered > p.rmq_rescue_size ||
+                        (float)best_cov < __fmul_rn((float)qlen, __fsub_rn(1.0f, p.rmq_rescue_ratio));
+    if (!rescue) break;
+    hit.flags |= 1u;
+    __syncwarp();
   }
-  if (lane == 0) {  // `cells` is warp-uniform
-    G.hits[r] = hit;
-    if (G.cells) atomicAdd(G.cells, cells);
-  }
+  chain_finish(G, r, lane, an, A, a0, qlen, m0, m1, best, bestA, bestB, hit, cells);
 }
 
 }  // namespace
@@ -336,7 +683,9 @@ int chain_batch(mm2_ctx* ctx, const ulonglong2* d_anchors, const u64* d_read_aof
   G.sum_span = d_sum_span; G.nreads = nreads; G.p = p; G.do_rescue = do_rescue; G.half_log = ctx->lut.as<float>();
   G.A = d_A; G.B = d_B; G.T = d_T; G.W = d_W; G.chain = d_chain; G.hits = d_hits; G.cells = d_cells;
   const int grid = (int)((nreads + CH_WARPS - 1) / CH_WARPS);
-  MM2_LAUNCH(ctx, chain_kernel, grid, CH_WARPS * 32, 0, G);
+  static const bool use_v1 = [] { const char* e = getenv("MM2_CHAIN"); return e && !strcmp(e, "v1"); }();   // comparison arm
+  if (use_v1) MM2_LAUNCH(ctx, chain_kernel, grid, CH_WARPS * 32, 0, G);
+  else MM2_LAUNCH(ctx, chain_ring_kernel, grid, CH_WARPS * 32, 0, G);
   CUDA_TRY(cudaGetLastError());
   return MM2_OK;
 }

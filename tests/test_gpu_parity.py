@@ -182,6 +182,46 @@ def test_chain_dp_all(ctx, orc, small_world):
                 _eq(cg, co, "chain")
 
 
+@pytest.mark.parametrize("density,max_skip,max_iter", [(5, 25, 5000), (40, 25, 5000), (40, 0, 5000), (40, 2, 31), (40, 25, 32), (40, 1, 33),
+                                                      (200, 25, 5000), (200, 3, 64), (200, 25, 1), (1000, 25, 5000), (1000, 5, 700)])
+def test_chain_dp_all_synthetic_windows(ctx, orc, density, max_skip, max_iter):
+    """anchors placed directly (no index): predecessor windows around and beyond the 32-slot register ring of the kernel,
+    collinear runs (marks -> max_chain_skip breaks), ties, both strands, several rids"""
+    import minimap2_rs_b200 as m
+    rng = np.random.default_rng(density * 1000 + max_skip * 10 + max_iter)
+    n = 6000
+    span = 15
+    parts = []
+    for rid, rev, cnt in ((0, 0, n // 2), (0, 1, n // 6), (2, 0, n // 6), (4, 1, n // 6)):
+        extent = cnt * 5000 // density          # ~density anchors per max_dist_x of target
+        rpos = np.sort(rng.integers(20, 20 + extent, cnt)).astype(np.int64)
+        diag = rng.choice([0, 0, 0, 7, -13, 400, -2500], cnt).astype(np.int64)
+        run = rng.integers(0, 4, cnt) == 0      # exact collinear repeats of the previous anchor's diagonal
+        diag[1:][run[1:]] = diag[:-1][run[1:]]
+        qpos = np.clip(rpos + diag + rng.integers(-3, 4, cnt) * (rng.integers(0, 3, cnt) == 0), 14, None)
+        x = (np.uint64(rev) << np.uint64(63)) | (np.uint64(rid) << np.uint64(32)) | rpos.astype(np.uint64)
+        y = (np.uint64(span) << np.uint64(32)) | qpos.astype(np.uint64)
+        parts.append(np.stack([x, y], axis=1))
+    xy = np.concatenate(parts)
+    order = np.lexsort((xy[:, 1], xy[:, 0]))
+    xy = xy[order]
+    a = np.zeros(xy.shape[0], dtype=orc.ANCHOR_DT)
+    a["x"], a["y"] = xy[:, 0], xy[:, 1]
+    p = orc.default_chain_params(15)
+    p.max_chain_skip, p.max_chain_iter = max_skip, max_iter
+    for bw in (p.bw, 100000):
+        p.bw = bw
+        o = orc.chain_dp_all(a, p)
+        gres = ctx.chain_dp_all(a, m.ChainParams.from_buffer_copy(bytes(p)))
+        _eq(gres["f"], o["f"], "f")
+        _eq(gres["pprev"], o["pprev"], "pprev")
+        _eq(gres["v"], o["v"], "v")
+        _eq(gres["scores"], o["scores"], "scores")
+        assert len(gres["chains"]) == len(o["chains"])
+        for cg, co in zip(gres["chains"], o["chains"]):
+            _eq(cg, co, "chain")
+
+
 # ---- the batched mapping path: PAF lines ---------------------------------------------------------------------------
 def _map_compare(ctx, mm2, orc, gi, oi, cat, roffs, names, opts_w_k=(10, 15), dump=True):
     w, k = opts_w_k
