@@ -437,7 +437,6 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
   MM2_TRY(ctx->keep.ensure(nm + 16));
   MM2_TRY(ctx->misc.ensure((nreads + 16) * 4 + 64));
   u32* d_sum_span = ctx->misc.as<u32>() + 16;
-  unsigned long long* d_cells = ctx->misc.as<unsigned long long>();
   CUDA_TRY(cudaMemsetAsync(ctx->misc.p, 0, 64, st));
   MM2_TRY(seeds_filter(ctx, so.key, so.seq_off, (u32)nreads, nm, o->q_occ_max, o->q_occ_frac, ctx->keep.as<u8>(), d_sum_span));
   ctx->timer.mark(st, "lookup");
@@ -497,13 +496,11 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
   }
   ctx->timer.mark(st, "chain");
   MM2_TRY(chain_batch(ctx, ctx->anchors.as<ulonglong2>(), ctx->read_aoff.as<u64>(), d_off, so.seq_off, so.val, d_sum_span, (u32)nreads,
-                      p, 1, ctx->dpA.as<int4>(), ctx->dpB.as<int4>(), ctx->dpT.as<int>(), ctx->dpW.as<int>(), nullptr, ctx->hits.as<ReadHit>(), d_cells));
+                      p, 1, ctx->dpA.as<int4>(), ctx->dpB.as<int4>(), ctx->dpT.as<int>(), ctx->dpW.as<int>(), nullptr, ctx->hits.as<ReadHit>(), nullptr));   // no cell counter: a diagnostic, costs ~20 % of the kernel
   ctx->timer.mark(st, "d2h");
   MM2_TRY(ctx->pin_out.ensure((nreads + 1) * sizeof(ReadHit) + 64));
   ReadHit* hits = ctx->pin_out.as<ReadHit>();
-  u64* h_cells = (u64*)(hits + nreads);
   if (nreads) CUDA_TRY(cudaMemcpyAsync(hits, ctx->hits.p, nreads * sizeof(ReadHit), cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(h_cells, d_cells, 8, cudaMemcpyDeviceToHost, st));
   ctx->timer.mark(st, "end");
   CUDA_TRY(cudaStreamSynchronize(st));
   ctx->timer.finish();
@@ -548,7 +545,6 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
   out->panic_reads = xmalloc<u32>(panics.size());
   if (!panics.empty()) memcpy(out->panic_reads, panics.data(), panics.size() * 4);
   out->n_minimizers_kept = 0;
-  (void)h_cells;
 
   if (o->want_stage_dump) {
     out->mini_offs = xmalloc<u64>(nreads + 1); out->minis = xmalloc<mm2_mini_t>(nm); out->mini_keep = xmalloc<u8>(nm);

@@ -444,8 +444,7 @@ __global__ void __launch_bounds__(CH_WARPS * 32) chain_ring_kernel(ChainArgs G) 
       if (i0 + 32 + lane < n) nxt = an[i0 + 32 + lane];          // next tile's anchors are in flight during this tile
       const int cx = (int)(u32)cur.x, cq = (int)(u32)cur.y, csp = (int)((cur.y >> 32) & 0xff);
       const u32 chi = (u32)(cur.x >> 32);
-      // state of this lane's anchor; final unless the anchor finds a predecessor (lchain.rs:77,89-90)
-      int nf = csp, npp = -1, nv = csp, ncnt = 1, nqs = wsub(cq, csp - 1), nts = wsub(cx, csp - 1), nfirst = i0 + lane;
+      const int own_qs = wsub(cq, csp - 1), own_ts = wsub(cx, csp - 1);
       // anchors whose window is not empty: the predicate of lchain.rs:75 is false for i - 1, and max_chain_iter >= 1
       u32 workmask;
       {
@@ -463,15 +462,17 @@ __global__ void __launch_bounds__(CH_WARPS * 32) chain_ring_kernel(ChainArgs G) 
         const int c = __ffs(workmask) - 1;
         workmask &= workmask - 1;
         const int i = i0 + c;
-        if (lane >= done && lane < c) {                          // the anchors before i that are not in the ring yet
-          rj = i0 + lane; rx = cx; rq = cq; rsp = csp; rhi = chi;
-          rf = nf; rpp = npp; rv = nv; rcnt = ncnt; rqs = nqs; rts = nts; rfirst = nfirst;
+        if (done < c) {
+          if (lane >= done && lane < c) {                        // anchors before i with an empty window (lchain.rs:77,89-90)
+            rj = i0 + lane; rx = cx; rq = cq; rsp = csp; rhi = chi;
+            rf = csp; rpp = -1; rv = csp; rcnt = 1; rqs = own_qs; rts = own_ts; rfirst = i0 + lane;
+          }
         }
-        done = c;
+        done = c + 1;
         const int ri = __shfl_sync(0xFFFFFFFFu, cx, c), qi = __shfl_sync(0xFFFFFFFFu, cq, c), spi = __shfl_sync(0xFFFFFFFFu, csp, c);
         const u32 hi_i = __shfl_sync(0xFFFFFFFFu, chi, c);
         const int low_iter = wsub(i, max_iter);                  // lchain.rs:78
-        const bool inwin = rj >= 0 && rj >= low_iter && rhi == hi_i && !(ri > wadd(rx, mdx));
+        const bool inwin = rj >= max(low_iter, 0) && rhi == hi_i && !(ri > wadd(rx, mdx));   // empty slots hold rj = -1
         int sc = NEG_INF;
         bool valid = false;
         if (inwin) {
@@ -489,22 +490,22 @@ __global__ void __launch_bounds__(CH_WARPS * 32) chain_ring_kernel(ChainArgs G) 
         if (vmask) {
           const int low_ring = max(i - 32, 0);
           const u32 markbits = __reduce_or_sync(0xFFFFFFFFu, (valid && rpp >= low_ring) ? (1u << (rpp & 31)) : 0u) & vmask;
-          // visiting order p <-> lane (c - 1 - p) & 31, i.e. bit p of brev(rotr(mask, c))
-          const u32 Ms = __brev(__funnelshift_r(markbits, markbits, c));
+          // visiting order p <-> lane (c - 1 - p) & 31, i.e. bit 31 - p of rotr(mask, c)
+          const u32 Mr = __funnelshift_r(markbits, markbits, c);
           const int m = __reduce_max_sync(0xFFFFFFFFu, sc);      // NEG_INF on the slots without a score
-          int pm = -1;                                           // first visited slot that reaches m
+          int hb = 32;                                           // 31 - (first visited slot that reaches m)
           if (m > spi) {
             const u32 eq = __ballot_sync(0xFFFFFFFFu, valid && sc == m);
-            pm = __clz(__funnelshift_r(eq, eq, c));
+            hb = 31 - __clz(__funnelshift_r(eq, eq, c));
           }
-          if (pm < 0 || (Ms & low_mask(pm)) == 0u) {
+          if (hb == 32 || (Mr & (0xFFFFFFFEu << hb)) == 0u) {
             // No record at all, or nothing marked before the slot that sets the final maximum: n_skip is still 0 there
             // (records only decrement it), that slot is the last record, and everything after it is a non-record.
-            if (pm >= 0) { max_f = m; max_j = i - 1 - pm; }
-            const u32 after = Ms & ~low_mask(pm + 1);
+            u32 after = Mr;
+            if (hb < 32) { max_f = m; max_j = i - 32 + hb; after = Mr & ((1u << hb) - 1u); }
             const int cnt = __popc(after), need = max(max_skip + 1, 1);
             if (cnt >= need) {                                   // lchain.rs:85: the need-th marked slot breaks the loop
-              if (count_cells) cells += (unsigned)(nth_set_bit(after, need) + 1);
+              if (count_cells) cells += (unsigned)(nth_set_bit(__brev(after), need) + 1);
               more = false;
             } else {
               n_skip = cnt;
@@ -514,7 +515,7 @@ __global__ void __launch_bounds__(CH_WARPS * 32) chain_ring_kernel(ChainArgs G) 
             const int sc_s = __shfl_sync(0xFFFFFFFFu, sc, (c - 1 - lane) & 31);
             const u32 Vs = __brev(__funnelshift_r(vmask, vmask, c)), As = __brev(__funnelshift_r(inmask, inmask, c));
             int rec_last;
-            const bool brk = chain_tile_walk(lane, Vs, Ms, As, sc_s, max_skip, max_f, n_skip, rec_last, cells);
+            const bool brk = chain_tile_walk(lane, Vs, __brev(Mr), As, sc_s, max_skip, max_f, n_skip, rec_last, cells);
             if (rec_last >= 0) max_j = i - 1 - rec_last;
             if (brk) more = false;
           }
@@ -588,34 +589,36 @@ __global__ void __launch_bounds__(CH_WARPS * 32) chain_ring_kernel(ChainArgs G) 
           }
         }
         // ---- lchain.rs:89-90 and the chain reductions of paf.rs:136-147 carried along the best-predecessor links -------
+        int mv = 0, mcnt = 0, mqs = 0, mts = 0, mfirst = 0;
         if (max_j >= 0) {
           const int L = max_j & 31;
-          int mv = __shfl_sync(0xFFFFFFFFu, rv, L), mcnt = __shfl_sync(0xFFFFFFFFu, rcnt, L), mqs = __shfl_sync(0xFFFFFFFFu, rqs, L);
-          int mts = __shfl_sync(0xFFFFFFFFu, rts, L), mfirst = __shfl_sync(0xFFFFFFFFu, rfirst, L);
-          if (lane == c) {
-            if (!from_ring) {
-              const int4 aj = A[max_j], bj = B[max_j];
-              mv = aj.z; mcnt = aj.w; mqs = bj.x; mts = bj.y; mfirst = bj.z;
-            }
-            nf = max_f; npp = max_j;
-            nv = mv > max_f ? mv : max_f;
-            ncnt = mcnt + 1;
-            nqs = min(mqs, nqs);
-            nts = min(mts, nts);
-            nfirst = mfirst;
+          mv = __shfl_sync(0xFFFFFFFFu, rv, L); mcnt = __shfl_sync(0xFFFFFFFFu, rcnt, L); mqs = __shfl_sync(0xFFFFFFFFu, rqs, L);
+          mts = __shfl_sync(0xFFFFFFFFu, rts, L); mfirst = __shfl_sync(0xFFFFFFFFu, rfirst, L);
+        }
+        if (lane == c) {                                         // anchor i takes over its ring slot
+          if (!from_ring) {
+            const int4 aj = A[max_j], bj = B[max_j];
+            mv = aj.z; mcnt = aj.w; mqs = bj.x; mts = bj.y; mfirst = bj.z;
           }
+          rj = i; rx = cx; rq = cq; rsp = csp; rhi = chi;
+          rf = max_f; rpp = max_j;
+          rv = (max_j >= 0 && mv > max_f) ? mv : max_f;
+          rcnt = max_j >= 0 ? mcnt + 1 : 1;
+          rqs = max_j >= 0 ? min(mqs, own_qs) : own_qs;
+          rts = max_j >= 0 ? min(mts, own_ts) : own_ts;
+          rfirst = max_j >= 0 ? mfirst : i;
         }
       }
       if (lane >= done && lane < tile_n) {
         rj = i0 + lane; rx = cx; rq = cq; rsp = csp; rhi = chi;
-        rf = nf; rpp = npp; rv = nv; rcnt = ncnt; rqs = nqs; rts = nts; rfirst = nfirst;
+        rf = csp; rpp = -1; rv = csp; rcnt = 1; rqs = own_qs; rts = own_ts; rfirst = i0 + lane;
       }
-      if (lane < tile_n) {
-        A[i0 + lane] = make_int4(nf, npp, nv, ncnt);
-        B[i0 + lane] = make_int4(nqs, nts, nfirst, 0);
+      if (lane < tile_n) {                                       // every lane now holds its own anchor of this tile
+        A[i0 + lane] = make_int4(rf, rpp, rv, rcnt);
+        B[i0 + lane] = make_int4(rqs, rts, rfirst, 0);
       }
       {  // lchain.rs:163: the LAST maximum of f
-        const int fl = lane < tile_n ? nf : NEG_INF * 4;
+        const int fl = lane < tile_n ? rf : NEG_INF * 4;
         const int m = __reduce_max_sync(0xFFFFFFFFu, fl);
         if (m >= bf) {
           const u32 eq = __ballot_sync(0xFFFFFFFFu, fl == m);
