@@ -522,6 +522,7 @@ __global__ void __launch_bounds__(CH_WARPS * 32) chain_ring_kernel(ChainArgs G) 
         } else if (count_cells) {
           cells += (unsigned)__popc(inmask);
         }
+        int mv = 0, mcnt = 0, mqs = 0, mts = 0, mfirst = 0;     // state of max_j
         if (more) {
           // ---- the window goes on beyond the ring: 32 predecessors at a time from global memory -------------------------
           if (!t_init) {
@@ -587,19 +588,18 @@ __global__ void __launch_bounds__(CH_WARPS * 32) chain_ring_kernel(ChainArgs G) 
             if (rec_last >= 0) { max_j = jb - rec_last; from_ring = false; }
             if (brk) break;
           }
+          if (!from_ring) {
+            const int4 aj = A[max_j], bj = B[max_j];
+            mv = aj.z; mcnt = aj.w; mqs = bj.x; mts = bj.y; mfirst = bj.z;
+          }
         }
         // ---- lchain.rs:89-90 and the chain reductions of paf.rs:136-147 carried along the best-predecessor links -------
-        int mv = 0, mcnt = 0, mqs = 0, mts = 0, mfirst = 0;
-        if (max_j >= 0) {
+        if (max_j >= 0 && from_ring) {
           const int L = max_j & 31;
           mv = __shfl_sync(0xFFFFFFFFu, rv, L); mcnt = __shfl_sync(0xFFFFFFFFu, rcnt, L); mqs = __shfl_sync(0xFFFFFFFFu, rqs, L);
           mts = __shfl_sync(0xFFFFFFFFu, rts, L); mfirst = __shfl_sync(0xFFFFFFFFu, rfirst, L);
         }
         if (lane == c) {                                         // anchor i takes over its ring slot
-          if (!from_ring) {
-            const int4 aj = A[max_j], bj = B[max_j];
-            mv = aj.z; mcnt = aj.w; mqs = bj.x; mts = bj.y; mfirst = bj.z;
-          }
           rj = i; rx = cx; rq = cq; rsp = csp; rhi = chi;
           rf = max_f; rpp = max_j;
           rv = (max_j >= 0 && mv > max_f) ? mv : max_f;
