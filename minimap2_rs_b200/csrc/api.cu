@@ -57,6 +57,9 @@ extern "C" int mm2_ctx_create(int device, mm2_ctx_t** out) {
   { const char* e = getenv("MM2_PIPELINE"); if (e && atoi(e) == 0) c->pipeline = false; }
   { const char* e = getenv("MM2_WORKERS"); if (e && atoi(e) >= 2 && atoi(e) <= 4) c->n_workers = atoi(e); }
   { const char* e = getenv("MM2_SUBBATCH_MB"); if (e && atoi(e) > 0) c->subbatch_bytes = (u64)atoi(e) << 20; }
+  // test hook: MM2_CHAIN_DENSE_MIN=n sends every read with >= n anchors to the CTA-per-read chaining kernel
+  { const char* e = getenv("MM2_CHAIN_DENSE_MIN"); if (e && atoi(e) > 0) { c->chain_dense_min = atoi(e); c->chain_dense_ratio5 = 0; } }
+  c->n_sm = prop.multiProcessorCount;
   *out = c;
   return MM2_OK;
 }
@@ -455,7 +458,7 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
     const u64 need = grow(ctx->anchors, na * 16) + grow(ctx->dpA, na * 16) + grow(ctx->dpB, na * 16) + grow(ctx->dpT, na * 4) +
                      grow(ctx->dpW, na * 4);
     size_t free_b = 0, total_b = 0;
-    bool have_info = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess;
+    bool have_info = need && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess;   // asked only when an arena must grow: the call takes milliseconds
     if (const char* e = getenv("MM2_ANCHOR_BUDGET_MB")) { free_b = (size_t)atoll(e) << 20; have_info = true; }  // test hook
     if (need && have_info && need > (u64)(free_b * 0.9) && nreads > 1 && !o->want_stage_dump) {
       const size_t mid = nreads / 2;

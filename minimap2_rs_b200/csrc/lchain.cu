@@ -37,6 +37,9 @@ struct ChainArgs {
   int4* A; int4* B; int* T; int* W; int* chain;
   ReadHit* hits;
   unsigned long long* cells;
+  u32* dense;        // [0] number of dense reads, [1] ticket, [2..] their read indices (chain_classify_kernel)
+  int dense_min;     // a read is dense when it has >= dense_min anchors and more than dense_ratio5 / 5 anchors per base
+  int dense_ratio5;
 };
 
 constexpr int CH_WARPS = 4;
@@ -320,7 +323,7 @@ __global__ void __launch_bounds__(CH_WARPS * 32) chain_kernel(ChainArgs G) {
 //  * Only when the ring was visited without a break AND the slot that anchor i overwrites (j = i - 32) is still inside
 //    the window does the loop continue, 32 predecessors at a time, on A/T in global memory.  On ONT-like reads the loop
 //    breaks inside the ring for nearly every anchor (about 27 visited predecessors: max_chain_skip = 25).
-// Same arithmetic and same order of decisions as chain_kernel; the tests compare both against the oracle.
+// Same arithmetic and same order of decisions as chain_kernel; tests/ compares both with the CPU restatement.
 
 __device__ __forceinline__ u32 low_mask(int n) { return n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u); }
 // position of the n-th (1-based) set bit of m; popc(m) >= n
@@ -396,10 +399,81 @@ __device__ __forceinline__ bool chain_sc(int ri, int qi, int rj, int qj, int spa
   return true;
 }
 
-__global__ void __launch_bounds__(CH_WARPS * 32) chain_ring_kernel(ChainArgs G) {
-  const u32 r = blockIdx.x * CH_WARPS + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
+__device__ __forceinline__ bool chain_is_dense(const ChainArgs& G, u32 r) {
+  const i64 n = (i64)(G.read_aoff[r + 1] - G.read_aoff[r]);
+  const i64 qlen = (i64)(G.read_off[r + 1] - G.read_off[r]);
+  return n >= (i64)G.dense_min && n <= 0x7fffffff && n * 5 > qlen * (i64)G.dense_ratio5;
+}
+
+// Reads with a dense anchor set (repeat-rich ultra-long reads: predecessor windows of thousands of anchors) are chained by
+// one CTA each (chain_dense_kernel); this kernel only lists them.
+__global__ void chain_classify_kernel(ChainArgs G) {
+  const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= G.nreads) return;
+  if (chain_is_dense(G, r)) G.dense[2 + atomicAdd(&G.dense[0], 1u)] = r;
+}
+
+// Shared state of a CTA that chains one dense read: warp 0 runs the ring algorithm; when a window goes on beyond the ring
+// it posts the anchor here and all NW warps evaluate the next 32 tiles (1024 predecessors) of the window in parallel.
+struct DenseSh {
+  int op;                      // 0: evaluate a round, 1: the read is done
+  int ri, qi, jb, start_j, mark, bw, mdx, mdy;
+  u32 hi_i;
+  u32 next;                    // next dense read of this CTA
+  u32 V[32], M[32], ACT[32];   // per tile: ballots of "has a score", "t[j] == i", "inside the window"
+  int tmax[32];                // per tile: best score
+  int sc[32][33];
+};
+constexpr int DENSE_WARPS = 8;
+
+template <int NW>
+__device__ __forceinline__ void dense_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory"); }
+
+// One round: tiles t = 0..31 cover j = jb - 32 t - lane; warp w takes tiles w, w + NW, ...  (all NW warps call this)
+template <int NW>
+__device__ __forceinline__ void dense_eval_round(const ChainArgs& G, DenseSh* sh, const ulonglong2* __restrict__ an, const int4* A, int* T,
+                                                 int wid, int lane) {
+  constexpr int TPW = 32 / NW;
+  const int ri = sh->ri, qi = sh->qi, jb = sh->jb, start_j = sh->start_j, mark = sh->mark, bw = sh->bw, mdx = sh->mdx, mdy = sh->mdy;
+  const u32 hi_i = sh->hi_i;
+  int sc2[TPW];
+  bool v2[TPW];
+#pragma unroll
+  for (int u = 0; u < TPW; ++u) {
+    const int j = jb - 32 * (wid + NW * u) - lane;
+    sc2[u] = NEG_INF; v2[u] = false;
+    if (j >= start_j) {
+      const ulonglong2 v = an[j];
+      if ((u32)(v.x >> 32) == hi_i) {                             // lchain.rs:81
+        int s0;
+        if (chain_sc(ri, qi, (int)(u32)v.x, (int)(u32)v.y, (int)((v.y >> 32) & 0xff), mdx, mdy, bw, G.p.chn_pen_gap, G.p.chn_pen_skip,
+                     G.half_log, s0)) {
+          const int2 fj = *reinterpret_cast<const int2*>(A + j);
+          sc2[u] = wadd(s0, fj.x);
+          v2[u] = true;
+          if (fj.y >= 0) T[fj.y] = mark;                          // lchain.rs:86: marks by slots past the break are never read
+        }
+      }
+    }
+  }
+  dense_bar<NW>();                                                // every mark of this round is visible
+#pragma unroll
+  for (int u = 0; u < TPW; ++u) {
+    const int t = wid + NW * u;
+    const int j = jb - 32 * t - lane;
+    const bool tm = v2[u] ? (T[j] == mark) : false;
+    const u32 Vb = __ballot_sync(0xFFFFFFFFu, v2[u]), Mb = __ballot_sync(0xFFFFFFFFu, tm), Ab = __ballot_sync(0xFFFFFFFFu, j >= start_j);
+    const int tmx = __reduce_max_sync(0xFFFFFFFFu, sc2[u]);
+    sh->sc[t][lane] = sc2[u];
+    if (lane == 0) { sh->V[t] = Vb; sh->M[t] = Mb; sh->ACT[t] = Ab; sh->tmax[t] = tmx; }
+  }
+  dense_bar<NW>();                                                // the tile summaries are in shared memory
+}
+
+// NW = 1: one warp per read (chain_ring_kernel).  NW > 1: one CTA of NW warps per read (chain_dense_kernel); warps 1.. only
+// serve dense_eval_round.
+template <int NW>
+__device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, const int lane, const int wid, DenseSh* sh) {
   const u64 a0 = G.read_aoff[r];
   const i64 n64 = (i64)(G.read_aoff[r + 1] - a0);
   const i32 qlen = (i32)(G.read_off[r + 1] - G.read_off[r]);
@@ -426,6 +500,18 @@ __global__ void __launch_bounds__(CH_WARPS * 32) chain_ring_kernel(ChainArgs G) 
   int best = 0;
   int4 bestA = make_int4(0, -1, 0, 0), bestB = make_int4(0, 0, 0, 0);
   bool t_init = false;
+  if constexpr (NW > 1) {
+    for (int x = wid * 32 + lane; x < n; x += NW * 32) T[x] = -1;
+    t_init = true;
+    dense_bar<NW>();
+    if (wid > 0) {
+      for (;;) {
+        dense_bar<NW>();                                          // a command is posted
+        if (sh->op != 0) return;
+        dense_eval_round<NW>(G, sh, an, A, T, wid, lane);
+      }
+    }
+  }
 
   for (int pass = 0; pass < 2; ++pass) {
     const int bw = pass == 0 ? p.bw : p.bw_long;                 // lchain.rs:327-328
@@ -561,32 +647,87 @@ __global__ void __launch_bounds__(CH_WARPS * 32) chain_ring_kernel(ChainArgs G) 
           }
           st = lo;
           const int start_j = low_iter > lo ? low_iter : lo;
-          for (int jb = i - 33; jb >= start_j; jb -= 32) {
-            const int j = jb - lane;
-            const bool act = j >= start_j;
-            bool v2 = false;
-            int sc2 = NEG_INF, ppj = -1;
-            if (act) {
-              const ulonglong2 v = an[j];
-              if ((u32)(v.x >> 32) == hi_i) {                     // lchain.rs:81
-                int s0;
-                if (chain_sc(ri, qi, (int)(u32)v.x, (int)(u32)v.y, (int)((v.y >> 32) & 0xff), mdx, mdy, bw, p.chn_pen_gap,
-                             p.chn_pen_skip, G.half_log, s0)) {
-                  const int2 fj = *reinterpret_cast<const int2*>(A + j);
-                  sc2 = wadd(s0, fj.x);
-                  ppj = fj.y;
-                  v2 = true;
+          if constexpr (NW > 1) {
+            // 32 tiles per round, evaluated by all warps; this warp then walks the tile summaries: lane t holds tile t
+            bool brk = false;
+            for (int jb = i - 33; jb >= start_j && !brk; jb -= 32 * 32) {
+              if (lane == 0) {
+                sh->op = 0; sh->ri = ri; sh->qi = qi; sh->hi_i = hi_i; sh->jb = jb; sh->start_j = start_j; sh->mark = mark;
+                sh->bw = bw; sh->mdx = mdx; sh->mdy = mdy;
+              }
+              dense_bar<NW>();
+              dense_eval_round<NW>(G, sh, an, A, T, 0, lane);
+              const int nround = min(32, (jb - start_j + 32) >> 5);   // tiles that reach into the window
+              const u32 tV = sh->V[lane], tM = sh->M[lane], tA = sh->ACT[lane];
+              const int tmx = lane < nround ? sh->tmax[lane] : NEG_INF;
+              int cur = 0;
+              while (cur < nround) {
+                // tiles [cur, tf) hold no score above max_f, i.e. no record (lchain.rs:84): n_skip only grows there
+                const u32 cand = __ballot_sync(0xFFFFFFFFu, lane >= cur && tmx > max_f);
+                const int tf = cand ? (__ffs(cand) - 1) : nround;
+                if (tf > cur) {
+                  const bool mine = lane >= cur && lane < tf;
+                  const int cnt = mine ? __popc(tM & tV) : 0;
+                  const int total = __reduce_add_sync(0xFFFFFFFFu, cnt);
+                  const int need = max(max_skip + 1 - n_skip, 1);
+                  if (total >= need) {                            // lchain.rs:85: the need-th marked slot breaks the loop
+                    if (count_cells) {
+                      int incl = cnt;
+#pragma unroll
+                      for (int d = 1; d < 32; d <<= 1) {
+                        const int o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                        if (lane >= d) incl += o;
+                      }
+                      const u32 hit_m = __ballot_sync(0xFFFFFFFFu, incl >= need);
+                      const int tb = __ffs(hit_m) - 1;
+                      const int before = __reduce_add_sync(0xFFFFFFFFu, (mine && lane < tb) ? __popc(tA) : 0);
+                      const int excl_tb = __shfl_sync(0xFFFFFFFFu, incl - cnt, tb);
+                      const u32 mtb = __shfl_sync(0xFFFFFFFFu, tM & tV, tb);
+                      cells += (unsigned)(before + nth_set_bit(mtb, need - excl_tb) + 1);
+                    }
+                    brk = true;
+                    break;
+                  }
+                  n_skip += total;
+                  if (count_cells) cells += (unsigned)__reduce_add_sync(0xFFFFFFFFu, mine ? __popc(tA) : 0);
                 }
+                if (tf >= nround) break;
+                int rec_last;
+                const bool b = chain_tile_walk(lane, sh->V[tf], sh->M[tf], sh->ACT[tf], sh->sc[tf][lane], max_skip, max_f, n_skip, rec_last,
+                                               cells);
+                if (rec_last >= 0) { max_j = jb - 32 * tf - rec_last; from_ring = false; }
+                if (b) { brk = true; break; }
+                cur = tf + 1;
               }
             }
-            if (v2 && ppj >= 0) T[ppj] = mark;                    // lchain.rs:86 (all lanes first, see the header)
-            __syncwarp();
-            const bool tm = v2 ? (T[j] == mark) : false;
-            const u32 V2 = __ballot_sync(0xFFFFFFFFu, v2), M2 = __ballot_sync(0xFFFFFFFFu, tm), A2 = __ballot_sync(0xFFFFFFFFu, act);
-            int rec_last;
-            const bool brk = chain_tile_walk(lane, V2, M2, A2, sc2, max_skip, max_f, n_skip, rec_last, cells);
-            if (rec_last >= 0) { max_j = jb - rec_last; from_ring = false; }
-            if (brk) break;
+          } else {
+            for (int jb = i - 33; jb >= start_j; jb -= 32) {
+              const int j = jb - lane;
+              const bool act = j >= start_j;
+              bool v2 = false;
+              int sc2 = NEG_INF, ppj = -1;
+              if (act) {
+                const ulonglong2 v = an[j];
+                if ((u32)(v.x >> 32) == hi_i) {                     // lchain.rs:81
+                  int s0;
+                  if (chain_sc(ri, qi, (int)(u32)v.x, (int)(u32)v.y, (int)((v.y >> 32) & 0xff), mdx, mdy, bw, p.chn_pen_gap,
+                               p.chn_pen_skip, G.half_log, s0)) {
+                    const int2 fj = *reinterpret_cast<const int2*>(A + j);
+                    sc2 = wadd(s0, fj.x);
+                    ppj = fj.y;
+                    v2 = true;
+                  }
+                }
+              }
+              if (v2 && ppj >= 0) T[ppj] = mark;                    // lchain.rs:86 (all lanes first, see the header)
+              __syncwarp();
+              const bool tm = v2 ? (T[j] == mark) : false;
+              const u32 V2 = __ballot_sync(0xFFFFFFFFu, v2), M2 = __ballot_sync(0xFFFFFFFFu, tm), A2 = __ballot_sync(0xFFFFFFFFu, act);
+              int rec_last;
+              const bool brk = chain_tile_walk(lane, V2, M2, A2, sc2, max_skip, max_f, n_skip, rec_last, cells);
+              if (rec_last >= 0) { max_j = jb - rec_last; from_ring = false; }
+              if (brk) break;
+            }
           }
           if (!from_ring) {
             const int4 aj = A[max_j], bj = B[max_j];
@@ -644,6 +785,31 @@ __global__ void __launch_bounds__(CH_WARPS * 32) chain_ring_kernel(ChainArgs G) 
     __syncwarp();
   }
   chain_finish(G, r, lane, an, A, a0, qlen, m0, m1, best, bestA, bestB, hit, cells);
+  if constexpr (NW > 1) {
+    if (lane == 0) sh->op = 1;
+    dense_bar<NW>();                                              // releases warps 1..
+  }
+}
+
+__global__ void __launch_bounds__(CH_WARPS * 32) chain_ring_kernel(ChainArgs G) {
+  const u32 r = blockIdx.x * CH_WARPS + (threadIdx.x >> 5);
+  if (r >= G.nreads) return;
+  if (chain_is_dense(G, r)) return;                               // chain_dense_kernel's
+  chain_read<1>(G, r, threadIdx.x & 31, 0, nullptr);
+}
+
+__global__ void __launch_bounds__(DENSE_WARPS * 32) chain_dense_kernel(ChainArgs G) {
+  __shared__ DenseSh sh;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const u32 ndense = G.dense[0];
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) sh.next = atomicAdd(&G.dense[1], 1u);
+    __syncthreads();
+    const u32 k = sh.next;
+    if (k >= ndense) return;
+    chain_read<DENSE_WARPS>(G, G.dense[2 + k], lane, wid, &sh);
+  }
 }
 
 }  // namespace
@@ -685,10 +851,22 @@ int chain_batch(mm2_ctx* ctx, const ulonglong2* d_anchors, const u64* d_read_aof
   G.anchors = d_anchors; G.read_aoff = d_read_aoff; G.read_off = d_read_off; G.mini_off = d_mini_off; G.mval = d_mval;
   G.sum_span = d_sum_span; G.nreads = nreads; G.p = p; G.do_rescue = do_rescue; G.half_log = ctx->lut.as<float>();
   G.A = d_A; G.B = d_B; G.T = d_T; G.W = d_W; G.chain = d_chain; G.hits = d_hits; G.cells = d_cells;
+  G.dense = nullptr; G.dense_min = 0x7fffffff; G.dense_ratio5 = 0;
   const int grid = (int)((nreads + CH_WARPS - 1) / CH_WARPS);
   static const bool use_v1 = [] { const char* e = getenv("MM2_CHAIN"); return e && !strcmp(e, "v1"); }();   // comparison arm
-  if (use_v1) MM2_LAUNCH(ctx, chain_kernel, grid, CH_WARPS * 32, 0, G);
-  else MM2_LAUNCH(ctx, chain_ring_kernel, grid, CH_WARPS * 32, 0, G);
+  if (use_v1) {
+    MM2_LAUNCH(ctx, chain_kernel, grid, CH_WARPS * 32, 0, G);
+  } else {
+    MM2_TRY(ctx->read_class.ensure(((size_t)nreads + 4) * 4));
+    G.dense = ctx->read_class.as<u32>();
+    G.dense_min = ctx->chain_dense_min;
+    G.dense_ratio5 = ctx->chain_dense_ratio5;
+    CUDA_TRY(cudaMemsetAsync(G.dense, 0, 8, ctx->stream));
+    MM2_LAUNCH(ctx, chain_classify_kernel, (int)((nreads + 255) / 256), 256, 0, G);
+    MM2_LAUNCH(ctx, chain_ring_kernel, grid, CH_WARPS * 32, 0, G);
+    // persistent CTAs, one dense read at a time each; with no dense read they exit at once
+    MM2_LAUNCH(ctx, chain_dense_kernel, (int)std::min<u64>(nreads, (u64)ctx->n_sm * 2), DENSE_WARPS * 32, 0, G);
+  }
   CUDA_TRY(cudaGetLastError());
   return MM2_OK;
 }

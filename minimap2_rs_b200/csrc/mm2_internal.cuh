@@ -126,6 +126,9 @@ struct mm2_ctx {
   bool pipeline = true;
   u64 subbatch_bytes = 64ull << 20;
   int lut_n = 0;        // entries of the chaining log table resident in `lut`
+  int n_sm = 148;
+  // chaining: reads with >= chain_dense_min anchors and more than chain_dense_ratio5 / 5 anchors per base get a CTA each
+  int chain_dense_min = 4096, chain_dense_ratio5 = 2;
   u64 mg_sorted_n = 0;  // records left in sort_keys2/sort_vals2 by mm2_mg_sketch_sort
 };
 

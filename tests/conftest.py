@@ -39,3 +39,15 @@ def ctx(mm2):
     c = mm2.Context(0)
     yield c
     c.close()
+
+
+@pytest.fixture(scope="session")
+def dense_ctx(mm2):
+    """a context whose chaining sends EVERY read with >= 1 anchors to the CTA-per-read kernel (chain_dense_kernel)"""
+    os.environ["MM2_CHAIN_DENSE_MIN"] = "1"
+    try:
+        c = mm2.Context(0)
+    finally:
+        del os.environ["MM2_CHAIN_DENSE_MIN"]
+    yield c
+    c.close()

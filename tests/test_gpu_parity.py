@@ -184,12 +184,15 @@ def test_chain_dp_all(ctx, orc, small_world):
 
 @pytest.mark.parametrize("density,max_skip,max_iter", [(5, 25, 5000), (40, 25, 5000), (40, 0, 5000), (40, 2, 31), (40, 25, 32), (40, 1, 33),
                                                       (200, 25, 5000), (200, 3, 64), (200, 25, 1), (1000, 25, 5000), (1000, 5, 700)])
-def test_chain_dp_all_synthetic_windows(ctx, orc, density, max_skip, max_iter):
+@pytest.mark.parametrize("which", ["warp_per_read", "cta_per_read"])
+def test_chain_dp_all_synthetic_windows(ctx, dense_ctx, orc, density, max_skip, max_iter, which):
     """anchors placed directly (no index): predecessor windows around and beyond the 32-slot register ring of the kernel,
     collinear runs (marks -> max_chain_skip breaks), ties, both strands, several rids"""
     import minimap2_rs_b200 as m
+    if which == "cta_per_read":
+        ctx = dense_ctx        # n >= 4096 would take that kernel anyway; the other arm keeps n below it
     rng = np.random.default_rng(density * 1000 + max_skip * 10 + max_iter)
-    n = 6000
+    n = 6000 if which == "cta_per_read" else 3600
     span = 15
     parts = []
     for rid, rev, cnt in ((0, 0, n // 2), (0, 1, n // 6), (2, 0, n // 6), (4, 1, n // 6)):
@@ -303,6 +306,24 @@ def test_map_batch_repeats_rescue_and_hifi_preset(ctx, mm2, orc, gen):
         chim.append(g[a:a + 4000].tobytes() + g[b:b + 3000].tobytes())
     cat2, roffs2 = cases.cat_offs([cat[int(roffs[i]):int(roffs[i + 1])].tobytes() for i in range(60)] + chim)
     res, st = _map_compare(ctx, mm2, orc, gi, oi, cat2, roffs2, ["h%d" % i for i in range(80)], (w, k))
+    assert st.n_rescued > 0
+
+
+def test_map_batch_cta_per_read_chaining(dense_ctx, mm2, orc, gen):
+    """the whole mapping path with every read chained by chain_dense_kernel (repeat-rich genome: long windows, rescue)"""
+    g = gen.repeat_genome(78, 1_500_000, 0.4, 0.2)
+    offs = np.array([0, g.size], dtype=np.uint64)
+    gi = mm2.Index.build(dense_ctx, g, offs, ["rep"])
+    oi = orc.Index.build(g, offs, ["rep"], threads=8)
+    cat, roffs = gen.reads(22, g, offs, 40, 12000, 0.02, 0.02, 0.02)
+    rng = np.random.default_rng(2)
+    chim = []
+    for i in range(6):   # chimeric reads force rescue_long_join's rerun (second DP pass of the same CTA)
+        a, b = int(rng.integers(0, g.size - 5000)), int(rng.integers(0, g.size - 5000))
+        chim.append(g[a:a + 4000].tobytes() + g[b:b + 1500].tobytes())
+    reads = [cat[int(roffs[i]):int(roffs[i + 1])].tobytes() for i in range(40)] + chim + [b"ACGT" * 10]
+    cat2, roffs2 = cases.cat_offs(reads)
+    res, st = _map_compare(dense_ctx, mm2, orc, gi, oi, cat2, roffs2, ["d%d" % i for i in range(len(reads))], dump=False)
     assert st.n_rescued > 0
 
 
