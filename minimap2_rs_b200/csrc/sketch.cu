@@ -391,6 +391,17 @@ __device__ __noinline__ u64 sk_emit_dups(const KT* s_key, const u8* s_z, int lo,
   return o;
 }
 
+// staged variant: the positions go to a shared list instead of global memory
+template <class KT, int PAD>
+__device__ __noinline__ u32 sk_list_dups(const KT* s_key, int lo, int hi, int excl, u16* s_list, u32 idx) {
+  const KT kv = s_key[excl + (excl >> PAD)];
+  for (int x = lo; x <= hi; ++x)
+    if (s_key[x + (x >> PAD)] == kv && x != excl) s_list[idx++] = (u16)x;
+  return idx;
+}
+
+constexpr int SK_LIST = 1024;   // staged minimizers per tile (a tile of random sequence emits ~380)
+
 template <class KT>
 __global__ void __launch_bounds__(SK_NT, 4) sketch_tile_kernel_v2(SketchParams P) {
   constexpr int PAD = KeyTraits<KT>::PAD;
@@ -403,6 +414,7 @@ __global__ void __launch_bounds__(SK_NT, 4) sketch_tile_kernel_v2(SketchParams P
   __shared__ u32 s_wsum[SK_NT / 32];
   __shared__ u32 s_tile;
   __shared__ u64 s_base;
+  __shared__ u16 s_list[SK_LIST];
 
   const int tid = threadIdx.x;
   const int w = P.w, k = P.k;
@@ -484,20 +496,36 @@ __global__ void __launch_bounds__(SK_NT, 4) sketch_tile_kernel_v2(SketchParams P
       const u32 cw = __funnelshift_r(s_pack[r0 >> 4], s_pack[(r0 >> 4) + 1], 2 * (r0 & 15));
       const u32 nb = __funnelshift_r(s_nm[r0 >> 5], s_nm[(r0 >> 5) + 1], r0 & 31);
       u32 zbits = 0;
+      if (l >= cap && (nb & 0xFFu) == 0u) {
+        // no N among these 8 bases and a full run before them: l stays at its cap, every k-mer is hashed
+        ge_cap = 0xFFu;
 #pragma unroll
-      for (int j = 0; j < SK_CH; ++j) {
-        const u32 c = (cw >> (2 * j)) & 3u;
-        l = ((nb >> j) & 1u) ? 0 : min(l + 1, cap);
-        fwd = (KT)(((fwd << 2) | (KT)c) & mask);
-        rev = (KT)((rev >> 2) | ((KT)(3u ^ c) << shift1));
-        const bool z = !(fwd < rev);
-        KT key = KMAX;
-        if (l >= k) key = hash_mix<KT>(z ? rev : fwd, mask);
-        K[j] = key;
-        s_key[KIDX(SK_CH * tid + j)] = key;
-        zbits |= (u32)z << j;
-        ge_cap |= (u32)(l >= cap) << j;
-        eq_capm1 |= (u32)(l == cap - 1) << j;
+        for (int j = 0; j < SK_CH; ++j) {
+          const u32 c = (cw >> (2 * j)) & 3u;
+          fwd = (KT)(((fwd << 2) | (KT)c) & mask);
+          rev = (KT)((rev >> 2) | ((KT)(3u ^ c) << shift1));
+          const bool z = !(fwd < rev);
+          const KT key = hash_mix<KT>(z ? rev : fwd, mask);
+          K[j] = key;
+          s_key[KIDX(SK_CH * tid + j)] = key;
+          zbits |= (u32)z << j;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < SK_CH; ++j) {
+          const u32 c = (cw >> (2 * j)) & 3u;
+          l = ((nb >> j) & 1u) ? 0 : min(l + 1, cap);
+          fwd = (KT)(((fwd << 2) | (KT)c) & mask);
+          rev = (KT)((rev >> 2) | ((KT)(3u ^ c) << shift1));
+          const bool z = !(fwd < rev);
+          KT key = KMAX;
+          if (l >= k) key = hash_mix<KT>(z ? rev : fwd, mask);
+          K[j] = key;
+          s_key[KIDX(SK_CH * tid + j)] = key;
+          zbits |= (u32)z << j;
+          ge_cap |= (u32)(l >= cap) << j;
+          eq_capm1 |= (u32)(l == cap - 1) << j;
+        }
       }
       s_z[tid] = (u8)zbits;
     }
@@ -534,41 +562,70 @@ __global__ void __launch_bounds__(SK_NT, 4) sketch_tile_kernel_v2(SketchParams P
         pk_prev = rk; ppd_prev = rpd;
         if (kx < rk) { pk_prev = kx; ppd_prev = t << 1; } else if (kx == rk) ppd_prev |= 1;
       }
-      KT fk = KMAX; int fpd = 0;  // prefix minima inside the chunk (newer element wins ties)
+      // Fast path: all 8 steps are inside the tile, every window involved is full (l >= w + k: the previous minimum is a
+      // real k-mer and sketch.rs:84/88 emit unconditionally) and no window holds its minimum twice.  Then step u emits
+      // the previous minimum exactly when it is replaced (new key <= old minimum) or slides out (its position is u - w).
+      bool slow = !(ge_cap == 0xFFu && c0 >= w && c0 + SK_CH - 1 <= u_last && !(last_tile && c0 + SK_CH - 1 == u_last));
+      if (!slow) {
+        const KT pk0 = pk_prev; const int ppd0 = ppd_prev;
+        KT fk = KMAX; int fpd = 0;
+        int odd = ppd_prev;
 #pragma unroll
-      for (int j = 0; j < SK_CH; ++j) {
-        const int u = c0 + j;
-        const KT ki = K[j];
-        if (ki <= fk) { fpd = (u << 1) | (ki == fk ? 1 : 0); fk = ki; }
-        // window [u-w+1, u] = older part (suffix) + newer part (prefix); the newer part wins ties
-        KT ck; int cpd;
-        if (fk <= Sk[j]) { ck = fk; cpd = fpd | (fk == Sk[j] ? 1 : 0); } else { ck = Sk[j]; cpd = Spd[j]; }
-        const int ppos = ppd_prev >> 1;
-        pp[j >> 1] |= (u32)ppos << (16 * (j & 1));
-        if (u >= w && u <= u_last) {
-          const KT kp = pk_prev;
-          const bool gc = (ge_cap >> j) & 1u, ec1 = (eq_capm1 >> j) & 1u;
-          if (kp != KMAX) {
-            if (ec1 && (ppd_prev & 1)) {
-              const u32 c1 = sk_count_dups<KT, PAD>(s_key, u - w + 1, u - 1, kp, ppos);
-              if (c1) { tot += c1; eflags |= 1u << (8 + j); }
-            }
-            if (ki <= kp) {
-              if (gc) { tot += 1; eflags |= 1u << j; }
-            } else if (ppos == u - w) {
-              if (gc || ec1) {
-                tot += 1; eflags |= 1u << j;
-                if (ck != KMAX && (cpd & 1)) {
-                  const u32 c3 = sk_count_dups<KT, PAD>(s_key, u - w + 1, u, ck, cpd >> 1);
-                  if (c3) { tot += c3; eflags |= 1u << (16 + j); }
+        for (int j = 0; j < SK_CH; ++j) {
+          const int u = c0 + j;
+          const KT ki = K[j];
+          if (ki <= fk) { fpd = (u << 1) | (ki == fk ? 1 : 0); fk = ki; }
+          KT ck; int cpd;
+          if (fk <= Sk[j]) { ck = fk; cpd = fpd | (fk == Sk[j] ? 1 : 0); } else { ck = Sk[j]; cpd = Spd[j]; }
+          const int ppos = ppd_prev >> 1;
+          pp[j >> 1] |= (u32)ppos << (16 * (j & 1));
+          const u32 em = (ki <= pk_prev || ppos == u - w) ? 1u : 0u;
+          tot += em; eflags |= em << j;
+          odd |= cpd;
+          pk_prev = ck; ppd_prev = cpd;
+        }
+        cur7 = ppd_prev >> 1;
+        if (odd & 1) {   // a repeated minimum somewhere: redo these 8 steps with the full rules
+          slow = true; tot = 0; eflags = 0; pp[0] = pp[1] = pp[2] = pp[3] = 0; pk_prev = pk0; ppd_prev = ppd0;
+        }
+      }
+      if (slow) {
+        KT fk = KMAX; int fpd = 0;  // prefix minima inside the chunk (newer element wins ties)
+  #pragma unroll
+        for (int j = 0; j < SK_CH; ++j) {
+          const int u = c0 + j;
+          const KT ki = K[j];
+          if (ki <= fk) { fpd = (u << 1) | (ki == fk ? 1 : 0); fk = ki; }
+          // window [u-w+1, u] = older part (suffix) + newer part (prefix); the newer part wins ties
+          KT ck; int cpd;
+          if (fk <= Sk[j]) { ck = fk; cpd = fpd | (fk == Sk[j] ? 1 : 0); } else { ck = Sk[j]; cpd = Spd[j]; }
+          const int ppos = ppd_prev >> 1;
+          pp[j >> 1] |= (u32)ppos << (16 * (j & 1));
+          if (u >= w && u <= u_last) {
+            const KT kp = pk_prev;
+            const bool gc = (ge_cap >> j) & 1u, ec1 = (eq_capm1 >> j) & 1u;
+            if (kp != KMAX) {
+              if (ec1 && (ppd_prev & 1)) {
+                const u32 c1 = sk_count_dups<KT, PAD>(s_key, u - w + 1, u - 1, kp, ppos);
+                if (c1) { tot += c1; eflags |= 1u << (8 + j); }
+              }
+              if (ki <= kp) {
+                if (gc) { tot += 1; eflags |= 1u << j; }
+              } else if (ppos == u - w) {
+                if (gc || ec1) {
+                  tot += 1; eflags |= 1u << j;
+                  if (ck != KMAX && (cpd & 1)) {
+                    const u32 c3 = sk_count_dups<KT, PAD>(s_key, u - w + 1, u, ck, cpd >> 1);
+                    if (c3) { tot += c3; eflags |= 1u << (16 + j); }
+                  }
                 }
               }
             }
+            if (last_tile && u == u_last && ck != KMAX) { tot += 1; eflags |= 1u << 24; }
           }
-          if (last_tile && u == u_last && ck != KMAX) { tot += 1; eflags |= 1u << 24; }
+          if (u == min(c0 + SK_CH - 1, u_last)) cur7 = cpd >> 1;
+          pk_prev = ck; ppd_prev = cpd;
         }
-        if (u == min(c0 + SK_CH - 1, u_last)) cur7 = cpd >> 1;
-        pk_prev = ck; ppd_prev = cpd;
       }
     }
 
@@ -620,10 +677,45 @@ __global__ void __launch_bounds__(SK_NT, 4) sketch_tile_kernel_v2(SketchParams P
     }
     __syncthreads();
 
-    // ---- write this thread's minimizers in step order ------------------------------------------------------------------
-    if (tot) {
+    // ---- write the minimizers in step order ------------------------------------------------------------------------------
+    const u64 rid_hi = (u64)(P.rid_base + q * P.rid_step) << 32;
+    if (tile_count <= (u32)SK_LIST) {
+      // usual case: every thread stages the tile positions it emits (shared list, in step order), then the CTA writes
+      // the records with coalesced stores
+      if (tot) {
+        u32 idx = my_off;
+        u32 jm = (eflags | (eflags >> 8) | (eflags >> 16)) & 0xFFu;  // steps of this thread that emit anything
+        while (jm) {
+          const int j = __ffs(jm) - 1;
+          jm &= jm - 1;
+          const int u = c0 + j;
+          const u32 pw = (j >> 1) == 0 ? pp[0] : (j >> 1) == 1 ? pp[1] : (j >> 1) == 2 ? pp[2] : pp[3];
+          const int ppos = (int)((pw >> (16 * (j & 1))) & 0xFFFFu);
+          if (eflags & (1u << (8 + j))) idx = sk_list_dups<KT, PAD>(s_key, u - w + 1, u - 1, ppos, s_list, idx);
+          if (eflags & (1u << j)) s_list[idx++] = (u16)ppos;
+          if (eflags & (1u << (16 + j))) {
+            const int j1 = j + 1;
+            const u32 pw1 = (j1 >> 1) == 0 ? pp[0] : (j1 >> 1) == 1 ? pp[1] : (j1 >> 1) == 2 ? pp[2] : pp[3];
+            const int cpos = (j == SK_CH - 1) ? cur7 : (int)((pw1 >> (16 * (j1 & 1))) & 0xFFFFu);
+            idx = sk_list_dups<KT, PAD>(s_key, u - w + 1, u, cpos, s_list, idx);
+          }
+        }
+        if (eflags & (1u << 24)) s_list[idx++] = (u16)cur7;
+      }
+      __syncthreads();
+      const u64 base = s_base;
+      for (u32 e2 = tid; e2 < tile_count; e2 += SK_NT) {
+        const int x = s_list[e2];
+        const u64 o = base + e2;
+        if (o < P.out_cap) {
+          const u32 z = (s_z[x >> 3] >> (x & 7)) & 1u;
+          P.out_key[o] = ((u64)s_key[KIDX(x)] << 8) | (u64)k;
+          P.out_val[o] = rid_hi | ((u64)(P0 + x) << 1) | (u64)z;
+        }
+      }
+    } else if (tot) {
+      // a tile that emits more than the list holds (windows full of repeated minima): each thread writes its own records
       u64 o = s_base + my_off;
-      const u64 rid_hi = (u64)(P.rid_base + q * P.rid_step) << 32;
       auto emit = [&](int x) {
         if (o < P.out_cap) {
           const u64 pos = (u64)(P0 + x);
@@ -633,7 +725,7 @@ __global__ void __launch_bounds__(SK_NT, 4) sketch_tile_kernel_v2(SketchParams P
         }
         ++o;
       };
-      u32 jm = (eflags | (eflags >> 8) | (eflags >> 16)) & 0xFFu;  // steps of this thread that emit anything
+      u32 jm = (eflags | (eflags >> 8) | (eflags >> 16)) & 0xFFu;
       while (jm) {
         const int j = __ffs(jm) - 1;
         jm &= jm - 1;
