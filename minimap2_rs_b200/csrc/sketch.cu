@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(SK_NT, 4) sketch_tile_kernel_v2(SketchParams P
   __shared__ __align__(16) u32 s_nm[SK_MAXCHUNK / 2 + 4];
   __shared__ u8 s_z[SK_NT];
   __shared__ u32 s_wsum[SK_NT / 32];
-  __shared__ u32 s_tile;
+  __shared__ u32 s_next[2];
   __shared__ u64 s_base;
   __shared__ u16 s_list[SK_LIST];
 
@@ -423,12 +423,13 @@ __global__ void __launch_bounds__(SK_NT, 4) sketch_tile_kernel_v2(SketchParams P
   const KT mask = (KT)((((u64)1) << (2 * k)) - 1);
   const int shift1 = 2 * (k - 1);
 
-  for (;;) {
-    __syncthreads();
-    if (tid == 0) s_tile = atomicAdd(P.ticket, 1u);
-    __syncthreads();
-    const u32 tile = s_tile;
-    if (tile >= P.ntiles) break;
+  // Tiles are handed out in order (the look-back below needs every earlier tile to be running or done).  The next ticket
+  // is taken by thread 0 right after its look-back, i.e. just before the tile's records are written: a ticket taken
+  // earlier would sit unprocessed while later tiles spin on it (measured: 2.7x slower).
+  if (tid == 0) s_next[0] = atomicAdd(P.ticket, 1u);
+  __syncthreads();
+  u32 tile = s_next[0];
+  for (int par = 0; tile < P.ntiles; par ^= 1) {
     const u32 q = P.tile_seq[tile];
     const u64 soff = P.seq_off[q];
     const i64 len = (i64)(P.seq_off[q + 1] - soff);
@@ -673,16 +674,17 @@ __global__ void __launch_bounds__(SK_NT, 4) sketch_tile_kernel_v2(SketchParams P
         s_base = excl;
         if (tile == P.tile_first[q]) P.seq_out_off[q] = excl;
         if (tile == P.ntiles - 1) P.seq_out_off[P.nseq] = excl + (u64)tile_count;
+        s_next[par ^ 1] = atomicAdd(P.ticket, 1u);   // read by everyone after the barrier below
       }
     }
-    __syncthreads();
 
     // ---- write the minimizers in step order ------------------------------------------------------------------------------
     const u64 rid_hi = (u64)(P.rid_base + q * P.rid_step) << 32;
-    if (tile_count <= (u32)SK_LIST) {
-      // usual case: every thread stages the tile positions it emits (shared list, in step order), then the CTA writes
-      // the records with coalesced stores
-      if (tot) {
+    const bool staged = tile_count <= (u32)SK_LIST;
+    {
+      // usual case: every thread stages the tile positions it emits (shared list, in step order; needs only the offsets
+      // inside the tile, so it overlaps warp 0's look-back), then the CTA writes the records with coalesced stores
+      if (staged && tot) {
         u32 idx = my_off;
         u32 jm = (eflags | (eflags >> 8) | (eflags >> 16)) & 0xFFu;  // steps of this thread that emit anything
         while (jm) {
@@ -702,7 +704,9 @@ __global__ void __launch_bounds__(SK_NT, 4) sketch_tile_kernel_v2(SketchParams P
         }
         if (eflags & (1u << 24)) s_list[idx++] = (u16)cur7;
       }
-      __syncthreads();
+    }
+    __syncthreads();   // s_base and the staged list are ready
+    if (staged) {
       const u64 base = s_base;
       for (u32 e2 = tid; e2 < tile_count; e2 += SK_NT) {
         const int x = s_list[e2];
@@ -744,6 +748,7 @@ __global__ void __launch_bounds__(SK_NT, 4) sketch_tile_kernel_v2(SketchParams P
       }
       if (eflags & (1u << 24)) emit(cur7);
     }
+    tile = s_next[par ^ 1];
   }
 #undef KIDX
 }
