@@ -222,7 +222,7 @@ def main():
         for kname, v in ctx.last_timings().items():
             stage_ms[kname] = stage_ms.get(kname, 0.0) + v / args.steps
         stats = dict(res.stats)
-        n_recs = int(res.recs.size)
+        n_recs = res.n_recs
         res.close()
     ev1.record(stream)
     barrier()

@@ -85,10 +85,11 @@ def lib():
     global _LIB
     if _LIB is not None:
         return _LIB
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("MM2_LIB_PATH", LIB_PATH)   # A/B builds of the same library (tools/, never a fallback)
+    if not os.path.exists(path):
         raise ImportError("libmm2b200.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(or `make -C minimap2_rs_b200/csrc`); minimap2_rs_b200 has no CPU fallback")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     vp, sz, u64p = C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)
     L.mm2_last_error.restype = C.c_char_p
     L.mm2_host_alloc.restype = vp
@@ -384,7 +385,8 @@ class MapResult:
         self._res = res
         self._idx = idx
         self.nreads = nreads
-        self.recs = _copy_out(res.recs, res.n_recs, PAF_DT, free=False)
+        self.n_recs = int(res.n_recs)
+        self._recs = None            # copied out of the library's buffer on first use (6.4 MB per 100k reads)
         self.panic_reads = _copy_out(res.panic_reads, res.n_panic, np.uint32, free=False)
         self.stats = dict(n_reads=res.n_reads, n_bases=res.n_bases, n_minimizers=res.n_minimizers,
                           n_minimizers_kept=res.n_minimizers_kept, n_anchors=res.n_anchors, n_rescued=res.n_rescued)
@@ -398,6 +400,15 @@ class MapResult:
                               anchors=_copy_out(res.anchors, na, ANCHOR_DT, free=False),
                               f=_copy_out(res.f, na, np.int32, free=False), v=_copy_out(res.v, na, np.int32, free=False),
                               pprev=_copy_out(res.pprev, na, np.int32, free=False))
+
+    @property
+    def recs(self):
+        """the PAF records (PAF_DT), one per kept chain, in read order"""
+        if self._recs is None:
+            if self._res is None:
+                raise Mm2Error(MM2_E_ARG, "MapResult is closed")
+            self._recs = _copy_out(self._res.recs, self._res.n_recs, PAF_DT, free=False)
+        return self._recs
 
     def paf_lines(self, qnames=None):
         """paf.rs:238 write_paf_many_with_scores for the whole batch -> list of lines"""

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <numeric>
 #include <mutex>
+#include <chrono>
 #include <thread>
 
 #include "stages.cuh"
@@ -419,6 +420,7 @@ static int build_record(const mm2_index* idx, const ReadHit& h, u32 r, i32 qlen,
 static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, const u64* d_off, const u64* h_off, size_t nreads,
                            const mm2_map_opts_t* o, mm2_map_result_t* out, bool timer_started) {
   cudaStream_t st = ctx->stream;
+  const auto wall0 = std::chrono::steady_clock::now();
   if (nreads > 0xFFFFFFF0ull) { mm2_set_error("too many reads in one batch"); return MM2_E_ARG; }
   // paf.rs:156 re-sketches the query with the INDEX's w/k for dv while everything else uses the CLI's
   const bool wk_mismatch = (o->w != idx->w || o->k != idx->k);
@@ -507,6 +509,7 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
   ctx->timer.mark(st, "end");
   CUDA_TRY(cudaStreamSynchronize(st));
   ctx->timer.finish();
+  const auto wall1 = std::chrono::steady_clock::now();
 
   // ---- records (paf.rs:130-222) ---------------------------------------------------------------------------------------------
   memset(out, 0, sizeof *out);
@@ -516,7 +519,7 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
   size_t nr = 0;
   {
     // host threads over contiguous read ranges; results are concatenated in read order
-    const int nth = nreads >= 16384 ? 8 : 1;
+    const int nth = nreads >= 16384 ? (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency())) : 1;
     std::vector<std::vector<mm2_paf_rec_t>> part((size_t)nth);
     std::vector<std::vector<u32>> ppan((size_t)nth);
     std::vector<u64> presc((size_t)nth, 0);
@@ -548,6 +551,11 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
   out->panic_reads = xmalloc<u32>(panics.size());
   if (!panics.empty()) memcpy(out->panic_reads, panics.data(), panics.size() * 4);
   out->n_minimizers_kept = 0;
+  {  // host wall clock of this call next to the device stage times: whole call up to here, and the record assembly alone
+    const auto wall2 = std::chrono::steady_clock::now();
+    ctx->timer.add_host("host_records", std::chrono::duration<float, std::milli>(wall2 - wall1).count());
+    ctx->timer.add_host("host_call", std::chrono::duration<float, std::milli>(wall2 - wall0).count());
+  }
 
   if (o->want_stage_dump) {
     out->mini_offs = xmalloc<u64>(nreads + 1); out->minis = xmalloc<mm2_mini_t>(nm); out->mini_keep = xmalloc<u8>(nm);

@@ -103,6 +103,12 @@ struct StageTimer {  // CUDA-event stopwatch on the context stream
     }
     names_blob.push_back('\0');
   }
+  void add_host(const char* name, float t) {  // a host-side wall-clock entry appended after finish()
+    if (!names_blob.empty()) names_blob.pop_back();
+    names_blob += name; names_blob.push_back('\0'); names_blob.push_back('\0');
+    ms.push_back(t);
+    names.push_back(name);
+  }
   ~StageTimer() { for (auto e : ev) cudaEventDestroy(e); }
 };
 

@@ -18,10 +18,13 @@
 
 namespace {
 
-constexpr int SK_NT = 256;                  // threads per CTA
+#ifndef MM2_SK_NT
+#define MM2_SK_NT 256
+#endif
+constexpr int SK_NT = MM2_SK_NT;            // threads per CTA
 constexpr int SK_CH = 8;                    // key positions per thread
 constexpr int SK_REGION = SK_NT * SK_CH;    // key positions held in shared memory: [s-w, s-w+2048)
-constexpr int SK_MAXCHUNK = 152;            // 16-byte chunks: (15 + 2048 + 255 + 28 + 15) / 16 rounded up + pad
+constexpr int SK_MAXCHUNK = ((15 + SK_REGION + 255 + 28 + 15 + 15) / 16 + 7) / 8 * 8;   // 16-byte chunks a tile can touch (+ pad)
 
 struct SketchParams {
   const u8* seq;          // concatenated ASCII bases
@@ -402,8 +405,11 @@ __device__ __noinline__ u32 sk_list_dups(const KT* s_key, int lo, int hi, int ex
 
 constexpr int SK_LIST = 1024;   // staged minimizers per tile (a tile of random sequence emits ~380)
 
+#ifndef MM2_SK_OCC
+#define MM2_SK_OCC 6   // CTAs per SM of the 32-bit-key kernel (40 registers; measured 10.3 / 9.3 / 8.9 ms per Gbase at 4 / 5 / 6)
+#endif
 template <class KT>
-__global__ void __launch_bounds__(SK_NT, 4) sketch_tile_kernel_v2(SketchParams P) {
+__global__ void __launch_bounds__(SK_NT, sizeof(KT) == 4 ? MM2_SK_OCC : 4) sketch_tile_kernel_v2(SketchParams P) {
   constexpr int PAD = KeyTraits<KT>::PAD;
   constexpr KT KMAX = (KT)~(KT)0;
 #define KIDX(u) ((u) + ((u) >> PAD))
@@ -939,7 +945,7 @@ int sketch_device(mm2_ctx* ctx, const u8* d_cat, const u64* d_off, const u64* h_
       P.seq_out_off = ctx->mini_off.as<u64>();
       P.tile_status = ctx->tile_status.as<u64>();
       P.ticket = (u32*)((u8*)ctx->tile_status.p + (size_t)ntiles * 8);
-      const int grid = (int)std::min<u64>(ntiles, (u64)num_sms(ctx->device) * 5);
+      const int grid = (int)std::min<u64>(ntiles, (u64)num_sms(ctx->device) * (MM2_SK_OCC + 1));
       if (w >= 9) {  // version 2: per-thread prefix/suffix window minima
         if (k <= 15) MM2_LAUNCH(ctx, sketch_tile_kernel_v2<u32>, grid, SK_NT, 0, P);
         else MM2_LAUNCH(ctx, sketch_tile_kernel_v2<u64>, grid, SK_NT, 0, P);
