@@ -7,7 +7,9 @@
 #include <cmath>
 #include <numeric>
 #include <mutex>
+#include <atomic>
 #include <chrono>
+#include <malloc.h>
 #include <thread>
 
 #include "stages.cuh"
@@ -121,6 +123,33 @@ inline int grid_for(u64 n, int block = 256) { return (int)std::max<u64>(1, std::
 
 template <class T>
 T* xmalloc(size_t n) { return (T*)malloc(std::max<size_t>(1, n) * sizeof(T)); }
+
+// The record array of a large batch is megabytes of freshly mapped pages on every call (a page fault per 4 KB, ~2 ms per
+// 100k reads).  mm2_map_result_free parks up to four such buffers here and the next batch takes one back.
+struct RecCache {
+  std::mutex mu;
+  struct Slot { void* p; size_t cap; } slot[4] = {{nullptr, 0}, {nullptr, 0}, {nullptr, 0}, {nullptr, 0}};
+  static constexpr size_t MIN_BYTES = 1u << 20;
+  void* take(size_t bytes) {
+    if (bytes >= MIN_BYTES) {
+      std::lock_guard<std::mutex> lk(mu);
+      for (auto& s : slot)
+        if (s.p && s.cap >= bytes && s.cap <= 2 * bytes) { void* p = s.p; s.p = nullptr; s.cap = 0; return p; }
+    }
+    return malloc(std::max<size_t>(1, bytes));
+  }
+  void give(void* p) {
+    if (!p) return;
+    const size_t cap = malloc_usable_size(p);
+    if (cap >= MIN_BYTES) {
+      std::lock_guard<std::mutex> lk(mu);
+      for (auto& s : slot)
+        if (!s.p) { s.p = p; s.cap = cap; return; }
+    }
+    free(p);
+  }
+};
+RecCache g_rec_cache;
 }  // namespace
 
 // ---- sketch ------------------------------------------------------------------------------------------------------------
@@ -372,7 +401,7 @@ static void merge_map_results(mm2_map_result_t* parts, const size_t* first, size
   memset(out, 0, sizeof *out);
   size_t nrec = 0, npan = 0;
   for (size_t i = 0; i < nparts; ++i) { nrec += parts[i].n_recs; npan += parts[i].n_panic; }
-  out->recs = xmalloc<mm2_paf_rec_t>(nrec);
+  out->recs = (mm2_paf_rec_t*)g_rec_cache.take(std::max<size_t>(1, nrec) * sizeof(mm2_paf_rec_t));
   out->panic_reads = xmalloc<u32>(npan);
   for (size_t i = 0; i < nparts; ++i) {
     mm2_map_result_t& p = parts[i];
@@ -514,34 +543,53 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
   // ---- records (paf.rs:130-222) ---------------------------------------------------------------------------------------------
   memset(out, 0, sizeof *out);
   out->n_reads = nreads; out->n_bases = nreads ? h_off[nreads] - h_off[0] : 0; out->n_minimizers = nm; out->n_anchors = na;
-  out->recs = xmalloc<mm2_paf_rec_t>(nreads);
+  out->recs = (mm2_paf_rec_t*)g_rec_cache.take(std::max<size_t>(1, nreads) * sizeof(mm2_paf_rec_t));
   std::vector<u32> panics;
   size_t nr = 0;
   {
-    // host threads over contiguous read ranges; results are concatenated in read order
+    // host threads over contiguous read ranges: count the records of each range, then write them in place in read order
     const int nth = nreads >= 16384 ? (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency())) : 1;
-    std::vector<std::vector<mm2_paf_rec_t>> part((size_t)nth);
+    std::vector<size_t> cnt((size_t)nth + 1, 0);
     std::vector<std::vector<u32>> ppan((size_t)nth);
     std::vector<u64> presc((size_t)nth, 0);
-    auto work = [&](int t) {
-      const size_t lo = nreads * (size_t)t / (size_t)nth, hi = nreads * (size_t)(t + 1) / (size_t)nth;
-      part[(size_t)t].reserve(hi - lo);
+    auto range = [&](int t, size_t& lo, size_t& hi) { lo = nreads * (size_t)t / (size_t)nth; hi = nreads * (size_t)(t + 1) / (size_t)nth; };
+    auto count = [&](int t) {
+      size_t lo, hi, c = 0; range(t, lo, hi);
+      for (size_t r = lo; r < hi; ++r) c += (hits[r].n_anchors != 0 && (hits[r].rid_rev & 0x7fffffffu) < idx->n_seq) ? 1 : 0;
+      cnt[(size_t)t + 1] = c;
+    };
+    auto fill = [&](int t) {
+      size_t lo, hi; range(t, lo, hi);
+      mm2_paf_rec_t* dst = out->recs + cnt[(size_t)t];
       for (size_t r = lo; r < hi; ++r) {
         const ReadHit& h = hits[r];
         if (h.flags & 1u) presc[(size_t)t] += 1;
-        mm2_paf_rec_t rec;
-        const int kind = build_record(idx, h, (u32)r, (i32)(h_off[r + 1] - h_off[r]), rec);
-        if (kind == 1) part[(size_t)t].push_back(rec);
+        const int kind = build_record(idx, h, (u32)r, (i32)(h_off[r + 1] - h_off[r]), *dst);
+        if (kind == 1) ++dst;
         else if (kind == 2) ppan[(size_t)t].push_back((u32)r);
       }
     };
-    std::vector<std::thread> th;
-    for (int t = 1; t < nth; ++t) th.emplace_back(work, t);
-    work(0);
-    for (auto& t : th) t.join();
+    auto run = [&](auto fn) {
+      std::vector<std::thread> th;
+      for (int t = 1; t < nth; ++t) th.emplace_back(fn, t);
+      fn(0);
+      for (auto& t : th) t.join();
+    };
+    if (nth == 1) { count(0); fill(0); }
+    else {
+      // one set of threads for both passes: a barrier on an atomic counter after the counts
+      std::atomic<int> arrived{0};
+      auto both = [&](int t) {
+        count(t);
+        if (arrived.fetch_add(1) + 1 == nth) { for (int x = 0; x < nth; ++x) cnt[(size_t)x + 1] += cnt[(size_t)x]; arrived.store(nth + 1); }
+        while (arrived.load() != nth + 1) std::this_thread::yield();
+        fill(t);
+      };
+      run(both);
+    }
+    if (nth == 1) cnt[1] += cnt[0];
+    nr = cnt[(size_t)nth];
     for (int t = 0; t < nth; ++t) {
-      if (!part[(size_t)t].empty()) memcpy(out->recs + nr, part[(size_t)t].data(), part[(size_t)t].size() * sizeof(mm2_paf_rec_t));
-      nr += part[(size_t)t].size();
       panics.insert(panics.end(), ppan[(size_t)t].begin(), ppan[(size_t)t].end());
       out->n_rescued += presc[(size_t)t];
     }
@@ -695,7 +743,7 @@ extern "C" int mm2_map_batch(mm2_ctx_t* ctx, const mm2_index_t* idx, const uint8
 
 extern "C" void mm2_map_result_free(mm2_map_result_t* r) {
   if (!r) return;
-  free(r->recs); free(r->panic_reads); free(r->mini_offs); free(r->minis); free(r->mini_keep); free(r->anchor_offs); free(r->anchors);
+  g_rec_cache.give(r->recs); free(r->panic_reads); free(r->mini_offs); free(r->minis); free(r->mini_keep); free(r->anchor_offs); free(r->anchors);
   free(r->f); free(r->v); free(r->pprev);
   memset(r, 0, sizeof *r);
 }

@@ -791,7 +791,10 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
   }
 }
 
-__global__ void __launch_bounds__(CH_WARPS * 32) chain_ring_kernel(ChainArgs G) {
+#ifndef MM2_CH_OCC
+#define MM2_CH_OCC 8   // CTAs per SM (64 registers; measured 7.5 / 6.8 / 8.0 ms per 100k reads at 6 / 8 / 10)
+#endif
+__global__ void __launch_bounds__(CH_WARPS * 32, MM2_CH_OCC) chain_ring_kernel(ChainArgs G) {
   const u32 r = blockIdx.x * CH_WARPS + (threadIdx.x >> 5);
   if (r >= G.nreads) return;
   if (chain_is_dense(G, r)) return;                               // chain_dense_kernel's
