@@ -760,6 +760,423 @@ __global__ void __launch_bounds__(SK_NT, sizeof(KT) == 4 ? MM2_SK_OCC : 4) sketc
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Version 3 (default): version 2 plus a ninth "scanner" warp per CTA.  In version 2 all eight warps wait at a barrier
+// while warp 0 does the decoupled look-back (40 % of the stall samples in profiles/).  Here the compute warps stage the
+// tile's records (key, pos << 1 | strand) in one of two shared buffers, publish the tile's count and go on with the next
+// tile; the scanner warp does the look-back, publishes the inclusive prefix and writes the staged records to global
+// memory with coalesced stores.  Named barriers: 1 = the 256 compute threads; FULL[b] = compute arrives, scanner
+// waits; EMPTY[b] = scanner arrives, compute waits before reusing buffer b; BASE = tiles too big to stage.
+#ifndef MM2_SK3_OCC
+#define MM2_SK3_OCC 5
+#endif
+constexpr int SK3_BAR_COMPUTE = 1, SK3_BAR_FULL = 2, SK3_BAR_EMPTY = 4, SK3_BAR_BASE = 6;
+__device__ __forceinline__ void sk3_bar_compute() { asm volatile("bar.sync %0, %1;" ::"n"(SK3_BAR_COMPUTE), "n"(SK_NT) : "memory"); }
+__device__ __forceinline__ void sk3_bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(SK_NT + 32) : "memory"); }
+__device__ __forceinline__ void sk3_bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(SK_NT + 32) : "memory"); }
+struct Sk3Meta { u32 tile, count, q, staged; };
+// staged variant of sk_emit_dups: key and pos << 1 | strand go to the shared buffers
+template <class KT, int PAD>
+__device__ __noinline__ u32 sk3_stage_dups(const KT* s_key, const u8* s_z, int lo, int hi, int excl, KT* okey, u32* opos, u32 idx, i64 P0) {
+  const KT kv = s_key[excl + (excl >> PAD)];
+  for (int x = lo; x <= hi; ++x)
+    if (s_key[x + (x >> PAD)] == kv && x != excl) {
+      okey[idx] = kv;
+      opos[idx] = ((u32)(P0 + x) << 1) | ((s_z[x >> 3] >> (x & 7)) & 1u);
+      ++idx;
+    }
+  return idx;
+}
+template <class KT>
+__global__ void __launch_bounds__(SK_NT + 32, sizeof(KT) == 4 ? MM2_SK3_OCC : 3) sketch_tile_kernel_v3(SketchParams P) {
+  constexpr int PAD = KeyTraits<KT>::PAD;
+  constexpr KT KMAX = (KT)~(KT)0;
+#define KIDX(u) ((u) + ((u) >> PAD))
+  __shared__ __align__(16) KT s_key[SK_REGION + (SK_REGION >> PAD) + 8];
+  __shared__ __align__(16) u32 s_pack[SK_MAXCHUNK + 4];
+  __shared__ __align__(16) u32 s_nm[SK_MAXCHUNK / 2 + 4];
+  __shared__ u8 s_z[SK_NT];
+  __shared__ u32 s_wsum[SK_NT / 32];
+  __shared__ u32 s_next[2];
+  __shared__ u64 s_base;
+  __shared__ __align__(16) KT s_okey[2][SK_LIST];
+  __shared__ __align__(16) u32 s_opos[2][SK_LIST];
+  __shared__ Sk3Meta s_meta[2];
+
+  const int tid = threadIdx.x;
+  const int w = P.w, k = P.k;
+  const int cap = w + k;
+  const int T = SK_REGION - w;
+  const KT mask = (KT)((((u64)1) << (2 * k)) - 1);
+  const int shift1 = 2 * (k - 1);
+
+  if (tid >= SK_NT) {
+    // ---- scanner warp: look-back, inclusive prefix, record write of the tiles this CTA has finished computing --------------
+    const int lane = tid - SK_NT;
+    volatile u64* st = P.tile_status;
+    for (u32 it = 0;; ++it) {
+      const int b = (int)(it & 1u);
+      sk3_bar_sync(SK3_BAR_FULL + b);
+      const u32 tile = s_meta[b].tile;
+      if (tile == 0xFFFFFFFFu) break;
+      const u32 tile_count = s_meta[b].count, q = s_meta[b].q;
+      const bool staged = s_meta[b].staged != 0;
+      u64 excl = 0;
+      if (tile != 0) {
+        i64 look = (i64)tile - 1;
+        for (;;) {
+          const i64 idx = look - lane;
+          u64 v;
+          if (idx >= 0) { do { v = st[idx]; } while ((v >> 62) == 0); } else v = (2ULL << 62);
+          const u32 incl_mask = __ballot_sync(0xFFFFFFFFu, (v >> 62) == 2);
+          const int first_incl = incl_mask ? (__ffs(incl_mask) - 1) : 32;
+          u64 contrib = (lane <= first_incl) ? (v & ((1ULL << 62) - 1)) : 0;
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xFFFFFFFFu, contrib, d);
+          excl += contrib;
+          if (incl_mask) break;
+          look -= 32;
+        }
+        if (lane == 0) st[tile] = (2ULL << 62) | (excl + (u64)tile_count);
+      }
+      if (lane == 0) {
+        if (tile == P.tile_first[q]) P.seq_out_off[q] = excl;
+        if (tile == P.ntiles - 1) P.seq_out_off[P.nseq] = excl + (u64)tile_count;
+      }
+      if (staged) {
+        const u64 rid_hi = (u64)(P.rid_base + q * P.rid_step) << 32;
+        for (u32 e2 = (u32)lane; e2 < tile_count; e2 += 32) {
+          const u64 o = excl + e2;
+          if (o < P.out_cap) {
+            P.out_key[o] = ((u64)s_okey[b][e2] << 8) | (u64)k;
+            P.out_val[o] = rid_hi | (u64)s_opos[b][e2];
+          }
+        }
+      } else {
+        if (lane == 0) s_base = excl;
+        __threadfence_block();
+        sk3_bar_arrive(SK3_BAR_BASE);
+      }
+      __threadfence_block();
+      sk3_bar_arrive(SK3_BAR_EMPTY + b);
+    }
+    return;
+  }
+
+  // Tiles are handed out in order (the look-back needs every earlier tile to be running or done); the next ticket is
+  // taken just before this tile's count is published.
+  if (tid == 0) s_next[0] = atomicAdd(P.ticket, 1u);
+  sk3_bar_compute();
+  u32 tile = s_next[0];
+  u32 it = 0;
+  for (int par = 0; tile < P.ntiles; par ^= 1) {
+    const u32 q = P.tile_seq[tile];
+    const u64 soff = P.seq_off[q];
+    const i64 len = (i64)(P.seq_off[q + 1] - soff);
+    const i64 s = (i64)(tile - P.tile_first[q]) * T;
+    const i64 e = min(len, s + (i64)T);
+    const int nsteps = (int)(e - s);
+    const i64 P0 = s - w;
+    const i64 a = P0 - cap;
+    const i64 gidx = (i64)soff + a;
+    const i64 g0 = (gidx >> 4) << 4;
+    const int delta = (int)(gidx - g0);
+    const int nchunks = (delta + SK_REGION + cap + 15) >> 4;
+
+    // ---- phase 1: 128-bit loads -> 2-bit packed codes + N mask (as in version 1) ---------------------------------
+    for (int c = tid; c < SK_MAXCHUNK + 4; c += SK_NT) {
+      u32 packed = 0, nmask = 0xFFFFu;
+      if (c < nchunks) {
+        const i64 gi = g0 + 16 * (i64)c;
+        u32 wd[4] = {0, 0, 0, 0};
+        if (P.vec_ok && gi >= 0 && gi + 16 <= (i64)P.buf_len) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(P.seq + gi));
+          wd[0] = v.x; wd[1] = v.y; wd[2] = v.z; wd[3] = v.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const i64 g = gi + j;
+            u32 b = (g >= 0 && g < (i64)P.buf_len) ? (u32)P.seq[g] : 0u;
+            wd[j >> 2] |= b << (8 * (j & 3));
+          }
+        }
+        nmask = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          u32 c4, vm;
+          nt4x4(wd[j], c4, vm);
+          packed |= pack4(c4) << (8 * j);
+          nmask |= nbits4(vm) << (4 * j);
+        }
+        const i64 pstart = a + 16 * (i64)c - delta;
+        const i64 lo = max((i64)0, -pstart), hi = min((i64)16, len - pstart);
+        u32 inseq = 0;
+        if (hi > lo) inseq = ((hi >= 16 ? 0x10000u : (1u << hi)) - 1u) & ~((1u << lo) - 1u);
+        nmask = (nmask | ~inseq) & 0xFFFFu;
+      }
+      s_pack[c] = packed;
+      reinterpret_cast<u16*>(s_nm)[c] = (u16)nmask;
+    }
+    sk3_bar_compute();
+
+    // ---- phase 2: 8 consecutive k-mers per thread -> keys (registers + shared), strand bits, l gates -----------------
+    KT K[SK_CH];
+    u32 ge_cap = 0, eq_capm1 = 0;
+    {
+      const int r0 = cap + SK_CH * tid + delta;
+      int l = run_len_at(s_nm, r0 - 1, cap);
+      const int rs = r0 - k;
+      const int wi = rs >> 4, sh = 2 * (rs & 15);
+      const u32 w0 = s_pack[wi], w1 = s_pack[wi + 1], w2 = s_pack[wi + 2];
+      const u32 flo = __funnelshift_r(w0, w1, sh), fhi = __funnelshift_r(w1, w2, sh);
+      const u64 field = (((u64)fhi << 32) | flo) & (u64)mask;
+      KT rev = (KT)((~field) & (u64)mask);
+      u64 br = __brevll(field);
+      br = ((br & 0x5555555555555555ULL) << 1) | ((br >> 1) & 0x5555555555555555ULL);
+      KT fwd = (KT)(br >> (64 - 2 * k));
+      const u32 cw = __funnelshift_r(s_pack[r0 >> 4], s_pack[(r0 >> 4) + 1], 2 * (r0 & 15));
+      const u32 nb = __funnelshift_r(s_nm[r0 >> 5], s_nm[(r0 >> 5) + 1], r0 & 31);
+      u32 zbits = 0;
+      if (l >= cap && (nb & 0xFFu) == 0u) {
+        // no N among these 8 bases and a full run before them: l stays at its cap, every k-mer is hashed
+        ge_cap = 0xFFu;
+#pragma unroll
+        for (int j = 0; j < SK_CH; ++j) {
+          const u32 c = (cw >> (2 * j)) & 3u;
+          fwd = (KT)(((fwd << 2) | (KT)c) & mask);
+          rev = (KT)((rev >> 2) | ((KT)(3u ^ c) << shift1));
+          const bool z = !(fwd < rev);
+          const KT key = hash_mix<KT>(z ? rev : fwd, mask);
+          K[j] = key;
+          s_key[KIDX(SK_CH * tid + j)] = key;
+          zbits |= (u32)z << j;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < SK_CH; ++j) {
+          const u32 c = (cw >> (2 * j)) & 3u;
+          l = ((nb >> j) & 1u) ? 0 : min(l + 1, cap);
+          fwd = (KT)(((fwd << 2) | (KT)c) & mask);
+          rev = (KT)((rev >> 2) | ((KT)(3u ^ c) << shift1));
+          const bool z = !(fwd < rev);
+          KT key = KMAX;
+          if (l >= k) key = hash_mix<KT>(z ? rev : fwd, mask);
+          K[j] = key;
+          s_key[KIDX(SK_CH * tid + j)] = key;
+          zbits |= (u32)z << j;
+          ge_cap |= (u32)(l >= cap) << j;
+          eq_capm1 |= (u32)(l == cap - 1) << j;
+        }
+      }
+      s_z[tid] = (u8)zbits;
+    }
+    sk3_bar_compute();
+
+    // ---- phase 3: window minima of this thread's 8 positions + emission decisions (sketch.rs:80-96) -----------------
+    const int c0 = SK_CH * tid;
+    const int u_last = w + nsteps - 1;
+    const bool last_tile = (e == len);
+    auto keyat = [&](int t) -> KT { return t >= 0 ? s_key[KIDX(t)] : KMAX; };
+    u32 tot = 0, eflags = 0;  // bits 0-7: emit prev; 8-15: first-window duplicates; 16-23: rescan duplicates; 24: end emit
+    u32 pp[4] = {0, 0, 0, 0};  // position of the previous minimum for each of the 8 steps (u16 x 8)
+    int cur7 = 0;              // position of the window minimum at this thread's last position
+    if (c0 + SK_CH > w && c0 < w + nsteps) {
+      // suffix minima over the w keys before this thread's chunk, newest position winning ties (sketch.rs:84,90-91).
+      // A range is (key, pd) with pd = pos << 1 | dup, dup = "the minimum occurs at least twice in the range".
+      KT rk = KMAX; int rpd = 0;
+      int t = c0 - 1;
+      for (; t > c0 - (w - 1) + 7; --t) {
+        const KT kx = keyat(t);
+        if (kx < rk) { rk = kx; rpd = t << 1; } else if (kx == rk) rpd |= 1;
+      }
+      KT Sk[SK_CH]; int Spd[SK_CH];
+#pragma unroll
+      for (int jj = SK_CH - 1; jj >= 0; --jj) {
+        const KT kx = keyat(t);
+        if (kx < rk) { rk = kx; rpd = t << 1; } else if (kx == rk) rpd |= 1;
+        Sk[jj] = rk; Spd[jj] = rpd;
+        --t;
+      }
+      KT pk_prev; int ppd_prev;  // window [c0-w, c0-1]
+      {
+        const KT kx = keyat(t);
+        pk_prev = rk; ppd_prev = rpd;
+        if (kx < rk) { pk_prev = kx; ppd_prev = t << 1; } else if (kx == rk) ppd_prev |= 1;
+      }
+      // Fast path: all 8 steps are inside the tile, every window involved is full (l >= w + k: the previous minimum is a
+      // real k-mer and sketch.rs:84/88 emit unconditionally) and no window holds its minimum twice.  Then step u emits
+      // the previous minimum exactly when it is replaced (new key <= old minimum) or slides out (its position is u - w).
+      bool slow = !(ge_cap == 0xFFu && c0 >= w && c0 + SK_CH - 1 <= u_last && !(last_tile && c0 + SK_CH - 1 == u_last));
+      if (!slow) {
+        const KT pk0 = pk_prev; const int ppd0 = ppd_prev;
+        KT fk = KMAX; int fpd = 0;
+        int odd = ppd_prev;
+#pragma unroll
+        for (int j = 0; j < SK_CH; ++j) {
+          const int u = c0 + j;
+          const KT ki = K[j];
+          if (ki <= fk) { fpd = (u << 1) | (ki == fk ? 1 : 0); fk = ki; }
+          KT ck; int cpd;
+          if (fk <= Sk[j]) { ck = fk; cpd = fpd | (fk == Sk[j] ? 1 : 0); } else { ck = Sk[j]; cpd = Spd[j]; }
+          const int ppos = ppd_prev >> 1;
+          pp[j >> 1] |= (u32)ppos << (16 * (j & 1));
+          const u32 em = (ki <= pk_prev || ppos == u - w) ? 1u : 0u;
+          tot += em; eflags |= em << j;
+          odd |= cpd;
+          pk_prev = ck; ppd_prev = cpd;
+        }
+        cur7 = ppd_prev >> 1;
+        if (odd & 1) {   // a repeated minimum somewhere: redo these 8 steps with the full rules
+          slow = true; tot = 0; eflags = 0; pp[0] = pp[1] = pp[2] = pp[3] = 0; pk_prev = pk0; ppd_prev = ppd0;
+        }
+      }
+      if (slow) {
+        KT fk = KMAX; int fpd = 0;  // prefix minima inside the chunk (newer element wins ties)
+  #pragma unroll
+        for (int j = 0; j < SK_CH; ++j) {
+          const int u = c0 + j;
+          const KT ki = K[j];
+          if (ki <= fk) { fpd = (u << 1) | (ki == fk ? 1 : 0); fk = ki; }
+          // window [u-w+1, u] = older part (suffix) + newer part (prefix); the newer part wins ties
+          KT ck; int cpd;
+          if (fk <= Sk[j]) { ck = fk; cpd = fpd | (fk == Sk[j] ? 1 : 0); } else { ck = Sk[j]; cpd = Spd[j]; }
+          const int ppos = ppd_prev >> 1;
+          pp[j >> 1] |= (u32)ppos << (16 * (j & 1));
+          if (u >= w && u <= u_last) {
+            const KT kp = pk_prev;
+            const bool gc = (ge_cap >> j) & 1u, ec1 = (eq_capm1 >> j) & 1u;
+            if (kp != KMAX) {
+              if (ec1 && (ppd_prev & 1)) {
+                const u32 c1 = sk_count_dups<KT, PAD>(s_key, u - w + 1, u - 1, kp, ppos);
+                if (c1) { tot += c1; eflags |= 1u << (8 + j); }
+              }
+              if (ki <= kp) {
+                if (gc) { tot += 1; eflags |= 1u << j; }
+              } else if (ppos == u - w) {
+                if (gc || ec1) {
+                  tot += 1; eflags |= 1u << j;
+                  if (ck != KMAX && (cpd & 1)) {
+                    const u32 c3 = sk_count_dups<KT, PAD>(s_key, u - w + 1, u, ck, cpd >> 1);
+                    if (c3) { tot += c3; eflags |= 1u << (16 + j); }
+                  }
+                }
+              }
+            }
+            if (last_tile && u == u_last && ck != KMAX) { tot += 1; eflags |= 1u << 24; }
+          }
+          if (u == min(c0 + SK_CH - 1, u_last)) cur7 = cpd >> 1;
+          pk_prev = ck; ppd_prev = cpd;
+        }
+      }
+    }
+
+    // ---- exclusive scan of the per-thread counts; the tile's count is published at once --------------------------------------
+    u32 inc = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u32 tt = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+      if ((tid & 31) >= d) inc += tt;
+    }
+    if ((tid & 31) == 31) s_wsum[tid >> 5] = inc;
+    if (tid == 0) s_next[par ^ 1] = atomicAdd(P.ticket, 1u);
+    sk3_bar_compute();
+    const u32 next_tile = s_next[par ^ 1];
+    u32 wbase = 0, tile_count = 0;
+#pragma unroll
+    for (int x = 0; x < SK_NT / 32; ++x) {
+      const u32 ws = s_wsum[x];
+      if (x < (tid >> 5)) wbase += ws;
+      tile_count += ws;
+    }
+    const u32 my_off = wbase + inc - tot;
+    const int b = (int)(it & 1u);
+    const bool staged = tile_count <= (u32)SK_LIST;
+    if (tid == 0) {
+      volatile u64* st = P.tile_status;
+      st[tile] = ((tile == 0 ? 2ULL : 1ULL) << 62) | (u64)tile_count;   // tile 0: its inclusive prefix; others: aggregate
+    }
+    if (it >= 2) sk3_bar_sync(SK3_BAR_EMPTY + b);   // the scanner is done with the tile that used this buffer before
+
+    // ---- stage the records in step order (shared buffer b); the scanner warp writes them out -----------------------------------
+    if (staged && tot) {
+      KT* okey = s_okey[b];
+      u32* opos = s_opos[b];
+      u32 idx = my_off;
+      auto put = [&](int x) {
+        okey[idx] = s_key[KIDX(x)];
+        opos[idx] = ((u32)(P0 + x) << 1) | ((s_z[x >> 3] >> (x & 7)) & 1u);
+        ++idx;
+      };
+      u32 jm = (eflags | (eflags >> 8) | (eflags >> 16)) & 0xFFu;  // steps of this thread that emit anything
+      while (jm) {
+        const int j = __ffs(jm) - 1;
+        jm &= jm - 1;
+        const int u = c0 + j;
+        const u32 pw = (j >> 1) == 0 ? pp[0] : (j >> 1) == 1 ? pp[1] : (j >> 1) == 2 ? pp[2] : pp[3];
+        const int ppos = (int)((pw >> (16 * (j & 1))) & 0xFFFFu);
+        if (eflags & (1u << (8 + j))) idx = sk3_stage_dups<KT, PAD>(s_key, s_z, u - w + 1, u - 1, ppos, okey, opos, idx, P0);
+        if (eflags & (1u << j)) put(ppos);
+        if (eflags & (1u << (16 + j))) {
+          const int j1 = j + 1;
+          const u32 pw1 = (j1 >> 1) == 0 ? pp[0] : (j1 >> 1) == 1 ? pp[1] : (j1 >> 1) == 2 ? pp[2] : pp[3];
+          const int cpos = (j == SK_CH - 1) ? cur7 : (int)((pw1 >> (16 * (j1 & 1))) & 0xFFFFu);
+          idx = sk3_stage_dups<KT, PAD>(s_key, s_z, u - w + 1, u, cpos, okey, opos, idx, P0);
+        }
+      }
+      if (eflags & (1u << 24)) put(cur7);
+    }
+    if (tid == 0) { s_meta[b].tile = tile; s_meta[b].count = tile_count; s_meta[b].q = q; s_meta[b].staged = staged ? 1u : 0u; }
+    __threadfence_block();
+    sk3_bar_arrive(SK3_BAR_FULL + b);
+    if (!staged) {
+      // a tile that emits more than a buffer holds (windows full of repeated minima): wait for the scanner's base and
+      // let each thread write its own records
+      sk3_bar_sync(SK3_BAR_BASE);
+      if (tot) {
+        const u64 rid_hi = (u64)(P.rid_base + q * P.rid_step) << 32;
+        u64 o = s_base + my_off;
+        auto emit = [&](int x) {
+          if (o < P.out_cap) {
+            const u64 pos = (u64)(P0 + x);
+            const u32 z = (s_z[x >> 3] >> (x & 7)) & 1u;
+            P.out_key[o] = ((u64)s_key[KIDX(x)] << 8) | (u64)k;
+            P.out_val[o] = rid_hi | (pos << 1) | (u64)z;
+          }
+          ++o;
+        };
+        u32 jm = (eflags | (eflags >> 8) | (eflags >> 16)) & 0xFFu;
+        while (jm) {
+          const int j = __ffs(jm) - 1;
+          jm &= jm - 1;
+          const int u = c0 + j;
+          const u32 pw = (j >> 1) == 0 ? pp[0] : (j >> 1) == 1 ? pp[1] : (j >> 1) == 2 ? pp[2] : pp[3];
+          const int ppos = (int)((pw >> (16 * (j & 1))) & 0xFFFFu);
+          if (eflags & (1u << (8 + j)))
+            o = sk_emit_dups<KT, PAD>(s_key, s_z, u - w + 1, u - 1, ppos, o, P.out_cap, P.out_key, P.out_val, rid_hi, P0, k);
+          if (eflags & (1u << j)) emit(ppos);
+          if (eflags & (1u << (16 + j))) {
+            const int j1 = j + 1;
+            const u32 pw1 = (j1 >> 1) == 0 ? pp[0] : (j1 >> 1) == 1 ? pp[1] : (j1 >> 1) == 2 ? pp[2] : pp[3];
+            const int cpos = (j == SK_CH - 1) ? cur7 : (int)((pw1 >> (16 * (j1 & 1))) & 0xFFFFu);
+            o = sk_emit_dups<KT, PAD>(s_key, s_z, u - w + 1, u, cpos, o, P.out_cap, P.out_key, P.out_val, rid_hi, P0, k);
+          }
+        }
+        if (eflags & (1u << 24)) emit(cur7);
+      }
+    }
+    tile = next_tile;
+    ++it;
+  }
+  {  // tell the scanner that this CTA has no more tiles
+    const int b = (int)(it & 1u);
+    if (it >= 2) sk3_bar_sync(SK3_BAR_EMPTY + b);
+    if (tid == 0) s_meta[b].tile = 0xFFFFFFFFu;
+    __threadfence_block();
+    sk3_bar_arrive(SK3_BAR_FULL + b);
+  }
+#undef KIDX
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Literal state machine (sketch.rs:29-100), one thread per sequence.  MODE 0: count only; MODE 1: write.
 __device__ __forceinline__ u32 nt4_dev(u8 b) {
   const u32 u = b & 0xDFu;
@@ -947,8 +1364,14 @@ int sketch_device(mm2_ctx* ctx, const u8* d_cat, const u64* d_off, const u64* h_
       P.ticket = (u32*)((u8*)ctx->tile_status.p + (size_t)ntiles * 8);
       const int grid = (int)std::min<u64>(ntiles, (u64)num_sms(ctx->device) * (MM2_SK_OCC + 1));
       if (w >= 9) {  // version 2: per-thread prefix/suffix window minima
-        if (k <= 15) MM2_LAUNCH(ctx, sketch_tile_kernel_v2<u32>, grid, SK_NT, 0, P);
-        else MM2_LAUNCH(ctx, sketch_tile_kernel_v2<u64>, grid, SK_NT, 0, P);
+        static const bool use_v2 = [] { const char* e = getenv("MM2_SKETCH"); return e && !strcmp(e, "v2"); }();   // comparison arm
+        if (use_v2) {
+          if (k <= 15) MM2_LAUNCH(ctx, sketch_tile_kernel_v2<u32>, grid, SK_NT, 0, P);
+          else MM2_LAUNCH(ctx, sketch_tile_kernel_v2<u64>, grid, SK_NT, 0, P);
+        } else {
+          if (k <= 15) MM2_LAUNCH(ctx, sketch_tile_kernel_v3<u32>, grid, SK_NT + 32, 0, P);
+          else MM2_LAUNCH(ctx, sketch_tile_kernel_v3<u64>, grid, SK_NT + 32, 0, P);
+        }
       } else {
         if (k <= 15) MM2_LAUNCH(ctx, sketch_tile_kernel<u32>, grid, SK_NT, 0, P);
         else MM2_LAUNCH(ctx, sketch_tile_kernel<u64>, grid, SK_NT, 0, P);
