@@ -204,8 +204,7 @@ __global__ void __launch_bounds__(NT) anchor_msort_kernel(ulonglong2* __restrict
   if (n64 <= lo_excl || n64 > hi_incl) return;
   const int n = (int)n64;
   ulonglong2* a = anchors + a0;
-  int m = 8;
-  while (m < n) m <<= 1;
+  const int m = (n + 7) & ~7;                 // records + padding up to a multiple of 8; runs need not be a power of two
   const int base = (int)threadIdx.x * 8;
   const bool active = base < m;
   const ulonglong2 PADV = make_ulonglong2(~0ULL, ~0ULL);
@@ -230,19 +229,20 @@ __global__ void __launch_bounds__(NT) anchor_msort_kernel(ulonglong2* __restrict
       const int pair0 = base & ~(2 * R - 1);
       const int d = base - pair0;                 // this thread's outputs are [d, d + 8) of the merged pair
       const int A0 = pair0, B0 = pair0 + R;   // runs A and B; one pad slot per 8 records keeps 128-bit accesses conflict-free
-      int lo = max(0, d - R), hi = min(d, R);     // merge path: how many of the first d outputs come from A (ties: A first)
+      const int LA = min(R, m - A0), LB = max(0, min(R, m - B0));   // the last pair of a pass may be short
+      int lo = max(0, d - LB), hi = min(d, LA);   // merge path: how many of the first d outputs come from A (ties: A first)
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         const ulonglong2 pa = sa[SIDX(A0 + mid)], pb = sa[SIDX(B0 + d - 1 - mid)];
         if (!a_less(pb.x, pb.y, pa.x, pa.y)) lo = mid + 1; else hi = mid;
       }
       int ai = lo, bi = d - lo;
-      ulonglong2 ka = ai < R ? sa[SIDX(A0 + ai)] : PADV, kb = bi < R ? sa[SIDX(B0 + bi)] : PADV;
+      ulonglong2 ka = ai < LA ? sa[SIDX(A0 + ai)] : PADV, kb = bi < LB ? sa[SIDX(B0 + bi)] : PADV;
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const bool take_a = bi >= R || (ai < R && !a_less(kb.x, kb.y, ka.x, ka.y));
+        const bool take_a = bi >= LB || (ai < LA && !a_less(kb.x, kb.y, ka.x, ka.y));
         v[e] = take_a ? ka : kb;
-        if (take_a) { ++ai; if (ai < R) ka = sa[SIDX(A0 + ai)]; } else { ++bi; if (bi < R) kb = sa[SIDX(B0 + bi)]; }
+        if (take_a) { ++ai; if (ai < LA) ka = sa[SIDX(A0 + ai)]; } else { ++bi; if (bi < LB) kb = sa[SIDX(B0 + bi)]; }
       }
     }
     __syncthreads();
