@@ -27,6 +27,13 @@ os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL_DEBU
 GENOME_SEED, READS_SEED = 0xB2000002, 0xB2001002
 W, K = 10, 15
 ERR = (0.0333, 0.0333, 0.0333)  # sub / ins / del
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch in the `ncu --set full` capture of tools/prof_step.py
+# (profiles/r01_ncu_v5.md): (bytes, units that launch processed, unit)
+NCU_TRAFFIC = {"sketch": (0.1011e9 + 0.2488e9, 100e6, "base"), "chain": (0.1388e9 + 0.1875e9, 6.978e6, "anchor"),
+               "lookup": (1.2243e9 + 0.2197e9, 18.628e6, "minimizer")}
+NCU_NOTE = {"sketch": "sketch_tile_kernel_v3 is instruction-issue bound (ncu: 65 % issue-active at 56 % occupancy, 5 % DRAM throughput), not HBM bound",
+            "chain": "chain_ring_kernel is warp-issue bound (ncu: 76 % issue-active at 40 % occupancy, 5 % DRAM throughput), not HBM bound",
+            "lookup": "lookup_count_kernel is DRAM bound on random 16-byte probes (ncu: 60 % DRAM throughput)"}
 
 
 def peaks():
@@ -258,8 +265,12 @@ def main():
         alg = {"sketch": n_bases + 16 * nm, "lookup": 32 * nm + 16 * na, "anchor_sort": 32 * na, "anchor_fill": 16 * nm + 16 * na,
                "filter": 9 * nm}
         kernels = {}
+        # device stages (CUDA-event timers on the launching stream) vs host wall-clock entries; shares are of the device stages
+        dev_stages = {kn: ms for kn, ms in stage_ms.items() if not kn.startswith("host_") and kn not in ("h2d", "d2h", "end")}
         for kname, ms in stage_ms.items():
-            e = {"ms": ms, "share": ms / max(1e-9, sum(stage_ms.values()))}
+            e = {"ms": ms}
+            if kname in dev_stages:
+                e["share"] = ms / max(1e-9, sum(dev_stages.values()))
             if kname in alg and ms > 0:
                 e["algorithmic_GB"] = alg[kname] / 1e9
                 e["achieved_GBps"] = alg[kname] / 1e9 / (ms / 1e3)
@@ -268,18 +279,17 @@ def main():
         # DRAM traffic per unit from the ncu --set full capture of the same kernels (profiles/r01_ncu_final.md, 200 Mbase
         # launch: sketch 0.744 GB / 200 Mbase, chain 1.360 GB / 13.96 M anchors, lookup 2.868 GB / 37.26 M minimizers),
         # scaled to the units of this launch
-        ncu_traffic = {"sketch": 0.744e9 / 200e6 * n_bases, "chain": 1.360e9 / 13.957e6 * na, "lookup": 2.868e9 / 37.257e6 * nm}
-        dom = max(stage_ms, key=stage_ms.get)
+        ncu_traffic = {k_: v_[0] / v_[1] * {"base": n_bases, "anchor": na, "minimizer": nm}[v_[2]] for k_, v_ in NCU_TRAFFIC.items()}
+        dom = max(dev_stages, key=dev_stages.get)
         if dom in alg:
             roof = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_GBps"], "peak": peak, "unit": "GB/s",
                     "frac": kernels[dom]["achieved_GBps"] / peak, "traffic": ncu_traffic.get(dom), "peak_source": peak_src,
-                    "note": "instruction-issue bound (ncu: 56 % issue-active, 4 % DRAM throughput); traffic scaled from the ncu capture"}
+                    "note": NCU_NOTE.get(dom, "") + "; traffic scaled from the ncu capture to the units of this launch"}
         else:  # chaining: integer-pipe / latency bound; credited with its HBM-visible algorithmic traffic (anchors + DP state)
             chain_bytes = na * (16 + 32 + 32 + 4)
             ach = chain_bytes / 1e9 / (stage_ms[dom] / 1e3)
             roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": ncu_traffic.get("chain"),
-                    "peak_source": peak_src, "note": "chain_kernel is warp-issue bound (ncu: 71 % issue-active, 6 % DRAM throughput), not HBM bound; "
-                    "algorithmic bytes = 84 B per anchor; traffic scaled from the ncu capture"}
+                    "peak_source": peak_src, "note": NCU_NOTE["chain"] + "; algorithmic bytes = 84 B per anchor; traffic scaled from the ncu capture"}
         line = {
             "metric": "mapped_bases_per_sec", "value": total_bases / (dev_ms / 1e3), "unit": "bases/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -25,7 +25,17 @@ kname = rows[0][1]
 hdr = rows[1]
 ci, si, so_ = hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Source")
 ti = hdr.index("Thread Instructions Executed")
-ins = [(r[so_].strip(), int(r[ci]), int(r[si]), int(r[ti])) for r in rows[2:] if len(r) > ci and r[ci].isdigit()]
+# the csv repeats the whole table once per matching launch: split on the repeated header, take launch MM2_NCU_LAUNCH (default: last)
+blocks, curb = [], []
+for r in rows[2:]:
+    if r and r[0] == "Kernel Name":
+        blocks.append(curb); curb = []
+        continue
+    if len(r) > ci and r[ci].isdigit():
+        curb.append((r[so_].strip(), int(r[ci]), int(r[si]), int(r[ti])))
+blocks.append(curb)
+blocks = [b for b in blocks if b]
+ins = blocks[int(os.environ.get("MM2_NCU_LAUNCH", "-1"))]
 # find the kernel's function in the disassembly: match by the mangled core name
 core = re.sub(r"[^A-Za-z0-9_]", "", kname.split("(")[0].split("::")[-1].split("<")[0])
 tmpls = re.findall(r"<([^<>]*)>", kname.split("(")[0])
