@@ -73,7 +73,7 @@ extern "C" void mm2_ctx_destroy(mm2_ctx_t* c) {
   cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->seq, &c->seq_off, &c->tile_seq, &c->tile_first, &c->tile_status, &c->misc, &c->mkey, &c->mval,
                     &c->mini_off, &c->keep, &c->occ_cnt, &c->occ_loc, &c->anchor_off_m, &c->scan_status, &c->anchors,
-                    &c->read_aoff, &c->read_class, &c->dpA, &c->dpB, &c->dpT, &c->dpW, &c->hits, &c->chain_idx, &c->lut, &c->sort_tmp,
+                    &c->read_aoff, &c->read_class, &c->read_flag, &c->read_nhit, &c->read_na, &c->flag_list, &c->dpA, &c->dpB, &c->dpT, &c->dpW, &c->hits, &c->chain_idx, &c->lut, &c->sort_tmp,
                     &c->sort_tmp2, &c->sort_keys2, &c->sort_vals2, &c->runidx, &c->run_start, &c->run_gp, &c->rs_counts, &c->rs_offs};
   for (DevBuf* b : bufs) b->release();
   c->pin_in.release(); c->pin_out.release(); c->pin_small.release(); c->pin_scalar.release();
@@ -248,26 +248,19 @@ extern "C" int mm2_build_anchors_filtered(mm2_ctx_t* ctx, const mm2_index_t* idx
   MM2_TRY(upload_minis(ctx, mv, n));
   MM2_TRY(ctx->mini_off.ensure(16));
   MM2_TRY(ctx->seq_off.ensure(16));
-  MM2_TRY(ctx->keep.ensure(n + 16));
-  MM2_TRY(ctx->occ_cnt.ensure((n + 16) * 4));
-  MM2_TRY(ctx->occ_loc.ensure((n + 16) * 8));
-  MM2_TRY(ctx->anchor_off_m.ensure((n + 2) * 8));
-  MM2_TRY(ctx->read_aoff.ensure(16));
+  MM2_TRY(ctx->misc.ensure(64));
   const u64 mo[2] = {0, (u64)n}, ro[2] = {0, (u64)(u32)qlen};
   CUDA_TRY(cudaMemcpyAsync(ctx->mini_off.p, mo, 16, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(ctx->seq_off.p, ro, 16, cudaMemcpyHostToDevice, st));
-  if (n) CUDA_TRY(cudaMemsetAsync(ctx->keep.p, 1, n, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   const IndexView V = idx->view();
-  MM2_TRY(seeds_lookup_count(ctx, V, ctx->mkey.as<u64>(), ctx->keep.as<u8>(), n, mid_occ, ctx->occ_cnt.as<u32>(), ctx->occ_loc.as<u64>()));
-  MM2_TRY(scan_u32_to_u64(ctx, ctx->occ_cnt.as<u32>(), ctx->anchor_off_m.as<u64>(), n));
   u64 na = 0;
-  MM2_TRY(read_scalar_u64(ctx, ctx->anchor_off_m.as<u64>() + n, &na));
+  // the minimizers are already filtered by the caller (seeds.rs:42-45): q_occ_frac = 0 switches the filter off
+  MM2_TRY(seeds_hits(ctx, V, ctx->mkey.as<u64>(), ctx->mval.as<u64>(), ctx->mini_off.as<u64>(), 1, n, 0, 0.0f, mid_occ, false,
+                     ctx->misc.as<u32>(), &na));
   MM2_TRY(ctx->anchors.ensure(std::max<u64>(1, na) * 16));
   // the deinterleave above used ctx->anchors as staging; it has completed (stream order), safe to reuse/grow
-  MM2_TRY(seeds_fill_and_sort(ctx, V, ctx->mkey.as<u64>(), ctx->mval.as<u64>(), ctx->mini_off.as<u64>(), ctx->seq_off.as<u64>(), 1,
-                              ctx->occ_cnt.as<u32>(), ctx->occ_loc.as<u64>(), ctx->anchor_off_m.as<u64>(),
-                              ctx->anchors.as<ulonglong2>(), ctx->read_aoff.as<u64>()));
+  MM2_TRY(seeds_fill_and_sort(ctx, V, ctx->mini_off.as<u64>(), ctx->seq_off.as<u64>(), 1, ctx->anchors.as<ulonglong2>()));
   mm2_anchor_t* h = xmalloc<mm2_anchor_t>(na);
   if (!h) { mm2_set_error("out of host memory"); return MM2_E_OOM; }
   if (na) CUDA_TRY(cudaMemcpyAsync(h, ctx->anchors.p, na * 16, cudaMemcpyDeviceToHost, st));
@@ -467,21 +460,14 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
   SketchOut so;
   MM2_TRY(sketch_device(ctx, d_cat, d_off, h_off, nreads, o->w, o->k, 0, 0, 0, &so));  // seeds.rs:7-11: rid 0, no HPC
   const u64 nm = so.total;
-  ctx->timer.mark(st, "filter");
-  MM2_TRY(ctx->keep.ensure(nm + 16));
+  ctx->timer.mark(st, "lookup");
   MM2_TRY(ctx->misc.ensure((nreads + 16) * 4 + 64));
   u32* d_sum_span = ctx->misc.as<u32>() + 16;
   CUDA_TRY(cudaMemsetAsync(ctx->misc.p, 0, 64, st));
-  MM2_TRY(seeds_filter(ctx, so.key, so.seq_off, (u32)nreads, nm, o->q_occ_max, o->q_occ_frac, ctx->keep.as<u8>(), d_sum_span));
-  ctx->timer.mark(st, "lookup");
-  MM2_TRY(ctx->occ_cnt.ensure((nm + 16) * 4));
-  MM2_TRY(ctx->occ_loc.ensure((nm + 16) * 8));
-  MM2_TRY(ctx->anchor_off_m.ensure((nm + 2) * 8));
   const IndexView V = idx->view();
-  MM2_TRY(seeds_lookup_count(ctx, V, so.key, ctx->keep.as<u8>(), nm, mid_occ, ctx->occ_cnt.as<u32>(), ctx->occ_loc.as<u64>()));
-  MM2_TRY(scan_u32_to_u64(ctx, ctx->occ_cnt.as<u32>(), ctx->anchor_off_m.as<u64>(), nm));
   u64 na = 0;
-  MM2_TRY(read_scalar_u64(ctx, ctx->anchor_off_m.as<u64>() + nm, &na));
+  MM2_TRY(seeds_hits(ctx, V, so.key, so.val, so.seq_off, (u32)nreads, nm, o->q_occ_max, o->q_occ_frac, mid_occ, o->want_stage_dump != 0,
+                     d_sum_span, &na));
   {
     // Anchors and DP state take 56 B per anchor.  If a batch of repeat-rich reads needs more than what is free, map its
     // two halves one after the other (reads are independent; the cheap stages above are simply redone per half).
@@ -505,9 +491,7 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
   }
   ctx->timer.mark(st, "anchor_fill");
   MM2_TRY(ctx->anchors.ensure(std::max<u64>(1, na) * 16));
-  MM2_TRY(ctx->read_aoff.ensure((nreads + 2) * 8));
-  MM2_TRY(seeds_fill_and_sort(ctx, V, so.key, so.val, so.seq_off, d_off, (u32)nreads, ctx->occ_cnt.as<u32>(), ctx->occ_loc.as<u64>(),
-                              ctx->anchor_off_m.as<u64>(), ctx->anchors.as<ulonglong2>(), ctx->read_aoff.as<u64>()));
+  MM2_TRY(seeds_fill_and_sort(ctx, V, so.seq_off, d_off, (u32)nreads, ctx->anchors.as<ulonglong2>()));
   MM2_TRY(ctx->dpA.ensure(std::max<u64>(1, na) * 16));
   MM2_TRY(ctx->dpB.ensure(std::max<u64>(1, na) * 16));
   MM2_TRY(ctx->dpT.ensure(std::max<u64>(1, na) * 4));

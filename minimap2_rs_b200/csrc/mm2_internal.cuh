@@ -123,6 +123,7 @@ struct mm2_ctx {
   DevBuf mkey, mval, mini_off;                                       // minimizers (SoA) + per-sequence offsets
   DevBuf keep, occ_cnt, occ_loc, anchor_off_m, scan_status;          // filter / lookup
   DevBuf anchors, read_aoff, read_class;                             // anchors
+  DevBuf read_flag, read_nhit, read_na, flag_list;                   // per-read seeding state (seeds.cu seed_hits_kernel)
   DevBuf dpA, dpB, dpT, dpW, hits, chain_idx, lut;                        // chaining
   DevBuf sort_tmp, sort_tmp2, sort_keys2, sort_vals2, runidx, run_start, run_gp, rs_counts, rs_offs;  // index build
   u64* sorted_k = nullptr; u64* sorted_v = nullptr;  // where the last index_sort_pairs left its result
@@ -207,4 +208,5 @@ int index_build_device(mm2_ctx* ctx, const u8* h_cat, const u64* h_off, const ch
                        int k, int b, int flag, mm2_index** out);
 
 // generic single-pass exclusive scan of u32 counts into u64 offsets (n+1 outputs; out[n] = total)
-int scan_u32_to_u64(mm2_ctx* ctx, const u32* d_in, u64* d_out, size_t n);
+// wide = true: tile sums are accumulated in 64 bits (inputs with no bound on their sum)
+int scan_u32_to_u64(mm2_ctx* ctx, const u32* d_in, u64* d_out, size_t n, bool wide = false);

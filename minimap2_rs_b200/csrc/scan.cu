@@ -6,9 +6,12 @@
 namespace {
 constexpr int SC_NT = 256, SC_PER = 8, SC_TILE = SC_NT * SC_PER;
 
+// ACC = u32: a tile of 2048 counts is known to sum below 2^32 (occurrence counts); ACC = u64: no such bound (per-read
+// anchor counts).
+template <class ACC>
 __global__ void __launch_bounds__(SC_NT) scan_kernel(const u32* __restrict__ in, u64* __restrict__ out, u64 n,
                                                      u64* status, u32* ticket) {
-  __shared__ u32 s_wsum[SC_NT / 32];
+  __shared__ ACC s_wsum[SC_NT / 32];
   __shared__ u32 s_tile;
   __shared__ u64 s_base;
   const int tid = threadIdx.x;
@@ -28,21 +31,21 @@ __global__ void __launch_bounds__(SC_NT) scan_kernel(const u32* __restrict__ in,
 #pragma unroll
       for (int j = 0; j < SC_PER; ++j) c[j] = (i0 + j < n) ? in[i0 + j] : 0u;
     }
-    u32 sum = 0;
+    ACC sum = 0;
 #pragma unroll
     for (int j = 0; j < SC_PER; ++j) sum += c[j];
-    u32 inc = sum;
+    ACC inc = sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      const u32 t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+      const ACC t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
       if ((tid & 31) >= d) inc += t;
     }
     if ((tid & 31) == 31) s_wsum[tid >> 5] = inc;
     __syncthreads();
-    u32 wbase = 0, tot = 0;
+    ACC wbase = 0, tot = 0;
 #pragma unroll
     for (int x = 0; x < SC_NT / 32; ++x) {
-      const u32 ws = s_wsum[x];
+      const ACC ws = s_wsum[x];
       if (x < (tid >> 5)) wbase += ws;
       tot += ws;
     }
@@ -87,7 +90,7 @@ __global__ void __launch_bounds__(SC_NT) scan_kernel(const u32* __restrict__ in,
 __global__ void scan_zero_total(u64* out) { out[0] = 0; }
 }  // namespace
 
-int scan_u32_to_u64(mm2_ctx* ctx, const u32* d_in, u64* d_out, size_t n) {
+int scan_u32_to_u64(mm2_ctx* ctx, const u32* d_in, u64* d_out, size_t n, bool wide) {
   if (n == 0) { MM2_LAUNCH(ctx, scan_zero_total, 1, 1, 0, d_out); return MM2_OK; }
   const size_t ntiles = (n + SC_TILE - 1) / SC_TILE;
   MM2_TRY(ctx->scan_status.ensure(ntiles * 8 + 16));
@@ -95,8 +98,10 @@ int scan_u32_to_u64(mm2_ctx* ctx, const u32* d_in, u64* d_out, size_t n) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
   const int grid = (int)std::min<size_t>(ntiles, (size_t)sms * 8);
-  MM2_LAUNCH(ctx, scan_kernel, grid, SC_NT, 0, d_in, d_out, (u64)n, ctx->scan_status.as<u64>(),
-             (u32*)((u8*)ctx->scan_status.p + ntiles * 8));
+  if (wide)
+    MM2_LAUNCH(ctx, scan_kernel<u64>, grid, SC_NT, 0, d_in, d_out, (u64)n, ctx->scan_status.as<u64>(), (u32*)((u8*)ctx->scan_status.p + ntiles * 8));
+  else
+    MM2_LAUNCH(ctx, scan_kernel<u32>, grid, SC_NT, 0, d_in, d_out, (u64)n, ctx->scan_status.as<u64>(), (u32*)((u8*)ctx->scan_status.p + ntiles * 8));
   CUDA_TRY(cudaGetLastError());
   return MM2_OK;
 }

@@ -20,11 +20,11 @@ static_assert(sizeof(ReadHit) == 64, "ReadHit layout");
 
 int seeds_filter(mm2_ctx* ctx, const u64* d_mkey, const u64* d_mini_off, u32 nreads, u64 n_mini, i32 q_occ_max, float q_occ_frac,
                  u8* d_keep, u32* d_sum_span);
-int seeds_lookup_count(mm2_ctx* ctx, const IndexView& V, const u64* d_mkey, const u8* d_keep, u64 n_mini, i32 mid_occ, u32* d_cnt,
-                       u64* d_loc);
-int seeds_fill_and_sort(mm2_ctx* ctx, const IndexView& V, const u64* d_mkey, const u64* d_mval, const u64* d_mini_off,
-                        const u64* d_read_off, u32 nreads, const u32* d_cnt, const u64* d_loc, const u64* d_aoff,
-                        ulonglong2* d_anchors, u64* d_read_aoff);
+// Query side, version 2 (seeds.cu): count sketch + exact filter where needed + Index::get + compact hit lists + per-read anchor
+// offsets (ctx->read_aoff); returns the batch's anchor count (synchronises).  Then anchors built and sorted per read.
+int seeds_hits(mm2_ctx* ctx, const IndexView& V, const u64* d_mkey, const u64* d_mval, const u64* d_mini_off, u32 nreads, u64 n_mini,
+               i32 q_occ_max, float q_occ_frac, i32 mid_occ, bool full_keep, u32* d_sum_span, u64* n_anchors);
+int seeds_fill_and_sort(mm2_ctx* ctx, const IndexView& V, const u64* d_mini_off, const u64* d_read_off, u32 nreads, ulonglong2* d_anchors);
 
 // lchain.rs:59-176 forward DP + fallback chain (+ rescue rerun, lchain.rs:321-330) for every read; one warp per read.
 // d_A/d_B: int4 per anchor ({f, pprev, v, cnt}, {qs_min, ts_min, first, window start}); d_T, d_W: int per anchor
