@@ -79,6 +79,9 @@ extern "C" void mm2_ctx_destroy(mm2_ctx_t* c) {
   c->pin_in.release(); c->pin_out.release(); c->pin_small.release(); c->pin_scalar.release();
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   for (int w = 0; w < 4; ++w) if (c->worker[w]) mm2_ctx_destroy(c->worker[w]);
+  for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
+  c->copy_events.clear();
+  if (c->copy_stream) { cudaStreamDestroy(c->copy_stream); c->copy_stream = nullptr; }
   delete c;
 }
 
@@ -439,6 +442,18 @@ static int build_record(const mm2_index* idx, const ReadHit& h, u32 r, i32 qlen,
   return 1;
 }
 
+// MM2_TRACE=1: host-clock timeline of the mapping calls on stderr (one line per event: ms since the first event, context,
+// event), to see how the sub-batch pipeline overlaps copies, kernels and record assembly
+static void mm2_trace(const mm2_ctx* ctx, const char* what) {
+  static const bool on = [] { const char* e = getenv("MM2_TRACE"); return e && *e == '1'; }();
+  if (!on) return;
+  static const auto t0 = std::chrono::steady_clock::now();
+  static std::mutex mu;
+  const float t = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  std::lock_guard<std::mutex> lk(mu);
+  fprintf(stderr, "[mm2 trace] %9.3f ctx=%p %s\n", t, (const void*)ctx, what);
+}
+
 static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, const u64* d_off, const u64* h_off, size_t nreads,
                            const mm2_map_opts_t* o, mm2_map_result_t* out, bool timer_started) {
   cudaStream_t st = ctx->stream;
@@ -458,7 +473,9 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
   if (!timer_started) ctx->timer.reset();
   ctx->timer.mark(st, "sketch");
   SketchOut so;
+  mm2_trace(ctx, "sketch issue");
   MM2_TRY(sketch_device(ctx, d_cat, d_off, h_off, nreads, o->w, o->k, 0, 0, 0, &so));  // seeds.rs:7-11: rid 0, no HPC
+  mm2_trace(ctx, "sketch done");
   const u64 nm = so.total;
   ctx->timer.mark(st, "lookup");
   MM2_TRY(ctx->misc.ensure((nreads + 16) * 4 + 64));
@@ -468,6 +485,7 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
   u64 na = 0;
   MM2_TRY(seeds_hits(ctx, V, so.key, so.val, so.seq_off, (u32)nreads, nm, o->q_occ_max, o->q_occ_frac, mid_occ, o->want_stage_dump != 0,
                      d_sum_span, &na));
+  mm2_trace(ctx, "hits done");
   {
     // Anchors and DP state take 56 B per anchor.  If a batch of repeat-rich reads needs more than what is free, map its
     // two halves one after the other (reads are independent; the cheap stages above are simply redone per half).
@@ -520,7 +538,9 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
   ReadHit* hits = ctx->pin_out.as<ReadHit>();
   if (nreads) CUDA_TRY(cudaMemcpyAsync(hits, ctx->hits.p, nreads * sizeof(ReadHit), cudaMemcpyDeviceToHost, st));
   ctx->timer.mark(st, "end");
+  mm2_trace(ctx, "chain issued");
   CUDA_TRY(cudaStreamSynchronize(st));
+  mm2_trace(ctx, "chain+d2h done");
   ctx->timer.finish();
   const auto wall1 = std::chrono::steady_clock::now();
 
@@ -589,6 +609,7 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
     ctx->timer.add_host("host_call", std::chrono::duration<float, std::milli>(wall2 - wall0).count());
   }
 
+  mm2_trace(ctx, "records done");
   if (o->want_stage_dump) {
     out->mini_offs = xmalloc<u64>(nreads + 1); out->minis = xmalloc<mm2_mini_t>(nm); out->mini_keep = xmalloc<u8>(nm);
     out->anchor_offs = xmalloc<u64>(nreads + 1); out->anchors = xmalloc<mm2_anchor_t>(na);
@@ -646,10 +667,12 @@ static int map_host_single(mm2_ctx* ctx, const mm2_index* idx, const u8* cat, co
     // keeps the workers in lock step (copy, copy, copy, then compute, compute, compute) instead of overlapping
     static std::mutex h2d_mutex;
     std::lock_guard<std::mutex> lk(h2d_mutex);
+    mm2_trace(ctx, "h2d start");
     if (total) CUDA_TRY(cudaMemcpyAsync(ctx->seq.p, cat + base, total, cudaMemcpyHostToDevice, st));
     memcpy(ctx->pin_in.p, off0.data(), (nreads + 1) * 8);  // pinned bounce: pageable sources serialise the streams
     CUDA_TRY(cudaMemcpyAsync(ctx->seq_off.p, ctx->pin_in.p, (nreads + 1) * 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    mm2_trace(ctx, "h2d done");
   }
   return map_device_impl(ctx, idx, ctx->seq.as<u8>(), ctx->seq_off.as<u64>(), off0.data(), nreads, opts, out, true);
 }
@@ -662,13 +685,29 @@ static int map_host_pipelined(mm2_ctx* ctx, const mm2_index* idx, const u8* cat,
   const int NW = ctx->n_workers;
   for (int w = 0; w < NW; ++w)
     if (!ctx->worker[w]) MM2_TRY(mm2_ctx_create(ctx->device, &ctx->worker[w]));
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (!ctx->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  while (ctx->copy_events.size() < nsub) {
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->copy_events.push_back(e);
+  }
+  // The whole batch gets one device buffer; a dedicated copy stream uploads it sub-batch by sub-batch, back to back, with an
+  // event after each, so the link never waits for a worker (before: a worker uploaded its own next sub-batch only after it
+  // had finished the previous one, and the copy engine idled ~35 % of the call).  Offsets stay absolute (rebased to the
+  // batch start): every stage only uses differences, and the sketch kernel's halo loads are bounded by the sub-batch end.
+  const u64 base = offs[0], total = offs[nreads] - base;
+  MM2_TRY(ctx->seq.ensure(total + 64));
+  MM2_TRY(ctx->seq_off.ensure((nreads + 1) * 8));
+  MM2_TRY(ctx->pin_in.ensure((nreads + 1) * 8));
+  u64* h_off0 = ctx->pin_in.as<u64>();
+  for (size_t i = 0; i <= nreads; ++i) h_off0[i] = offs[i] - base;
   // sub-batch boundaries balanced by bases
   std::vector<size_t> cut(nsub + 1, nreads);
   cut[0] = 0;
-  const u64 base = offs[0], total = offs[nreads] - base;
   for (size_t sidx = 1; sidx < nsub; ++sidx) {
-    const u64 target = base + total * sidx / nsub;
-    cut[sidx] = (size_t)(std::lower_bound(offs, offs + nreads + 1, target) - offs);
+    const u64 target = total * sidx / nsub;
+    cut[sidx] = (size_t)(std::lower_bound(h_off0, h_off0 + nreads + 1, target) - h_off0);
     if (cut[sidx] < cut[sidx - 1]) cut[sidx] = cut[sidx - 1];
   }
   std::vector<mm2_map_result_t> part(nsub);
@@ -676,11 +715,17 @@ static int map_host_pipelined(mm2_ctx* ctx, const mm2_index* idx, const u8* cat,
   int rc[4] = {MM2_OK, MM2_OK, MM2_OK, MM2_OK};
   std::string err[4];
   std::vector<std::vector<float>> ms_sum(4);
+  std::atomic<size_t> n_issued{0};   // sub-batches whose upload (and event) has been enqueued on the copy stream
+  std::atomic<int> copy_rc{MM2_OK};
   auto work = [&](int w) {
     mm2_ctx* c = ctx->worker[w];
+    cudaSetDevice(c->device);
     for (size_t sidx = (size_t)w; sidx < nsub; sidx += (size_t)NW) {
       const size_t lo = cut[sidx], hi = cut[sidx + 1];
-      const int r = map_host_single(c, idx, cat, offs + lo, hi - lo, opts, &part[sidx]);
+      while (n_issued.load(std::memory_order_acquire) <= sidx && copy_rc.load() == MM2_OK) std::this_thread::yield();
+      if (copy_rc.load() != MM2_OK) { rc[w] = copy_rc.load(); err[w] = "host to device copy failed"; return; }
+      if (cudaStreamWaitEvent(c->stream, ctx->copy_events[sidx], 0) != cudaSuccess) { rc[w] = MM2_E_CUDA; err[w] = "cudaStreamWaitEvent failed"; return; }
+      const int r = map_device_impl(c, idx, ctx->seq.as<u8>(), ctx->seq_off.as<u64>() + lo, h_off0 + lo, hi - lo, opts, &part[sidx], false);
       if (r != MM2_OK) { rc[w] = r; err[w] = mm2_last_error(); return; }
       if (ms_sum[w].size() < c->timer.ms.size()) ms_sum[w].resize(c->timer.ms.size(), 0.f);
       for (size_t i = 0; i < c->timer.ms.size(); ++i) ms_sum[w][i] += c->timer.ms[i];
@@ -689,9 +734,20 @@ static int map_host_pipelined(mm2_ctx* ctx, const mm2_index* idx, const u8* cat,
   u64 l0 = 0, l1 = 0;
   for (int w = 0; w < NW; ++w) l0 += ctx->worker[w]->launches;
   std::vector<std::thread> th;
-  for (int w = 1; w < NW; ++w) th.emplace_back(work, w);
-  work(0);
+  for (int w = 0; w < NW; ++w) th.emplace_back(work, w);
+  {  // this thread feeds the copy stream (a pageable source makes cudaMemcpyAsync block, so the workers are already running)
+    cudaStream_t cs = ctx->copy_stream;
+    cudaError_t e = cudaMemcpyAsync(ctx->seq_off.p, h_off0, (nreads + 1) * 8, cudaMemcpyHostToDevice, cs);
+    for (size_t sidx = 0; sidx < nsub && e == cudaSuccess; ++sidx) {
+      const u64 b0 = h_off0[cut[sidx]], b1 = h_off0[cut[sidx + 1]];
+      if (b1 > b0) e = cudaMemcpyAsync(ctx->seq.as<u8>() + b0, cat + base + b0, b1 - b0, cudaMemcpyHostToDevice, cs);
+      if (e == cudaSuccess) e = cudaEventRecord(ctx->copy_events[sidx], cs);
+      if (e == cudaSuccess) n_issued.store(sidx + 1, std::memory_order_release);
+    }
+    if (e != cudaSuccess) { copy_rc.store(MM2_E_CUDA); cudaGetLastError(); }
+  }
   for (auto& t : th) t.join();
+  cudaStreamSynchronize(ctx->copy_stream);
   for (int w = 0; w < NW; ++w) l1 += ctx->worker[w]->launches;
   ctx->launches += l1 - l0;
   for (int w = 0; w < NW; ++w)
@@ -721,7 +777,32 @@ extern "C" int mm2_map_batch(mm2_ctx_t* ctx, const mm2_index_t* idx, const uint8
   // sub-batches of ~64 Mbase (MM2_SUBBATCH_MB) over 4 worker contexts (MM2_WORKERS): measured best on configs[1]; small batches and stage dumps take the single-context path
   size_t nsub = (size_t)std::min<u64>(64, total / ctx->subbatch_bytes);
   if (nsub > nreads) nsub = nreads;
-  if (nsub >= 2 && !opts->want_stage_dump && ctx->pipeline) return map_host_pipelined(ctx, idx, cat, offs, nreads, opts, out, nsub);
+  if (nsub >= 2 && !opts->want_stage_dump && ctx->pipeline) {
+    // the pipelined path keeps the whole batch resident: batches above MM2_RESIDENT_MB (default 4096) go through it in pieces
+    const char* e_res = getenv("MM2_RESIDENT_MB");
+    const u64 resident = (u64)(e_res && atoll(e_res) > 0 ? atoll(e_res) : 4096) << 20;
+    if (total <= resident) return map_host_pipelined(ctx, idx, cat, offs, nreads, opts, out, nsub);
+    std::vector<size_t> first;
+    std::vector<mm2_map_result_t> part;
+    size_t lo = 0;
+    while (lo < nreads) {
+      size_t hi = (size_t)(std::upper_bound(offs + lo, offs + nreads + 1, offs[lo] + resident) - offs) - 1;
+      if (hi <= lo) hi = lo + 1;
+      if (hi > nreads) hi = nreads;
+      const u64 piece = offs[hi] - offs[lo];
+      size_t ns = (size_t)std::min<u64>(64, piece / ctx->subbatch_bytes);
+      if (ns > hi - lo) ns = hi - lo;
+      mm2_map_result_t r;
+      memset(&r, 0, sizeof r);
+      const int rc = ns >= 2 ? map_host_pipelined(ctx, idx, cat, offs + lo, hi - lo, opts, &r, ns) : map_host_single(ctx, idx, cat, offs + lo, hi - lo, opts, &r);
+      if (rc != MM2_OK) { for (auto& p : part) mm2_map_result_free(&p); return rc; }
+      part.push_back(r); first.push_back(lo);
+      lo = hi;
+    }
+    first.push_back(nreads);
+    merge_map_results(part.data(), first.data(), part.size(), out);
+    return MM2_OK;
+  }
   return map_host_single(ctx, idx, cat, offs, nreads, opts, out);
 }
 

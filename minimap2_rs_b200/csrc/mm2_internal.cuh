@@ -129,6 +129,8 @@ struct mm2_ctx {
   u64* sorted_k = nullptr; u64* sorted_v = nullptr;  // where the last index_sort_pairs left its result
   PinBuf pin_in, pin_out, pin_small, pin_scalar;  // pin_scalar: 8-byte device->host reads (pageable targets serialise streams)
   mm2_ctx* worker[4] = {nullptr, nullptr, nullptr, nullptr};  // sub-batch pipeline of mm2_map_batch (host buffers)
+  cudaStream_t copy_stream = nullptr;             // uploads of the pipelined host path
+  std::vector<cudaEvent_t> copy_events;           // one per sub-batch
   int n_workers = 4;
   bool pipeline = true;
   u64 subbatch_bytes = 64ull << 20;

@@ -456,6 +456,16 @@ def test_map_batch_pipelined_equals_single(mm2, orc, gen):
     names = ["n%d" % i for i in range(3000)]
     want, _ = oi.align_batch(cat, roffs, names, threads=8)
     assert r1.paf_lines(names) == want
+    # batches larger than the resident limit go through the pipeline in pieces (here 4 MB pieces of 2 sub-batches each)
+    os.environ["MM2_RESIDENT_MB"] = "4"
+    try:
+        r3 = c.map_batch(gi, cat, roffs)
+    finally:
+        del os.environ["MM2_RESIDENT_MB"]
+    assert (r3.recs == r2.recs).all() and r3.stats["n_anchors"] == r2.stats["n_anchors"]
+    # a batch that does not start at offset 0 of its buffer
+    r4 = c.map_batch(gi, cat, roffs[1000:])
+    assert r4.recs.size == 2000 and r4.paf_lines(names[1000:]) == want[1000:]
     c.close()
 
 
