@@ -323,9 +323,6 @@ __device__ __forceinline__ bool a_less(u64 x1, u64 y1, u64 x2, u64 y2) { return 
 // a merge-path binary search and merges them serially.  Moves ~2.5x fewer bytes through shared memory than the bitonic
 // network below, which was bound by it (profiles/: short-scoreboard and MIO-throttle stalls).  Slots past n hold the
 // all-ones record; a real record with that bit pattern is identical to the padding, so the first n outputs are right.
-__device__ __forceinline__ void a_cswap(ulonglong2& p, ulonglong2& q) {
-  if (a_less(q.x, q.y, p.x, p.y)) { const ulonglong2 t = p; p = q; q = t; }
-}
 
 #define SIDX(i) ((i) + ((i) >> 3))
 // where a sort kernel finds the hit lists when it builds the read's anchors itself (seeds.rs:44-57 fused into the sort)
@@ -334,6 +331,101 @@ struct HitSrc {
   const u64* hit_loc; const u64* hit_q; const u16* hit_aux;
   const u64* mini_off; const u64* read_off; const u32* read_nhit;
 };
+
+// record types of the merge sort: the anchor itself (128-bit lexicographic (x, y)) or an order-preserving 64-bit key
+__device__ __forceinline__ bool rec_less(const ulonglong2& p, const ulonglong2& q) { return a_less(p.x, p.y, q.x, q.y); }
+__device__ __forceinline__ bool rec_less(const u64& p, const u64& q) { return p < q; }
+template <class T> __device__ __forceinline__ T rec_pad();
+template <> __device__ __forceinline__ ulonglong2 rec_pad<ulonglong2>() { return make_ulonglong2(~0ULL, ~0ULL); }
+template <> __device__ __forceinline__ u64 rec_pad<u64>() { return ~0ULL; }
+template <class T> __device__ __forceinline__ void rec_cswap(T& p, T& q) {
+  if (rec_less(q, p)) { const T t = p; p = q; q = t; }
+}
+
+// v[0..8) = this thread's 8 consecutive records (slots base..base+7 of m, padding included) -> the same slots of the sorted
+// sequence.  The caller has made sure nobody still reads `sa`.
+template <class T>
+__device__ __forceinline__ void msort_core(T (&v)[8], T* sa, const int m, const int base, const bool active) {
+  const T PADV = rec_pad<T>();
+  if (active) {
+    rec_cswap(v[0], v[1]); rec_cswap(v[2], v[3]); rec_cswap(v[4], v[5]); rec_cswap(v[6], v[7]);
+    rec_cswap(v[0], v[2]); rec_cswap(v[1], v[3]); rec_cswap(v[4], v[6]); rec_cswap(v[5], v[7]);
+    rec_cswap(v[1], v[2]); rec_cswap(v[5], v[6]);
+    rec_cswap(v[0], v[4]); rec_cswap(v[1], v[5]); rec_cswap(v[2], v[6]); rec_cswap(v[3], v[7]);
+    rec_cswap(v[2], v[4]); rec_cswap(v[3], v[5]);
+    rec_cswap(v[1], v[2]); rec_cswap(v[3], v[4]); rec_cswap(v[5], v[6]);
+  }
+  for (int R = 8; R < m; R <<= 1) {
+    if (active) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sa[SIDX(base + e)] = v[e];
+    }
+    __syncthreads();
+    if (active) {
+      const int pair0 = base & ~(2 * R - 1);
+      const int d = base - pair0;                 // this thread's outputs are [d, d + 8) of the merged pair
+      const int A0 = pair0, B0 = pair0 + R;   // runs A and B; one pad slot per 8 records keeps the wide accesses conflict-free
+      const int LA = min(R, m - A0), LB = max(0, min(R, m - B0));   // the last pair of a pass may be short
+      int lo = max(0, d - LB), hi = min(d, LA);   // merge path: how many of the first d outputs come from A (ties: A first)
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const T pa = sa[SIDX(A0 + mid)], pb = sa[SIDX(B0 + d - 1 - mid)];
+        if (!rec_less(pb, pa)) lo = mid + 1; else hi = mid;
+      }
+      int ai = lo, bi = d - lo;
+      T ka = ai < LA ? sa[SIDX(A0 + ai)] : PADV, kb = bi < LB ? sa[SIDX(B0 + bi)] : PADV;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const bool take_a = bi >= LB || (ai < LA && !rec_less(kb, ka));
+        v[e] = take_a ? ka : kb;
+        if (take_a) { ++ai; if (ai < LA) ka = sa[SIDX(A0 + ai)]; } else { ++bi; if (bi < LB) kb = sa[SIDX(B0 + bi)]; }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// The read's anchors made straight into shared memory from its compact hit list (seeds.rs:44-57).  K64: as 64-bit keys
+// rev | rid (32 - qb bits) | rpos (31 bits) | qpos (qb bits), which order exactly like (x, y) when every anchor of the read
+// has rpos >= 0, 0 <= qpos < 2^qb, rid < 2^(32 - qb) and the same span; returns false if some anchor does not fit.
+template <int NT, bool K64>
+__device__ __forceinline__ bool msort_fill(const HitSrc& H, const u32 r, void* smem, u32* s_o, const int qb, const u32 span0) {
+  ulonglong2* sa = reinterpret_cast<ulonglong2*>(smem);
+  u64* sk = reinterpret_cast<u64*>(smem);
+  const u64 m0 = H.mini_off[r];
+  const u32 nh = H.read_nhit[r];
+  const i32 qlen = (i32)(H.read_off[r + 1] - H.read_off[r]);
+  bool ok = true;
+  auto put = [&](int o, u64 x, u64 y) {
+    if (K64) {
+      const u64 rid = (x >> 32) & 0x7fffffffULL;
+      ok = ok && !(x & 0x80000000ULL) && (y >> 32) == (u64)span0 && ((u32)y >> qb) == 0u && (rid >> (32 - qb)) == 0;
+      sk[SIDX(o)] = (x & (1ULL << 63)) | (rid << (31 + qb)) | ((x & 0x7fffffffULL) << qb) | (y & 0xffffffffULL);
+    } else {
+      sa[SIDX(o)] = make_ulonglong2(x, y);
+    }
+  };
+  if (threadIdx.x == 0) *s_o = 0;
+  __syncthreads();
+  for (u32 h = threadIdx.x; h < nh; h += NT) {
+    const u64 loc = H.hit_loc[m0 + h], q = H.hit_q[m0 + h];
+    const u32 aux = H.hit_aux[m0 + h];
+    const u32 c = (u32)(q >> 32);
+    const u64 ks = aux & 0xffu, rps = (q & 0xffffffffULL) | ((u64)(aux >> 8) << 32);
+    const int o = (int)atomicAdd(s_o, c);
+    u64 x, y;
+    if (c == 1) {
+      make_anchor(loc, ks, rps, qlen, x, y);
+      put(o, x, y);
+    } else {
+      for (u32 t = 0; t < c; ++t) {
+        make_anchor(H.V.p[loc + t], ks, rps, qlen, x, y);
+        put(o + (int)t, x, y);
+      }
+    }
+  }
+  return __syncthreads_and(ok) != 0;
+}
 
 template <int NT, bool FUSED>
 __device__ __forceinline__ void anchor_msort_read(ulonglong2* __restrict__ anchors, const u64* __restrict__ read_aoff, const u32 r,
@@ -344,74 +436,40 @@ __device__ __forceinline__ void anchor_msort_read(ulonglong2* __restrict__ ancho
   const int m = (n + 7) & ~7;                 // records + padding up to a multiple of 8; runs need not be a power of two
   const int base = (int)threadIdx.x * 8;
   const bool active = base < m;
-  const ulonglong2 PADV = make_ulonglong2(~0ULL, ~0ULL);
-  ulonglong2 v[8];
   if (FUSED) {
-    // the read's anchors are made here, straight into shared memory, from its compact hit list
-    const u64 m0 = H.mini_off[r];
-    const u32 nh = H.read_nhit[r];
     const i32 qlen = (i32)(H.read_off[r + 1] - H.read_off[r]);
-    if (threadIdx.x == 0) *s_o = 0;
-    __syncthreads();
-    for (u32 h = threadIdx.x; h < nh; h += NT) {
-      const u64 loc = H.hit_loc[m0 + h], q = H.hit_q[m0 + h];
-      const u32 aux = H.hit_aux[m0 + h];
-      const u32 c = (u32)(q >> 32);
-      const u64 ks = aux & 0xffu, rps = (q & 0xffffffffULL) | ((u64)(aux >> 8) << 32);
-      const int o = (int)atomicAdd(s_o, c);
-      if (c == 1) {
-        u64 x, y;
-        make_anchor(loc, ks, rps, qlen, x, y);
-        sa[SIDX(o)] = make_ulonglong2(x, y);
-      } else {
-        for (u32 t = 0; t < c; ++t) {
-          u64 x, y;
-          make_anchor(H.V.p[loc + t], ks, rps, qlen, x, y);
-          sa[SIDX(o + (int)t)] = make_ulonglong2(x, y);
-        }
+    const int qb = max(1, 32 - __clz(max(qlen, 1)));       // qpos < qlen < 2^qb for every well-formed anchor
+    const u32 span0 = H.hit_aux[H.mini_off[r]] & 0xffu;    // n >= 1, so the read has a first hit
+    if (qb <= 31 && msort_fill<NT, true>(H, r, sa, s_o, qb, span0)) {
+      u64* sk = reinterpret_cast<u64*>(sa);
+      u64 kv[8];
+      if (active) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) kv[e] = base + e < n ? sk[SIDX(base + e)] : ~0ULL;
       }
+      __syncthreads();   // everyone has taken its 8 keys out of shared memory
+      msort_core<u64>(kv, sk, m, base, active);
+      if (active) {
+        const u64 qmask = (1ULL << qb) - 1, rmask = (1ULL << (32 - qb)) - 1;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (base + e < n) {
+            const u64 kx = kv[e];
+            a[base + e] = make_ulonglong2((kx & (1ULL << 63)) | (((kx >> (31 + qb)) & rmask) << 32) | ((kx >> qb) & 0x7fffffffULL),
+                                          ((u64)span0 << 32) | (kx & qmask));
+          }
+      }
+      return;
     }
-    __syncthreads();
+    msort_fill<NT, false>(H, r, sa, s_o, 0, 0);   // some anchor does not fit the 64-bit key: sort the anchors themselves
   }
+  ulonglong2 v[8];
   if (active) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = base + e < n ? (FUSED ? sa[SIDX(base + e)] : a[base + e]) : PADV;
-    a_cswap(v[0], v[1]); a_cswap(v[2], v[3]); a_cswap(v[4], v[5]); a_cswap(v[6], v[7]);
-    a_cswap(v[0], v[2]); a_cswap(v[1], v[3]); a_cswap(v[4], v[6]); a_cswap(v[5], v[7]);
-    a_cswap(v[1], v[2]); a_cswap(v[5], v[6]);
-    a_cswap(v[0], v[4]); a_cswap(v[1], v[5]); a_cswap(v[2], v[6]); a_cswap(v[3], v[7]);
-    a_cswap(v[2], v[4]); a_cswap(v[3], v[5]);
-    a_cswap(v[1], v[2]); a_cswap(v[3], v[4]); a_cswap(v[5], v[6]);
+    for (int e = 0; e < 8; ++e) v[e] = base + e < n ? (FUSED ? sa[SIDX(base + e)] : a[base + e]) : rec_pad<ulonglong2>();
   }
   if (FUSED) __syncthreads();   // everyone has taken its 8 records out of shared memory
-  for (int R = 8; R < m; R <<= 1) {
-    if (active) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) sa[SIDX(base + e)] = v[e];
-    }
-    __syncthreads();
-    if (active) {
-      const int pair0 = base & ~(2 * R - 1);
-      const int d = base - pair0;                 // this thread's outputs are [d, d + 8) of the merged pair
-      const int A0 = pair0, B0 = pair0 + R;   // runs A and B; one pad slot per 8 records keeps 128-bit accesses conflict-free
-      const int LA = min(R, m - A0), LB = max(0, min(R, m - B0));   // the last pair of a pass may be short
-      int lo = max(0, d - LB), hi = min(d, LA);   // merge path: how many of the first d outputs come from A (ties: A first)
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        const ulonglong2 pa = sa[SIDX(A0 + mid)], pb = sa[SIDX(B0 + d - 1 - mid)];
-        if (!a_less(pb.x, pb.y, pa.x, pa.y)) lo = mid + 1; else hi = mid;
-      }
-      int ai = lo, bi = d - lo;
-      ulonglong2 ka = ai < LA ? sa[SIDX(A0 + ai)] : PADV, kb = bi < LB ? sa[SIDX(B0 + bi)] : PADV;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const bool take_a = bi >= LB || (ai < LA && !a_less(kb.x, kb.y, ka.x, ka.y));
-        v[e] = take_a ? ka : kb;
-        if (take_a) { ++ai; if (ai < LA) ka = sa[SIDX(A0 + ai)]; } else { ++bi; if (bi < LB) kb = sa[SIDX(B0 + bi)]; }
-      }
-    }
-    __syncthreads();
-  }
+  msort_core<ulonglong2>(v, sa, m, base, active);
   if (active) {
 #pragma unroll
     for (int e = 0; e < 8; ++e)
@@ -558,7 +616,6 @@ __global__ void __launch_bounds__(NT) anchor_sort_gmem_kernel(ulonglong2* __rest
   anchor_sort_gmem_read<NT>(anchors, read_aoff, r);
 }
 
-inline int grid_for(u64 n, int block = 256) { return (int)std::max<u64>(1, std::min<u64>((n + block - 1) / block, 148ull * 32)); }
 bool g_attr_done = false;
 void seeds_set_attrs() {
   if (g_attr_done) return;
