@@ -531,12 +531,18 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
     return rc;
   }
   ctx->timer.mark(st, "chain");
-  MM2_TRY(chain_batch(ctx, ctx->anchors.as<ulonglong2>(), ctx->read_aoff.as<u64>(), d_off, so.seq_off, so.val, d_sum_span, (u32)nreads,
-                      p, 1, ctx->dpA.as<int4>(), ctx->dpB.as<int4>(), ctx->dpT.as<int>(), ctx->dpW.as<int>(), nullptr, ctx->hits.as<ReadHit>(), nullptr));   // no cell counter: a diagnostic, costs ~20 % of the kernel
-  ctx->timer.mark(st, "d2h");
+  // The 64-byte per-read results are written by the chain kernels straight into page-locked host memory (zero-copy:
+  // cudaMallocHost memory is device-addressable under unified addressing): one posted PCIe write per read while the kernel
+  // runs, instead of a device buffer plus a separate D2H copy at the end (measured 0.8 ms per 100k reads).
+  // MM2_HITS=copy keeps the device buffer + copy as the comparison arm.
   MM2_TRY(ctx->pin_out.ensure((nreads + 1) * sizeof(ReadHit) + 64));
   ReadHit* hits = ctx->pin_out.as<ReadHit>();
-  if (nreads) CUDA_TRY(cudaMemcpyAsync(hits, ctx->hits.p, nreads * sizeof(ReadHit), cudaMemcpyDeviceToHost, st));
+  static const bool hits_copy = [] { const char* e = getenv("MM2_HITS"); return e && !strcmp(e, "copy"); }();
+  MM2_TRY(chain_batch(ctx, ctx->anchors.as<ulonglong2>(), ctx->read_aoff.as<u64>(), d_off, so.seq_off, so.val, d_sum_span, (u32)nreads,
+                      p, 1, ctx->dpA.as<int4>(), ctx->dpB.as<int4>(), ctx->dpT.as<int>(), ctx->dpW.as<int>(), nullptr,
+                      hits_copy ? ctx->hits.as<ReadHit>() : hits, nullptr));   // no cell counter: a diagnostic, costs ~20 % of the kernel
+  ctx->timer.mark(st, "d2h");
+  if (nreads && hits_copy) CUDA_TRY(cudaMemcpyAsync(hits, ctx->hits.p, nreads * sizeof(ReadHit), cudaMemcpyDeviceToHost, st));
   ctx->timer.mark(st, "end");
   mm2_trace(ctx, "chain issued");
   CUDA_TRY(cudaStreamSynchronize(st));

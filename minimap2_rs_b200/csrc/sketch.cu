@@ -1106,23 +1106,37 @@ __global__ void __launch_bounds__(SK_NT + 32, sizeof(KT) == 4 ? MM2_SK3_OCC : 3)
         opos[idx] = ((u32)(P0 + x) << 1) | ((s_z[x >> 3] >> (x & 7)) & 1u);
         ++idx;
       };
-      u32 jm = (eflags | (eflags >> 8) | (eflags >> 16)) & 0xFFu;  // steps of this thread that emit anything
-      while (jm) {
-        const int j = __ffs(jm) - 1;
-        jm &= jm - 1;
-        const int u = c0 + j;
-        const u32 pw = (j >> 1) == 0 ? pp[0] : (j >> 1) == 1 ? pp[1] : (j >> 1) == 2 ? pp[2] : pp[3];
-        const int ppos = (int)((pw >> (16 * (j & 1))) & 0xFFFFu);
-        if (eflags & (1u << (8 + j))) idx = sk3_stage_dups<KT, PAD>(s_key, s_z, u - w + 1, u - 1, ppos, okey, opos, idx, P0);
-        if (eflags & (1u << j)) put(ppos);
-        if (eflags & (1u << (16 + j))) {
-          const int j1 = j + 1;
-          const u32 pw1 = (j1 >> 1) == 0 ? pp[0] : (j1 >> 1) == 1 ? pp[1] : (j1 >> 1) == 2 ? pp[2] : pp[3];
-          const int cpos = (j == SK_CH - 1) ? cur7 : (int)((pw1 >> (16 * (j1 & 1))) & 0xFFFFu);
-          idx = sk3_stage_dups<KT, PAD>(s_key, s_z, u - w + 1, u, cpos, okey, opos, idx, P0);
+      if ((eflags >> 8) == 0u) {
+        // only "previous minimum" emissions (every clean run): step j's record goes to my_off + the number of this
+        // thread's emitting steps before j -- no serial loop, no dynamic indexing of pp[]
+#pragma unroll
+        for (int j = 0; j < SK_CH; ++j) {
+          if (eflags & (1u << j)) {
+            const int x = (int)((pp[j >> 1] >> (16 * (j & 1))) & 0xFFFFu);
+            const u32 o = my_off + (u32)__popc(eflags & ((1u << j) - 1u));
+            okey[o] = s_key[KIDX(x)];
+            opos[o] = ((u32)(P0 + x) << 1) | ((s_z[x >> 3] >> (x & 7)) & 1u);
+          }
         }
+      } else {
+        u32 jm = (eflags | (eflags >> 8) | (eflags >> 16)) & 0xFFu;  // steps of this thread that emit anything
+        while (jm) {
+          const int j = __ffs(jm) - 1;
+          jm &= jm - 1;
+          const int u = c0 + j;
+          const u32 pw = (j >> 1) == 0 ? pp[0] : (j >> 1) == 1 ? pp[1] : (j >> 1) == 2 ? pp[2] : pp[3];
+          const int ppos = (int)((pw >> (16 * (j & 1))) & 0xFFFFu);
+          if (eflags & (1u << (8 + j))) idx = sk3_stage_dups<KT, PAD>(s_key, s_z, u - w + 1, u - 1, ppos, okey, opos, idx, P0);
+          if (eflags & (1u << j)) put(ppos);
+          if (eflags & (1u << (16 + j))) {
+            const int j1 = j + 1;
+            const u32 pw1 = (j1 >> 1) == 0 ? pp[0] : (j1 >> 1) == 1 ? pp[1] : (j1 >> 1) == 2 ? pp[2] : pp[3];
+            const int cpos = (j == SK_CH - 1) ? cur7 : (int)((pw1 >> (16 * (j1 & 1))) & 0xFFFFu);
+            idx = sk3_stage_dups<KT, PAD>(s_key, s_z, u - w + 1, u, cpos, okey, opos, idx, P0);
+          }
+        }
+        if (eflags & (1u << 24)) put(cur7);
       }
-      if (eflags & (1u << 24)) put(cur7);
     }
     if (tid == 0) { s_meta[b].tile = tile; s_meta[b].count = tile_count; s_meta[b].q = q; s_meta[b].staged = staged ? 1u : 0u; }
     __threadfence_block();
