@@ -415,16 +415,34 @@ __global__ void chain_classify_kernel(ChainArgs G) {
 
 // Shared state of a CTA that chains one dense read: warp 0 runs the ring algorithm; when a window goes on beyond the ring
 // it posts the anchor here and all NW warps evaluate the next 32 tiles (1024 predecessors) of the window in parallel.
+// Window ring of a dense read in shared memory: the static fields and the DP result (f, pprev) of the last DENSE_CAP
+// anchors that have left the register ring, slot = j % DENSE_CAP, plus one mark bit per slot (lchain.rs:86 `t[pprev] = i`,
+// cleared for every anchor).  Every far predecessor of a window of at most max_chain_iter <= DENSE_CAP - 64 anchors is in
+// there, so a DP cell costs shared-memory loads instead of L2 round trips (the kernel was bound by those: 48 B per cell,
+// 2,800 cells per anchor on configs[4]).  Larger max_chain_iter values fall back to the arrays in global memory.
+#ifdef MM2_DENSE_PROF
+// build with -DMM2_DENSE_PROF: cycles of warp 0 per phase of the dense path, printed by chain_batch (diagnostic only)
+__device__ unsigned long long g_dense_prof[8];
+#define DPROF_T(v) const long long v = clock64()
+#define DPROF_ADD(k, a, b) do { if (NW > 1 && lane == 0) dprof[k] += (unsigned long long)((b) - (a)); } while (0)
+#define DPROF_INC(k) do { if (NW > 1 && lane == 0) dprof[k] += 1ull; } while (0)
+#else
+#define DPROF_T(v)
+#define DPROF_ADD(k, a, b)
+#define DPROF_INC(k)
+#endif
+constexpr int DENSE_CAP = 5120;
 struct DenseSh {
   int op;                      // 0: evaluate a round, 1: the read is done
   int ri, qi, jb, start_j, mark, bw, mdx, mdy;
   u32 hi_i;
   u32 next;                    // next dense read of this CTA
+  int use_sm;                  // the window ring below is in use (max_chain_iter fits)
+  int* sx; int* sq; int* sf; int* sp; u8* ss; u32* mk;   // DENSE_CAP entries each (mk: DENSE_CAP / 32 words)
   u32 V[32], M[32], ACT[32];   // per tile: ballots of "has a score", "t[j] == i", "inside the window"
   int tmax[32];                // per tile: best score
   int sc[32][33];
 };
-constexpr int DENSE_WARPS = 8;
 
 template <int NW>
 __device__ __forceinline__ void dense_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory"); }
@@ -438,6 +456,40 @@ __device__ __forceinline__ void dense_eval_round(const ChainArgs& G, DenseSh* sh
   const u32 hi_i = sh->hi_i;
   int sc2[TPW];
   bool v2[TPW];
+  if (sh->use_sm) {
+    const int* __restrict__ sx = sh->sx; const int* __restrict__ sq = sh->sq; const int* __restrict__ sf = sh->sf;
+    const int* __restrict__ sp = sh->sp; const u8* __restrict__ ss = sh->ss;
+    u32* mk = sh->mk;
+#pragma unroll
+    for (int u = 0; u < TPW; ++u) {
+      const int j = jb - 32 * (wid + NW * u) - lane;
+      sc2[u] = NEG_INF; v2[u] = false;
+      if (j >= start_j) {                                           // same rid/strand as anchor i: start_j is inside its block
+        const int slot = j % DENSE_CAP;
+        int s0;
+        if (chain_sc(ri, qi, sx[slot], sq[slot], (int)ss[slot], mdx, mdy, bw, G.p.chn_pen_gap, G.p.chn_pen_skip, G.half_log, s0)) {
+          sc2[u] = wadd(s0, sf[slot]);
+          v2[u] = true;
+          const int pp = sp[slot];
+          if (pp >= start_j) { const int ps = pp % DENSE_CAP; atomicOr(&mk[ps >> 5], 1u << (ps & 31)); }   // lchain.rs:86; marks below the window are never read
+        }
+      }
+    }
+    dense_bar<NW>();                                                // every mark of this round is visible
+#pragma unroll
+    for (int u = 0; u < TPW; ++u) {
+      const int t = wid + NW * u;
+      const int j = jb - 32 * t - lane;
+      bool tm = false;
+      if (v2[u]) { const int slot = j % DENSE_CAP; tm = (mk[slot >> 5] >> (slot & 31)) & 1u; }
+      const u32 Vb = __ballot_sync(0xFFFFFFFFu, v2[u]), Mb = __ballot_sync(0xFFFFFFFFu, tm), Ab = __ballot_sync(0xFFFFFFFFu, j >= start_j);
+      const int tmx = __reduce_max_sync(0xFFFFFFFFu, sc2[u]);
+      sh->sc[t][lane] = sc2[u];
+      if (lane == 0) { sh->V[t] = Vb; sh->M[t] = Mb; sh->ACT[t] = Ab; sh->tmax[t] = tmx; }
+    }
+    dense_bar<NW>();                                                // the tile summaries are in shared memory
+    return;
+  }
 #pragma unroll
   for (int u = 0; u < TPW; ++u) {
     const int j = jb - 32 * (wid + NW * u) - lane;
@@ -500,8 +552,20 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
   int best = 0;
   int4 bestA = make_int4(0, -1, 0, 0), bestB = make_int4(0, 0, 0, 0);
   bool t_init = false;
+#ifdef MM2_DENSE_PROF
+  unsigned long long dprof[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // 0 ring phase, 1 window search + marks, 2 eval rounds, 3 walk, 4 anchors, 5 rounds, 6 record tiles, 7 total
+  const long long dprof_t0 = clock64();
+#endif
+  bool use_sm = false;
+  int blk_start = 0;   // first anchor of the rid/strand block that holds the last anchor of the previous tile
   if constexpr (NW > 1) {
-    for (int x = wid * 32 + lane; x < n; x += NW * 32) T[x] = -1;
+    use_sm = max_iter <= DENSE_CAP - 64;
+    if (wid == 0 && lane == 0) sh->use_sm = use_sm ? 1 : 0;
+    if (use_sm) {
+      for (int x = wid * 32 + lane; x < DENSE_CAP / 32; x += NW * 32) sh->mk[x] = 0;
+    } else {
+      for (int x = wid * 32 + lane; x < n; x += NW * 32) T[x] = -1;
+    }
     t_init = true;
     dense_bar<NW>();
     if (wid > 0) {
@@ -533,6 +597,7 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
       const int own_qs = wsub(cq, csp - 1), own_ts = wsub(cx, csp - 1);
       // anchors whose window is not empty: the predicate of lchain.rs:75 is false for i - 1, and max_chain_iter >= 1
       u32 workmask;
+      u32 bnd = 0;   // lanes whose anchor starts a new rid/strand block (NW > 1 only)
       {
         int px = __shfl_up_sync(0xFFFFFFFFu, cx, 1);
         u32 phi = __shfl_up_sync(0xFFFFFFFFu, chi, 1);
@@ -542,12 +607,15 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
         const int i = i0 + lane;
         const bool work = lane < tile_n && i > 0 && (i - 1) >= wsub(i, max_iter) && phi == chi && !(cx > wadd(px, mdx));
         workmask = __ballot_sync(0xFFFFFFFFu, work);
+        if constexpr (NW > 1) bnd = __ballot_sync(0xFFFFFFFFu, lane < tile_n && (i == 0 || phi != chi));
       }
       int done = 0;   // lanes [0, done) of this tile are committed to the ring
       while (workmask) {
         const int c = __ffs(workmask) - 1;
         workmask &= workmask - 1;
         const int i = i0 + c;
+        DPROF_T(tp0);
+        DPROF_INC(4);
         if (done < c) {
           if (lane >= done && lane < c) {                        // anchors before i with an empty window (lchain.rs:77,89-90)
             rj = i0 + lane; rx = cx; rq = cq; rsp = csp; rhi = chi;
@@ -609,6 +677,8 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
           cells += (unsigned)__popc(inmask);
         }
         int mv = 0, mcnt = 0, mqs = 0, mts = 0, mfirst = 0;     // state of max_j
+        DPROF_T(tp1);
+        DPROF_ADD(0, tp0, tp1);
         if (more) {
           // ---- the window goes on beyond the ring: 32 predecessors at a time from global memory -------------------------
           if (!t_init) {
@@ -618,9 +688,42 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
           }
           const int mark = mark_base + i;
           const int hi_known = i - 32;                           // inside the window
+          bool sm_path = false;
+          if constexpr (NW > 1) sm_path = use_sm;
+          int lo = st;
+          if (sm_path) {
+            // window start on the shared ring.  Inside the rid/strand block of anchor i (it starts at blk0) the predicate of
+            // lchain.rs:75 is `rpos(i) > rpos(j) + max_dist_x`; anchors below i - max_chain_iter are outside the window
+            // whatever the predicate says (lchain.rs:78) and may already be overwritten in the ring, so the search starts there.
+            const u32 bm = bnd & low_mask(c + 1);
+            const int blk0 = bm ? i0 + 31 - __clz(bm) : blk_start;
+            lo = max(max(st, blk0), max(low_iter, 0));
+            const int* __restrict__ sx = sh->sx;
+            int rounds = 0;
+            for (;;) {
+              const int j = lo + lane;
+              bool adv = false;
+              if (j < hi_known) adv = ri > wadd(sx[j % DENSE_CAP], mdx);
+              const u32 b = __ballot_sync(0xFFFFFFFFu, !adv);
+              if (b) { lo += __ffs(b) - 1; break; }
+              lo += 32;
+              if (++rounds == 2) {
+                int hi = hi_known;
+                while (lo < hi) {
+                  const int mid = (lo + hi) >> 1;
+                  if (ri > wadd(sx[mid % DENSE_CAP], mdx)) lo = mid + 1; else hi = mid;
+                }
+                break;
+              }
+            }
+            // marks of this anchor start from a clean mask; the ring slots mark their in-window predecessors
+            for (int x = lane; x < DENSE_CAP / 32; x += 32) sh->mk[x] = 0;
+            __syncwarp();
+            const int sj = low_iter > lo ? low_iter : lo;
+            if (valid && rpp >= sj && rpp < hi_known) { const int ps = rpp % DENSE_CAP; atomicOr(&sh->mk[ps >> 5], 1u << (ps & 31)); }
+          } else {
           if (valid && rpp >= 0 && rpp < hi_known) T[rpp] = mark;   // marks of the ring slots on older anchors
           // window start: first j in [st, i - 32] for which the predicate of lchain.rs:75 is false
-          int lo = st;
           {
             int rounds = 0;
             for (;;) {
@@ -645,8 +748,11 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
               }
             }
           }
+          }
           st = lo;
           const int start_j = low_iter > lo ? low_iter : lo;
+          DPROF_T(tp2);
+          DPROF_ADD(1, tp1, tp2);
           if constexpr (NW > 1) {
             // 32 tiles per round, evaluated by all warps; this warp then walks the tile summaries: lane t holds tile t
             bool brk = false;
@@ -655,8 +761,12 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
                 sh->op = 0; sh->ri = ri; sh->qi = qi; sh->hi_i = hi_i; sh->jb = jb; sh->start_j = start_j; sh->mark = mark;
                 sh->bw = bw; sh->mdx = mdx; sh->mdy = mdy;
               }
+              DPROF_T(tp3);
               dense_bar<NW>();
               dense_eval_round<NW>(G, sh, an, A, T, 0, lane);
+              DPROF_T(tp4);
+              DPROF_ADD(2, tp3, tp4);
+              DPROF_INC(5);
               const int nround = min(32, (jb - start_j + 32) >> 5);   // tiles that reach into the window
               const u32 tV = sh->V[lane], tM = sh->M[lane], tA = sh->ACT[lane];
               const int tmx = lane < nround ? sh->tmax[lane] : NEG_INF;
@@ -692,6 +802,7 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
                   if (count_cells) cells += (unsigned)__reduce_add_sync(0xFFFFFFFFu, mine ? __popc(tA) : 0);
                 }
                 if (tf >= nround) break;
+                DPROF_INC(6);
                 int rec_last;
                 const bool b = chain_tile_walk(lane, sh->V[tf], sh->M[tf], sh->ACT[tf], sh->sc[tf][lane], max_skip, max_f, n_skip, rec_last,
                                                cells);
@@ -699,6 +810,8 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
                 if (b) { brk = true; break; }
                 cur = tf + 1;
               }
+              DPROF_T(tp5);
+              DPROF_ADD(3, tp4, tp5);
             }
           } else {
             for (int jb = i - 33; jb >= start_j; jb -= 32) {
@@ -758,6 +871,13 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
         A[i0 + lane] = make_int4(rf, rpp, rv, rcnt);
         B[i0 + lane] = make_int4(rqs, rts, rfirst, 0);
       }
+      if constexpr (NW > 1) {
+        if (use_sm && lane < tile_n) {                           // ... and they enter the shared window ring
+          const int slot = (i0 + lane) % DENSE_CAP;
+          sh->sx[slot] = rx; sh->sq[slot] = rq; sh->ss[slot] = (u8)rsp; sh->sf[slot] = rf; sh->sp[slot] = rpp;
+        }
+        if (bnd) blk_start = i0 + 31 - __clz(bnd);
+      }
       {  // lchain.rs:163: the LAST maximum of f
         const int fl = lane < tile_n ? rf : NEG_INF * 4;
         const int m = __reduce_max_sync(0xFFFFFFFFu, fl);
@@ -788,6 +908,12 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
   if constexpr (NW > 1) {
     if (lane == 0) sh->op = 1;
     dense_bar<NW>();                                              // releases warps 1..
+#ifdef MM2_DENSE_PROF
+    if (lane == 0) {
+      dprof[7] = (unsigned long long)(clock64() - dprof_t0);
+      for (int x = 0; x < 8; ++x) atomicAdd(&g_dense_prof[x], dprof[x]);
+    }
+#endif
   }
 }
 
@@ -801,17 +927,30 @@ __global__ void __launch_bounds__(CH_WARPS * 32, MM2_CH_OCC) chain_ring_kernel(C
   chain_read<1>(G, r, threadIdx.x & 31, 0, nullptr);
 }
 
-__global__ void __launch_bounds__(DENSE_WARPS * 32) chain_dense_kernel(ChainArgs G) {
+// NW warps per dense read, MINB resident CTAs per SM (register cap 65536 / (NW * 32 * MINB)).  A dense read is bound by the
+// latency of its anchor-after-anchor dependency, so the throughput of an SM is (reads resident on it) / (latency per anchor):
+// few dense reads want wide CTAs (short latency), many dense reads want many narrow CTAs.  The host launches the variants
+// whose [lo, hi) range of dense-read counts it wants; the CTAs of the others return at once.
+template <int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB) chain_dense_kernel(ChainArgs G, u32 nd_lo, u32 nd_hi) {
   __shared__ DenseSh sh;
+  extern __shared__ __align__(16) unsigned char dense_dyn[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const u32 ndense = G.dense[0];
+  if (ndense < nd_lo || ndense >= nd_hi) return;
+  if (threadIdx.x == 0) {
+    int* base = reinterpret_cast<int*>(dense_dyn);
+    sh.sx = base; sh.sq = base + DENSE_CAP; sh.sf = base + 2 * DENSE_CAP; sh.sp = base + 3 * DENSE_CAP;
+    sh.mk = reinterpret_cast<u32*>(base + 4 * DENSE_CAP);
+    sh.ss = reinterpret_cast<u8*>(base + 4 * DENSE_CAP + DENSE_CAP / 32);
+  }
   for (;;) {
     __syncthreads();
     if (threadIdx.x == 0) sh.next = atomicAdd(&G.dense[1], 1u);
     __syncthreads();
     const u32 k = sh.next;
     if (k >= ndense) return;
-    chain_read<DENSE_WARPS>(G, G.dense[2 + k], lane, wid, &sh);
+    chain_read<NW>(G, G.dense[2 + k], lane, wid, &sh);
   }
 }
 
@@ -868,8 +1007,32 @@ int chain_batch(mm2_ctx* ctx, const ulonglong2* d_anchors, const u64* d_read_aof
     MM2_LAUNCH(ctx, chain_classify_kernel, (int)((nreads + 255) / 256), 256, 0, G);
     MM2_LAUNCH(ctx, chain_ring_kernel, grid, CH_WARPS * 32, 0, G);
     // persistent CTAs, one dense read at a time each; with no dense read they exit at once
-    MM2_LAUNCH(ctx, chain_dense_kernel, (int)std::min<u64>(nreads, (u64)ctx->n_sm * 2), DENSE_WARPS * 32, 0, G);
+    const u32 sm = (u32)ctx->n_sm;
+    constexpr int DENSE_DYN = 4 * DENSE_CAP * 4 + DENSE_CAP / 32 * 4 + DENSE_CAP;   // window ring (see DenseSh)
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(chain_dense_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_DYN);
+      cudaFuncSetAttribute(chain_dense_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_DYN);
+      cudaFuncSetAttribute(chain_dense_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_DYN);
+      attr_done = true;
+    }
+    static const int force_nw = [] { const char* e = getenv("MM2_DENSE_NW"); return e ? atoi(e) : 0; }();   // experiment knob: warps per dense read
+    const int dgrid = (int)std::min<u64>(nreads, (u64)sm * 2);
+    if (force_nw == 16) MM2_LAUNCH(ctx, (chain_dense_kernel<16, 2>), dgrid, 16 * 32, DENSE_DYN, G, 1u, 0xFFFFFFFFu);
+    else if (force_nw == 4) MM2_LAUNCH(ctx, (chain_dense_kernel<4, 2>), dgrid, 4 * 32, DENSE_DYN, G, 1u, 0xFFFFFFFFu);
+    else MM2_LAUNCH(ctx, (chain_dense_kernel<8, 2>), dgrid, 8 * 32, DENSE_DYN, G, 1u, 0xFFFFFFFFu);
   }
+#ifdef MM2_DENSE_PROF
+  {
+    cudaStreamSynchronize(ctx->stream);
+    unsigned long long h[8];
+    cudaMemcpyFromSymbol(h, g_dense_prof, sizeof h);
+    if (h[4]) fprintf(stderr, "[dense prof] anchors %llu rounds %llu record-tiles %llu | cycles per anchor: ring %.0f search+marks %.0f eval %.0f walk %.0f total %.0f\n",
+                      h[4], h[5], h[6], (double)h[0] / h[4], (double)h[1] / h[4], (double)h[2] / h[4], (double)h[3] / h[4], (double)h[7] / h[4]);
+    memset(h, 0, sizeof h);
+    cudaMemcpyToSymbol(g_dense_prof, h, sizeof h);
+  }
+#endif
   CUDA_TRY(cudaGetLastError());
   return MM2_OK;
 }
