@@ -10,7 +10,7 @@ cat, roffs = gen.reads(0xB2001002, g, goffs, 100_000, 10_000, 0.0333, 0.0333, 0.
 pin = mm2.PinnedBuffer(cat.size); pr = pin.array(np.uint8, cat.size); pr[:] = cat
 c0 = mm2.Context(0)
 gi = mm2.Index.build(c0, g, goffs, ["chr8"])
-for workers, mb in [(2, 96), (2, 32), (2, 250), (3, 64), (3, 128), (4, 64), (4, 128), (0, 0)]:
+for workers, mb in [(4, 64), (4, 32), (4, 48), (4, 24), (3, 32), (4, 96), (2, 64)]:
     if workers:
         os.environ["MM2_WORKERS"] = str(workers); os.environ["MM2_SUBBATCH_MB"] = str(mb); os.environ["MM2_PIPELINE"] = "1"
     else:
