@@ -28,12 +28,13 @@ GENOME_SEED, READS_SEED = 0xB2000002, 0xB2001002
 W, K = 10, 15
 ERR = (0.0333, 0.0333, 0.0333)  # sub / ins / del
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch in the `ncu --set full` capture of tools/prof_step.py
-# (profiles/r01_ncu_v5.md): (bytes, units that launch processed, unit)
-NCU_TRAFFIC = {"sketch": (0.1011e9 + 0.2488e9, 100e6, "base"), "chain": (0.1388e9 + 0.1875e9, 6.978e6, "anchor"),
-               "lookup": (1.2243e9 + 0.2197e9, 18.628e6, "minimizer")}
-NCU_NOTE = {"sketch": "sketch_tile_kernel_v3 is instruction-issue bound (ncu: 65 % issue-active at 56 % occupancy, 5 % DRAM throughput), not HBM bound",
+# (profiles/r01_ncu_v11.md): (bytes, units that launch processed, unit)
+NCU_TRAFFIC = {"sketch": (0.1011e9 + 0.2471e9, 100e6, "base"), "chain": (0.1393e9 + 0.1882e9, 6.978e6, "anchor"),
+               "lookup": (1.2007e9 + 0.0907e9, 18.628e6, "minimizer"), "anchor_sort": (0.1637e9 + 0.0725e9, 6.978e6, "anchor")}
+NCU_NOTE = {"sketch": "sketch_tile_kernel_v3 is instruction-issue bound (ncu: 63 % issue-active at 56 % occupancy, 5 % DRAM throughput), not HBM bound",
             "chain": "chain_ring_kernel is warp-issue bound (ncu: 76 % issue-active at 40 % occupancy, 5 % DRAM throughput), not HBM bound",
-            "lookup": "lookup_count_kernel is DRAM bound on random 16-byte probes (ncu: 60 % DRAM throughput)"}
+            "lookup": "seed_hits_kernel is DRAM bound on random 16-byte probes that cost a 64-byte access each (ncu: 48 % DRAM throughput)",
+            "anchor_sort": "anchor_msort_kernel is issue / shared-memory bound (ncu: 60 % issue-active)"}
 
 
 def peaks():
@@ -261,9 +262,9 @@ def main():
     if rank == 0:
         peak, peak_src = peaks()
         nm, na = stats["n_minimizers"], stats["n_anchors"]
-        # algorithmic bytes per launch (SURVEY.md §8d / DESIGN.md): sketch L + 16 n_min; lookup 32 n_min + 16 n_anchor; sort 32 n_anchor
-        alg = {"sketch": n_bases + 16 * nm, "lookup": 32 * nm + 16 * na, "anchor_sort": 32 * na, "anchor_fill": 16 * nm + 16 * na,
-               "filter": 9 * nm}
+        # algorithmic bytes per launch (SURVEY.md §8d / DESIGN.md): sketch L + 16 n_min; lookup 16 n_min + 16 n_min; anchors 8 per occurrence + sort 32 n_anchor
+        # (the lookup stage now ends at the compact hit lists; the anchors are built, sorted and written once by the sort stage)
+        alg = {"sketch": n_bases + 16 * nm, "lookup": 32 * nm, "anchor_sort": 8 * na + 32 * na}
         kernels = {}
         # device stages (CUDA-event timers on the launching stream) vs host wall-clock entries; shares are of the device stages
         dev_stages = {kn: ms for kn, ms in stage_ms.items() if not kn.startswith("host_") and kn not in ("h2d", "d2h", "end")}

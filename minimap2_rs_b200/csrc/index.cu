@@ -266,7 +266,8 @@ int index_build_table(mm2_ctx* ctx, mm2_index* idx) {
   // Bloom filter in front of the table, only while it fits comfortably in the 126 MB L2
   idx->has_bloom = false;
   u64 nblk = 1024;
-  while (nblk < idx->n_keys / 16) nblk <<= 1;  // <= 16 keys x 4 bits per 128-bit block: ~2-3 % false positives
+  static const u64 keys_per_blk = [] { const char* e = getenv("MM2_BLOOM_KPB"); return (u64)(e && atoi(e) > 0 ? atoi(e) : 16); }();   // experiment knob
+  while (nblk < idx->n_keys / keys_per_blk) nblk <<= 1;  // <= 16 keys x 4 bits per 128-bit block: ~2-3 % false positives
   if (idx->n_keys && nblk * 16 <= (40ull << 20) && !getenv("MM2_NO_BLOOM")) {  // must stay L2-resident next to streaming traffic
     MM2_TRY(idx->bloom.ensure(nblk * 16));
     idx->bloom_mask = nblk - 1;
