@@ -303,7 +303,7 @@ def main():
             "work": {"reads": args.reads * world, "bases_per_step": total_bases, "minimizers": int(nm), "anchors": int(na), "paf_records": n_recs,
                      "rescued": int(stats["n_rescued"])},
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # the CPU leg is an N = 1 measurement (rank 0's host cores are shared with the other ranks otherwise)
             from oracle import orc
             t0 = time.time()
             oi = orc.Index.build(g, goffs, ["chr8"], w=W, k=K, threads=os.cpu_count() or 1)

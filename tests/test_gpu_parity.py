@@ -309,6 +309,26 @@ def test_map_batch_repeats_rescue_and_hifi_preset(ctx, mm2, orc, gen):
     assert st.n_rescued > 0
 
 
+def test_map_batch_anchor_classes_and_exact_filter(ctx, mm2, orc, gen):
+    """one batch that exercises every anchor-count class of the seeding stage (fused fill + merge sort up to 1024 and up to 4096
+    anchors, device-built lists for the shared-memory and global-memory bitonic classes above) and the exact query filter
+    behind the count sketch (reads listed by seed_hits_kernel<0>, filtered by filter_list_kernel, looked up by <1>)"""
+    g = gen.repeat_genome(79, 2_000_000, 0.4, 0.2)
+    offs = np.array([0, g.size], dtype=np.uint64)
+    gi = mm2.Index.build(ctx, g, offs, ["rep"])
+    oi = orc.Index.build(g, offs, ["rep"], threads=8)
+    reads = []
+    for seed, n, ln in ((31, 30, 700), (32, 30, 3000), (33, 20, 9000), (34, 8, 30000)):
+        c, ro = gen.reads(seed, g, offs, n, ln, 0.02, 0.02, 0.02)
+        reads += [c[int(ro[i]):int(ro[i + 1])].tobytes() for i in range(n)]
+    reads += [b"AC" * 4000, b"ACGTTGCA" * 1500]                     # low-complexity reads: the same few k-mers hundreds of times
+    cat, roffs = cases.cat_offs(reads)
+    res, st = _map_compare(ctx, mm2, orc, gi, oi, cat, roffs, ["c%d" % i for i in range(len(reads))])
+    na = np.diff(res.stage["anchor_offs"].astype(np.int64))
+    assert (na <= 1024).any() and ((na > 1024) & (na <= 4096)).any() and ((na > 4096) & (na <= 12288)).any() and (na > 12288).any(), np.sort(na)
+    assert st.n_minimizers_kept < st.n_minimizers                      # the exact filter dropped something
+
+
 def test_map_batch_cta_per_read_chaining(dense_ctx, mm2, orc, gen):
     """the whole mapping path with every read chained by chain_dense_kernel (repeat-rich genome: long windows, rescue)"""
     g = gen.repeat_genome(78, 1_500_000, 0.4, 0.2)
