@@ -409,6 +409,27 @@ static void merge_map_results(mm2_map_result_t* parts, const size_t* first, size
   }
 }
 
+// Same, for parts whose records were written straight into one destination array (part i at base + first[i], read ids and
+// panic ids already global): close the gaps left by reads without a record; nothing is copied when every read has one.
+static void merge_in_place(mm2_map_result_t* parts, const size_t* first, size_t nparts, mm2_paf_rec_t* base, mm2_map_result_t* out) {
+  memset(out, 0, sizeof *out);
+  out->recs = base;
+  size_t npan = 0, w = 0;
+  for (size_t i = 0; i < nparts; ++i) npan += parts[i].n_panic;
+  out->panic_reads = xmalloc<u32>(npan);
+  for (size_t i = 0; i < nparts; ++i) {
+    mm2_map_result_t& p = parts[i];
+    if (p.n_recs && base + first[i] != base + w) memmove(base + w, base + first[i], p.n_recs * sizeof(mm2_paf_rec_t));
+    w += p.n_recs;
+    for (size_t j = 0; j < p.n_panic; ++j) out->panic_reads[out->n_panic++] = p.panic_reads[j];
+    out->n_reads += p.n_reads; out->n_bases += p.n_bases; out->n_minimizers += p.n_minimizers;
+    out->n_minimizers_kept += p.n_minimizers_kept; out->n_anchors += p.n_anchors; out->n_rescued += p.n_rescued;
+    p.recs = nullptr;   // not owned by the part
+    mm2_map_result_free(&p);
+  }
+  out->n_recs = w;
+}
+
 // paf.rs:130-222 for the single reported chain of a read: 0 = no record (no anchors, main.rs:211-213), 1 = record,
 // 2 = the reference panics on this read (idx.seq[rid0] out of bounds after the odd-rid sign extension, F5)
 static int build_record(const mm2_index* idx, const ReadHit& h, u32 r, i32 qlen, mm2_paf_rec_t& rec) {
@@ -454,8 +475,11 @@ static void mm2_trace(const mm2_ctx* ctx, const char* what) {
   fprintf(stderr, "[mm2 trace] %9.3f ctx=%p %s\n", t, (const void*)ctx, what);
 }
 
+// rec_dst != NULL: the records (at most one per read on this path) go to rec_dst[0 .. nreads) -- a slice of the caller's
+// array, not owned by *out -- and read / panic ids are offset by read_id_base.  Ignored by the general multi-chain tail.
 static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, const u64* d_off, const u64* h_off, size_t nreads,
-                           const mm2_map_opts_t* o, mm2_map_result_t* out, bool timer_started) {
+                           const mm2_map_opts_t* o, mm2_map_result_t* out, bool timer_started, mm2_paf_rec_t* rec_dst = nullptr,
+                           u32 read_id_base = 0) {
   cudaStream_t st = ctx->stream;
   const auto wall0 = std::chrono::steady_clock::now();
   if (nreads > 0xFFFFFFF0ull) { mm2_set_error("too many reads in one batch"); return MM2_E_ARG; }
@@ -499,10 +523,17 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
       const size_t mid = nreads / 2;
       mm2_map_result_t part[2];
       memset(part, 0, sizeof part);
+      const size_t first[2] = {0, mid};
+      if (rec_dst) {
+        int rc = map_device_impl(ctx, idx, d_cat, d_off, h_off, mid, o, &part[0], true, rec_dst, read_id_base);
+        if (rc == MM2_OK) rc = map_device_impl(ctx, idx, d_cat, d_off + mid, h_off + mid, nreads - mid, o, &part[1], true, rec_dst + mid, read_id_base + (u32)mid);
+        if (rc != MM2_OK) { part[0].recs = part[1].recs = nullptr; mm2_map_result_free(&part[0]); mm2_map_result_free(&part[1]); return rc; }
+        merge_in_place(part, first, 2, rec_dst, out);
+        return MM2_OK;
+      }
       int rc = map_device_impl(ctx, idx, d_cat, d_off, h_off, mid, o, &part[0], true);
       if (rc == MM2_OK) rc = map_device_impl(ctx, idx, d_cat, d_off + mid, h_off + mid, nreads - mid, o, &part[1], true);
       if (rc != MM2_OK) { mm2_map_result_free(&part[0]); mm2_map_result_free(&part[1]); return rc; }
-      const size_t first[2] = {0, mid};
       merge_map_results(part, first, 2, out);
       return MM2_OK;
     }
@@ -553,7 +584,7 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
   // ---- records (paf.rs:130-222) ---------------------------------------------------------------------------------------------
   memset(out, 0, sizeof *out);
   out->n_reads = nreads; out->n_bases = nreads ? h_off[nreads] - h_off[0] : 0; out->n_minimizers = nm; out->n_anchors = na;
-  out->recs = (mm2_paf_rec_t*)g_rec_cache.take(std::max<size_t>(1, nreads) * sizeof(mm2_paf_rec_t));
+  out->recs = rec_dst ? rec_dst : (mm2_paf_rec_t*)g_rec_cache.take(std::max<size_t>(1, nreads) * sizeof(mm2_paf_rec_t));
   std::vector<u32> panics;
   size_t nr = 0;
   {
@@ -574,9 +605,9 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
       for (size_t r = lo; r < hi; ++r) {
         const ReadHit& h = hits[r];
         if (h.flags & 1u) presc[(size_t)t] += 1;
-        const int kind = build_record(idx, h, (u32)r, (i32)(h_off[r + 1] - h_off[r]), *dst);
+        const int kind = build_record(idx, h, (u32)r + read_id_base, (i32)(h_off[r + 1] - h_off[r]), *dst);
         if (kind == 1) ++dst;
-        else if (kind == 2) ppan[(size_t)t].push_back((u32)r);
+        else if (kind == 2) ppan[(size_t)t].push_back((u32)r + read_id_base);
       }
     };
     auto run = [&](auto fn) {
@@ -721,6 +752,10 @@ static int map_host_pipelined(mm2_ctx* ctx, const mm2_index* idx, const u8* cat,
   int rc[4] = {MM2_OK, MM2_OK, MM2_OK, MM2_OK};
   std::string err[4];
   std::vector<std::vector<float>> ms_sum(4);
+  // one record array for the whole batch, written in place by the workers (the default path reports at most one chain per
+  // read); the general multi-chain tail keeps per-part arrays that are concatenated afterwards
+  const bool direct = !(opts->min_cnt < 2 || opts->w != idx->w || opts->k != idx->k);
+  mm2_paf_rec_t* final_recs = direct ? (mm2_paf_rec_t*)g_rec_cache.take(std::max<size_t>(1, nreads) * sizeof(mm2_paf_rec_t)) : nullptr;
   std::atomic<size_t> n_issued{0};   // sub-batches whose upload (and event) has been enqueued on the copy stream
   std::atomic<int> copy_rc{MM2_OK};
   auto work = [&](int w) {
@@ -731,7 +766,8 @@ static int map_host_pipelined(mm2_ctx* ctx, const mm2_index* idx, const u8* cat,
       while (n_issued.load(std::memory_order_acquire) <= sidx && copy_rc.load() == MM2_OK) std::this_thread::yield();
       if (copy_rc.load() != MM2_OK) { rc[w] = copy_rc.load(); err[w] = "host to device copy failed"; return; }
       if (cudaStreamWaitEvent(c->stream, ctx->copy_events[sidx], 0) != cudaSuccess) { rc[w] = MM2_E_CUDA; err[w] = "cudaStreamWaitEvent failed"; return; }
-      const int r = map_device_impl(c, idx, ctx->seq.as<u8>(), ctx->seq_off.as<u64>() + lo, h_off0 + lo, hi - lo, opts, &part[sidx], false);
+      const int r = map_device_impl(c, idx, ctx->seq.as<u8>(), ctx->seq_off.as<u64>() + lo, h_off0 + lo, hi - lo, opts, &part[sidx], false,
+                                    final_recs ? final_recs + lo : nullptr, final_recs ? (u32)lo : 0u);
       if (r != MM2_OK) { rc[w] = r; err[w] = mm2_last_error(); return; }
       if (ms_sum[w].size() < c->timer.ms.size()) ms_sum[w].resize(c->timer.ms.size(), 0.f);
       for (size_t i = 0; i < c->timer.ms.size(); ++i) ms_sum[w][i] += c->timer.ms[i];
@@ -758,7 +794,8 @@ static int map_host_pipelined(mm2_ctx* ctx, const mm2_index* idx, const u8* cat,
   ctx->launches += l1 - l0;
   for (int w = 0; w < NW; ++w)
     if (rc[w] != MM2_OK) {
-      for (auto& p : part) mm2_map_result_free(&p);
+      for (auto& p : part) { if (final_recs) p.recs = nullptr; mm2_map_result_free(&p); }
+      g_rec_cache.give(final_recs);
       mm2_set_error("%s", err[w].c_str());
       return rc[w];
     }
@@ -771,7 +808,8 @@ static int map_host_pipelined(mm2_ctx* ctx, const mm2_index* idx, const u8* cat,
   ctx->timer.names_blob.clear();
   for (size_t i = 0; i < ctx->timer.ms.size() && i < ctx->timer.names.size(); ++i) { ctx->timer.names_blob += ctx->timer.names[i]; ctx->timer.names_blob.push_back('\0'); }
   ctx->timer.names_blob.push_back('\0');
-  merge_map_results(part.data(), cut.data(), nsub, out);
+  if (final_recs) merge_in_place(part.data(), cut.data(), nsub, final_recs, out);
+  else merge_map_results(part.data(), cut.data(), nsub, out);
   return MM2_OK;
 }
 
