@@ -724,7 +724,7 @@ static int map_host_pipelined(mm2_ctx* ctx, const mm2_index* idx, const u8* cat,
     if (!ctx->worker[w]) MM2_TRY(mm2_ctx_create(ctx->device, &ctx->worker[w]));
   CUDA_TRY(cudaSetDevice(ctx->device));
   if (!ctx->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-  while (ctx->copy_events.size() < nsub) {
+  while (ctx->copy_events.size() < nsub + 1) {   // + 1: the first sub-batch may be split below
     cudaEvent_t e;
     CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     ctx->copy_events.push_back(e);
@@ -739,11 +739,14 @@ static int map_host_pipelined(mm2_ctx* ctx, const mm2_index* idx, const u8* cat,
   MM2_TRY(ctx->pin_in.ensure((nreads + 1) * 8));
   u64* h_off0 = ctx->pin_in.as<u64>();
   for (size_t i = 0; i <= nreads; ++i) h_off0[i] = offs[i] - base;
-  // sub-batch boundaries balanced by bases
+  // sub-batch boundaries balanced by bases; the first sub-batch is split 1/4 + 3/4 so that the kernels start after a quarter
+  // of a sub-batch has been uploaded instead of a whole one
+  const size_t nunit = nsub;
+  if (nsub >= 4) nsub += 1;
   std::vector<size_t> cut(nsub + 1, nreads);
   cut[0] = 0;
   for (size_t sidx = 1; sidx < nsub; ++sidx) {
-    const u64 target = total * sidx / nsub;
+    const u64 target = nsub == nunit ? total * sidx / nunit : (sidx == 1 ? total / (4 * nunit) : total * (sidx - 1) / nunit);
     cut[sidx] = (size_t)(std::lower_bound(h_off0, h_off0 + nreads + 1, target) - h_off0);
     if (cut[sidx] < cut[sidx - 1]) cut[sidx] = cut[sidx - 1];
   }
