@@ -228,7 +228,7 @@ __device__ __forceinline__ void seed_hits_read(const SeedHitArgs& G, const u32 r
 // threshold); reads that need the exact filter go on the list, all others are looked up right away.
 // MODE 1: the reads on the list, after filter_list_kernel wrote their keep flags.
 template <int MODE>
-__global__ void __launch_bounds__(SH_NT, 12) seed_hits_kernel(SeedHitArgs G) {
+__global__ void __launch_bounds__(SH_NT, 16) seed_hits_kernel(SeedHitArgs G) {
   __shared__ u32 s_bins[MODE == 0 ? 2048 : 1];
   __shared__ u32 s_red[SH_NT / 32];
   __shared__ u32 s_nh;
@@ -479,7 +479,7 @@ __device__ __forceinline__ void anchor_msort_read(ulonglong2* __restrict__ ancho
 
 // LIST = false: CTA r sorts read r if lo_excl < n <= hi_incl.  LIST = true: the CTAs walk a device-built list of reads.
 template <int NT, bool FUSED, bool LIST>
-__global__ void __launch_bounds__(NT, NT >= 512 ? 2 : 1) anchor_msort_kernel(ulonglong2* __restrict__ anchors, const u64* __restrict__ read_aoff, u32 nreads,
+__global__ void __launch_bounds__(NT, NT >= 512 ? 2 : 12) anchor_msort_kernel(ulonglong2* __restrict__ anchors, const u64* __restrict__ read_aoff, u32 nreads,
                                                           u32 lo_excl, u32 hi_incl, HitSrc H, const u32* __restrict__ list,
                                                           const u32* __restrict__ n_list) {
   extern __shared__ __align__(16) unsigned char as_smem[];
