@@ -423,22 +423,45 @@ int index_build_device(mm2_ctx* ctx, const u8* h_cat, const u64* h_off, const ch
   for (size_t i = 0; i <= nseq && nseq; ++i) off0[i] = h_off[i] - h_off[0];
   IB_TRY(ctx->seq.ensure(total + 64));
   IB_TRY(ctx->seq_off.ensure((nseq + 1) * 8));
-  if (total) IB_CUDA(cudaMemcpyAsync(ctx->seq.p, h_cat + (nseq ? h_off[0] : 0), total, cudaMemcpyHostToDevice, st));
-  IB_CUDA(cudaMemcpyAsync(ctx->seq_off.p, off0.data(), (nseq + 1) * 8, cudaMemcpyHostToDevice, st));
-  IB_CUDA(cudaStreamSynchronize(st));  // off0 is a stack vector
+  IB_TRY(ctx->pin_in.ensure((nseq + 1) * 8));
+  memcpy(ctx->pin_in.p, off0.data(), (nseq + 1) * 8);   // pinned bounce: the copy below must not need a stream sync
+  IB_CUDA(cudaMemcpyAsync(ctx->seq_off.p, ctx->pin_in.p, (nseq + 1) * 8, cudaMemcpyHostToDevice, st));
+  // The genome goes up in chunks on the copy stream, an event after each; the sketch kernel is launched once per chunk on the
+  // tiles that are already resident (sketch_device, SketchFeed), so the 2.6 ms upload of a 145 Mbp genome overlaps the
+  // sketch instead of preceding it.
+  if (!ctx->copy_stream) IB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  const int nchunks = (int)std::max<u64>(1, std::min<u64>(8, total / (16ull << 20)));
+  while (ctx->copy_events.size() < (size_t)nchunks) {
+    cudaEvent_t e;
+    IB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->copy_events.push_back(e);
+  }
+  std::vector<u64> chunk_end((size_t)nchunks, total);
+  {
+    const u8* src = h_cat + (nseq ? h_off[0] : 0);
+    u64 b0 = 0;
+    for (int c = 0; c < nchunks; ++c) {
+      const u64 b1 = c + 1 == nchunks ? total : ((total * (u64)(c + 1) / (u64)nchunks) & ~(u64)15);
+      chunk_end[(size_t)c] = b1;
+      if (b1 > b0) IB_CUDA(cudaMemcpyAsync(ctx->seq.as<u8>() + b0, src + b0, b1 - b0, cudaMemcpyHostToDevice, ctx->copy_stream));
+      IB_CUDA(cudaEventRecord(ctx->copy_events[(size_t)c], ctx->copy_stream));
+      b0 = b1;
+    }
+  }
   IB_TRY(idx->seq_len.ensure(std::max<size_t>(1, nseq) * 4));
   if (nseq) IB_CUDA(cudaMemcpyAsync(idx->seq_len.p, idx->lens.data(), nseq * 4, cudaMemcpyHostToDevice, st));
-  ctx->timer.mark(st, "pack");
   const u64 words_used = (total + 7) / 8;
   idx->S_words_alloc = total ? kroundup64((size_t)words_used) : 0;
   IB_TRY(idx->S.ensure(std::max<u64>(1, idx->S_words_alloc) * 4));
+  ctx->timer.mark(st, "sketch");
+  SketchOut so;
+  SketchFeed feed{nchunks, chunk_end.data(), ctx->copy_events.data()};
+  IB_TRY(sketch_device(ctx, ctx->seq.as<u8>(), ctx->seq_off.as<u64>(), off0.data(), nseq, w, k, 0, 1, flag & 1, &so, &feed));
+  ctx->timer.mark(st, "pack");   // every chunk has been waited for on this stream by now
   if (idx->S_words_alloc) {
     MM2_LAUNCH(ctx, pack_seq4_kernel, grid_for(idx->S_words_alloc), 256, 0, ctx->seq.as<u8>(), total, idx->S.as<u32>(), idx->S_words_alloc);
     IB_CUDA(cudaGetLastError());
   }
-  ctx->timer.mark(st, "sketch");
-  SketchOut so;
-  IB_TRY(sketch_device(ctx, ctx->seq.as<u8>(), ctx->seq_off.as<u64>(), off0.data(), nseq, w, k, 0, 1, flag & 1, &so));
   ctx->timer.mark(st, "sort");
   IB_TRY(index_finish_from_minimizers(ctx, idx, so.total));
   ctx->timer.mark(st, "end");

@@ -203,8 +203,11 @@ struct SketchOut {  // device SoA minimizers of a batch
 };
 // Sketch nseq sequences resident on the device (d_cat/d_off) into ctx->mkey/mval/mini_off.  h_off is the host copy
 // of the offsets.  Synchronises the stream once (to learn the total / handle capacity overflow).
+// feed (optional): d_cat is still being uploaded by another stream; ev[c] fires when bytes [0, chunk_end[c]) of it (relative
+// to the first sequence) are resident.  The tile kernel is then launched once per chunk so that it overlaps the upload.
+struct SketchFeed { int nchunks; const u64* chunk_end; cudaEvent_t* ev; };
 int sketch_device(mm2_ctx* ctx, const u8* d_cat, const u64* d_off, const u64* h_off, size_t nseq, int w, int k,
-                  u32 rid_base, u32 rid_step, int is_hpc, SketchOut* out);
+                  u32 rid_base, u32 rid_step, int is_hpc, SketchOut* out, const SketchFeed* feed = nullptr);
 
 int index_build_device(mm2_ctx* ctx, const u8* h_cat, const u64* h_off, const char* const* names, size_t nseq, int w,
                        int k, int b, int flag, mm2_index** out);

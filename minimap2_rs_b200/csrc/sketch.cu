@@ -40,6 +40,7 @@ struct SketchParams {
   u64* seq_out_off;       // nseq+1
   u64* tile_status;       // ntiles, zero-initialised; [63:62] 1 = aggregate, 2 = inclusive prefix
   u32* ticket;            // zero-initialised
+  u32 tile_base;          // first tile of this launch (tickets count from it; v3 kernel only, 0 elsewhere)
 };
 
 // invertible integer mix of sketch.rs:4-13, in the narrowest type that holds 2k bits
@@ -864,7 +865,7 @@ __global__ void __launch_bounds__(SK_NT + 32, sizeof(KT) == 4 ? MM2_SK3_OCC : 3)
 
   // Tiles are handed out in order (the look-back needs every earlier tile to be running or done); the next ticket is
   // taken just before this tile's count is published.
-  if (tid == 0) s_next[0] = atomicAdd(P.ticket, 1u);
+  if (tid == 0) s_next[0] = P.tile_base + atomicAdd(P.ticket, 1u);
   sk3_bar_compute();
   u32 tile = s_next[0];
   u32 it = 0;
@@ -1077,7 +1078,7 @@ __global__ void __launch_bounds__(SK_NT + 32, sizeof(KT) == 4 ? MM2_SK3_OCC : 3)
       if ((tid & 31) >= d) inc += tt;
     }
     if ((tid & 31) == 31) s_wsum[tid >> 5] = inc;
-    if (tid == 0) s_next[par ^ 1] = atomicAdd(P.ticket, 1u);
+    if (tid == 0) s_next[par ^ 1] = P.tile_base + atomicAdd(P.ticket, 1u);
     sk3_bar_compute();
     const u32 next_tile = s_next[par ^ 1];
     u32 wbase = 0, tile_count = 0;
@@ -1332,7 +1333,7 @@ static int num_sms(int device) {
 }
 
 int sketch_device(mm2_ctx* ctx, const u8* d_cat, const u64* d_off, const u64* h_off, size_t nseq, int w, int k,
-                  u32 rid_base, u32 rid_step, int is_hpc, SketchOut* out) {
+                  u32 rid_base, u32 rid_step, int is_hpc, SketchOut* out, const SketchFeed* feed) {
   if (!(w > 0 && w < 256) || !(k > 0 && k <= 28)) { mm2_set_error("sketch: need 0<w<256 and 0<k<=28 (sketch.rs:31-32)"); return MM2_E_ARG; }
   if (nseq == 0) { out->key = out->val = nullptr; out->seq_off = nullptr; out->total = 0; return MM2_OK; }
   if (nseq >= 0xFFFFFFFFull) { mm2_set_error("sketch: too many sequences"); return MM2_E_ARG; }
@@ -1355,7 +1356,7 @@ int sketch_device(mm2_ctx* ctx, const u8* d_cat, const u64* d_off, const u64* h_
     // queue behind another context's bulk read upload on the copy engine and stall this stream)
     MM2_TRY(ctx->tile_first.ensure((nseq + 4) * 8 + (nseq + 8) * 4));
     MM2_TRY(ctx->tile_seq.ensure((size_t)ntiles * 4));
-    MM2_TRY(ctx->tile_status.ensure((size_t)ntiles * 8 + 16));
+    MM2_TRY(ctx->tile_status.ensure((size_t)ntiles * 8 + 16 + 4 * 64));   // + one ticket counter per launch of a fed sketch
     u64* d_tf64 = ctx->tile_first.as<u64>();
     u32* d_tcnt = (u32*)((u8*)ctx->tile_first.p + ((((nseq + 2) * 8) + 15) / 16) * 16);  // 16-byte aligned for the scan's vector loads
     MM2_LAUNCH(ctx, tile_count_kernel, (int)((nseq + 255) / 256), 256, 0, d_off, (u32)nseq, T, d_tcnt);
@@ -1365,8 +1366,9 @@ int sketch_device(mm2_ctx* ctx, const u8* d_cat, const u64* d_off, const u64* h_
     for (int attempt = 0; attempt < 2; ++attempt) {
       MM2_TRY(ctx->mkey.ensure(cap * 8));
       MM2_TRY(ctx->mval.ensure(cap * 8));
-      CUDA_TRY(cudaMemsetAsync(ctx->tile_status.p, 0, (size_t)ntiles * 8 + 16, st));
+      CUDA_TRY(cudaMemsetAsync(ctx->tile_status.p, 0, (size_t)ntiles * 8 + 16 + 4 * 64, st));
       SketchParams P;
+      P.tile_base = 0;
       P.seq = d_cat; P.seq_off = d_off; P.buf_len = h_off[nseq];
       P.tile_seq = ctx->tile_seq.as<u32>(); P.tile_first = d_tf64;
       P.nseq = (u32)nseq; P.ntiles = ntiles; P.w = w; P.k = k;
@@ -1377,8 +1379,37 @@ int sketch_device(mm2_ctx* ctx, const u8* d_cat, const u64* d_off, const u64* h_
       P.tile_status = ctx->tile_status.as<u64>();
       P.ticket = (u32*)((u8*)ctx->tile_status.p + (size_t)ntiles * 8);
       const int grid = (int)std::min<u64>(ntiles, (u64)num_sms(ctx->device) * (MM2_SK_OCC + 1));
-      if (w >= 9) {  // version 2: per-thread prefix/suffix window minima
-        static const bool use_v2 = [] { const char* e = getenv("MM2_SKETCH"); return e && !strcmp(e, "v2"); }();   // comparison arm
+      static const bool use_v2 = [] { const char* e = getenv("MM2_SKETCH"); return e && !strcmp(e, "v2"); }();   // comparison arm
+      if (feed && attempt == 0 && w >= 9 && !use_v2 && feed->nchunks >= 1 && feed->nchunks <= 64) {
+        // The sequence is still being uploaded (index build): one launch per uploaded chunk over the tiles that lie entirely
+        // inside it.  The launches share the tile status array, so the look-back of a launch's first tile finds the
+        // inclusive prefix the previous launch left; every launch has its own ticket counter.
+        u32 t_prev = 0;
+        for (int c = 0; c < feed->nchunks; ++c) {
+          u64 t_end = ntiles;
+          if (c + 1 < feed->nchunks) {
+            const u64 B = feed->chunk_end[c];
+            t_end = 0;
+            for (size_t q = 0; q < nseq; ++q) {
+              const u64 so = h_off[q] - h_off[0], len = h_off[q + 1] - h_off[q];
+              const u64 ntq = std::max<u64>(1, (len + T - 1) / T);
+              if (so + len + 16 <= B) { t_end += ntq; continue; }
+              if (B > so + 16) t_end += std::min<u64>(ntq - 1, (B - so - 16) / (u64)T);   // tiles that end (with a 16-byte margin) below B
+              break;                                                                   // later sequences lie above B
+            }
+          }
+          CUDA_TRY(cudaStreamWaitEvent(st, feed->ev[c], 0));
+          if (t_end > t_prev) {
+            P.tile_base = t_prev; P.ntiles = (u32)t_end;
+            P.ticket = (u32*)((u8*)ctx->tile_status.p + (size_t)ntiles * 8 + 16) + c;
+            const int g = (int)std::min<u64>(t_end - t_prev, (u64)num_sms(ctx->device) * (MM2_SK_OCC + 1));
+            if (k <= 15) MM2_LAUNCH(ctx, sketch_tile_kernel_v3<u32>, g, SK_NT + 32, 0, P);
+            else MM2_LAUNCH(ctx, sketch_tile_kernel_v3<u64>, g, SK_NT + 32, 0, P);
+            t_prev = (u32)t_end;
+          }
+        }
+      } else if (w >= 9) {  // version 2: per-thread prefix/suffix window minima
+        if (feed && attempt == 0) for (int c = 0; c < feed->nchunks; ++c) CUDA_TRY(cudaStreamWaitEvent(st, feed->ev[c], 0));
         if (use_v2) {
           if (k <= 15) MM2_LAUNCH(ctx, sketch_tile_kernel_v2<u32>, grid, SK_NT, 0, P);
           else MM2_LAUNCH(ctx, sketch_tile_kernel_v2<u64>, grid, SK_NT, 0, P);
@@ -1387,6 +1418,7 @@ int sketch_device(mm2_ctx* ctx, const u8* d_cat, const u64* d_off, const u64* h_
           else MM2_LAUNCH(ctx, sketch_tile_kernel_v3<u64>, grid, SK_NT + 32, 0, P);
         }
       } else {
+        if (feed && attempt == 0) for (int c = 0; c < feed->nchunks; ++c) CUDA_TRY(cudaStreamWaitEvent(st, feed->ev[c], 0));
         if (k <= 15) MM2_LAUNCH(ctx, sketch_tile_kernel<u32>, grid, SK_NT, 0, P);
         else MM2_LAUNCH(ctx, sketch_tile_kernel<u64>, grid, SK_NT, 0, P);
       }
@@ -1400,6 +1432,7 @@ int sketch_device(mm2_ctx* ctx, const u8* d_cat, const u64* d_off, const u64* h_
     }
   } else {
     // literal path: count, scan, write
+    if (feed) for (int c = 0; c < feed->nchunks; ++c) CUDA_TRY(cudaStreamWaitEvent(st, feed->ev[c], 0));
     MM2_TRY(ctx->misc.ensure((nseq + 1) * 8 + nseq * 2 * (size_t)w * 8));
     u64* d_counts = ctx->misc.as<u64>();
     u64* d_win = d_counts + nseq + 1;
