@@ -58,6 +58,7 @@ extern "C" int mm2_ctx_create(int device, mm2_ctx_t** out) {
   if (e != cudaSuccess) { delete c; mm2_set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); return MM2_E_CUDA; }
   c->own_stream = true;
   { const char* e = getenv("MM2_PIPELINE"); if (e && atoi(e) == 0) c->pipeline = false; }
+  { const char* e = getenv("MM2_SYNC"); if (e && !strcmp(e, "block")) c->block_sync = true; }
   { const char* e = getenv("MM2_WORKERS"); if (e && atoi(e) >= 2 && atoi(e) <= 4) c->n_workers = atoi(e); }
   { const char* e = getenv("MM2_SUBBATCH_MB"); if (e && atoi(e) > 0) c->subbatch_bytes = (u64)atoi(e) << 20; }
   // test hook: MM2_CHAIN_DENSE_MIN=n sends every read with >= n anchors to the CTA-per-read chaining kernel
@@ -79,6 +80,7 @@ extern "C" void mm2_ctx_destroy(mm2_ctx_t* c) {
   c->pin_in.release(); c->pin_out.release(); c->pin_small.release(); c->pin_scalar.release();
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   for (int w = 0; w < 4; ++w) if (c->worker[w]) mm2_ctx_destroy(c->worker[w]);
+  if (c->sync_event) { cudaEventDestroy(c->sync_event); c->sync_event = nullptr; }
   for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
   c->copy_events.clear();
   if (c->copy_stream) { cudaStreamDestroy(c->copy_stream); c->copy_stream = nullptr; }
@@ -576,7 +578,7 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
   if (nreads && hits_copy) CUDA_TRY(cudaMemcpyAsync(hits, ctx->hits.p, nreads * sizeof(ReadHit), cudaMemcpyDeviceToHost, st));
   ctx->timer.mark(st, "end");
   mm2_trace(ctx, "chain issued");
-  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(mm2_stream_wait(ctx));
   mm2_trace(ctx, "chain+d2h done");
   ctx->timer.finish();
   const auto wall1 = std::chrono::steady_clock::now();

@@ -131,6 +131,8 @@ struct mm2_ctx {
   mm2_ctx* worker[4] = {nullptr, nullptr, nullptr, nullptr};  // sub-batch pipeline of mm2_map_batch (host buffers)
   cudaStream_t copy_stream = nullptr;             // uploads of the pipelined host path
   std::vector<cudaEvent_t> copy_events;           // one per sub-batch
+  bool block_sync = false;                         // MM2_SYNC=block: sleep in the three per-batch waits instead of spinning
+  cudaEvent_t sync_event = nullptr;
   int n_workers = 4;
   bool pipeline = true;
   u64 subbatch_bytes = 64ull << 20;
@@ -140,6 +142,15 @@ struct mm2_ctx {
   int chain_dense_min = 4096, chain_dense_ratio5 = 2;
   u64 mg_sorted_n = 0;  // records left in sort_keys2/sort_vals2 by mm2_mg_sketch_sort
 };
+
+// The waits of the mapping path (minimizer total, anchor total, end of the batch).  cudaStreamSynchronize spins a host core; with
+// several ranks x 5 threads on one box that oversubscribes the cores, so MM2_SYNC=block waits on a blocking event instead.
+inline cudaError_t mm2_stream_wait(mm2_ctx* ctx) {
+  if (!ctx->block_sync) return cudaStreamSynchronize(ctx->stream);
+  if (!ctx->sync_event) { cudaError_t e = cudaEventCreateWithFlags(&ctx->sync_event, cudaEventBlockingSync | cudaEventDisableTiming); if (e != cudaSuccess) return e; }
+  cudaError_t e = cudaEventRecord(ctx->sync_event, ctx->stream);
+  return e != cudaSuccess ? e : cudaEventSynchronize(ctx->sync_event);
+}
 
 #define MM2_LAUNCH(ctx, kern, grid, block, smem, ...)                         \
   do {                                                                         \

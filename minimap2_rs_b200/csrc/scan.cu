@@ -109,7 +109,7 @@ int scan_u32_to_u64(mm2_ctx* ctx, const u32* d_in, u64* d_out, size_t n, bool wi
 int read_scalar_u64(mm2_ctx* ctx, const u64* d_src, u64* out) {
   MM2_TRY(ctx->pin_scalar.ensure(64));
   CUDA_TRY(cudaMemcpyAsync(ctx->pin_scalar.p, d_src, 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(mm2_stream_wait(ctx));
   *out = *ctx->pin_scalar.as<u64>();
   return MM2_OK;
 }

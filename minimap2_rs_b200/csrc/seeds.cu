@@ -678,7 +678,7 @@ int seeds_hits(mm2_ctx* ctx, const IndexView& V, const u64* d_mkey, const u64* d
   MM2_TRY(scan_u32_to_u64(ctx, ctx->read_na.as<u32>(), d_aoff, nreads, true));
   MM2_TRY(ctx->pin_scalar.ensure(64));
   CUDA_TRY(cudaMemcpyAsync(ctx->pin_scalar.p, d_aoff + nreads, 16, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(mm2_stream_wait(ctx));
   const u64 total = ctx->pin_scalar.as<u64>()[0];
   const u32 err = (u32)(ctx->pin_scalar.as<u64>()[1] >> 32);
   if (err) { mm2_set_error("a read has 2^32 or more anchors"); return MM2_E_OOM; }
