@@ -770,6 +770,9 @@ __global__ void __launch_bounds__(SK_NT, sizeof(KT) == 4 ? MM2_SK_OCC : 4) sketc
 #ifndef MM2_SK3_OCC
 #define MM2_SK3_OCC 5
 #endif
+#ifndef MM2_SK3_OCC64
+#define MM2_SK3_OCC64 4   // 64-bit keys (k > 15): 56 registers; measured 13.55 / 13.16 ms per Gbase of HiFi reads at 3 / 4
+#endif
 constexpr int SK3_BAR_COMPUTE = 1, SK3_BAR_FULL = 2, SK3_BAR_EMPTY = 4, SK3_BAR_BASE = 6;
 __device__ __forceinline__ void sk3_bar_compute() { asm volatile("bar.sync %0, %1;" ::"n"(SK3_BAR_COMPUTE), "n"(SK_NT) : "memory"); }
 __device__ __forceinline__ void sk3_bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(SK_NT + 32) : "memory"); }
@@ -788,7 +791,7 @@ __device__ __noinline__ u32 sk3_stage_dups(const KT* s_key, const u8* s_z, int l
   return idx;
 }
 template <class KT>
-__global__ void __launch_bounds__(SK_NT + 32, sizeof(KT) == 4 ? MM2_SK3_OCC : 3) sketch_tile_kernel_v3(SketchParams P) {
+__global__ void __launch_bounds__(SK_NT + 32, sizeof(KT) == 4 ? MM2_SK3_OCC : MM2_SK3_OCC64) sketch_tile_kernel_v3(SketchParams P) {
   constexpr int PAD = KeyTraits<KT>::PAD;
   constexpr KT KMAX = (KT)~(KT)0;
 #define KIDX(u) ((u) + ((u) >> PAD))
