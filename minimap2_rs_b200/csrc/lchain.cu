@@ -417,7 +417,7 @@ __global__ void chain_classify_kernel(ChainArgs G) {
 // it posts the anchor here and all NW warps evaluate the next 32 tiles (1024 predecessors) of the window in parallel.
 // Window ring of a dense read in shared memory: the static fields and the DP result (f, pprev) of the last DENSE_CAP
 // anchors that have left the register ring, slot = j % DENSE_CAP, plus one mark bit per slot (lchain.rs:86 `t[pprev] = i`,
-// cleared for every anchor).  Every far predecessor of a window of at most max_chain_iter <= DENSE_CAP - 64 anchors is in
+// see `tg`).  Every far predecessor of a window of at most max_chain_iter <= DENSE_CAP - 64 anchors is in
 // there, so a DP cell costs shared-memory loads instead of L2 round trips (the kernel was bound by those: 48 B per cell,
 // 2,800 cells per anchor on configs[4]).  Larger max_chain_iter values fall back to the arrays in global memory.
 #ifdef MM2_DENSE_PROF
@@ -438,7 +438,10 @@ struct DenseSh {
   u32 hi_i;
   u32 next;                    // next dense read of this CTA
   int use_sm;                  // the window ring below is in use (max_chain_iter fits)
-  int* sx; int* sq; int* sf; int* sp; u8* ss; u32* mk;   // DENSE_CAP entries each (mk: DENSE_CAP / 32 words)
+  int* sx; int* sq; int* sf; int* sp; u8* ss;   // DENSE_CAP entries each
+  u16* tg;                      // mark of lchain.rs:86 per slot: tag of the last anchor that marked it (0 = none); tag(i) = i % 65535 + 1
+                                // is unique among the anchors that can have marked a live slot, so nothing is cleared per anchor
+  int tag;                      // tag of the anchor being evaluated
   u32 V[32], M[32], ACT[32];   // per tile: ballots of "has a score", "t[j] == i", "inside the window"
   int tmax[32];                // per tile: best score
   int sc[32][33];
@@ -459,20 +462,35 @@ __device__ __forceinline__ void dense_eval_round(const ChainArgs& G, DenseSh* sh
   if (sh->use_sm) {
     const int* __restrict__ sx = sh->sx; const int* __restrict__ sq = sh->sq; const int* __restrict__ sf = sh->sf;
     const int* __restrict__ sp = sh->sp; const u8* __restrict__ ss = sh->ss;
-    u32* mk = sh->mk;
+    u16* tg = sh->tg;
+    const u16 tag = (u16)sh->tag;
+    const float pen_gap = G.p.chn_pen_gap, pen_skip = G.p.chn_pen_skip;
+    const float* __restrict__ half_log = G.half_log;
+    int slot_b = jb % DENSE_CAP;                                    // slots go down with j and wrap at most once (window <= DENSE_CAP)
+    // The cells of one lane are written without branches (comput_sc's early returns become one predicate, lchain.rs:17-34), so
+    // that the loads and the arithmetic of the TPW cells overlap instead of running one after the other.
 #pragma unroll
     for (int u = 0; u < TPW; ++u) {
-      const int j = jb - 32 * (wid + NW * u) - lane;
-      sc2[u] = NEG_INF; v2[u] = false;
-      if (j >= start_j) {                                           // same rid/strand as anchor i: start_j is inside its block
-        const int slot = j % DENSE_CAP;
-        int s0;
-        if (chain_sc(ri, qi, sx[slot], sq[slot], (int)ss[slot], mdx, mdy, bw, G.p.chn_pen_gap, G.p.chn_pen_skip, G.half_log, s0)) {
-          sc2[u] = wadd(s0, sf[slot]);
-          v2[u] = true;
-          const int pp = sp[slot];
-          if (pp >= start_j) { const int ps = pp % DENSE_CAP; atomicOr(&mk[ps >> 5], 1u << (ps & 31)); }   // lchain.rs:86; marks below the window are never read
-        }
+      const int back = 32 * (wid + NW * u) + lane;                  // j = jb - back
+      const int j = jb - back;
+      const bool act = j >= start_j;                                // same rid/strand as anchor i: start_j is inside its block
+      int slot = slot_b - back; if (slot < 0) slot += DENSE_CAP;
+      if (!act) slot = 0;
+      const int rj = sx[slot], qj = sq[slot], span_j = (int)ss[slot], fj = sf[slot], pp = sp[slot];
+      const int dq = wsub(qi, qj), dr = wsub(ri, rj);
+      int dd = wsub(dr, dq); if (dd < 0) dd = wsub(0, dd);
+      const bool ok = act && dq > 0 && dq <= mdx && dr != 0 && dq <= mdy && dd <= bw && dd >= 0;
+      const int dg = min(dr, dq);
+      int s0 = min(span_j, dg);
+      const int ddc = ok ? dd : 0;
+      const float lin = __fadd_rn(__fmul_rn(pen_gap, (float)ddc), __fmul_rn(pen_skip, (float)dg));
+      const int pen = __float2int_rz(__fadd_rn(lin, half_log[ddc]));
+      if (ddc != 0 || dg > span_j) s0 = wsub(s0, pen);
+      sc2[u] = ok ? wadd(s0, fj) : NEG_INF;
+      v2[u] = ok;
+      if (ok && pp >= start_j) {                                    // lchain.rs:86; marks below the window are never read
+        int ps = slot - (j - pp); if (ps < 0) ps += DENSE_CAP;
+        tg[ps] = tag;
       }
     }
     dense_bar<NW>();                                                // every mark of this round is visible
@@ -481,7 +499,7 @@ __device__ __forceinline__ void dense_eval_round(const ChainArgs& G, DenseSh* sh
       const int t = wid + NW * u;
       const int j = jb - 32 * t - lane;
       bool tm = false;
-      if (v2[u]) { const int slot = j % DENSE_CAP; tm = (mk[slot >> 5] >> (slot & 31)) & 1u; }
+      if (v2[u]) { int slot = slot_b - 32 * t - lane; if (slot < 0) slot += DENSE_CAP; tm = tg[slot] == tag; }
       const u32 Vb = __ballot_sync(0xFFFFFFFFu, v2[u]), Mb = __ballot_sync(0xFFFFFFFFu, tm), Ab = __ballot_sync(0xFFFFFFFFu, j >= start_j);
       const int tmx = __reduce_max_sync(0xFFFFFFFFu, sc2[u]);
       sh->sc[t][lane] = sc2[u];
@@ -562,7 +580,7 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
     use_sm = max_iter <= DENSE_CAP - 64;
     if (wid == 0 && lane == 0) sh->use_sm = use_sm ? 1 : 0;
     if (use_sm) {
-      for (int x = wid * 32 + lane; x < DENSE_CAP / 32; x += NW * 32) sh->mk[x] = 0;
+      for (int x = wid * 32 + lane; x < DENSE_CAP; x += NW * 32) sh->tg[x] = 0;
     } else {
       for (int x = wid * 32 + lane; x < n; x += NW * 32) T[x] = -1;
     }
@@ -716,11 +734,11 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
                 break;
               }
             }
-            // marks of this anchor start from a clean mask; the ring slots mark their in-window predecessors
-            for (int x = lane; x < DENSE_CAP / 32; x += 32) sh->mk[x] = 0;
-            __syncwarp();
+            // the ring slots mark their in-window predecessors with this anchor's tag
             const int sj = low_iter > lo ? low_iter : lo;
-            if (valid && rpp >= sj && rpp < hi_known) { const int ps = rpp % DENSE_CAP; atomicOr(&sh->mk[ps >> 5], 1u << (ps & 31)); }
+            const int tag = i % 65535 + 1;
+            if (lane == 0) sh->tag = tag;
+            if (valid && rpp >= sj && rpp < hi_known) sh->tg[rpp % DENSE_CAP] = (u16)tag;
           } else {
           if (valid && rpp >= 0 && rpp < hi_known) T[rpp] = mark;   // marks of the ring slots on older anchors
           // window start: first j in [st, i - 32] for which the predicate of lchain.rs:75 is false
@@ -875,6 +893,7 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
         if (use_sm && lane < tile_n) {                           // ... and they enter the shared window ring
           const int slot = (i0 + lane) % DENSE_CAP;
           sh->sx[slot] = rx; sh->sq[slot] = rq; sh->ss[slot] = (u8)rsp; sh->sf[slot] = rf; sh->sp[slot] = rpp;
+          sh->tg[slot] = 0;                                      // a new anchor lives here: nobody has marked it yet
         }
         if (bnd) blk_start = i0 + 31 - __clz(bnd);
       }
@@ -941,8 +960,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) chain_dense_kernel(ChainArgs G,
   if (threadIdx.x == 0) {
     int* base = reinterpret_cast<int*>(dense_dyn);
     sh.sx = base; sh.sq = base + DENSE_CAP; sh.sf = base + 2 * DENSE_CAP; sh.sp = base + 3 * DENSE_CAP;
-    sh.mk = reinterpret_cast<u32*>(base + 4 * DENSE_CAP);
-    sh.ss = reinterpret_cast<u8*>(base + 4 * DENSE_CAP + DENSE_CAP / 32);
+    sh.tg = reinterpret_cast<u16*>(base + 4 * DENSE_CAP);
+    sh.ss = reinterpret_cast<u8*>(base + 4 * DENSE_CAP + DENSE_CAP / 2);
   }
   for (;;) {
     __syncthreads();
@@ -1008,7 +1027,7 @@ int chain_batch(mm2_ctx* ctx, const ulonglong2* d_anchors, const u64* d_read_aof
     MM2_LAUNCH(ctx, chain_ring_kernel, grid, CH_WARPS * 32, 0, G);
     // persistent CTAs, one dense read at a time each; with no dense read they exit at once
     const u32 sm = (u32)ctx->n_sm;
-    constexpr int DENSE_DYN = 4 * DENSE_CAP * 4 + DENSE_CAP / 32 * 4 + DENSE_CAP;   // window ring (see DenseSh)
+    constexpr int DENSE_DYN = 4 * DENSE_CAP * 4 + DENSE_CAP * 2 + DENSE_CAP;   // window ring (see DenseSh)
     static bool attr_done = false;
     if (!attr_done) {
       cudaFuncSetAttribute(chain_dense_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_DYN);
