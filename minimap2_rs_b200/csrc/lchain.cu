@@ -399,6 +399,23 @@ __device__ __forceinline__ bool chain_sc(int ri, int qi, int rj, int qj, int spa
   return true;
 }
 
+// The same without branches (one predicate instead of the early returns): used where every lane of the warp evaluates a cell,
+// so the warp executes the whole body anyway and the branch / reconvergence instructions are pure overhead.  `act` = the lane
+// has a cell at all; the table index is clamped for the lanes that do not.
+__device__ __forceinline__ bool chain_sc_flat(bool act, int ri, int qi, int rj, int qj, int span_j, int mdx, int mdy, int bw, float pen_gap,
+                                              float pen_skip, const float* __restrict__ half_log, int& s0) {
+  const int dq = wsub(qi, qj), dr = wsub(ri, rj);
+  int dd = wsub(dr, dq); if (dd < 0) dd = wsub(0, dd);
+  const bool ok = act && dq > 0 && dq <= mdx && dr != 0 && dq <= mdy && dd <= bw && dd >= 0;
+  const int dg = min(dr, dq);
+  s0 = min(span_j, dg);
+  const int ddc = ok ? dd : 0;
+  const float lin = __fadd_rn(__fmul_rn(pen_gap, (float)ddc), __fmul_rn(pen_skip, (float)dg));
+  const int pen = __float2int_rz(__fadd_rn(lin, half_log[ddc]));
+  if (ddc != 0 || dg > span_j) s0 = wsub(s0, pen);
+  return ok;
+}
+
 __device__ __forceinline__ bool chain_is_dense(const ChainArgs& G, u32 r) {
   const i64 n = (i64)(G.read_aoff[r + 1] - G.read_aoff[r]);
   const i64 qlen = (i64)(G.read_off[r + 1] - G.read_off[r]);
@@ -645,15 +662,9 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
         const u32 hi_i = __shfl_sync(0xFFFFFFFFu, chi, c);
         const int low_iter = wsub(i, max_iter);                  // lchain.rs:78
         const bool inwin = rj >= max(low_iter, 0) && rhi == hi_i && !(ri > wadd(rx, mdx));   // empty slots hold rj = -1
-        int sc = NEG_INF;
-        bool valid = false;
-        if (inwin) {
-          int s0;
-          if (chain_sc(ri, qi, rx, rq, rsp, mdx, mdy, bw, p.chn_pen_gap, p.chn_pen_skip, G.half_log, s0)) {
-            sc = wadd(s0, rf);
-            valid = true;
-          }
-        }
+        int s0;
+        const bool valid = chain_sc_flat(inwin, ri, qi, rx, rq, rsp, mdx, mdy, bw, p.chn_pen_gap, p.chn_pen_skip, G.half_log, s0);
+        const int sc = valid ? wadd(s0, rf) : NEG_INF;
         const u32 inmask = __ballot_sync(0xFFFFFFFFu, inwin);
         const u32 vmask = __ballot_sync(0xFFFFFFFFu, valid);
         int max_f = spi, max_j = -1, n_skip = 0;
