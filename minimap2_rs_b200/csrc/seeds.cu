@@ -374,11 +374,17 @@ __device__ __forceinline__ void msort_core(T (&v)[8], T* sa, const int m, const 
       }
       int ai = lo, bi = d - lo;
       T ka = ai < LA ? sa[SIDX(A0 + ai)] : PADV, kb = bi < LB ? sa[SIDX(B0 + bi)] : PADV;
+      // one load per output, no divergent paths: the run that gave the output is refilled (an exhausted run keeps its stale head,
+      // which the bi >= LB / ai < LA tests of the next step never pick)
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const bool take_a = bi >= LB || (ai < LA && !rec_less(kb, ka));
         v[e] = take_a ? ka : kb;
-        if (take_a) { ++ai; if (ai < LA) ka = sa[SIDX(A0 + ai)]; } else { ++bi; if (bi < LB) kb = sa[SIDX(B0 + bi)]; }
+        ai += take_a ? 1 : 0; bi += take_a ? 0 : 1;
+        const int nidx = take_a ? A0 + ai : B0 + bi;
+        const bool more = take_a ? ai < LA : bi < LB;
+        const T nv = sa[SIDX(more ? nidx : pair0)];
+        if (take_a) { if (more) ka = nv; } else { if (more) kb = nv; }
       }
     }
     __syncthreads();
