@@ -466,11 +466,18 @@ def test_map_batch_pipelined_equals_single(mm2, orc, gen):
     del os.environ["MM2_SUBBATCH_MB"]
     gi = mm2.Index.build(c, g, offs, ["p"])
     cat, roffs = gen.reads(8, g, offs, 3000, 4000, 0.03, 0.03, 0.03)   # 12 MB -> 6 sub-batches
+    # every 7th read is replaced by random sequence: no anchors, no record -> the workers' in-place record slices have gaps
+    # that the final compaction must close
+    rng = np.random.default_rng(5)
+    cat = cat.copy()
+    for i in range(3, 3000, 7):
+        lo, hi = int(roffs[i]), int(roffs[i + 1])
+        cat[lo:hi] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, hi - lo)]
     r1 = c.map_batch(gi, cat, roffs)
     o = mm2.default_map_opts()
     o.want_stage_dump = 1                                              # forces the single-context path
     r2 = c.map_batch(gi, cat, roffs, o)
-    assert r1.recs.size == r2.recs.size == 3000 and (r1.recs == r2.recs).all()
+    assert r1.recs.size == r2.recs.size and 2000 < r1.recs.size < 3000 and (r1.recs == r2.recs).all()
     assert r1.stats["n_anchors"] == r2.stats["n_anchors"] and r1.stats["n_minimizers"] == r2.stats["n_minimizers"]
     oi = orc.Index.build(g, offs, ["p"], threads=8)
     names = ["n%d" % i for i in range(3000)]
@@ -485,7 +492,8 @@ def test_map_batch_pipelined_equals_single(mm2, orc, gen):
     assert (r3.recs == r2.recs).all() and r3.stats["n_anchors"] == r2.stats["n_anchors"]
     # a batch that does not start at offset 0 of its buffer
     r4 = c.map_batch(gi, cat, roffs[1000:])
-    assert r4.recs.size == 2000 and r4.paf_lines(names[1000:]) == want[1000:]
+    want4 = [l for l in want if int(l.split("\t")[0][1:]) >= 1000]
+    assert r4.recs.size == len(want4) and r4.paf_lines(names[1000:]) == want4
     c.close()
 
 
