@@ -28,9 +28,55 @@ struct Fasta {
   std::vector<uint64_t> offs;
 };
 // noodles-like record semantics (name = up to the first whitespace; sequence lines concatenated)
+// Extension (the reference reads FASTA only): a query file whose first byte is '@' is read as FASTQ --
+// '@name ...', sequence lines up to a line starting with '+', then as many quality characters as there were bases.
+bool read_fastq(FILE* fp, bool first_only, Fasta& fa) {
+  std::vector<char> buf(1 << 20);
+  enum { HEADER, SEQ, PLUS, QUAL } st = QUAL;
+  bool line_start = true, name_done = false;
+  size_t n, need_q = 0, nrec = 0;
+  while ((n = fread(buf.data(), 1, buf.size(), fp)) > 0) {
+    for (size_t i = 0; i < n; ++i) {
+      const char c = buf[i];
+      if (c == '\r') continue;
+      switch (st) {
+        case HEADER:
+          if (c == '\n') { st = SEQ; line_start = true; }
+          else if (!name_done) { if (c == ' ' || c == '\t') name_done = true; else fa.names.back().push_back(c); }
+          break;
+        case SEQ:
+          if (c == '\n') { line_start = true; break; }
+          if (line_start && c == '+') { st = PLUS; need_q = fa.cat.size() - fa.offs.back(); break; }
+          line_start = false;
+          fa.cat.push_back((uint8_t)c);
+          break;
+        case PLUS:
+          if (c == '\n') { st = QUAL; line_start = true; }
+          break;
+        case QUAL:
+          if (need_q) { if (c != '\n') --need_q; break; }
+          if (c == '\n') { line_start = true; break; }
+          if (c == '@') {   // quality strings may contain '@', but only inside their need_q characters
+            if (nrec && first_only) { fa.offs.push_back(fa.cat.size()); return true; }
+            ++nrec; st = HEADER; name_done = false;
+            fa.names.emplace_back(); fa.offs.push_back(fa.cat.size());
+          }
+          break;
+      }
+    }
+  }
+  fa.offs.push_back(fa.cat.size());
+  return true;
+}
+
 bool read_fasta(const std::string& path, bool first_only, Fasta& fa) {
   FILE* fp = fopen(path.c_str(), "rb");
   if (!fp) return false;
+  {
+    const int c0 = fgetc(fp);
+    if (c0 != EOF) ungetc(c0, fp);
+    if (c0 == '@') { const bool ok = read_fastq(fp, first_only, fa); fclose(fp); return ok; }
+  }
   std::vector<char> buf(1 << 20);
   bool in_header = false, line_start = true, have = false, name_done = false, stop = false;
   size_t n;

@@ -439,6 +439,16 @@ def test_cli_index_align_anchors_chain(ctx, mm2, orc, gen, tmp_path):
     pf = str(tmp_path / "o.paf")
     out = subprocess.run([exe, "align", fa, qa, "--all-reads", "-o", pf, "-x", "map-ont"], capture_output=True, text=True)
     assert out.returncode == 0 and open(pf).read() == "\n".join(want) + "\n", out.stderr
+    # extension: the same reads as FASTQ (multi-line sequence, '@' and '+' inside the qualities) give the same PAF
+    qq = str(tmp_path / "q.fq")
+    with open(qq, "wb") as f:
+        for i in range(3):
+            sq = rc[int(ro[i]):int(ro[i + 1])].tobytes()
+            f.write(b"@read%d some comment\n" % i + sq[:1000] + b"\n" + sq[1000:] + b"\n+\n" + b"@+" * (len(sq) // 2) + b"I" * (len(sq) % 2) + b"\n")
+    out = subprocess.run([exe, "align", mmi, qq, "--all-reads"], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout == "\n".join(want) + "\n", out.stderr
+    out = subprocess.run([exe, "align", mmi, qq], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout == want[0] + "\n"
     # anchors / chain debug subcommands
     q0 = rc[int(ro[0]):int(ro[1])]
     a = oi.anchors(orc.filter_query_minimizers(orc.sketch(q0, 10, 15)), q0.size, max(10, oi.calc_mid_occ()))
