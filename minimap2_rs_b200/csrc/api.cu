@@ -52,6 +52,7 @@ extern "C" int mm2_ctx_create(int device, mm2_ctx_t** out) {
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
   }
+  MM2_TRY(lchain_init_device()); MM2_TRY(radix_init_device()); MM2_TRY(seeds_init_device());
   mm2_ctx* c = new mm2_ctx();
   c->device = device;
   e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
@@ -437,7 +438,7 @@ static void merge_in_place(mm2_map_result_t* parts, const size_t* first, size_t 
 static int build_record(const mm2_index* idx, const ReadHit& h, u32 r, i32 qlen, mm2_paf_rec_t& rec) {
   if (h.n_anchors == 0) return 0;
   const u32 rid0 = h.rid_rev & 0x7fffffffu;
-  if (rid0 >= idx->n_seq) return 2;
+  if (rid0 >= idx->lens.size()) return 2;   // idx.seq[rid0] (paf.rs:149): bounded by the table actually held
   const bool rev = (h.rid_rev >> 31) != 0;
   rec.read_id = r; rec.rid = rid0; rec.qlen = (u32)qlen; rec.qstart = (u32)h.qs; rec.qend = (u32)h.qe;
   rec.tlen = idx->lens[rid0]; rec.tstart = (u32)h.ts; rec.tend = (u32)h.te;
@@ -598,7 +599,7 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
     auto range = [&](int t, size_t& lo, size_t& hi) { lo = nreads * (size_t)t / (size_t)nth; hi = nreads * (size_t)(t + 1) / (size_t)nth; };
     auto count = [&](int t) {
       size_t lo, hi, c = 0; range(t, lo, hi);
-      for (size_t r = lo; r < hi; ++r) c += (hits[r].n_anchors != 0 && (hits[r].rid_rev & 0x7fffffffu) < idx->n_seq) ? 1 : 0;
+      for (size_t r = lo; r < hi; ++r) c += (hits[r].n_anchors != 0 && (hits[r].rid_rev & 0x7fffffffu) < idx->lens.size()) ? 1 : 0;
       cnt[(size_t)t + 1] = c;
     };
     auto fill = [&](int t) {

@@ -145,7 +145,7 @@ bool paf_record(const mm2_index* idx, const mm2_anchor_t* a, const std::vector<u
   i32 qs, qe, ts, te;
   qrange(a, chain, &qs, &qe); trange(a, chain, &ts, &te);
   const u32 rid0 = (u32)((a[chain[0]].x >> 32) & 0x7fffffffULL);
-  if (rid0 >= idx->n_seq) return false;
+  if (rid0 >= idx->lens.size()) return false;
   rec.rid = rid0; rec.qlen = (u32)qlen; rec.qstart = (u32)qs; rec.qend = (u32)qe; rec.tlen = idx->lens[rid0];
   rec.tstart = (u32)ts; rec.tend = (u32)te; rec.nm = (u32)std::max(wsub(qe, qs), 0); rec.blen = (u32)std::max(wsub(te, ts), 0);
   rec.cm = (u32)chain.size(); rec.s1 = rec.s2 = 0; rec.rl = 0; rec.strand = rev ? '-' : '+'; rec.mapq = 60; rec.tp = primary ? 'P' : 'S';

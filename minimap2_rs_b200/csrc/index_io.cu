@@ -57,7 +57,10 @@ struct FileW {
 };
 struct MemR {  // bounds-checked little-endian reader over a whole file in memory
   const u8* p; size_t n, o = 0; bool ok = true;
-  bool need(size_t k) { if (o + k > n) { ok = false; return false; } return true; }
+  bool need(size_t k) { if (k > n - o) { ok = false; return false; } return true; }   // o <= n always; no wrap-around
+  size_t left() const { return n - o; }
+  // k records of `rec` bytes each, with the multiplication checked against what is left in the file
+  const u8* take_recs(size_t k, size_t rec) { if (k > (n - o) / rec) { ok = false; return nullptr; } return take(k * rec); }
   u8 u8_() { if (!need(1)) return 0; return p[o++]; }
   u32 u32_() { if (!need(4)) return 0; u32 v; memcpy(&v, p + o, 4); o += 4; return v; }
   i32 i32_() { return (i32)u32_(); }
@@ -236,13 +239,13 @@ extern "C" int mm2_index_load_mmi(mm2_ctx_t* ctx, const char* path, mm2_index_t*
   std::vector<std::pair<u64, u64>> ent;
   for (size_t bi = 0; bi < nb && rd.ok; ++bi) {
     const size_t n = rd.u32_();
-    const u8* pp = rd.take(n * 8);
+    const u8* pp = rd.take_recs(n, 8);
     if (!rd.ok) break;
     h.poff[bi] = h.p.size();
     h.p.resize(h.p.size() + n);
     if (n) memcpy(h.p.data() + h.poff[bi], pp, n * 8);
     const size_t size = rd.u32_();
-    const u8* ee = rd.take(size * 16);
+    const u8* ee = rd.take_recs(size, 16);
     if (!rd.ok) break;
     h.koff[bi] = h.hkeys.size();
     ent.resize(size);
@@ -253,7 +256,7 @@ extern "C" int mm2_index_load_mmi(mm2_ctx_t* ctx, const char* path, mm2_index_t*
   if (!rd.ok) return fail(MM2_E_FORMAT, "truncated MMI bucket table");
   h.koff[nb] = h.hkeys.size(); h.poff[nb] = h.p.size();
   const size_t words = (size_t)((sum_len + 7) / 8);
-  const u8* sp = rd.take(words * 4);
+  const u8* sp = rd.take_recs(words, 4);
   if (!rd.ok) return fail(MM2_E_FORMAT, "truncated MMI sequence array");
   h.S.resize(words);
   if (words) memcpy(h.S.data(), sp, words * 4);
@@ -335,7 +338,7 @@ extern "C" int mm2_index_load_native(mm2_ctx_t* ctx, const char* path, mm2_index
   idx->total_len = total;
   HostIndex h;
   const size_t s_words = (size_t)rd.u64_();
-  const u8* sp = rd.take(s_words * 4);
+  const u8* sp = rd.take_recs(s_words, 4);
   if (!rd.ok) return fail(MM2_E_FORMAT, "truncated index sequence array");
   h.S.resize(s_words);
   if (s_words) memcpy(h.S.data(), sp, s_words * 4);
@@ -345,7 +348,7 @@ extern "C" int mm2_index_load_native(mm2_ctx_t* ctx, const char* path, mm2_index
   std::vector<std::pair<u64, u64>> ent;
   for (size_t bi = 0; bi < nb && rd.ok; ++bi) {
     const size_t n = (size_t)rd.u64_();
-    const u8* pp = rd.take(n * 8);
+    const u8* pp = rd.take_recs(n, 8);
     if (!rd.ok) break;
     h.poff[bi] = h.p.size();
     h.p.resize(h.p.size() + n);
@@ -353,7 +356,7 @@ extern "C" int mm2_index_load_native(mm2_ctx_t* ctx, const char* path, mm2_index
     h.koff[bi] = h.hkeys.size();
     if (rd.u8_() != 0) {
       const size_t size = (size_t)rd.u64_();
-      const u8* ee = rd.take(size * 16);
+      const u8* ee = rd.take_recs(size, 16);
       if (!rd.ok) break;
       ent.resize(size);
       for (size_t q = 0; q < size; ++q) { memcpy(&ent[q].first, ee + q * 16, 8); memcpy(&ent[q].second, ee + q * 16 + 8, 8); }

@@ -984,7 +984,17 @@ __global__ void __launch_bounds__(NW * 32, MINB) chain_dense_kernel(ChainArgs G,
   }
 }
 
+constexpr int DENSE_DYN = 4 * DENSE_CAP * 4 + DENSE_CAP * 2 + DENSE_CAP;   // window ring (see DenseSh)
 }  // namespace
+
+// Opt-in to more than 48 KB of dynamic shared memory.  The attribute is per device, so mm2_ctx_create calls this for
+// every context (after cudaSetDevice) instead of once per process.
+int lchain_init_device() {
+  CUDA_TRY(cudaFuncSetAttribute(chain_dense_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_DYN));
+  CUDA_TRY(cudaFuncSetAttribute(chain_dense_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_DYN));
+  CUDA_TRY(cudaFuncSetAttribute(chain_dense_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_DYN));
+  return MM2_OK;
+}
 
 // host-built table of 0.5 * mg_log2(dd + 1) (lchain.rs:15,30-31): glibc logf, division by f32 LN_2, exact halving
 static std::vector<float> build_half_log(int n) {
@@ -1038,14 +1048,6 @@ int chain_batch(mm2_ctx* ctx, const ulonglong2* d_anchors, const u64* d_read_aof
     MM2_LAUNCH(ctx, chain_ring_kernel, grid, CH_WARPS * 32, 0, G);
     // persistent CTAs, one dense read at a time each; with no dense read they exit at once
     const u32 sm = (u32)ctx->n_sm;
-    constexpr int DENSE_DYN = 4 * DENSE_CAP * 4 + DENSE_CAP * 2 + DENSE_CAP;   // window ring (see DenseSh)
-    static bool attr_done = false;
-    if (!attr_done) {
-      cudaFuncSetAttribute(chain_dense_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_DYN);
-      cudaFuncSetAttribute(chain_dense_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_DYN);
-      cudaFuncSetAttribute(chain_dense_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_DYN);
-      attr_done = true;
-    }
     static const int force_nw = [] { const char* e = getenv("MM2_DENSE_NW"); return e ? atoi(e) : 0; }();   // experiment knob: warps per dense read
     const int dgrid = (int)std::min<u64>(nreads, (u64)sm * 2);
     if (force_nw == 16) MM2_LAUNCH(ctx, (chain_dense_kernel<16, 2>), dgrid, 16 * 32, DENSE_DYN, G, 1u, 0xFFFFFFFFu);

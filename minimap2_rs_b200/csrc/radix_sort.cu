@@ -134,13 +134,16 @@ __global__ void __launch_bounds__(RS_NT) rs_scatter_kernel(const u64* __restrict
 
 }  // namespace
 
+int radix_init_device() {   // per device (see lchain_init_device)
+  CUDA_TRY(cudaFuncSetAttribute(rs_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TILE * 16));
+  return MM2_OK;
+}
+
 // Sorts n pairs by key bits [0, end_bit).  The passes ping-pong between buffer A = (a_keys, a_vals), which holds the input
 // and is overwritten, and buffer B; *res_keys / *res_vals say which one holds the result.
 int radix_sort_pairs(mm2_ctx* ctx, u64* a_keys, u64* a_vals, u64* b_keys, u64* b_vals, u64 n, int end_bit, u64** res_keys, u64** res_vals) {
   *res_keys = a_keys; *res_vals = a_vals;
   if (n == 0) return MM2_OK;
-  static bool attr_done = false;
-  if (!attr_done) { cudaFuncSetAttribute(rs_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TILE * 16); attr_done = true; }
   const int npass = std::max(1, (end_bit + RS_BITS - 1) / RS_BITS);
   const u32 ntiles = (u32)((n + RS_TILE - 1) / RS_TILE);
   const size_t ncnt = (size_t)ntiles * RS_BINS;

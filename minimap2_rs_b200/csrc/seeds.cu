@@ -622,23 +622,22 @@ __global__ void __launch_bounds__(NT) anchor_sort_gmem_kernel(ulonglong2* __rest
   anchor_sort_gmem_read<NT>(anchors, read_aoff, r);
 }
 
-bool g_attr_done = false;
-void seeds_set_attrs() {
-  if (g_attr_done) return;
+int seeds_set_attrs() {
   cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FL_SLOTS * 12);
   cudaFuncSetAttribute(filter_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FL_SLOTS * 12);
   cudaFuncSetAttribute(anchor_sort_smem_kernel<1024, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 16);
   cudaFuncSetAttribute(anchor_sort_smem_kernel<4096, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16);
   cudaFuncSetAttribute(anchor_sort_smem_kernel<12288, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12288 * 16);
-  cudaFuncSetAttribute(anchor_msort_kernel<512, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4608 * 16);
-  g_attr_done = true;
+  CUDA_TRY(cudaFuncSetAttribute(anchor_msort_kernel<512, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4608 * 16));
+  return MM2_OK;
 }
 
 }  // namespace
 
+int seeds_init_device() { return seeds_set_attrs(); }   // per device (see lchain_init_device)
+
 int seeds_filter(mm2_ctx* ctx, const u64* d_mkey, const u64* d_mini_off, u32 nreads, u64 n_mini, i32 q_occ_max, float q_occ_frac,
                  u8* d_keep, u32* d_sum_span) {
-  seeds_set_attrs();
   if (n_mini) CUDA_TRY(cudaMemsetAsync(d_keep, 1, n_mini, ctx->stream));
   if (nreads) MM2_LAUNCH(ctx, filter_kernel, nreads, FL_NT, FL_SLOTS * 12, d_mkey, d_mini_off, nreads, q_occ_max, q_occ_frac, d_keep, d_sum_span);
   CUDA_TRY(cudaGetLastError());
@@ -652,7 +651,6 @@ int seeds_filter(mm2_ctx* ctx, const u64* d_mkey, const u64* d_mini_off, u32 nre
 int seeds_hits(mm2_ctx* ctx, const IndexView& V, const u64* d_mkey, const u64* d_mval, const u64* d_mini_off, u32 nreads, u64 n_mini,
                i32 q_occ_max, float q_occ_frac, i32 mid_occ, bool full_keep, u32* d_sum_span, u64* n_anchors) {
   cudaStream_t st = ctx->stream;
-  seeds_set_attrs();
   *n_anchors = 0;
   MM2_TRY(ctx->keep.ensure(n_mini + 16));
   MM2_TRY(ctx->occ_loc.ensure((n_mini + 16) * 8));

@@ -39,3 +39,8 @@ int index_build_table(mm2_ctx* ctx, mm2_index* idx);
 int map_general_finish(mm2_ctx* ctx, const mm2_index* idx, const u64* d_read_off, const u64* h_off, size_t nreads,
                        const mm2_map_opts_t* o, const mm2_chain_params_t& p, const SketchOut& so, const u32* d_sum_span, u64 nm, u64 na,
                        mm2_map_result_t* out);
+
+// per-device kernel attributes (dynamic shared memory opt-ins); called by mm2_ctx_create after cudaSetDevice
+int lchain_init_device();
+int radix_init_device();
+int seeds_init_device();

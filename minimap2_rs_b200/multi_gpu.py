@@ -106,6 +106,7 @@ def build_index_sharded(ctx, cat, offs, names, w=10, k=15, b=14, flag=0, group=N
     words_used = (total + 7) // 8
     s_alloc = _kroundup64(words_used) if total else 0
     S = torch.zeros(max(1, s_alloc), dtype=torch.int32, device=dev)
+    torch.cuda.current_stream(dev).synchronize()   # the zero fill runs on torch's stream, mg_pack_seq on the context's
     ranges = [_word_range(offs, *shard.shard_reads(offs, world, r), words_used) for r in range(world)]
     w0, w1 = ranges[rank]
     ctx.mg_pack_seq(cat, total, w0, w1, S.data_ptr())
@@ -180,6 +181,7 @@ def build_index_sharded_emulated(ctx, cat, offs, names, w=10, k=15, b=14, flag=0
     words_used = (total + 7) // 8
     s_alloc = _kroundup64(words_used) if total else 0
     S = torch.zeros(max(1, s_alloc), dtype=torch.int32, device=dev)
+    torch.cuda.current_stream(dev).synchronize()   # see build_index_sharded
     for rank in range(world):
         w0, w1 = _word_range(offs, *shard.shard_reads(offs, world, rank), words_used)
         ctx.mg_pack_seq(cat, total, w0, w1, S.data_ptr())
