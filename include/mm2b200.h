@@ -55,11 +55,7 @@ const char* mm2_last_error(void);
 void mm2_free(void* p);               /* releases any `**out` array */
 void* mm2_host_alloc(size_t bytes);   /* page-locked host buffer (fast H2D/D2H); NULL on failure */
 void mm2_host_free(void* p);
-/* number of kernels launched by this context since creation (bench.py's gpu_launches claim) */
-uint64_t mm2_ctx_launch_count(const mm2_ctx_t* ctx);
-/* per-stage device time of the last batched call, in milliseconds (CUDA events on the context stream).
- * names: NUL-separated, double-NUL terminated list matching ms[0..n) */
-int mm2_ctx_last_timings(const mm2_ctx_t* ctx, const char** names, const float** ms, int* n);
+/* (launch counters, stage timers and the DP-cell counter used by bench.py are diagnostics: see mm2b200_diag.h) */
 
 /* ---- sketch (sketch.rs:29 sketch_sequence) -------------------------------------------------------------- */
 int mm2_sketch(mm2_ctx_t* ctx, const uint8_t* seq, size_t len, int w, int k, uint32_t rid, int is_hpc,
@@ -97,34 +93,30 @@ int mm2_index_get_ref_subseq(const mm2_index_t* idx, uint32_t rid, int32_t st, i
 /* device-time breakdown of the build that produced idx (ms): sketch, sort, bucket build, pack, total; genome bases */
 int mm2_index_build_timings(const mm2_index_t* idx, float* ms5, uint64_t* n_bases, uint64_t* n_minimizers);
 
-/* ---- multi-GPU index build building blocks (index.rs:427-475 split over ranks) --------------------------
- * One process per GPU.  Rank r sketches a contiguous range of sequences, sorts its minimizers bucket-major, sends each
- * bucket owner its slice (all-to-all), builds the buckets it owns, and the finished ranges are replicated to every GPU.
- * The exchange itself is done by the caller (minimap2_rs_b200/multi_gpu.py over torch.distributed / NCCL). */
-typedef struct {
-  uint64_t n_keys, n_p, n_minimizers, S_words;
-  const void *hkeys, *hvals, *p, *bkt_koff, *bkt_poff, *S;  /* device pointers, valid until mm2_index_free */
-  const uint64_t* occ_hist;                                  /* host, 65536 entries */
-  size_t n_occ_big; const uint32_t* occ_big;                 /* host */
-} mm2_index_raw_t;
-/* sketch sequences [seq_lo, seq_hi) (rid = global sequence number), sort by (bucket, key); counts[r] = records owned by rank r */
-int mm2_mg_sketch_sort(mm2_ctx_t* ctx, const uint8_t* cat, const uint64_t* offs, size_t nseq, size_t seq_lo, size_t seq_hi, int w,
-                       int k, int b, int flag, int nranks, uint64_t* counts);
-/* copy the n sorted (key, position) records of the last mm2_mg_sketch_sort into caller-owned device buffers */
-int mm2_mg_export_sorted(mm2_ctx_t* ctx, void* d_ckey, void* d_y, size_t n);
-/* received records (device, source-rank order; the two buffers are used as sort scratch) -> the buckets this rank owns
- * (index.rs:74-109), no lookup table */
-int mm2_mg_build_partial(mm2_ctx_t* ctx, void* d_ckey, void* d_y, size_t n, int w, int k, int b, int flag,
-                         mm2_index_t** out);
-/* 4-bit pack (index.rs:11-19) words [word_lo, word_hi) of the genome into d_S (a device array of all S words) */
-int mm2_mg_pack_seq(mm2_ctx_t* ctx, const uint8_t* cat, uint64_t total_len, uint64_t word_lo, uint64_t word_hi, void* d_S);
-int mm2_device_copy(mm2_ctx_t* ctx, void* dst, const void* src, size_t nbytes);
-int mm2_index_raw(const mm2_index_t* idx, mm2_index_raw_t* out);
-/* build the replicated index object from fully gathered device arrays (+ summed occurrence histogram) */
-int mm2_index_assemble(mm2_ctx_t* ctx, const uint64_t* offs, const char* const* names, size_t nseq, int w, int k, int b, int flag,
-                       uint64_t n_keys, uint64_t n_p, const void* d_hkeys, const void* d_hvals, const void* d_p, const void* d_koff,
-                       const void* d_poff, const void* d_S, uint64_t S_words, const uint64_t* occ_hist, const uint32_t* occ_big,
-                       size_t n_occ_big, mm2_index_t** out);
+/* ---- multi-GPU index build (index.rs:427-475 split over the GPUs of one box) ------------------------------
+ * One rank per GPU.  The genome is sketched in shares (split INSIDE sequences, by tiles with a 2w+k halo), the minimizers
+ * are sorted locally and routed to the owner of their hash-prefix bucket (all-to-all over NCCL / NVLink), every rank builds
+ * the buckets it owns (index.rs:74-109), and the finished ranges are all-gathered so that every GPU ends up with the whole
+ * index (mapping shards the READS, not the index).  The result is byte-identical to the single-GPU / CPU build.
+ * The communicator lives in the library: NCCL is bound at run time (dlopen), the 128-byte unique id travels by whatever
+ * the caller has (torch.distributed, MPI, a file). */
+typedef struct mm2_comm mm2_comm_t;
+#define MM2_COMM_ID_BYTES 128
+int mm2_comm_get_unique_id(void* id128);                 /* rank 0: ncclGetUniqueId */
+int mm2_comm_create(mm2_ctx_t* ctx, const void* id128, int nranks, int rank, mm2_comm_t** out);   /* collective */
+void mm2_comm_destroy(mm2_comm_t* comm);
+int mm2_comm_rank(const mm2_comm_t* comm, int* rank, int* nranks);
+int mm2_comm_barrier(mm2_comm_t* comm);                  /* device work of every rank's context is complete on return */
+/* collective: every rank passes the same host arrays (as mm2_index_build_seqs) and gets its replica of the index */
+int mm2_index_build_sharded(mm2_ctx_t* ctx, mm2_comm_t* comm, const uint8_t* cat, const uint64_t* offs, const char* const* names,
+                            size_t nseq, int w, int k, int b, int flag, mm2_index_t** out);
+/* the same phases for `nranks` virtual ranks on ONE GPU (the exchange steps are device copies): single-GPU test of the path */
+int mm2_index_build_sharded_emulated(mm2_ctx_t* ctx, int nranks, const uint8_t* cat, const uint64_t* offs, const char* const* names,
+                                     size_t nseq, int w, int k, int b, int flag, mm2_index_t** out);
+/* one process, several GPUs: ctxs[i] on distinct devices; a private host thread per context runs the sharded build over a
+ * communicator of its own; out[i] = the replica on ctxs[i]'s device (`mm2rs index --gpus N`) */
+int mm2_index_build_multi(mm2_ctx_t* const* ctxs, int nctx, const uint8_t* cat, const uint64_t* offs, const char* const* names,
+                          size_t nseq, int w, int k, int b, int flag, mm2_index_t** out);
 
 /* ---- seeds (seeds.rs) -------------------------------------------------------------------------------------- */
 /* seeds.rs:13 filter_query_minimizers: in place, *n updated */

@@ -49,13 +49,6 @@ class _Chains(C.Structure):
                 ("f", C.c_void_p), ("v", C.c_void_p), ("pprev", C.c_void_p)]
 
 
-class IndexRaw(C.Structure):  # mm2_index_raw_t
-    _fields_ = [("n_keys", C.c_uint64), ("n_p", C.c_uint64), ("n_minimizers", C.c_uint64), ("S_words", C.c_uint64),
-                ("hkeys", C.c_void_p), ("hvals", C.c_void_p), ("p", C.c_void_p), ("bkt_koff", C.c_void_p),
-                ("bkt_poff", C.c_void_p), ("S", C.c_void_p), ("occ_hist", C.c_void_p), ("n_occ_big", C.c_size_t),
-                ("occ_big", C.c_void_p)]
-
-
 class _MapResult(C.Structure):
     _fields_ = [("n_recs", C.c_size_t), ("recs", C.c_void_p), ("n_panic", C.c_size_t), ("panic_reads", C.c_void_p),
                 ("n_reads", C.c_uint64), ("n_bases", C.c_uint64), ("n_minimizers", C.c_uint64),
@@ -67,15 +60,18 @@ class _MapResult(C.Structure):
 # every symbol include/mm2b200.h declares (tests check that the library exports all of them)
 ABI_SYMBOLS = [
     "mm2_ctx_create", "mm2_ctx_destroy", "mm2_ctx_set_stream", "mm2_ctx_synchronize", "mm2_last_error", "mm2_free",
-    "mm2_host_alloc", "mm2_host_free", "mm2_ctx_launch_count", "mm2_ctx_last_timings", "mm2_sketch", "mm2_sketch_batch",
+    "mm2_host_alloc", "mm2_host_free", "mm2_sketch", "mm2_sketch_batch",
     "mm2_index_build_fasta", "mm2_index_build_seqs", "mm2_index_save_mmi", "mm2_index_load_mmi", "mm2_index_save_native",
     "mm2_index_load_native", "mm2_index_load_auto", "mm2_index_free", "mm2_index_get", "mm2_index_stats",
     "mm2_index_calc_mid_occ", "mm2_index_params", "mm2_index_seq", "mm2_index_get_ref_subseq", "mm2_index_build_timings",
     "mm2_filter_query_minimizers", "mm2_build_anchors_filtered", "mm2_chain_dp_all", "mm2_chains_free",
     "mm2_default_chain_params", "mm2_default_map_opts", "mm2_map_batch", "mm2_map_batch_device", "mm2_map_result_free",
-    "mm2_paf_format", "mm2_paf_format_batch", "mm2_mg_sketch_sort", "mm2_mg_export_sorted", "mm2_mg_build_partial",
-    "mm2_mg_pack_seq", "mm2_device_copy", "mm2_index_raw", "mm2_index_assemble",
+    "mm2_paf_format", "mm2_paf_format_batch", "mm2_comm_get_unique_id", "mm2_comm_create", "mm2_comm_destroy", "mm2_comm_rank",
+    "mm2_comm_barrier", "mm2_index_build_sharded", "mm2_index_build_sharded_emulated", "mm2_index_build_multi",
 ]
+
+# include/mm2b200_diag.h (diagnostics: bench / profiling, not part of the drop-in boundary)
+DIAG_SYMBOLS = ["mm2_ctx_launch_count", "mm2_ctx_last_timings", "mm2_ctx_count_cells", "mm2_ctx_last_cells", "mm2_shard_plan"]
 
 _LIB = None
 
@@ -103,6 +99,9 @@ def lib():
     L.mm2_ctx_launch_count.restype = C.c_uint64
     L.mm2_ctx_launch_count.argtypes = [vp]
     L.mm2_ctx_last_timings.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int)]
+    L.mm2_ctx_count_cells.argtypes = [vp, C.c_int]
+    L.mm2_ctx_last_cells.restype = C.c_uint64
+    L.mm2_ctx_last_cells.argtypes = [vp]
     L.mm2_sketch.argtypes = [vp, vp, sz, C.c_int, C.c_int, C.c_uint32, C.c_int, C.POINTER(vp), C.POINTER(sz)]
     L.mm2_sketch_batch.argtypes = [vp, vp, vp, sz, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(vp), C.POINTER(vp)]
     L.mm2_index_build_fasta.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
@@ -133,14 +132,16 @@ def lib():
     L.mm2_map_result_free.argtypes = [C.POINTER(_MapResult)]
     L.mm2_paf_format.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p, sz]
     L.mm2_paf_format_batch.argtypes = [vp, C.POINTER(_MapResult), vp, C.POINTER(vp), C.POINTER(sz)]
-    L.mm2_mg_sketch_sort.argtypes = [vp, vp, vp, sz, sz, sz, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
-    L.mm2_mg_export_sorted.argtypes = [vp, vp, vp, sz]
-    L.mm2_mg_build_partial.argtypes = [vp, vp, vp, sz, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
-    L.mm2_mg_pack_seq.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, vp]
-    L.mm2_device_copy.argtypes = [vp, vp, vp, sz]
-    L.mm2_index_raw.argtypes = [vp, C.POINTER(IndexRaw)]
-    L.mm2_index_assemble.argtypes = [vp, vp, vp, sz, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp,
-                                     vp, C.c_uint64, vp, vp, sz, C.POINTER(vp)]
+    L.mm2_comm_get_unique_id.argtypes = [vp]
+    L.mm2_comm_create.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(vp)]
+    L.mm2_comm_destroy.argtypes = [vp]
+    L.mm2_comm_destroy.restype = None
+    L.mm2_comm_rank.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.mm2_comm_barrier.argtypes = [vp]
+    L.mm2_index_build_sharded.argtypes = [vp, vp, vp, vp, vp, sz, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.mm2_index_build_sharded_emulated.argtypes = [vp, C.c_int, vp, vp, vp, sz, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.mm2_index_build_multi.argtypes = [vp, C.c_int, vp, vp, vp, sz, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    L.mm2_shard_plan.argtypes = [vp, sz, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     _LIB = L
     return L
 
@@ -173,7 +174,7 @@ def as_u8(seq):
 class PinnedBuffer:
     """page-locked host memory (mm2_host_alloc) exposed as numpy arrays; keep the object alive while arrays are in use"""
 
-    def __init__(self, nbytes):
+    def __init__(self, nbytes, device=None):
         self.nbytes = max(1, int(nbytes))
         self.p = lib().mm2_host_alloc(self.nbytes)
         if not self.p:
@@ -243,6 +244,14 @@ class Context:
     @property
     def launch_count(self):
         return int(lib().mm2_ctx_launch_count(self.h))
+
+    def count_cells(self, on=True):
+        """diagnostic: make the chaining kernels count DP cells (lchain.rs:80 iterations); read with last_cells"""
+        _check(lib().mm2_ctx_count_cells(self.h, 1 if on else 0))
+
+    @property
+    def last_cells(self):
+        return int(lib().mm2_ctx_last_cells(self.h))
 
     def last_timings(self):
         names, ms, n = C.c_void_p(), C.c_void_p(), C.c_int()
@@ -331,43 +340,6 @@ class Context:
                                               offs.ctypes.data, offs.size - 1, C.byref(opts), C.byref(res)))
         return MapResult(idx, res, offs.size - 1)
 
-    # ---- multi-GPU index build building blocks (orchestrated by minimap2_rs_b200.multi_gpu) ----------------------
-    def mg_sketch_sort(self, cat, offs, seq_lo, seq_hi, w, k, b, flag, nranks):
-        cat = cat if isinstance(cat, np.ndarray) and cat.dtype == np.uint8 else as_u8(cat)
-        offs = np.ascontiguousarray(offs, dtype=np.uint64)
-        counts = np.zeros(nranks, dtype=np.uint64)
-        _check(lib().mm2_mg_sketch_sort(self.h, cat.ctypes.data, offs.ctypes.data, offs.size - 1, seq_lo, seq_hi, w, k, b, flag,
-                                        nranks, counts.ctypes.data))
-        return counts
-
-    def mg_export_sorted(self, d_ckey, d_y, n):
-        _check(lib().mm2_mg_export_sorted(self.h, C.c_void_p(d_ckey), C.c_void_p(d_y), n))
-
-    def mg_build_partial(self, d_ckey, d_y, n, w, k, b, flag):
-        h = C.c_void_p()
-        _check(lib().mm2_mg_build_partial(self.h, C.c_void_p(d_ckey), C.c_void_p(d_y), n, w, k, b, flag, C.byref(h)))
-        return Index(h)
-
-    def mg_pack_seq(self, cat, total_len, word_lo, word_hi, d_S):
-        cat = cat if isinstance(cat, np.ndarray) and cat.dtype == np.uint8 else as_u8(cat)
-        _check(lib().mm2_mg_pack_seq(self.h, cat.ctypes.data, total_len, word_lo, word_hi, C.c_void_p(d_S)))
-
-    def device_copy(self, dst, src, nbytes):
-        _check(lib().mm2_device_copy(self.h, C.c_void_p(dst), C.c_void_p(src), nbytes))
-
-    def index_assemble(self, offs, names, w, k, b, flag, n_keys, n_p, d_hkeys, d_hvals, d_p, d_koff, d_poff, d_S, S_words, occ_hist,
-                       occ_big):
-        offs = np.ascontiguousarray(offs, dtype=np.uint64)
-        enc = [n.encode() if isinstance(n, str) else bytes(n) for n in names]
-        arr = (C.c_char_p * len(enc))(*enc)
-        occ_hist = np.ascontiguousarray(occ_hist, dtype=np.uint64)
-        occ_big = np.ascontiguousarray(occ_big, dtype=np.uint32)
-        h = C.c_void_p()
-        _check(lib().mm2_index_assemble(self.h, offs.ctypes.data, arr, len(enc), w, k, b, flag, n_keys, n_p, C.c_void_p(d_hkeys),
-                                        C.c_void_p(d_hvals), C.c_void_p(d_p), C.c_void_p(d_koff), C.c_void_p(d_poff),
-                                        C.c_void_p(d_S), S_words, occ_hist.ctypes.data, occ_big.ctypes.data, occ_big.size, C.byref(h)))
-        return Index(h)
-
     def close(self):
         if getattr(self, "h", None):
             lib().mm2_ctx_destroy(self.h)
@@ -378,6 +350,54 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+class Comm:
+    """the library's NCCL communicator for one context (mm2_comm_t): one rank per GPU"""
+
+    def __init__(self, ctx, unique_id, nranks, rank):
+        self.h = C.c_void_p()
+        self.ctx = ctx
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        _check(lib().mm2_comm_create(ctx.h, buf, nranks, rank, C.byref(self.h)))
+        self.nranks, self.rank = nranks, rank
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_char * 128)()
+        _check(lib().mm2_comm_get_unique_id(buf))
+        return bytes(buf.raw)
+
+    @classmethod
+    def from_torch(cls, ctx, dist, group=None):
+        """collective over a torch.distributed group: rank 0's unique id is broadcast through the group's store"""
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [cls.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        return cls(ctx, box[0], world, rank)
+
+    def barrier(self):
+        _check(lib().mm2_comm_barrier(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().mm2_comm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def shard_plan(offs, w, k, flag, nranks, rank):
+    """diagnostic (host only): the share of `rank` in the sharded index build"""
+    offs = np.ascontiguousarray(offs, dtype=np.uint64)
+    out = np.zeros(8, dtype=np.uint64)
+    _check(lib().mm2_shard_plan(offs.ctypes.data, offs.size - 1, w, k, flag, nranks, rank, out.ctypes.data))
+    keys = ("tile_path", "lo", "hi", "sketch_byte_lo", "sketch_byte_hi", "word_lo", "word_hi", "upload_bytes")
+    return dict(zip(keys, (int(x) for x in out)))
 
 
 class MapResult:
@@ -456,6 +476,40 @@ class Index:
         return cls(h)
 
     @classmethod
+    def build_sharded(cls, ctx, comm, cat, offs, names, w=10, k=15, b=14, flag=0):
+        """collective over `comm` (mm2_index_build_sharded): every rank passes the same host arrays and gets its replica"""
+        cat = cat if isinstance(cat, np.ndarray) and cat.dtype == np.uint8 else as_u8(cat)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        enc = [n.encode() if isinstance(n, str) else bytes(n) for n in names]
+        arr = (C.c_char_p * len(enc))(*enc)
+        h = C.c_void_p()
+        _check(lib().mm2_index_build_sharded(ctx.h, comm.h, cat.ctypes.data, offs.ctypes.data, arr, len(enc), w, k, b, flag, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def build_sharded_emulated(cls, ctx, nranks, cat, offs, names, w=10, k=15, b=14, flag=0):
+        """the sharded build's phases for `nranks` virtual ranks on one GPU (single-GPU test of that path)"""
+        cat = cat if isinstance(cat, np.ndarray) and cat.dtype == np.uint8 else as_u8(cat)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        enc = [n.encode() if isinstance(n, str) else bytes(n) for n in names]
+        arr = (C.c_char_p * len(enc))(*enc)
+        h = C.c_void_p()
+        _check(lib().mm2_index_build_sharded_emulated(ctx.h, nranks, cat.ctypes.data, offs.ctypes.data, arr, len(enc), w, k, b, flag, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def build_multi(cls, ctxs, cat, offs, names, w=10, k=15, b=14, flag=0):
+        """one process, several GPUs (mm2_index_build_multi): -> one replica per context"""
+        cat = cat if isinstance(cat, np.ndarray) and cat.dtype == np.uint8 else as_u8(cat)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        enc = [n.encode() if isinstance(n, str) else bytes(n) for n in names]
+        arr = (C.c_char_p * len(enc))(*enc)
+        hs = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+        out = (C.c_void_p * len(ctxs))()
+        _check(lib().mm2_index_build_multi(hs, len(ctxs), cat.ctypes.data, offs.ctypes.data, arr, len(enc), w, k, b, flag, out))
+        return [cls(C.c_void_p(o)) for o in out]
+
+    @classmethod
     def build_from_fasta(cls, ctx, path, w=10, k=15, b=14, flag=0):
         h = C.c_void_p()
         _check(lib().mm2_index_build_fasta(ctx.h, path.encode(), w, k, b, flag, C.byref(h)))
@@ -511,15 +565,6 @@ class Index:
         out, n = C.c_void_p(), C.c_size_t()
         _check(lib().mm2_index_get_ref_subseq(self.h, rid, st, en, C.byref(out), C.byref(n)))
         return _copy_out(out.value, n.value, np.uint8).tobytes()
-
-    def raw(self):
-        """device pointers and counts of the flat arrays (mm2_index_raw_t) + host copies of the occurrence histogram"""
-        r = IndexRaw()
-        _check(lib().mm2_index_raw(self.h, C.byref(r)))
-        hist = np.frombuffer((C.c_char * (65536 * 8)).from_address(r.occ_hist), dtype=np.uint64, count=65536).copy()
-        big = (np.frombuffer((C.c_char * (r.n_occ_big * 4)).from_address(r.occ_big), dtype=np.uint32, count=r.n_occ_big).copy()
-               if r.n_occ_big else np.zeros(0, dtype=np.uint32))
-        return r, hist, big
 
     def build_timings(self):
         ms = (C.c_float * 5)()

@@ -76,7 +76,7 @@ extern "C" void mm2_ctx_destroy(mm2_ctx_t* c) {
   DevBuf* bufs[] = {&c->seq, &c->seq_off, &c->tile_seq, &c->tile_first, &c->tile_status, &c->misc, &c->mkey, &c->mval,
                     &c->mini_off, &c->keep, &c->occ_cnt, &c->occ_loc, &c->anchor_off_m, &c->scan_status, &c->anchors,
                     &c->read_aoff, &c->read_class, &c->read_flag, &c->read_nhit, &c->read_na, &c->flag_list, &c->dpA, &c->dpB, &c->dpT, &c->dpW, &c->hits, &c->chain_idx, &c->lut, &c->sort_tmp,
-                    &c->sort_tmp2, &c->sort_keys2, &c->sort_vals2, &c->runidx, &c->run_start, &c->run_gp, &c->rs_counts, &c->rs_offs};
+                    &c->sort_tmp2, &c->sort_keys2, &c->sort_vals2, &c->runidx, &c->run_start, &c->run_gp, &c->rs_counts, &c->rs_offs, &c->diag, &c->mg_recv_k, &c->mg_recv_v};
   for (DevBuf* b : bufs) b->release();
   c->pin_in.release(); c->pin_out.release(); c->pin_small.release(); c->pin_scalar.release();
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -108,6 +108,13 @@ extern "C" int mm2_ctx_synchronize(mm2_ctx_t* c) {
   return MM2_OK;
 }
 extern "C" uint64_t mm2_ctx_launch_count(const mm2_ctx_t* c) { return c ? c->launches : 0; }
+extern "C" int mm2_ctx_count_cells(mm2_ctx_t* c, int on) {
+  if (!c) { mm2_set_error("NULL ctx"); return MM2_E_ARG; }
+  c->count_cells = on != 0;
+  for (int w = 0; w < 4; ++w) if (c->worker[w]) c->worker[w]->count_cells = c->count_cells;
+  return MM2_OK;
+}
+extern "C" uint64_t mm2_ctx_last_cells(const mm2_ctx_t* c) { return c ? c->last_cells : 0; }
 extern "C" int mm2_ctx_last_timings(const mm2_ctx_t* c, const char** names, const float** ms, int* n) {
   if (!c || !names || !ms || !n) { mm2_set_error("NULL argument"); return MM2_E_ARG; }
   *names = c->timer.names_blob.c_str(); *ms = c->timer.ms.data(); *n = (int)c->timer.ms.size();
@@ -509,9 +516,9 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
   u32* d_sum_span = ctx->misc.as<u32>() + 16;
   CUDA_TRY(cudaMemsetAsync(ctx->misc.p, 0, 64, st));
   const IndexView V = idx->view();
-  u64 na = 0;
+  u64 na = 0, n_dropped = 0;
   MM2_TRY(seeds_hits(ctx, V, so.key, so.val, so.seq_off, (u32)nreads, nm, o->q_occ_max, o->q_occ_frac, mid_occ, o->want_stage_dump != 0,
-                     d_sum_span, &na));
+                     d_sum_span, &na, &n_dropped));
   mm2_trace(ctx, "hits done");
   {
     // Anchors and DP state take 56 B per anchor.  If a batch of repeat-rich reads needs more than what is free, map its
@@ -561,7 +568,7 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
       MM2_TRY(seeds_filter(ctx, dvs.key, dvs.seq_off, (u32)nreads, nm_dv, 0, 0.0f, ctx->keep.as<u8>(), d_sum_span));  // sum of spans only
     }
     const int rc = map_general_finish(ctx, idx, d_off, h_off, nreads, o, p, dvs, d_sum_span, nm_dv, na, out);
-    if (rc == MM2_OK) out->n_minimizers = nm;
+    if (rc == MM2_OK) { out->n_minimizers = nm; out->n_minimizers_kept = nm - n_dropped; }
     return rc;
   }
   ctx->timer.mark(st, "chain");
@@ -572,9 +579,15 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
   MM2_TRY(ctx->pin_out.ensure((nreads + 1) * sizeof(ReadHit) + 64));
   ReadHit* hits = ctx->pin_out.as<ReadHit>();
   static const bool hits_copy = [] { const char* e = getenv("MM2_HITS"); return e && !strcmp(e, "copy"); }();
+  unsigned long long* d_cells = nullptr;
+  if (ctx->count_cells) {
+    MM2_TRY(ctx->diag.ensure(64));
+    d_cells = ctx->diag.as<unsigned long long>();
+    CUDA_TRY(cudaMemsetAsync(d_cells, 0, 8, st));
+  }
   MM2_TRY(chain_batch(ctx, ctx->anchors.as<ulonglong2>(), ctx->read_aoff.as<u64>(), d_off, so.seq_off, so.val, d_sum_span, (u32)nreads,
                       p, 1, ctx->dpA.as<int4>(), ctx->dpB.as<int4>(), ctx->dpT.as<int>(), ctx->dpW.as<int>(), nullptr,
-                      hits_copy ? ctx->hits.as<ReadHit>() : hits, nullptr));   // no cell counter: a diagnostic, costs ~20 % of the kernel
+                      hits_copy ? ctx->hits.as<ReadHit>() : hits, d_cells));   // cell counter: a diagnostic (mm2b200_diag.h), off by default
   ctx->timer.mark(st, "d2h");
   if (nreads && hits_copy) CUDA_TRY(cudaMemcpyAsync(hits, ctx->hits.p, nreads * sizeof(ReadHit), cudaMemcpyDeviceToHost, st));
   ctx->timer.mark(st, "end");
@@ -582,6 +595,7 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
   CUDA_TRY(mm2_stream_wait(ctx));
   mm2_trace(ctx, "chain+d2h done");
   ctx->timer.finish();
+  if (d_cells) { u64 c = 0; MM2_TRY(read_scalar_u64(ctx, (const u64*)d_cells, &c)); ctx->last_cells = c; }
   const auto wall1 = std::chrono::steady_clock::now();
 
   // ---- records (paf.rs:130-222) ---------------------------------------------------------------------------------------------
@@ -642,7 +656,7 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
   out->n_panic = panics.size();
   out->panic_reads = xmalloc<u32>(panics.size());
   if (!panics.empty()) memcpy(out->panic_reads, panics.data(), panics.size() * 4);
-  out->n_minimizers_kept = 0;
+  out->n_minimizers_kept = nm - n_dropped;   // seeds.rs:13-36 survivors (counted by the exact-filter passes)
   {  // host wall clock of this call next to the device stage times: whole call up to here, and the record assembly alone
     const auto wall2 = std::chrono::steady_clock::now();
     ctx->timer.add_host("host_records", std::chrono::duration<float, std::milli>(wall2 - wall1).count());
@@ -725,6 +739,7 @@ static int map_host_pipelined(mm2_ctx* ctx, const mm2_index* idx, const u8* cat,
   const int NW = ctx->n_workers;
   for (int w = 0; w < NW; ++w)
     if (!ctx->worker[w]) MM2_TRY(mm2_ctx_create(ctx->device, &ctx->worker[w]));
+  for (int w = 0; w < NW; ++w) { ctx->worker[w]->count_cells = ctx->count_cells; ctx->worker[w]->last_cells = 0; }
   CUDA_TRY(cudaSetDevice(ctx->device));
   if (!ctx->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   while (ctx->copy_events.size() < nsub + 1) {   // + 1: the first sub-batch may be split below
@@ -758,6 +773,7 @@ static int map_host_pipelined(mm2_ctx* ctx, const mm2_index* idx, const u8* cat,
   int rc[4] = {MM2_OK, MM2_OK, MM2_OK, MM2_OK};
   std::string err[4];
   std::vector<std::vector<float>> ms_sum(4);
+  u64 cells_sum[4] = {0, 0, 0, 0};
   // one record array for the whole batch, written in place by the workers (the default path reports at most one chain per
   // read); the general multi-chain tail keeps per-part arrays that are concatenated afterwards
   const bool direct = !(opts->min_cnt < 2 || opts->w != idx->w || opts->k != idx->k);
@@ -775,6 +791,7 @@ static int map_host_pipelined(mm2_ctx* ctx, const mm2_index* idx, const u8* cat,
       const int r = map_device_impl(c, idx, ctx->seq.as<u8>(), ctx->seq_off.as<u64>() + lo, h_off0 + lo, hi - lo, opts, &part[sidx], false,
                                     final_recs ? final_recs + lo : nullptr, final_recs ? (u32)lo : 0u);
       if (r != MM2_OK) { rc[w] = r; err[w] = mm2_last_error(); return; }
+      cells_sum[w] += c->last_cells;
       if (ms_sum[w].size() < c->timer.ms.size()) ms_sum[w].resize(c->timer.ms.size(), 0.f);
       for (size_t i = 0; i < c->timer.ms.size(); ++i) ms_sum[w][i] += c->timer.ms[i];
     }
@@ -798,6 +815,7 @@ static int map_host_pipelined(mm2_ctx* ctx, const mm2_index* idx, const u8* cat,
   cudaStreamSynchronize(ctx->copy_stream);
   for (int w = 0; w < NW; ++w) l1 += ctx->worker[w]->launches;
   ctx->launches += l1 - l0;
+  ctx->last_cells = cells_sum[0] + cells_sum[1] + cells_sum[2] + cells_sum[3];
   for (int w = 0; w < NW; ++w)
     if (rc[w] != MM2_OK) {
       for (auto& p : part) { if (final_recs) p.recs = nullptr; mm2_map_result_free(&p); }

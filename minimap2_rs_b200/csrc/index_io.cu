@@ -91,9 +91,10 @@ int download(const mm2_index* idx, HostIndex& h, bool want_S) {
   CUDA_TRY(cudaSetDevice(idx->device));
   const size_t nb = (size_t)1 << idx->b;
   h.hkeys.resize(idx->n_keys); h.hvals.resize(idx->n_keys); h.koff.resize(nb + 1); h.poff.resize(nb + 1); h.p.resize(idx->n_p);
-  if (idx->n_keys) {
-    CUDA_TRY(cudaMemcpy(h.hkeys.data(), idx->hkeys.p, idx->n_keys * 8, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(h.hvals.data(), idx->hvals.p, idx->n_keys * 8, cudaMemcpyDeviceToHost));
+  if (idx->n_keys) {   // device layout: interleaved {key, value} records
+    std::vector<u64> kv((size_t)idx->n_keys * 2);
+    CUDA_TRY(cudaMemcpy(kv.data(), idx->kv.p, idx->n_keys * 16, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < idx->n_keys; ++i) { h.hkeys[i] = kv[2 * i]; h.hvals[i] = kv[2 * i + 1]; }
   }
   CUDA_TRY(cudaMemcpy(h.koff.data(), idx->bkt_koff.p, (nb + 1) * 8, cudaMemcpyDeviceToHost));
   CUDA_TRY(cudaMemcpy(h.poff.data(), idx->bkt_poff.p, (nb + 1) * 8, cudaMemcpyDeviceToHost));
@@ -109,16 +110,16 @@ int download(const mm2_index* idx, HostIndex& h, bool want_S) {
 int upload(mm2_ctx* ctx, mm2_index* idx, HostIndex& h) {
   const size_t nb = (size_t)1 << idx->b;
   idx->n_keys = h.hkeys.size(); idx->n_p = h.p.size();
-  MM2_TRY(idx->hkeys.ensure(std::max<size_t>(1, idx->n_keys) * 8));
-  MM2_TRY(idx->hvals.ensure(std::max<size_t>(1, idx->n_keys) * 8));
+  MM2_TRY(idx->kv.ensure(std::max<size_t>(1, idx->n_keys) * 16));
   MM2_TRY(idx->p.ensure(std::max<size_t>(1, idx->n_p) * 8));
   MM2_TRY(idx->bkt_koff.ensure((nb + 1) * 8));
   MM2_TRY(idx->bkt_poff.ensure((nb + 1) * 8));
   MM2_TRY(idx->S.ensure(std::max<size_t>(1, h.S.size()) * 4));
   MM2_TRY(idx->seq_len.ensure(std::max<size_t>(1, idx->lens.size()) * 4));
   if (idx->n_keys) {
-    CUDA_TRY(cudaMemcpy(idx->hkeys.p, h.hkeys.data(), idx->n_keys * 8, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(idx->hvals.p, h.hvals.data(), idx->n_keys * 8, cudaMemcpyHostToDevice));
+    std::vector<u64> kv((size_t)idx->n_keys * 2);
+    for (size_t i = 0; i < idx->n_keys; ++i) { kv[2 * i] = h.hkeys[i]; kv[2 * i + 1] = h.hvals[i]; }
+    CUDA_TRY(cudaMemcpy(idx->kv.p, kv.data(), idx->n_keys * 16, cudaMemcpyHostToDevice));
   }
   if (idx->n_p) CUDA_TRY(cudaMemcpy(idx->p.p, h.p.data(), idx->n_p * 8, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(idx->bkt_koff.p, h.koff.data(), (nb + 1) * 8, cudaMemcpyHostToDevice));
@@ -136,7 +137,7 @@ int upload(mm2_ctx* ctx, mm2_index* idx, HostIndex& h) {
   }
   std::sort(idx->occ_big.begin(), idx->occ_big.end());
   idx->n_minimizers = sum_occ;
-  MM2_TRY(index_build_table(ctx, idx));
+  MM2_TRY(index_build_lookup(ctx, idx));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return MM2_OK;
 }
@@ -151,8 +152,8 @@ bool ends_with(const char* s, const char* suf) {
 extern "C" void mm2_index_free(mm2_index_t* idx) {
   if (!idx) return;
   cudaSetDevice(idx->device);
-  idx->S.release(); idx->hkeys.release(); idx->hvals.release(); idx->bkt_koff.release(); idx->bkt_poff.release();
-  idx->p.release(); idx->seq_len.release(); idx->tab.release(); idx->bloom.release();
+  idx->S.release(); idx->kv.release(); idx->bkt_koff.release(); idx->bkt_poff.release();
+  idx->p.release(); idx->seq_len.release(); idx->fine_off.release(); idx->bloom.release();
   delete idx;
 }
 

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "mm2b200.h"
+#include "mm2b200_diag.h"
 
 typedef uint64_t u64;
 typedef uint32_t u32;
@@ -141,6 +142,10 @@ struct mm2_ctx {
   // chaining: reads with >= chain_dense_min anchors and more than chain_dense_ratio5 / 5 anchors per base get a CTA each
   int chain_dense_min = 4096, chain_dense_ratio5 = 2;
   u64 mg_sorted_n = 0;  // records left in sort_keys2/sort_vals2 by mm2_mg_sketch_sort
+  bool count_cells = false;  // diagnostics (mm2b200_diag.h): DP-cell counter of the chaining kernels
+  u64 last_cells = 0;
+  DevBuf diag;
+  DevBuf mg_recv_k, mg_recv_v;   // sharded index build: records received from the other ranks
 };
 
 // The waits of the mapping path (minimizer total, anchor total, end of the batch).  cudaStreamSynchronize spins a host core; with
@@ -164,20 +169,35 @@ struct IndexView {
   int w, k, b, flag;
   u32 n_seq;
   u64 n_keys, n_p;
-  const u64* hkeys;      // n_keys: (minier>>b)<<1 | is_single, ascending inside each bucket
-  const u64* hvals;      // n_keys: y (single) or start_in_bucket_p<<32 | n
+  const ulonglong2* kv;  // n_keys: {(minier>>b)<<1 | is_single, y (single) or start_in_bucket_p<<32 | n}, ascending key inside each bucket
   const u64* bkt_koff;   // (1<<b)+1
   const u64* bkt_poff;   // (1<<b)+1
   const u64* p;          // n_p
   const u32* seq_len;    // n_seq
-  // open-addressing table over all keys: slot = {tag = minier<<1|is_single (0 = empty slot marker ~0), val}
-  const ulonglong2* tab;
-  u64 tab_mask;
+  // Seed lookup: the keys are sorted by (bucket, minier>>b), so a FINE bucket = (bucket, top bits of a monotone
+  // equalising map of minier>>b) is a contiguous range of kv[]; fine_off[f] is its first entry (index_fine_id below).
+  const u32* fine_off;   // (1 << (b + fine_j)) + 1
+  int fine_j, fine_pw, R;   // fine bits per bucket; squarings of the equalising map; R = bits of minier>>b (max(2k-b, 0))
   // blocked Bloom filter over the keys (one 16-byte block per key, 4 bits), small enough to live in L2: answers most
-  // of the ~80 % of query minimizers that are absent from the index without touching the table in HBM.  NULL = disabled.
+  // of the ~80 % of query minimizers that are absent from the index without touching HBM.  NULL = disabled.
   const uint4* bloom;
   u64 bloom_mask;
 };
+
+// Monotone map of hk = minier>>b (R bits) onto fine_j bits.  Minimizer hashes are window MINIMA, so hk is skewed towards 0
+// with density ~ w (1-x)^(w-1); u = 1 - (1-x)^(2^pw) (integer arithmetic: exactly monotone, identical wherever it is
+// evaluated) spreads the keys of a bucket roughly evenly over its 2^fine_j fine buckets.  Only balance depends on it.
+__host__ __device__ __forceinline__ u32 index_fine_cdf(u64 hk, int R, int j, int pw) {
+  if (j <= 0) return 0u;
+  const u64 t = (R >= 64 ? ~0ULL : ((1ULL << R) - 1)) - hk;
+  u32 t32 = R >= 32 ? (u32)(t >> (R - 32)) : (u32)(t << (32 - R));
+  for (int s = 0; s < pw; ++s) t32 = (u32)(((u64)t32 * (u64)t32) >> 32);
+  return (~t32) >> (32 - j);
+}
+__host__ __device__ __forceinline__ u64 index_fine_id(const IndexView& V, u64 minier) {
+  const u64 bkt = minier & ((1ULL << V.b) - 1);
+  return (bkt << V.fine_j) | (u64)index_fine_cdf(minier >> V.b, V.R, V.fine_j, V.fine_pw);
+}
 
 struct mm2_index {
   int device = 0;
@@ -189,16 +209,17 @@ struct mm2_index {
   std::vector<u64> seq_offset;  // index.rs:29 IndexSeq.offset
   std::vector<u8> is_alt;
   u64 total_len = 0;
-  u64 S_words_alloc = 0;       // kroundup64((total+7)/8) as allocated by build (native format writes all of it)
+  u64 S_words_alloc = 0;       // kroundup64((total+7)/8) as allocated by build (native format writes all of it); 0 = no sequence array
   u64 n_keys = 0, n_p = 0, n_minimizers = 0;
-  DevBuf S, hkeys, hvals, bkt_koff, bkt_poff, p, seq_len, tab, bloom;
-  u64 tab_mask = 0, bloom_mask = 0;
+  DevBuf S, kv, bkt_koff, bkt_poff, p, seq_len, fine_off, bloom;
+  int fine_j = 0, fine_pw = 0;
+  u64 bloom_mask = 0;
   bool has_bloom = false;
   // occurrence histogram for calc_mid_occ/stats (index.rs:111-141): hist[c] = #keys with count c (c < 65536)
   std::vector<u64> occ_hist;
   std::vector<u32> occ_big;     // counts >= 65536
   float build_ms[5] = {0, 0, 0, 0, 0};
-  mm2_index() { S.pooled = hkeys.pooled = hvals.pooled = bkt_koff.pooled = bkt_poff.pooled = p.pooled = seq_len.pooled = tab.pooled = bloom.pooled = true; }
+  mm2_index() { S.pooled = kv.pooled = bkt_koff.pooled = bkt_poff.pooled = p.pooled = seq_len.pooled = fine_off.pooled = bloom.pooled = true; }
   IndexView view() const;
 };
 
@@ -217,11 +238,20 @@ struct SketchOut {  // device SoA minimizers of a batch
 // feed (optional): d_cat is still being uploaded by another stream; ev[c] fires when bytes [0, chunk_end[c]) of it (relative
 // to the first sequence) are resident.  The tile kernel is then launched once per chunk so that it overlaps the upload.
 struct SketchFeed { int nchunks; const u64* chunk_end; cudaEvent_t* ev; };
+// shard (optional, tile kernels only): sketch just the tiles [tile_lo, tile_hi) of the batch's global tile list (the sharded
+// index build splits INSIDE sequences this way: a tile depends only on its own bases plus a 2w+k halo).  Only the bytes
+// sketch_tile_bytes() names need to be resident; out->total = minimizers of the shard, in global emission order.
+struct SketchShard { u64 tile_lo, tile_hi; };
+u64 sketch_tile_count(const u64* h_off, size_t nseq, int w);
+void sketch_tile_bytes(const u64* h_off, size_t nseq, int w, int k, u64 tile_lo, u64 tile_hi, u64* byte_lo, u64* byte_hi);
 int sketch_device(mm2_ctx* ctx, const u8* d_cat, const u64* d_off, const u64* h_off, size_t nseq, int w, int k,
-                  u32 rid_base, u32 rid_step, int is_hpc, SketchOut* out, const SketchFeed* feed = nullptr);
+                  u32 rid_base, u32 rid_step, int is_hpc, SketchOut* out, const SketchFeed* feed = nullptr,
+                  const SketchShard* shard = nullptr);
 
 int index_build_device(mm2_ctx* ctx, const u8* h_cat, const u64* h_off, const char* const* names, size_t nseq, int w,
                        int k, int b, int flag, mm2_index** out);
+// seed-lookup structures (fine offsets + Bloom filter) from kv / bkt_koff; after build, load and sharded assembly
+int index_build_lookup(mm2_ctx* ctx, mm2_index* idx);
 
 // generic single-pass exclusive scan of u32 counts into u64 offsets (n+1 outputs; out[n] = total)
 // wide = true: tile sums are accumulated in 64 bits (inputs with no bound on their sum)

@@ -18,7 +18,7 @@ constexpr int FL_PER_PASS = FL_SLOTS / 4;  // expected distinct keys per pass (l
 template <bool INIT_KEEP>
 __device__ __forceinline__ void filter_read(const u32 r, const u64* __restrict__ mkey, const u64* __restrict__ mini_off,
                                             i32 q_occ_max, float q_occ_frac, u8* __restrict__ keep, u32* __restrict__ sum_span,
-                                            unsigned char* fl_smem, u32* s_red) {
+                                            unsigned char* fl_smem, u32* s_red, unsigned long long* __restrict__ n_dropped) {
   unsigned long long* hk = reinterpret_cast<unsigned long long*>(fl_smem);
   u32* hc = reinterpret_cast<u32*>(fl_smem + FL_SLOTS * 8);
   const u64 m0 = mini_off[r], m1 = mini_off[r + 1];
@@ -54,6 +54,7 @@ __device__ __forceinline__ void filter_read(const u32 r, const u64* __restrict__
   if (INIT_KEEP)
     for (u64 i = m0 + tid; i < m1; i += FL_NT) keep[i] = 1;
   const u32 npass = (u32)((n + FL_PER_PASS - 1) / FL_PER_PASS);
+  u32 dropped = 0;
   for (u32 pass = 0; pass < npass; ++pass) {
     __syncthreads();
     for (int s = tid; s < FL_SLOTS; s += FL_NT) { hk[s] = ~0ULL; hc[s] = 0; }
@@ -76,8 +77,13 @@ __device__ __forceinline__ void filter_read(const u32 r, const u64* __restrict__
       if ((u32)((h >> 40) % npass) != pass) continue;
       u32 slot = (u32)(h >> 20) & (FL_SLOTS - 1);
       while (hk[slot] != key) slot = (slot + 1) & (FL_SLOTS - 1);
-      if ((u64)hc[slot] > thr) keep[i] = 0;
+      if ((u64)hc[slot] > thr) { keep[i] = 0; ++dropped; }
     }
+  }
+  if (n_dropped) {   // work counter of the batch (n_minimizers_kept); only reads that reach the exact passes get here
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) dropped += __shfl_xor_sync(0xFFFFFFFFu, dropped, d);
+    if ((tid & 31) == 0 && dropped) atomicAdd(n_dropped, (unsigned long long)dropped);
   }
 }
 
@@ -87,28 +93,23 @@ __global__ void __launch_bounds__(FL_NT) filter_kernel(const u64* __restrict__ m
   extern __shared__ __align__(16) unsigned char fl_smem[];
   __shared__ u32 s_red[FL_NT / 32];
   if (blockIdx.x >= nreads) return;
-  filter_read<false>(blockIdx.x, mkey, mini_off, q_occ_max, q_occ_frac, keep, sum_span, fl_smem, s_red);
+  filter_read<false>(blockIdx.x, mkey, mini_off, q_occ_max, q_occ_frac, keep, sum_span, fl_smem, s_red, nullptr);
 }
 
 // the exact passes for the reads seed_hits_kernel<0> put on the list (their count sketch had a bin over the threshold)
 __global__ void __launch_bounds__(FL_NT) filter_list_kernel(const u64* __restrict__ mkey, const u64* __restrict__ mini_off,
                                                             const u32* __restrict__ list, const u32* __restrict__ n_list,
                                                             i32 q_occ_max, float q_occ_frac, u8* __restrict__ keep,
-                                                            u32* __restrict__ sum_span) {
+                                                            u32* __restrict__ sum_span, unsigned long long* __restrict__ n_dropped) {
   extern __shared__ __align__(16) unsigned char fl_smem[];
   __shared__ u32 s_red[FL_NT / 32];
   const u32 nl = *n_list;
   for (u32 j = blockIdx.x; j < nl; j += gridDim.x) {
     __syncthreads();   // the previous read's shared state is no longer in use
-    filter_read<true>(list[j], mkey, mini_off, q_occ_max, q_occ_frac, keep, sum_span, fl_smem, s_red);
+    filter_read<true>(list[j], mkey, mini_off, q_occ_max, q_occ_frac, keep, sum_span, fl_smem, s_red, n_dropped);
   }
 }
 
-// ---- index.rs:143-154 Index::get for every kept minimizer: occurrence count + where the occurrences live -------------
-__device__ __forceinline__ u64 tab_hash(u64 minier) {
-  u64 x = minier * 0x9E3779B97F4A7C15ULL;
-  return x ^ (x >> 29);
-}
 
 // ---- seeds.rs:62-79 push_anchor ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void make_anchor(u64 r, u64 key_span, u64 rps, i32 qlen, u64& x, u64& y) {
@@ -185,23 +186,26 @@ __device__ __forceinline__ void seed_hits_read(const SeedHitArgs& G, const u32 r
       for (int q = 0; q < 4; ++q) { const u32 b = (u32)(h >> (7 * q)) & 127u; maybe = maybe && ((wd[b >> 5] >> (b & 31)) & 1u); }
     }
     if (!maybe) continue;
-    u64 slot = tab_hash(minier) & G.V.tab_mask;
+    // Index::get (index.rs:143-154): the key's fine bucket is a short contiguous run of kv[] (ascending keys)
+    const u64 hk = minier >> G.V.b;
+    const u64 f = ((minier & bmask) << G.V.fine_j) | (u64)index_fine_cdf(hk, G.V.R, G.V.fine_j, G.V.fine_pw);
+    const u32 e0 = __ldg(G.V.fine_off + f), e1 = __ldg(G.V.fine_off + f + 1);
     u32 cnt = 0; u64 loc = 0;
-    for (;;) {
-      const ulonglong2 e = ld_hint_v2(&G.V.tab[slot], pol_stream);
-      if (e.x == ~0ULL) break;
-      if ((e.x >> 1) == minier) {
-        if (e.x & 1) { cnt = 1; loc = e.y; }                     // Occurrences::Single (never skipped, seeds.rs:47)
+    for (u32 e = e0; e < e1; ++e) {
+      const ulonglong2 kv = ld_hint_v2(&G.V.kv[e], pol_stream);
+      const u64 kk = kv.x >> 1;
+      if (kk < hk) continue;
+      if (kk == hk) {
+        if (kv.x & 1) { cnt = 1; loc = kv.y; }                   // Occurrences::Single (never skipped, seeds.rs:47)
         else {
-          const u64 c = e.y & 0xffffffffULL;
+          const u64 c = kv.y & 0xffffffffULL;
           if (!((i32)(u32)c > G.mid_occ)) {                      // seeds.rs:51 `slice.len() as i32 > mid_occ`
             cnt = (u32)c;
-            loc = G.V.bkt_poff[minier & bmask] + (e.y >> 32);
+            loc = G.V.bkt_poff[minier & bmask] + (kv.y >> 32);
           }
         }
-        break;
       }
-      slot = (slot + 1) & G.V.tab_mask;
+      break;
     }
     if (cnt) {
       const u64 rps = __ldcs(G.mval + i);
@@ -649,9 +653,10 @@ int seeds_filter(mm2_ctx* ctx, const u64* d_mkey, const u64* d_mini_off, u32 nre
 // minimizer afterwards (stage dump), not only inside the reads that went through the exact filter.  Synchronises the
 // stream once to return the batch's anchor count.
 int seeds_hits(mm2_ctx* ctx, const IndexView& V, const u64* d_mkey, const u64* d_mval, const u64* d_mini_off, u32 nreads, u64 n_mini,
-               i32 q_occ_max, float q_occ_frac, i32 mid_occ, bool full_keep, u32* d_sum_span, u64* n_anchors) {
+               i32 q_occ_max, float q_occ_frac, i32 mid_occ, bool full_keep, u32* d_sum_span, u64* n_anchors, u64* n_dropped) {
   cudaStream_t st = ctx->stream;
   *n_anchors = 0;
+  if (n_dropped) *n_dropped = 0;
   MM2_TRY(ctx->keep.ensure(n_mini + 16));
   MM2_TRY(ctx->occ_loc.ensure((n_mini + 16) * 8));
   MM2_TRY(ctx->anchor_off_m.ensure((n_mini + 16) * 8));
@@ -661,8 +666,8 @@ int seeds_hits(mm2_ctx* ctx, const IndexView& V, const u64* d_mkey, const u64* d
   MM2_TRY(ctx->read_na.ensure(((u64)nreads + 16) * 4));
   MM2_TRY(ctx->read_aoff.ensure(((u64)nreads + 4) * 8));
   u64* d_aoff = ctx->read_aoff.as<u64>();
-  u32* d_hdr = reinterpret_cast<u32*>(d_aoff + nreads + 1);   // {number of listed reads, error flag}, read back with the total
-  CUDA_TRY(cudaMemsetAsync(d_hdr, 0, 8, st));
+  u32* d_hdr = reinterpret_cast<u32*>(d_aoff + nreads + 1);   // {number of listed reads, error flag}, then the u64 count of
+  CUDA_TRY(cudaMemsetAsync(d_hdr, 0, 16, st));                  // minimizers dropped by the exact filter; read back with the total
   if (full_keep && n_mini) CUDA_TRY(cudaMemsetAsync(ctx->keep.p, 1, n_mini, st));
   SeedHitArgs G;
   G.V = V; G.mkey = d_mkey; G.mval = d_mval; G.mini_off = d_mini_off; G.nreads = nreads;
@@ -675,18 +680,19 @@ int seeds_hits(mm2_ctx* ctx, const IndexView& V, const u64* d_mkey, const u64* d
     if (q_occ_frac > 0.0f && q_occ_max > 0) {   // otherwise nothing can be on the list (seeds.rs:14)
       const int lgrid = (int)std::min<u32>(nreads, (u32)ctx->n_sm * 4u);
       MM2_LAUNCH(ctx, filter_list_kernel, lgrid, FL_NT, FL_SLOTS * 12, d_mkey, d_mini_off, G.list, G.n_list, q_occ_max, q_occ_frac,
-                 ctx->keep.as<u8>(), d_sum_span);
+                 ctx->keep.as<u8>(), d_sum_span, reinterpret_cast<unsigned long long*>(d_aoff + nreads + 2));
       MM2_LAUNCH(ctx, seed_hits_kernel<1>, (int)std::min<u32>(nreads, (u32)ctx->n_sm * 12u), SH_NT, 0, G);
     }
   }
   MM2_TRY(scan_u32_to_u64(ctx, ctx->read_na.as<u32>(), d_aoff, nreads, true));
   MM2_TRY(ctx->pin_scalar.ensure(64));
-  CUDA_TRY(cudaMemcpyAsync(ctx->pin_scalar.p, d_aoff + nreads, 16, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(ctx->pin_scalar.p, d_aoff + nreads, 24, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(mm2_stream_wait(ctx));
   const u64 total = ctx->pin_scalar.as<u64>()[0];
   const u32 err = (u32)(ctx->pin_scalar.as<u64>()[1] >> 32);
   if (err) { mm2_set_error("a read has 2^32 or more anchors"); return MM2_E_OOM; }
   *n_anchors = total;
+  if (n_dropped) *n_dropped = ctx->pin_scalar.as<u64>()[2];
   CUDA_TRY(cudaGetLastError());
   return MM2_OK;
 }

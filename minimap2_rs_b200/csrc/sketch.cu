@@ -40,7 +40,7 @@ struct SketchParams {
   u64* seq_out_off;       // nseq+1
   u64* tile_status;       // ntiles, zero-initialised; [63:62] 1 = aggregate, 2 = inclusive prefix
   u32* ticket;            // zero-initialised
-  u32 tile_base;          // first tile of this launch (tickets count from it; v3 kernel only, 0 elsewhere)
+  u32 tile_base;          // first tile of this launch (tickets count from it)
 };
 
 // invertible integer mix of sketch.rs:4-13, in the narrowest type that holds 2k bits
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(SK_NT) sketch_tile_kernel(SketchParams P) {
 
   for (;;) {
     __syncthreads();  // protects s_tile / all tile state of the previous iteration
-    if (tid == 0) s_tile = atomicAdd(P.ticket, 1u);
+    if (tid == 0) s_tile = P.tile_base + atomicAdd(P.ticket, 1u);
     __syncthreads();
     const u32 tile = s_tile;
     if (tile >= P.ntiles) break;
@@ -367,9 +367,9 @@ __global__ void __launch_bounds__(SK_NT) sketch_tile_kernel(SketchParams P) {
 
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Version 2 of the tile kernel (used for w >= 9): same phases 1-2, but the window argmin is computed per thread with
-// prefix/suffix minima over its 8 consecutive positions (3 merges per position instead of w compares), the emission
-// decisions are taken in registers, and the minimizers are written by the thread that decided them.
+// The tile kernel used for w >= 9 (below): same phases 1-2, but the window argmin is computed per thread with
+// prefix/suffix minima over its 8 consecutive positions (3 merges per position instead of w compares) and the emission
+// decisions are taken in registers.
 // Window minima are kept as (key, pos << 1 | dup): among equal keys the NEWEST position wins (sketch.rs:84,90-91) and
 // `dup` says whether the minimum occurs at least twice in the range.
 
@@ -395,374 +395,11 @@ __device__ __noinline__ u64 sk_emit_dups(const KT* s_key, const u8* s_z, int lo,
   return o;
 }
 
-// staged variant: the positions go to a shared list instead of global memory
-template <class KT, int PAD>
-__device__ __noinline__ u32 sk_list_dups(const KT* s_key, int lo, int hi, int excl, u16* s_list, u32 idx) {
-  const KT kv = s_key[excl + (excl >> PAD)];
-  for (int x = lo; x <= hi; ++x)
-    if (s_key[x + (x >> PAD)] == kv && x != excl) s_list[idx++] = (u16)x;
-  return idx;
-}
-
 constexpr int SK_LIST = 1024;   // staged minimizers per tile (a tile of random sequence emits ~380)
 
-#ifndef MM2_SK_OCC
-#define MM2_SK_OCC 6   // CTAs per SM of the 32-bit-key kernel (40 registers; measured 10.3 / 9.3 / 8.9 ms per Gbase at 4 / 5 / 6)
-#endif
-template <class KT>
-__global__ void __launch_bounds__(SK_NT, sizeof(KT) == 4 ? MM2_SK_OCC : 4) sketch_tile_kernel_v2(SketchParams P) {
-  constexpr int PAD = KeyTraits<KT>::PAD;
-  constexpr KT KMAX = (KT)~(KT)0;
-#define KIDX(u) ((u) + ((u) >> PAD))
-  __shared__ __align__(16) KT s_key[SK_REGION + (SK_REGION >> PAD) + 8];
-  __shared__ __align__(16) u32 s_pack[SK_MAXCHUNK + 4];
-  __shared__ __align__(16) u32 s_nm[SK_MAXCHUNK / 2 + 4];
-  __shared__ u8 s_z[SK_NT];
-  __shared__ u32 s_wsum[SK_NT / 32];
-  __shared__ u32 s_next[2];
-  __shared__ u64 s_base;
-  __shared__ u16 s_list[SK_LIST];
-
-  const int tid = threadIdx.x;
-  const int w = P.w, k = P.k;
-  const int cap = w + k;
-  const int T = SK_REGION - w;
-  const KT mask = (KT)((((u64)1) << (2 * k)) - 1);
-  const int shift1 = 2 * (k - 1);
-
-  // Tiles are handed out in order (the look-back below needs every earlier tile to be running or done).  The next ticket
-  // is taken by thread 0 right after its look-back, i.e. just before the tile's records are written: a ticket taken
-  // earlier would sit unprocessed while later tiles spin on it (measured: 2.7x slower).
-  if (tid == 0) s_next[0] = atomicAdd(P.ticket, 1u);
-  __syncthreads();
-  u32 tile = s_next[0];
-  for (int par = 0; tile < P.ntiles; par ^= 1) {
-    const u32 q = P.tile_seq[tile];
-    const u64 soff = P.seq_off[q];
-    const i64 len = (i64)(P.seq_off[q + 1] - soff);
-    const i64 s = (i64)(tile - P.tile_first[q]) * T;
-    const i64 e = min(len, s + (i64)T);
-    const int nsteps = (int)(e - s);
-    const i64 P0 = s - w;
-    const i64 a = P0 - cap;
-    const i64 gidx = (i64)soff + a;
-    const i64 g0 = (gidx >> 4) << 4;
-    const int delta = (int)(gidx - g0);
-    const int nchunks = (delta + SK_REGION + cap + 15) >> 4;
-
-    // ---- phase 1: 128-bit loads -> 2-bit packed codes + N mask (as in version 1) ---------------------------------
-    for (int c = tid; c < SK_MAXCHUNK + 4; c += SK_NT) {
-      u32 packed = 0, nmask = 0xFFFFu;
-      if (c < nchunks) {
-        const i64 gi = g0 + 16 * (i64)c;
-        u32 wd[4] = {0, 0, 0, 0};
-        if (P.vec_ok && gi >= 0 && gi + 16 <= (i64)P.buf_len) {
-          const uint4 v = __ldg(reinterpret_cast<const uint4*>(P.seq + gi));
-          wd[0] = v.x; wd[1] = v.y; wd[2] = v.z; wd[3] = v.w;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const i64 g = gi + j;
-            u32 b = (g >= 0 && g < (i64)P.buf_len) ? (u32)P.seq[g] : 0u;
-            wd[j >> 2] |= b << (8 * (j & 3));
-          }
-        }
-        nmask = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          u32 c4, vm;
-          nt4x4(wd[j], c4, vm);
-          packed |= pack4(c4) << (8 * j);
-          nmask |= nbits4(vm) << (4 * j);
-        }
-        const i64 pstart = a + 16 * (i64)c - delta;
-        const i64 lo = max((i64)0, -pstart), hi = min((i64)16, len - pstart);
-        u32 inseq = 0;
-        if (hi > lo) inseq = ((hi >= 16 ? 0x10000u : (1u << hi)) - 1u) & ~((1u << lo) - 1u);
-        nmask = (nmask | ~inseq) & 0xFFFFu;
-      }
-      s_pack[c] = packed;
-      reinterpret_cast<u16*>(s_nm)[c] = (u16)nmask;
-    }
-    __syncthreads();
-
-    // ---- phase 2: 8 consecutive k-mers per thread -> keys (registers + shared), strand bits, l gates -----------------
-    KT K[SK_CH];
-    u32 ge_cap = 0, eq_capm1 = 0;
-    {
-      const int r0 = cap + SK_CH * tid + delta;
-      int l = run_len_at(s_nm, r0 - 1, cap);
-      const int rs = r0 - k;
-      const int wi = rs >> 4, sh = 2 * (rs & 15);
-      const u32 w0 = s_pack[wi], w1 = s_pack[wi + 1], w2 = s_pack[wi + 2];
-      const u32 flo = __funnelshift_r(w0, w1, sh), fhi = __funnelshift_r(w1, w2, sh);
-      const u64 field = (((u64)fhi << 32) | flo) & (u64)mask;
-      KT rev = (KT)((~field) & (u64)mask);
-      u64 br = __brevll(field);
-      br = ((br & 0x5555555555555555ULL) << 1) | ((br >> 1) & 0x5555555555555555ULL);
-      KT fwd = (KT)(br >> (64 - 2 * k));
-      const u32 cw = __funnelshift_r(s_pack[r0 >> 4], s_pack[(r0 >> 4) + 1], 2 * (r0 & 15));
-      const u32 nb = __funnelshift_r(s_nm[r0 >> 5], s_nm[(r0 >> 5) + 1], r0 & 31);
-      u32 zbits = 0;
-      if (l >= cap && (nb & 0xFFu) == 0u) {
-        // no N among these 8 bases and a full run before them: l stays at its cap, every k-mer is hashed
-        ge_cap = 0xFFu;
-#pragma unroll
-        for (int j = 0; j < SK_CH; ++j) {
-          const u32 c = (cw >> (2 * j)) & 3u;
-          fwd = (KT)(((fwd << 2) | (KT)c) & mask);
-          rev = (KT)((rev >> 2) | ((KT)(3u ^ c) << shift1));
-          const bool z = !(fwd < rev);
-          const KT key = hash_mix<KT>(z ? rev : fwd, mask);
-          K[j] = key;
-          s_key[KIDX(SK_CH * tid + j)] = key;
-          zbits |= (u32)z << j;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < SK_CH; ++j) {
-          const u32 c = (cw >> (2 * j)) & 3u;
-          l = ((nb >> j) & 1u) ? 0 : min(l + 1, cap);
-          fwd = (KT)(((fwd << 2) | (KT)c) & mask);
-          rev = (KT)((rev >> 2) | ((KT)(3u ^ c) << shift1));
-          const bool z = !(fwd < rev);
-          KT key = KMAX;
-          if (l >= k) key = hash_mix<KT>(z ? rev : fwd, mask);
-          K[j] = key;
-          s_key[KIDX(SK_CH * tid + j)] = key;
-          zbits |= (u32)z << j;
-          ge_cap |= (u32)(l >= cap) << j;
-          eq_capm1 |= (u32)(l == cap - 1) << j;
-        }
-      }
-      s_z[tid] = (u8)zbits;
-    }
-    __syncthreads();
-
-    // ---- phase 3: window minima of this thread's 8 positions + emission decisions (sketch.rs:80-96) -----------------
-    const int c0 = SK_CH * tid;
-    const int u_last = w + nsteps - 1;
-    const bool last_tile = (e == len);
-    auto keyat = [&](int t) -> KT { return t >= 0 ? s_key[KIDX(t)] : KMAX; };
-    u32 tot = 0, eflags = 0;  // bits 0-7: emit prev; 8-15: first-window duplicates; 16-23: rescan duplicates; 24: end emit
-    u32 pp[4] = {0, 0, 0, 0};  // position of the previous minimum for each of the 8 steps (u16 x 8)
-    int cur7 = 0;              // position of the window minimum at this thread's last position
-    if (c0 + SK_CH > w && c0 < w + nsteps) {
-      // suffix minima over the w keys before this thread's chunk, newest position winning ties (sketch.rs:84,90-91).
-      // A range is (key, pd) with pd = pos << 1 | dup, dup = "the minimum occurs at least twice in the range".
-      KT rk = KMAX; int rpd = 0;
-      int t = c0 - 1;
-      for (; t > c0 - (w - 1) + 7; --t) {
-        const KT kx = keyat(t);
-        if (kx < rk) { rk = kx; rpd = t << 1; } else if (kx == rk) rpd |= 1;
-      }
-      KT Sk[SK_CH]; int Spd[SK_CH];
-#pragma unroll
-      for (int jj = SK_CH - 1; jj >= 0; --jj) {
-        const KT kx = keyat(t);
-        if (kx < rk) { rk = kx; rpd = t << 1; } else if (kx == rk) rpd |= 1;
-        Sk[jj] = rk; Spd[jj] = rpd;
-        --t;
-      }
-      KT pk_prev; int ppd_prev;  // window [c0-w, c0-1]
-      {
-        const KT kx = keyat(t);
-        pk_prev = rk; ppd_prev = rpd;
-        if (kx < rk) { pk_prev = kx; ppd_prev = t << 1; } else if (kx == rk) ppd_prev |= 1;
-      }
-      // Fast path: all 8 steps are inside the tile, every window involved is full (l >= w + k: the previous minimum is a
-      // real k-mer and sketch.rs:84/88 emit unconditionally) and no window holds its minimum twice.  Then step u emits
-      // the previous minimum exactly when it is replaced (new key <= old minimum) or slides out (its position is u - w).
-      bool slow = !(ge_cap == 0xFFu && c0 >= w && c0 + SK_CH - 1 <= u_last && !(last_tile && c0 + SK_CH - 1 == u_last));
-      if (!slow) {
-        const KT pk0 = pk_prev; const int ppd0 = ppd_prev;
-        KT fk = KMAX; int fpd = 0;
-        int odd = ppd_prev;
-#pragma unroll
-        for (int j = 0; j < SK_CH; ++j) {
-          const int u = c0 + j;
-          const KT ki = K[j];
-          if (ki <= fk) { fpd = (u << 1) | (ki == fk ? 1 : 0); fk = ki; }
-          KT ck; int cpd;
-          if (fk <= Sk[j]) { ck = fk; cpd = fpd | (fk == Sk[j] ? 1 : 0); } else { ck = Sk[j]; cpd = Spd[j]; }
-          const int ppos = ppd_prev >> 1;
-          pp[j >> 1] |= (u32)ppos << (16 * (j & 1));
-          const u32 em = (ki <= pk_prev || ppos == u - w) ? 1u : 0u;
-          tot += em; eflags |= em << j;
-          odd |= cpd;
-          pk_prev = ck; ppd_prev = cpd;
-        }
-        cur7 = ppd_prev >> 1;
-        if (odd & 1) {   // a repeated minimum somewhere: redo these 8 steps with the full rules
-          slow = true; tot = 0; eflags = 0; pp[0] = pp[1] = pp[2] = pp[3] = 0; pk_prev = pk0; ppd_prev = ppd0;
-        }
-      }
-      if (slow) {
-        KT fk = KMAX; int fpd = 0;  // prefix minima inside the chunk (newer element wins ties)
-  #pragma unroll
-        for (int j = 0; j < SK_CH; ++j) {
-          const int u = c0 + j;
-          const KT ki = K[j];
-          if (ki <= fk) { fpd = (u << 1) | (ki == fk ? 1 : 0); fk = ki; }
-          // window [u-w+1, u] = older part (suffix) + newer part (prefix); the newer part wins ties
-          KT ck; int cpd;
-          if (fk <= Sk[j]) { ck = fk; cpd = fpd | (fk == Sk[j] ? 1 : 0); } else { ck = Sk[j]; cpd = Spd[j]; }
-          const int ppos = ppd_prev >> 1;
-          pp[j >> 1] |= (u32)ppos << (16 * (j & 1));
-          if (u >= w && u <= u_last) {
-            const KT kp = pk_prev;
-            const bool gc = (ge_cap >> j) & 1u, ec1 = (eq_capm1 >> j) & 1u;
-            if (kp != KMAX) {
-              if (ec1 && (ppd_prev & 1)) {
-                const u32 c1 = sk_count_dups<KT, PAD>(s_key, u - w + 1, u - 1, kp, ppos);
-                if (c1) { tot += c1; eflags |= 1u << (8 + j); }
-              }
-              if (ki <= kp) {
-                if (gc) { tot += 1; eflags |= 1u << j; }
-              } else if (ppos == u - w) {
-                if (gc || ec1) {
-                  tot += 1; eflags |= 1u << j;
-                  if (ck != KMAX && (cpd & 1)) {
-                    const u32 c3 = sk_count_dups<KT, PAD>(s_key, u - w + 1, u, ck, cpd >> 1);
-                    if (c3) { tot += c3; eflags |= 1u << (16 + j); }
-                  }
-                }
-              }
-            }
-            if (last_tile && u == u_last && ck != KMAX) { tot += 1; eflags |= 1u << 24; }
-          }
-          if (u == min(c0 + SK_CH - 1, u_last)) cur7 = cpd >> 1;
-          pk_prev = ck; ppd_prev = cpd;
-        }
-      }
-    }
-
-    // ---- exclusive scan of the per-thread counts, then decoupled look-back for the tile's global base --------------------
-    u32 inc = tot;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const u32 tt = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-      if ((tid & 31) >= d) inc += tt;
-    }
-    if ((tid & 31) == 31) s_wsum[tid >> 5] = inc;
-    __syncthreads();
-    u32 wbase = 0, tile_count = 0;
-#pragma unroll
-    for (int x = 0; x < SK_NT / 32; ++x) {
-      const u32 ws = s_wsum[x];
-      if (x < (tid >> 5)) wbase += ws;
-      tile_count += ws;
-    }
-    const u32 my_off = wbase + inc - tot;
-    if (tid < 32) {
-      volatile u64* st = P.tile_status;
-      u64 excl = 0;
-      if (tile == 0) {
-        if (tid == 0) st[0] = (2ULL << 62) | (u64)tile_count;
-      } else {
-        if (tid == 0) st[tile] = (1ULL << 62) | (u64)tile_count;
-        i64 look = (i64)tile - 1;
-        for (;;) {
-          const i64 idx = look - tid;
-          u64 v;
-          if (idx >= 0) { do { v = st[idx]; } while ((v >> 62) == 0); } else v = (2ULL << 62);
-          const u32 incl_mask = __ballot_sync(0xFFFFFFFFu, (v >> 62) == 2);
-          const int first_incl = incl_mask ? (__ffs(incl_mask) - 1) : 32;
-          u64 contrib = (tid <= first_incl) ? (v & ((1ULL << 62) - 1)) : 0;
-#pragma unroll
-          for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xFFFFFFFFu, contrib, d);
-          excl += contrib;
-          if (incl_mask) break;
-          look -= 32;
-        }
-        if (tid == 0) st[tile] = (2ULL << 62) | (excl + (u64)tile_count);
-      }
-      if (tid == 0) {
-        s_base = excl;
-        if (tile == P.tile_first[q]) P.seq_out_off[q] = excl;
-        if (tile == P.ntiles - 1) P.seq_out_off[P.nseq] = excl + (u64)tile_count;
-        s_next[par ^ 1] = atomicAdd(P.ticket, 1u);   // read by everyone after the barrier below
-      }
-    }
-
-    // ---- write the minimizers in step order ------------------------------------------------------------------------------
-    const u64 rid_hi = (u64)(P.rid_base + q * P.rid_step) << 32;
-    const bool staged = tile_count <= (u32)SK_LIST;
-    {
-      // usual case: every thread stages the tile positions it emits (shared list, in step order; needs only the offsets
-      // inside the tile, so it overlaps warp 0's look-back), then the CTA writes the records with coalesced stores
-      if (staged && tot) {
-        u32 idx = my_off;
-        u32 jm = (eflags | (eflags >> 8) | (eflags >> 16)) & 0xFFu;  // steps of this thread that emit anything
-        while (jm) {
-          const int j = __ffs(jm) - 1;
-          jm &= jm - 1;
-          const int u = c0 + j;
-          const u32 pw = (j >> 1) == 0 ? pp[0] : (j >> 1) == 1 ? pp[1] : (j >> 1) == 2 ? pp[2] : pp[3];
-          const int ppos = (int)((pw >> (16 * (j & 1))) & 0xFFFFu);
-          if (eflags & (1u << (8 + j))) idx = sk_list_dups<KT, PAD>(s_key, u - w + 1, u - 1, ppos, s_list, idx);
-          if (eflags & (1u << j)) s_list[idx++] = (u16)ppos;
-          if (eflags & (1u << (16 + j))) {
-            const int j1 = j + 1;
-            const u32 pw1 = (j1 >> 1) == 0 ? pp[0] : (j1 >> 1) == 1 ? pp[1] : (j1 >> 1) == 2 ? pp[2] : pp[3];
-            const int cpos = (j == SK_CH - 1) ? cur7 : (int)((pw1 >> (16 * (j1 & 1))) & 0xFFFFu);
-            idx = sk_list_dups<KT, PAD>(s_key, u - w + 1, u, cpos, s_list, idx);
-          }
-        }
-        if (eflags & (1u << 24)) s_list[idx++] = (u16)cur7;
-      }
-    }
-    __syncthreads();   // s_base and the staged list are ready
-    if (staged) {
-      const u64 base = s_base;
-      for (u32 e2 = tid; e2 < tile_count; e2 += SK_NT) {
-        const int x = s_list[e2];
-        const u64 o = base + e2;
-        if (o < P.out_cap) {
-          const u32 z = (s_z[x >> 3] >> (x & 7)) & 1u;
-          P.out_key[o] = ((u64)s_key[KIDX(x)] << 8) | (u64)k;
-          P.out_val[o] = rid_hi | ((u64)(P0 + x) << 1) | (u64)z;
-        }
-      }
-    } else if (tot) {
-      // a tile that emits more than the list holds (windows full of repeated minima): each thread writes its own records
-      u64 o = s_base + my_off;
-      auto emit = [&](int x) {
-        if (o < P.out_cap) {
-          const u64 pos = (u64)(P0 + x);
-          const u32 z = (s_z[x >> 3] >> (x & 7)) & 1u;
-          P.out_key[o] = ((u64)s_key[KIDX(x)] << 8) | (u64)k;
-          P.out_val[o] = rid_hi | (pos << 1) | (u64)z;
-        }
-        ++o;
-      };
-      u32 jm = (eflags | (eflags >> 8) | (eflags >> 16)) & 0xFFu;
-      while (jm) {
-        const int j = __ffs(jm) - 1;
-        jm &= jm - 1;
-        const int u = c0 + j;
-        const u32 pw = (j >> 1) == 0 ? pp[0] : (j >> 1) == 1 ? pp[1] : (j >> 1) == 2 ? pp[2] : pp[3];
-        const int ppos = (int)((pw >> (16 * (j & 1))) & 0xFFFFu);
-        if (eflags & (1u << (8 + j)))
-          o = sk_emit_dups<KT, PAD>(s_key, s_z, u - w + 1, u - 1, ppos, o, P.out_cap, P.out_key, P.out_val, rid_hi, P0, k);
-        if (eflags & (1u << j)) emit(ppos);
-        if (eflags & (1u << (16 + j))) {
-          const int j1 = j + 1;
-          const u32 pw1 = (j1 >> 1) == 0 ? pp[0] : (j1 >> 1) == 1 ? pp[1] : (j1 >> 1) == 2 ? pp[2] : pp[3];
-          const int cpos = (j == SK_CH - 1) ? cur7 : (int)((pw1 >> (16 * (j1 & 1))) & 0xFFFFu);
-          o = sk_emit_dups<KT, PAD>(s_key, s_z, u - w + 1, u, cpos, o, P.out_cap, P.out_key, P.out_val, rid_hi, P0, k);
-        }
-      }
-      if (eflags & (1u << 24)) emit(cur7);
-    }
-    tile = s_next[par ^ 1];
-  }
-#undef KIDX
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
-// Version 3 (default): version 2 plus a ninth "scanner" warp per CTA.  In version 2 all eight warps wait at a barrier
-// while warp 0 does the decoupled look-back (40 % of the stall samples in profiles/).  Here the compute warps stage the
+// The tile kernel for w >= 9: eight compute warps plus a ninth "scanner" warp per CTA (with the look-back done by a compute
+// warp, all eight waited at a barrier for it: 40 % of the stall samples in round 1's profile).  The compute warps stage the
 // tile's records (key, pos << 1 | strand) in one of two shared buffers, publish the tile's count and go on with the next
 // tile; the scanner warp does the look-back, publishes the inclusive prefix and writes the staged records to global
 // memory with coalesced stores.  Named barriers: 1 = the 256 compute threads; FULL[b] = compute arrives, scanner
@@ -1335,8 +972,44 @@ static int num_sms(int device) {
   return g_num_sms;
 }
 
+// Tiles of the odd-k / non-HPC kernels: T = SK_REGION - w steps each, at least one per sequence.
+u64 sketch_tile_count(const u64* h_off, size_t nseq, int w) {
+  const u64 T = (u64)(SK_REGION - w);
+  u64 nt = 0;
+  for (size_t i = 0; i < nseq; ++i) nt += std::max<u64>(1, (h_off[i + 1] - h_off[i] + T - 1) / T);
+  return nt;
+}
+// bytes of the concatenated sequences (relative to h_off[0]) that the tiles [tile_lo, tile_hi) read, halo included
+void sketch_tile_bytes(const u64* h_off, size_t nseq, int w, int k, u64 tile_lo, u64 tile_hi, u64* byte_lo, u64* byte_hi) {
+  const u64 T = (u64)(SK_REGION - w), total = h_off[nseq] - h_off[0];
+  *byte_lo = *byte_hi = 0;
+  if (tile_hi <= tile_lo) return;
+  u64 t0 = 0, lo = ~0ULL, hi = 0;
+  for (size_t q = 0; q < nseq; ++q) {
+    const u64 so = h_off[q] - h_off[0], len = h_off[q + 1] - h_off[q];
+    const u64 ntq = std::max<u64>(1, (len + T - 1) / T);
+    const u64 a = std::max(t0, tile_lo), b = std::min(t0 + ntq, tile_hi);
+    if (a < b) {
+      const u64 s = so + (a - t0) * T, e = so + std::min(len, (b - t0) * T);
+      const u64 halo = (u64)(2 * w + k) + 32;
+      lo = std::min(lo, s > halo ? s - halo : 0);
+      hi = std::max(hi, std::min(total, e + 32));
+    }
+    t0 += ntq;
+    if (t0 >= tile_hi) break;
+  }
+  if (lo == ~0ULL) return;
+  *byte_lo = lo & ~(u64)15; *byte_hi = hi;
+}
+
+namespace {
+// "inclusive prefix 0" in the 32 status slots in front of a shard's first tile (one look-back window: every lane must
+// find a published value)
+__global__ void sketch_seed_prefix_kernel(u64* st, u32 t_lo) { if (threadIdx.x < t_lo && threadIdx.x < 32) st[t_lo - 1 - threadIdx.x] = 2ULL << 62; }
+}
+
 int sketch_device(mm2_ctx* ctx, const u8* d_cat, const u64* d_off, const u64* h_off, size_t nseq, int w, int k,
-                  u32 rid_base, u32 rid_step, int is_hpc, SketchOut* out, const SketchFeed* feed) {
+                  u32 rid_base, u32 rid_step, int is_hpc, SketchOut* out, const SketchFeed* feed, const SketchShard* shard) {
   if (!(w > 0 && w < 256) || !(k > 0 && k <= 28)) { mm2_set_error("sketch: need 0<w<256 and 0<k<=28 (sketch.rs:31-32)"); return MM2_E_ARG; }
   if (nseq == 0) { out->key = out->val = nullptr; out->seq_off = nullptr; out->total = 0; return MM2_OK; }
   if (nseq >= 0xFFFFFFFFull) { mm2_set_error("sketch: too many sequences"); return MM2_E_ARG; }
@@ -1344,17 +1017,16 @@ int sketch_device(mm2_ctx* ctx, const u8* d_cat, const u64* d_off, const u64* h_
   cudaStream_t st = ctx->stream;
   MM2_TRY(ctx->mini_off.ensure((nseq + 1) * 8));
   const bool tile_path = (k & 1) && !is_hpc;
-  // capacity guess: random sequence gives 2/(w+1) minimizers per base; retried at the exact size if too small
-  u64 cap = (u64)((double)total_len * 2.0 / (double)(w + 1) * 1.25) + 2 * nseq + 1024;
+  if (shard && !tile_path) { mm2_set_error("sketch: tile shards need the tile kernels (odd k, no HPC)"); return MM2_E_ARG; }
   if (tile_path) {
     const int T = SK_REGION - w;
-    u64 nt = 0;
-    for (size_t i = 0; i < nseq; ++i) {
-      const u64 len = h_off[i + 1] - h_off[i];
-      nt += std::max<u64>(1, (len + T - 1) / T);
-      if (nt >= 0xFFFFFFF0ull) { mm2_set_error("sketch: too many tiles"); return MM2_E_ARG; }
-    }
+    const u64 nt = sketch_tile_count(h_off, nseq, w);
+    if (nt >= 0xFFFFFFF0ull) { mm2_set_error("sketch: too many tiles"); return MM2_E_ARG; }
     const u32 ntiles = (u32)nt;
+    const u32 t_lo = shard ? (u32)std::min<u64>(shard->tile_lo, ntiles) : 0u, t_hi = shard ? (u32)std::min<u64>(shard->tile_hi, ntiles) : ntiles;
+    // capacity guess: random sequence gives 2/(w+1) minimizers per base; retried at the exact size if too small
+    const u64 len_eff = shard ? std::min<u64>(total_len, (u64)(t_hi - t_lo) * (u64)T) : total_len;
+    u64 cap = (u64)((double)len_eff * 2.0 / (double)(w + 1) * 1.25) + 2 * (shard ? 1 : nseq) + 1024;
     // tile -> sequence tables are derived ON the device from the resident offsets (no small H2D copies: they would
     // queue behind another context's bulk read upload on the copy engine and stall this stream)
     MM2_TRY(ctx->tile_first.ensure((nseq + 4) * 8 + (nseq + 8) * 4));
@@ -1366,24 +1038,29 @@ int sketch_device(mm2_ctx* ctx, const u8* d_cat, const u64* d_off, const u64* h_
     MM2_TRY(scan_u32_to_u64(ctx, d_tcnt, d_tf64, nseq));
     MM2_LAUNCH(ctx, tile_seq_kernel, (int)std::min<u64>(((u64)ntiles + 255) / 256, 148ull * 32), 256, 0, d_tf64, (u32)nseq, ntiles,
                ctx->tile_seq.as<u32>());
+    if (t_hi <= t_lo) {   // an empty shard
+      MM2_TRY(ctx->mkey.ensure(64)); MM2_TRY(ctx->mval.ensure(64));
+      out->total = 0; out->key = ctx->mkey.as<u64>(); out->val = ctx->mval.as<u64>(); out->seq_off = ctx->mini_off.as<u64>();
+      return MM2_OK;
+    }
     for (int attempt = 0; attempt < 2; ++attempt) {
       MM2_TRY(ctx->mkey.ensure(cap * 8));
       MM2_TRY(ctx->mval.ensure(cap * 8));
       CUDA_TRY(cudaMemsetAsync(ctx->tile_status.p, 0, (size_t)ntiles * 8 + 16 + 4 * 64, st));
+      if (t_lo > 0) MM2_LAUNCH(ctx, sketch_seed_prefix_kernel, 1, 32, 0, ctx->tile_status.as<u64>(), t_lo);
       SketchParams P;
-      P.tile_base = 0;
+      P.tile_base = t_lo;
       P.seq = d_cat; P.seq_off = d_off; P.buf_len = h_off[nseq];
       P.tile_seq = ctx->tile_seq.as<u32>(); P.tile_first = d_tf64;
-      P.nseq = (u32)nseq; P.ntiles = ntiles; P.w = w; P.k = k;
+      P.nseq = (u32)nseq; P.ntiles = t_hi; P.w = w; P.k = k;
       P.vec_ok = ((uintptr_t)d_cat & 15) == 0;
       P.rid_base = rid_base; P.rid_step = rid_step;
       P.out_key = ctx->mkey.as<u64>(); P.out_val = ctx->mval.as<u64>(); P.out_cap = cap;
       P.seq_out_off = ctx->mini_off.as<u64>();
       P.tile_status = ctx->tile_status.as<u64>();
       P.ticket = (u32*)((u8*)ctx->tile_status.p + (size_t)ntiles * 8);
-      const int grid = (int)std::min<u64>(ntiles, (u64)num_sms(ctx->device) * (MM2_SK_OCC + 1));
-      static const bool use_v2 = [] { const char* e = getenv("MM2_SKETCH"); return e && !strcmp(e, "v2"); }();   // comparison arm
-      if (feed && attempt == 0 && w >= 9 && !use_v2 && feed->nchunks >= 1 && feed->nchunks <= 64) {
+      const int grid = (int)std::min<u64>(t_hi - t_lo, (u64)num_sms(ctx->device) * (MM2_SK3_OCC + 2));
+      if (feed && !shard && attempt == 0 && w >= 9 && feed->nchunks >= 1 && feed->nchunks <= 64) {
         // The sequence is still being uploaded (index build): one launch per uploaded chunk over the tiles that lie entirely
         // inside it.  The launches share the tile status array, so the look-back of a launch's first tile finds the
         // inclusive prefix the previous launch left; every launch has its own ticket counter.
@@ -1405,25 +1082,21 @@ int sketch_device(mm2_ctx* ctx, const u8* d_cat, const u64* d_off, const u64* h_
           if (t_end > t_prev) {
             P.tile_base = t_prev; P.ntiles = (u32)t_end;
             P.ticket = (u32*)((u8*)ctx->tile_status.p + (size_t)ntiles * 8 + 16) + c;
-            const int g = (int)std::min<u64>(t_end - t_prev, (u64)num_sms(ctx->device) * (MM2_SK_OCC + 1));
+            const int g = (int)std::min<u64>(t_end - t_prev, (u64)num_sms(ctx->device) * (MM2_SK3_OCC + 2));
             if (k <= 15) MM2_LAUNCH(ctx, sketch_tile_kernel_v3<u32>, g, SK_NT + 32, 0, P);
             else MM2_LAUNCH(ctx, sketch_tile_kernel_v3<u64>, g, SK_NT + 32, 0, P);
             t_prev = (u32)t_end;
           }
         }
-      } else if (w >= 9) {  // version 2: per-thread prefix/suffix window minima
-        if (feed && attempt == 0) for (int c = 0; c < feed->nchunks; ++c) CUDA_TRY(cudaStreamWaitEvent(st, feed->ev[c], 0));
-        if (use_v2) {
-          if (k <= 15) MM2_LAUNCH(ctx, sketch_tile_kernel_v2<u32>, grid, SK_NT, 0, P);
-          else MM2_LAUNCH(ctx, sketch_tile_kernel_v2<u64>, grid, SK_NT, 0, P);
-        } else {
-          if (k <= 15) MM2_LAUNCH(ctx, sketch_tile_kernel_v3<u32>, grid, SK_NT + 32, 0, P);
-          else MM2_LAUNCH(ctx, sketch_tile_kernel_v3<u64>, grid, SK_NT + 32, 0, P);
-        }
       } else {
         if (feed && attempt == 0) for (int c = 0; c < feed->nchunks; ++c) CUDA_TRY(cudaStreamWaitEvent(st, feed->ev[c], 0));
-        if (k <= 15) MM2_LAUNCH(ctx, sketch_tile_kernel<u32>, grid, SK_NT, 0, P);
-        else MM2_LAUNCH(ctx, sketch_tile_kernel<u64>, grid, SK_NT, 0, P);
+        if (w >= 9) {   // per-thread prefix/suffix window minima + scanner warp
+          if (k <= 15) MM2_LAUNCH(ctx, sketch_tile_kernel_v3<u32>, grid, SK_NT + 32, 0, P);
+          else MM2_LAUNCH(ctx, sketch_tile_kernel_v3<u64>, grid, SK_NT + 32, 0, P);
+        } else {        // small windows: the O(w) window scan
+          if (k <= 15) MM2_LAUNCH(ctx, sketch_tile_kernel<u32>, grid, SK_NT, 0, P);
+          else MM2_LAUNCH(ctx, sketch_tile_kernel<u64>, grid, SK_NT, 0, P);
+        }
       }
       CUDA_TRY(cudaGetLastError());
       u64 total = 0;
@@ -1449,7 +1122,7 @@ int sketch_device(mm2_ctx* ctx, const u8* d_cat, const u64* d_off, const u64* h_
     MM2_LAUNCH(ctx, excl_scan_u64_small, 1, 1, 0, d_counts, ctx->mini_off.as<u64>(), (u32)nseq);
     u64 total = 0;
     MM2_TRY(read_scalar_u64(ctx, ctx->mini_off.as<u64>() + nseq, &total));
-    cap = total + 16;
+    const u64 cap = total + 16;
     MM2_TRY(ctx->mkey.ensure(cap * 8));
     MM2_TRY(ctx->mval.ensure(cap * 8));
     P.out_key = ctx->mkey.as<u64>(); P.out_val = ctx->mval.as<u64>(); P.out_cap = cap;

@@ -23,7 +23,7 @@ int seeds_filter(mm2_ctx* ctx, const u64* d_mkey, const u64* d_mini_off, u32 nre
 // Query side, version 2 (seeds.cu): count sketch + exact filter where needed + Index::get + compact hit lists + per-read anchor
 // offsets (ctx->read_aoff); returns the batch's anchor count (synchronises).  Then anchors built and sorted per read.
 int seeds_hits(mm2_ctx* ctx, const IndexView& V, const u64* d_mkey, const u64* d_mval, const u64* d_mini_off, u32 nreads, u64 n_mini,
-               i32 q_occ_max, float q_occ_frac, i32 mid_occ, bool full_keep, u32* d_sum_span, u64* n_anchors);
+               i32 q_occ_max, float q_occ_frac, i32 mid_occ, bool full_keep, u32* d_sum_span, u64* n_anchors, u64* n_dropped = nullptr);
 int seeds_fill_and_sort(mm2_ctx* ctx, const IndexView& V, const u64* d_mini_off, const u64* d_read_off, u32 nreads, ulonglong2* d_anchors);
 
 // lchain.rs:59-176 forward DP + fallback chain (+ rescue rerun, lchain.rs:321-330) for every read; one warp per read.
@@ -33,7 +33,6 @@ int seeds_fill_and_sort(mm2_ctx* ctx, const IndexView& V, const u64* d_mini_off,
 int chain_batch(mm2_ctx* ctx, const ulonglong2* d_anchors, const u64* d_read_aoff, const u64* d_read_off, const u64* d_mini_off,
                 const u64* d_mval, const u32* d_sum_span, u32 nreads, const mm2_chain_params_t& p, int do_rescue,
                 int4* d_A, int4* d_B, int* d_T, int* d_W, int* d_chain, ReadHit* d_hits, unsigned long long* d_cells);
-int index_build_table(mm2_ctx* ctx, mm2_index* idx);
 
 // general.cu: the multi-chain tail of main.rs:209-218 (only reachable with -n < 2)
 int map_general_finish(mm2_ctx* ctx, const mm2_index* idx, const u64* d_read_off, const u64* h_off, size_t nreads,

@@ -14,6 +14,10 @@ def test_library_exports_every_declared_symbol(mm2):
     missing = [s for s in sorted(declared) if not hasattr(L, s)]
     assert not missing, missing
     assert declared == set(mm2.ABI_SYMBOLS)
+    diag = open(os.path.join(root, "include", "mm2b200_diag.h")).read()
+    ddecl = set(re.findall(r"\b(mm2_[a-z0-9_]+)\s*\(", diag))
+    assert ddecl == set(mm2.DIAG_SYMBOLS) and not [s for s in ddecl if not hasattr(L, s)]
+    assert not (ddecl & declared)   # diagnostics stay out of the drop-in header
 
 
 def test_no_cpu_fallback(mm2):

@@ -507,27 +507,74 @@ def test_map_batch_pipelined_equals_single(mm2, orc, gen):
     c.close()
 
 
-@pytest.mark.parametrize("world,k,b", [(2, 15, 14), (3, 19, 10), (8, 15, 14)])
-def test_multi_gpu_index_build_emulated_ranks(ctx, mm2, orc, gen, tmp_path, world, k, b):
-    """bucket-partitioned build with R virtual ranks on one GPU: byte-identical .mmi"""
-    from minimap2_rs_b200 import multi_gpu
+@pytest.mark.parametrize("world,k,b,w,hpc", [(2, 15, 14, 10, 0), (3, 19, 10, 10, 0), (8, 15, 14, 10, 0), (5, 17, 12, 5, 0), (4, 14, 12, 10, 0), (3, 15, 14, 10, 1)])
+def test_multi_gpu_index_build_emulated_ranks(ctx, mm2, orc, gen, tmp_path, world, k, b, w, hpc):
+    """bucket-sharded build with R virtual ranks on one GPU: byte-identical .mmi.
+    Odd k / no HPC shards the sketch by TILES, i.e. inside sequences (every virtual rank only uploads its own bytes plus the
+    halo; the rest of the sequence buffer is poisoned with N); even k and HPC shard by whole sequences."""
     g = gen.repeat_genome(61, 900_000, 0.3, 0.2)
     cuts = [0, 200_003, 200_004, 450_000, 450_017, 700_001, 900_000]
     seqs = [g[cuts[i]:cuts[i + 1]].tobytes() for i in range(len(cuts) - 1)]
     names = ["s%d" % i for i in range(len(seqs))]
     cat, offs = cases.cat_offs(seqs)
-    gi = multi_gpu.build_index_sharded_emulated(ctx, cat, offs, names, w=10, k=k, b=b, world=world)
-    oi = orc.Index.build(cat, offs, names, w=10, k=k, b=b, threads=8)
+    gi = mm2.Index.build_sharded_emulated(ctx, world, cat, offs, names, w=w, k=k, b=b, flag=hpc)
+    oi = orc.Index.build(cat, offs, names, w=w, k=k, b=b, flag=hpc, threads=8)
     assert gi.stats() == oi.stats() and gi.calc_mid_occ() == oi.calc_mid_occ()
     pg, po = str(tmp_path / "g.mmi"), str(tmp_path / "o.mmi")
     gi.save_to_mmi(pg)
     oi.save_mmi(po)
     assert open(pg, "rb").read() == open(po, "rb").read()
+    if hpc:
+        return
     # and it maps like the single-GPU index
     rc, ro = gen.reads(2, g[:200_000], np.array([0, 200_000], dtype=np.uint64), 20, 3000, 0.02, 0.02, 0.02)
-    res = ctx.map_batch(gi, rc, ro, mm2.default_map_opts(10, k))
-    want, _ = oi.align_batch(rc, ro, ["m%d" % i for i in range(20)], orc.AlignOpts.default(10, k), threads=4)
+    res = ctx.map_batch(gi, rc, ro, mm2.default_map_opts(w, k))
+    want, _ = oi.align_batch(rc, ro, ["m%d" % i for i in range(20)], orc.AlignOpts.default(w, k), threads=4)
     assert res.paf_lines(["m%d" % i for i in range(20)]) == want
+
+
+def test_multi_gpu_single_sequence_genome_is_split_inside_the_sequence(ctx, mm2, orc, gen, tmp_path):
+    """one chromosome, 8 virtual ranks: every rank sketches 1/8 of it (the reference's rayon split cannot, index.rs:442-452)"""
+    g = gen.genome(63, 3_000_000, 1e-3, 30.0)
+    offs = np.array([0, g.size], dtype=np.uint64)
+    plans = [mm2.shard_plan(offs, 10, 15, 0, 8, r) for r in range(8)]
+    assert all(p["tile_path"] == 1 for p in plans) and plans[0]["lo"] == 0
+    assert all(plans[r]["hi"] == plans[r + 1]["lo"] for r in range(7))
+    assert max(p["upload_bytes"] for p in plans) < g.size // 8 + 5000
+    gi = mm2.Index.build_sharded_emulated(ctx, 8, g, offs, ["chr1"])
+    oi = orc.Index.build(g, offs, ["chr1"], threads=8)
+    pg, po = str(tmp_path / "g.mmi"), str(tmp_path / "o.mmi")
+    gi.save_to_mmi(pg)
+    oi.save_mmi(po)
+    assert open(pg, "rb").read() == open(po, "rb").read()
+
+
+def test_two_contexts_on_two_devices_in_one_process(mm2, orc, gen, tmp_path):
+    """per-device kernel attributes (dynamic shared memory opt-ins) and mm2_index_build_multi: needs >= 2 GPUs"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    g = gen.repeat_genome(65, 1_500_000, 0.3, 0.2)
+    offs = np.array([0, g.size], dtype=np.uint64)
+    cs = [mm2.Context(0), mm2.Context(1)]
+    gis = mm2.Index.build_multi(cs, g, offs, ["m"])
+    oi = orc.Index.build(g, offs, ["m"], threads=8)
+    cat, roffs = gen.reads(3, g, offs, 50, 12000, 0.02, 0.02, 0.02)
+    names = ["t%d" % i for i in range(50)]
+    want, _ = oi.align_batch(cat, roffs, names, threads=8)
+    os.environ["MM2_CHAIN_DENSE_MIN"] = "1"      # the CTA-per-read kernel needs the 95 KB opt-in on BOTH devices
+    try:
+        ds = [mm2.Context(0), mm2.Context(1)]
+    finally:
+        del os.environ["MM2_CHAIN_DENSE_MIN"]
+    for c, gi in list(zip(cs, gis)) + list(zip(ds, gis)):
+        assert gi.stats() == oi.stats()
+        assert c.map_batch(gi, cat, roffs).paf_lines(names) == want
+    p0, p1, po = (str(tmp_path / n) for n in ("0.mmi", "1.mmi", "o.mmi"))
+    gis[0].save_to_mmi(p0)
+    gis[1].save_to_mmi(p1)
+    oi.save_mmi(po)
+    assert open(p0, "rb").read() == open(po, "rb").read() == open(p1, "rb").read()
 
 
 @pytest.mark.parametrize("min_cnt,min_score,extra", [(1, 10, {}), (1, 40, {}), (1, 5, dict(best_n=2, pri_ratio=0.5, mask_level=0.9)), (1, 10, dict(bw=100, bw_long=3000))])
@@ -645,3 +692,77 @@ def test_fuzz_map_options(ctx, mm2, orc, gen):
             res = ctx.map_batch(gi, rc, ro, o)
             want, _ = oi.align_batch(rc, ro, qn, oo, threads=8)
             assert res.paf_lines(qn) == want, "fuzz k=%d it=%d opts=%s" % (k, it, {f: getattr(o, f) for f, _ in o._fields_})
+
+
+@pytest.mark.parametrize("w,k", [(10, 14), (10, 16), (5, 20), (11, 28)])
+def test_map_batch_even_k_matching_index(ctx, mm2, orc, gen, w, k):
+    """even k with the SAME w/k on the index and the query: the default (closed-form dv) record path, not the w/k-mismatch
+    tail.  Palindromic k-mers are skipped by the sketch (sketch.rs:67), so the literal sketch kernel, the lookup and the
+    rank-based dv (paf.rs:174-191) all see them."""
+    g = gen.repeat_genome(131, 900_000, 0.3, 0.2) if k < 20 else gen.genome(132, 900_000, 1e-3, 30.0)
+    # palindrome-rich inserts: (AT)n / ACGT-repeat blocks make many k-mers equal to their reverse complement
+    g = g.copy()
+    for p in range(10_000, 800_000, 90_000):
+        g[p:p + 300] = np.frombuffer((b"ACGT" * 75), dtype=np.uint8)
+        g[p + 1000:p + 1200] = np.frombuffer((b"AT" * 100), dtype=np.uint8)
+    offs = np.array([0, g.size], dtype=np.uint64)
+    gi = mm2.Index.build(ctx, g, offs, ["ev"], w=w, k=k)
+    oi = orc.Index.build(g, offs, ["ev"], w=w, k=k, threads=8)
+    assert gi.stats() == oi.stats()
+    cat, roffs = gen.reads(k, g, offs, 60, 3000, 0.01, 0.01, 0.01)
+    reads = [cat[int(roffs[i]):int(roffs[i + 1])].tobytes() for i in range(60)]
+    reads += [g[9_500:12_000].tobytes(), g[99_800:101_500].tobytes()]          # reads across the palindromic blocks
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    reads += [g[189_000:192_000].tobytes().translate(comp)[::-1]]
+    cat2, ro2 = cases.cat_offs(reads)
+    names = ["e%d" % i for i in range(len(reads))]
+    res, st = _map_compare(ctx, mm2, orc, gi, oi, cat2, ro2, names, (w, k))
+    assert res.recs.size >= 55
+    # and without the stage dump (the pipelined / in-place record path)
+    _map_compare(ctx, mm2, orc, gi, oi, cat2, ro2, names, (w, k), dump=False)
+
+
+def test_config1_full_size_mmi_and_600bp_read(ctx, mm2, orc, gen, tmp_path):
+    """BASELINE configs[0] at its stated size (SURVEY.md §8d C1 stand-in): one 145,138,636-bp sequence `chr8`, index k=15 w=10;
+    the .mmi written by the GPU build must be byte-identical (sha256 over the whole file) to the CPU oracle's, and the 600-bp
+    read genome[5,999,340 .. 5,999,940) with 4 substitutions must give the same PAF line."""
+    import hashlib
+    L = 145_138_636
+    g = gen.genome(0xB2000002, L)
+    offs = np.array([0, L], dtype=np.uint64)
+    gi = mm2.Index.build(ctx, g, offs, ["chr8"], w=10, k=15, b=14)
+    oi = orc.Index.build(g, offs, ["chr8"], w=10, k=15, b=14, threads=os.cpu_count() or 8)
+    assert gi.stats() == oi.stats()
+    assert gi.calc_mid_occ(2e-4) == oi.calc_mid_occ(2e-4)
+
+    def sha(path):
+        h = hashlib.sha256()
+        with open(path, "rb") as f:
+            while True:
+                blk = f.read(1 << 24)
+                if not blk:
+                    break
+                h.update(blk)
+        return h.hexdigest(), os.path.getsize(path)
+
+    pg, po = str(tmp_path / "g.mmi"), str(tmp_path / "o.mmi")
+    gi.save_to_mmi(pg)
+    hg = sha(pg)
+    os.remove(pg)
+    oi.save_mmi(po)
+    ho = sha(po)
+    os.remove(po)
+    assert hg == ho, (hg, ho)
+    q = bytearray(g[5_999_340:5_999_940].tobytes())
+    for p in (57, 211, 388, 540):
+        q[p] = ord("ACGT"[("ACGT".index(chr(q[p])) + 1) % 4])
+    qc, qo = cases.cat_offs([bytes(q)])
+    res = ctx.map_batch(gi, qc, qo)
+    want, _ = oi.align_batch(qc, qo, ["read600"])
+    got = res.paf_lines(["read600"])
+    assert got == want and len(got) == 1
+    f = got[0].split("\t")
+    assert f[5] == "chr8" and int(f[6]) == L and abs(int(f[7]) - 5_999_340) < 40 and f[4] == "+"
+    # a sample of BASELINE configs[1] reads on the same full-size index, every stage compared
+    cat, roffs = gen.reads(0xB2001002, g, offs, 200, 10_000, 0.0333, 0.0333, 0.0333)
+    _map_compare(ctx, mm2, orc, gi, oi, cat, roffs, ["r%06d" % i for i in range(200)])

@@ -67,3 +67,63 @@ def test_gloo_world2_gather_in_input_order():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert ok
+
+
+def _plan_worker(rank, world, port, q):
+    """every rank computes ITS share of the sharded index build (mm2_shard_plan, pure host code in libmm2b200.so); the shares
+    are gathered over gloo and checked on rank 0"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    import minimap2_rs_b200 as mm2
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lens = [193_750_000, 1, 193_750_000, 1, 50_000, 7, 0, 2038, 2039, 300_000_000]
+    offs = np.zeros(len(lens) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum(lens)
+    res = {}
+    for (w, k, flag) in ((10, 15, 0), (10, 19, 0), (5, 21, 0), (10, 14, 0), (10, 15, 1)):
+        mine = mm2.shard_plan(offs, w, k, flag, world, rank)
+        box = [None] * world
+        dist.all_gather_object(box, mine)
+        res[(w, k, flag)] = box
+    if rank == 0:
+        ok = True
+        total = int(offs[-1])
+        words = 1
+        while words < (total + 7) // 8:
+            words *= 2
+        for (w, k, flag), plans in res.items():
+            tile = (k % 2 == 1) and not flag
+            ok &= all(p["tile_path"] == int(tile) for p in plans)
+            ok &= plans[0]["lo"] == 0 and all(plans[r]["hi"] == plans[r + 1]["lo"] for r in range(world - 1))   # shares tile the list
+            if tile:
+                T = 2048 - w
+                ntiles = sum(max(1, (l + T - 1) // T) for l in lens)
+                ok &= plans[-1]["hi"] == ntiles
+                # a rank uploads about 1 / world of the genome although sequences are far from balanced
+                ok &= all(abs(p["upload_bytes"] - total / world) < 0.02 * total for p in plans)
+                for p in plans:   # halo: the sketch reads from 2w+k (+ alignment slack) before its first step
+                    ok &= p["sketch_byte_lo"] % 16 == 0 and p["sketch_byte_hi"] <= total
+            else:
+                ok &= plans[-1]["hi"] == len(lens)
+            ok &= plans[0]["word_lo"] == 0 and plans[-1]["word_hi"] == words
+            ok &= all(plans[r]["word_hi"] == plans[r + 1]["word_lo"] for r in range(world - 1))
+        q.put(bool(ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_sharded_build_plan():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    ps = [ctx.Process(target=_plan_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    ok = q.get(timeout=120)
+    for p in ps:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert ok

@@ -104,7 +104,9 @@ void mm2gen_repeat_genome(uint64_t seed, uint8_t* out, size_t len, double tandem
 // Reads of exactly read_len bases drawn from sequences [seq_offs[i], seq_offs[i+1]) of `genome` (only sequences with
 // length >= 4*read_len are used), 50 % reverse-complemented, iid substitution/insertion/deletion errors.
 // out must hold nreads*read_len bytes.  src_seq/src_pos/src_rev (nreads each, may be NULL) record the truth.
-void mm2gen_reads(uint64_t seed, const uint8_t* genome, const uint64_t* seq_offs, size_t nseq, size_t nreads, size_t read_len,
+// `first`: index of the first read of this call within the read set (read i depends only on (seed, i)), so that ranks can
+// generate disjoint shards of one read set.
+void mm2gen_reads_from(uint64_t seed, const uint8_t* genome, const uint64_t* seq_offs, size_t nseq, size_t first, size_t nreads, size_t read_len,
                   double p_sub, double p_ins, double p_del, uint8_t* out, uint32_t* src_seq, uint64_t* src_pos, uint8_t* src_rev) {
   std::vector<size_t> ok;
   std::vector<uint64_t> cum;
@@ -120,7 +122,7 @@ void mm2gen_reads(uint64_t seed, const uint8_t* genome, const uint64_t* seq_offs
     th.emplace_back([&, t]() {
       std::vector<uint8_t> tmp(read_len);
       for (size_t rd = t; rd < nreads; rd += nt) {
-        Rng r(seed * 0x9e3779b97f4a7c15ULL + rd * 2 + 1);
+        Rng r(seed * 0x9e3779b97f4a7c15ULL + (first + rd) * 2 + 1);
         uint64_t x = r.below(tot);
         size_t si = std::upper_bound(cum.begin(), cum.end(), x) - cum.begin();
         uint64_t base = si ? cum[si - 1] : 0;
@@ -146,6 +148,11 @@ void mm2gen_reads(uint64_t seed, const uint8_t* genome, const uint64_t* seq_offs
       }
     });
   for (auto& x : th) x.join();
+}
+
+void mm2gen_reads(uint64_t seed, const uint8_t* genome, const uint64_t* seq_offs, size_t nseq, size_t nreads, size_t read_len,
+                  double p_sub, double p_ins, double p_del, uint8_t* out, uint32_t* src_seq, uint64_t* src_pos, uint8_t* src_rev) {
+  mm2gen_reads_from(seed, genome, seq_offs, nseq, 0, nreads, read_len, p_sub, p_ins, p_del, out, src_seq, src_pos, src_rev);
 }
 
 }  // extern "C"

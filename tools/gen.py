@@ -25,6 +25,7 @@ def lib():
         L.mm2gen_genome.argtypes = [C.c_uint64, vp, sz, C.c_double, C.c_double]
         L.mm2gen_repeat_genome.argtypes = [C.c_uint64, vp, sz, C.c_double, C.c_double]
         L.mm2gen_reads.argtypes = [C.c_uint64, vp, vp, sz, sz, sz, C.c_double, C.c_double, C.c_double, vp, vp, vp, vp]
+        L.mm2gen_reads_from.argtypes = [C.c_uint64, vp, vp, sz, sz, sz, sz, C.c_double, C.c_double, C.c_double, vp, vp, vp, vp]
         _LIB = L
     return _LIB
 
@@ -41,14 +42,15 @@ def repeat_genome(seed, length, tandem_frac=0.4, dispersed_frac=0.2):
     return g
 
 
-def reads(seed, genome_cat, seq_offs, nreads, read_len, p_sub, p_ins, p_del, out=None, truth=False):
-    """returns (cat uint8[nreads*read_len], offs uint64[nreads+1]) (+ (src_seq, src_pos, src_rev) if truth)"""
+def reads(seed, genome_cat, seq_offs, nreads, read_len, p_sub, p_ins, p_del, out=None, truth=False, first=0):
+    """returns (cat uint8[nreads*read_len], offs uint64[nreads+1]) (+ (src_seq, src_pos, src_rev) if truth); `first` = index of
+    the first read within the seeded read set (reads [first, first + nreads) of it)"""
     seq_offs = np.ascontiguousarray(seq_offs, dtype=np.uint64)
     cat = out if out is not None else np.empty(nreads * read_len, dtype=np.uint8)
     ss = np.zeros(nreads, dtype=np.uint32)
     sp = np.zeros(nreads, dtype=np.uint64)
     sr = np.zeros(nreads, dtype=np.uint8)
-    lib().mm2gen_reads(seed, genome_cat.ctypes.data, seq_offs.ctypes.data, seq_offs.size - 1, nreads, read_len,
-                       p_sub, p_ins, p_del, cat.ctypes.data, ss.ctypes.data, sp.ctypes.data, sr.ctypes.data)
+    lib().mm2gen_reads_from(seed, genome_cat.ctypes.data, seq_offs.ctypes.data, seq_offs.size - 1, first, nreads, read_len,
+                            p_sub, p_ins, p_del, cat.ctypes.data, ss.ctypes.data, sp.ctypes.data, sr.ctypes.data)
     offs = np.arange(nreads + 1, dtype=np.uint64) * np.uint64(read_len)
     return (cat, offs, (ss, sp, sr)) if truth else (cat, offs)
