@@ -76,7 +76,7 @@ extern "C" void mm2_ctx_destroy(mm2_ctx_t* c) {
   DevBuf* bufs[] = {&c->seq, &c->seq_off, &c->tile_seq, &c->tile_first, &c->tile_status, &c->misc, &c->mkey, &c->mval,
                     &c->mini_off, &c->keep, &c->occ_cnt, &c->occ_loc, &c->anchor_off_m, &c->scan_status, &c->anchors,
                     &c->read_aoff, &c->read_class, &c->read_flag, &c->read_nhit, &c->read_na, &c->flag_list, &c->dpA, &c->dpB, &c->dpT, &c->dpW, &c->hits, &c->chain_idx, &c->lut, &c->sort_tmp,
-                    &c->sort_tmp2, &c->sort_keys2, &c->sort_vals2, &c->runidx, &c->run_start, &c->run_gp, &c->rs_counts, &c->rs_offs, &c->diag, &c->mg_recv_k, &c->mg_recv_v};
+                    &c->sort_tmp2, &c->sort_keys2, &c->sort_vals2, &c->runidx, &c->run_start, &c->run_gp, &c->rs_counts, &c->rs_offs, &c->diag, &c->mg_recv_k, &c->mg_recv_v, &c->fine_tmp};
   for (DevBuf* b : bufs) b->release();
   c->pin_in.release(); c->pin_out.release(); c->pin_small.release(); c->pin_scalar.release();
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -575,10 +575,8 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
   // The 64-byte per-read results are written by the chain kernels straight into page-locked host memory (zero-copy:
   // cudaMallocHost memory is device-addressable under unified addressing): one posted PCIe write per read while the kernel
   // runs, instead of a device buffer plus a separate D2H copy at the end (measured 0.8 ms per 100k reads).
-  // MM2_HITS=copy keeps the device buffer + copy as the comparison arm.
   MM2_TRY(ctx->pin_out.ensure((nreads + 1) * sizeof(ReadHit) + 64));
   ReadHit* hits = ctx->pin_out.as<ReadHit>();
-  static const bool hits_copy = [] { const char* e = getenv("MM2_HITS"); return e && !strcmp(e, "copy"); }();
   unsigned long long* d_cells = nullptr;
   if (ctx->count_cells) {
     MM2_TRY(ctx->diag.ensure(64));
@@ -587,9 +585,8 @@ static int map_device_impl(mm2_ctx* ctx, const mm2_index* idx, const u8* d_cat, 
   }
   MM2_TRY(chain_batch(ctx, ctx->anchors.as<ulonglong2>(), ctx->read_aoff.as<u64>(), d_off, so.seq_off, so.val, d_sum_span, (u32)nreads,
                       p, 1, ctx->dpA.as<int4>(), ctx->dpB.as<int4>(), ctx->dpT.as<int>(), ctx->dpW.as<int>(), nullptr,
-                      hits_copy ? ctx->hits.as<ReadHit>() : hits, d_cells));   // cell counter: a diagnostic (mm2b200_diag.h), off by default
+                      hits, d_cells));   // cell counter: a diagnostic (mm2b200_diag.h), off by default
   ctx->timer.mark(st, "d2h");
-  if (nreads && hits_copy) CUDA_TRY(cudaMemcpyAsync(hits, ctx->hits.p, nreads * sizeof(ReadHit), cudaMemcpyDeviceToHost, st));
   ctx->timer.mark(st, "end");
   mm2_trace(ctx, "chain issued");
   CUDA_TRY(mm2_stream_wait(ctx));

@@ -8,10 +8,10 @@
 //   bkt_koff[2^b+1]  first key of each bucket;  bkt_poff[2^b+1] first p entry of each bucket
 //   p[n_p]           positions of multi-occurrence keys, per bucket in ascending key order, each run ascending
 //   S[...]           4-bit packed sequence (index.rs:11-19), only needed for .mmi / get_ref_subseq
-//   fine_off[...]    seed lookup: first kv entry of every FINE bucket (bucket, equalised top bits of minier>>b); because
-//                    kv is sorted by (bucket, key) a fine bucket is a contiguous run of ~1 entries, so Index::get is one
-//                    offset load + one short scan, the structure is built by a streaming pass (no random claims in a
-//                    GiB-sized table as in round 1) and it shards by bucket owner like everything else
+//   tab[...]         seed lookup: one 32-byte line per FINE bucket (bucket, equalised top bits of minier>>b) holding the
+//                    first two records of the bucket's run in kv (or the first + a pointer to the rest).  kv is sorted by
+//                    (bucket, key), so a fine bucket is a contiguous run: the table is written by a streaming pass (no
+//                    random claims in a GiB-sized table as in round 1) and Index::get is one 32-byte access
 //   bloom[...]       blocked Bloom filter over the keys (only while it fits in L2)
 // The per-bucket Vec<Minimizer> + stable sort + HashMap of the reference become ONE device radix sort on the
 // re-keyed minimizers (bucket in the high bits, minier>>b below; stable, so equal keys keep ascending y) followed
@@ -236,12 +236,27 @@ inline int grid_for(u64 n, int block = 256) { return (int)std::min<u64>((n + blo
 
 }  // namespace
 
+// one 32-byte table line per fine bucket from the fine offsets (see IndexView::tab)
+__global__ void __launch_bounds__(256) tab_fill_kernel(const ulonglong2* __restrict__ kv, const u32* __restrict__ fine_off, u64 F,
+                                                       ulonglong2* __restrict__ tab) {
+  for (u64 f = blockIdx.x * (u64)blockDim.x + threadIdx.x; f < F; f += (u64)gridDim.x * blockDim.x) {
+    const u32 lo = fine_off[f], hi = fine_off[f + 1];
+    const u32 n = hi - lo;
+    ulonglong2 e0 = make_ulonglong2(TAB_EMPTY, TAB_EMPTY), e1 = e0;
+    if (n >= 1) e0 = kv[lo];
+    if (n == 2) e1 = kv[lo + 1];
+    else if (n > 2) e1 = make_ulonglong2(TAB_MORE, ((u64)(n - 1) << 32) | (u64)(lo + 1));
+    tab[2 * f] = e0;
+    tab[2 * f + 1] = e1;
+  }
+}
+
 IndexView mm2_index::view() const {
   IndexView v;
   v.w = w; v.k = k; v.b = b; v.flag = flag; v.n_seq = n_seq; v.n_keys = n_keys; v.n_p = n_p;
   v.kv = kv.as<ulonglong2>(); v.bkt_koff = bkt_koff.as<u64>(); v.bkt_poff = bkt_poff.as<u64>();
   v.p = p.as<u64>(); v.seq_len = seq_len.as<u32>();
-  v.fine_off = fine_off.as<u32>(); v.fine_j = fine_j; v.fine_pw = fine_pw; v.R = std::max(2 * k - b, 0);
+  v.tab = tab.as<ulonglong2>(); v.fine_j = fine_j; v.fine_pw = fine_pw; v.R = std::max(2 * k - b, 0);
   v.bloom = has_bloom ? bloom.as<uint4>() : nullptr; v.bloom_mask = bloom_mask;
   return v;
 }
@@ -250,7 +265,8 @@ IndexView mm2_index::view() const {
 int index_build_lookup(mm2_ctx* ctx, mm2_index* idx) {
   if (idx->n_keys >= 0xFFFFFFFFull) { mm2_set_error("index: %llu distinct minimizers do not fit the 32-bit fine offsets", (unsigned long long)idx->n_keys); return MM2_E_UNSUPPORTED; }
   const int R = std::max(2 * idx->k - idx->b, 0);
-  // fine buckets: the smallest power of two >= n_keys (mean occupancy in (0.5, 1]), at most R bits below the bucket
+  // fine buckets: the smallest power of two >= n_keys (mean occupancy in (0.5, 1]: ~4 % of the runs are longer than the two
+  // records a table line holds), at most R bits below the bucket
   int j = 0;
   while (j < R && j < 30 && (1ULL << (idx->b + j)) < idx->n_keys) ++j;
   idx->fine_j = j;
@@ -259,7 +275,8 @@ int index_build_lookup(mm2_ctx* ctx, mm2_index* idx) {
   while (pw < 5 && (1 << pw) * (1 << pw) * 2 <= idx->w * idx->w) ++pw;   // 2^pw <= w / sqrt(2)
   idx->fine_pw = pw;
   const u64 nb = 1ULL << idx->b, F = nb << j;
-  MM2_TRY(idx->fine_off.ensure((F + 1) * 4));
+  MM2_TRY(ctx->fine_tmp.ensure((F + 1) * 4));
+  MM2_TRY(idx->tab.ensure(F * 32));
   // Bloom filter in front of the lookup, only while it fits comfortably in the 126 MB L2
   idx->has_bloom = false;
   u64 nblk = 1024;
@@ -272,7 +289,9 @@ int index_build_lookup(mm2_ctx* ctx, mm2_index* idx) {
   }
   const int grid = (int)std::max<u64>(1, std::min<u64>((nb + 7) / 8, 148ull * 64));
   MM2_LAUNCH(ctx, lookup_build_kernel, grid, 256, 0, idx->kv.as<ulonglong2>(), idx->bkt_koff.as<u64>(), nb, idx->b, R, j, pw,
-             idx->fine_off.as<u32>(), idx->has_bloom ? idx->bloom.as<u32>() : (u32*)nullptr, idx->bloom_mask);
+             ctx->fine_tmp.as<u32>(), idx->has_bloom ? idx->bloom.as<u32>() : (u32*)nullptr, idx->bloom_mask);
+  MM2_LAUNCH(ctx, tab_fill_kernel, (int)std::max<u64>(1, std::min<u64>((F + 255) / 256, 148ull * 32)), 256, 0, idx->kv.as<ulonglong2>(),
+             ctx->fine_tmp.as<u32>(), F, idx->tab.as<ulonglong2>());
   CUDA_TRY(cudaGetLastError());
   return MM2_OK;
 }

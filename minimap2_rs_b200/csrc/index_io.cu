@@ -153,7 +153,7 @@ extern "C" void mm2_index_free(mm2_index_t* idx) {
   if (!idx) return;
   cudaSetDevice(idx->device);
   idx->S.release(); idx->kv.release(); idx->bkt_koff.release(); idx->bkt_poff.release();
-  idx->p.release(); idx->seq_len.release(); idx->fine_off.release(); idx->bloom.release();
+  idx->p.release(); idx->seq_len.release(); idx->tab.release(); idx->bloom.release();
   delete idx;
 }
 

@@ -96,215 +96,6 @@ __device__ __forceinline__ void chain_finish(const ChainArgs& G, u32 r, int lane
   }
 }
 
-__global__ void __launch_bounds__(CH_WARPS * 32) chain_kernel(ChainArgs G) {
-  const u32 r = blockIdx.x * CH_WARPS + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (r >= G.nreads) return;
-  const u64 a0 = G.read_aoff[r];
-  const i64 n64 = (i64)(G.read_aoff[r + 1] - a0);
-  const i32 qlen = (i32)(G.read_off[r + 1] - G.read_off[r]);
-  const u64 m0 = G.mini_off[r], m1 = G.mini_off[r + 1];
-  ReadHit hit;
-  hit.rid_rev = 0xFFFFFFFFu; hit.qs = hit.qe = hit.ts = hit.te = 0; hit.cm = 0; hit.score = 0;
-  hit.n_anchors = (u32)n64; hit.n_mini = (u32)(m1 - m0); hit.sum_span = G.sum_span[r];
-  hit.st_rank = hit.en_rank = -1; hit.flags = 0; hit.best = -1; hit.pad0 = hit.pad1 = 0;
-  if (n64 <= 0 || n64 > 0x7fffffff) {
-    if (lane == 0) G.hits[r] = hit;
-    return;
-  }
-  const int n = (int)n64;
-  const ulonglong2* an = G.anchors + a0;
-  int4* A = G.A + a0;
-  int4* B = G.B + a0;
-  int* T = G.T + a0;
-  int* W = G.W + a0;
-  const mm2_chain_params_t& p = G.p;
-  unsigned long long cells = 0;
-  int best = 0;
-  int4 bestA = make_int4(0, -1, 0, 0), bestB = make_int4(0, 0, 0, 0);
-
-  for (int pass = 0; pass < 2; ++pass) {
-    const int bw = pass == 0 ? p.bw : p.bw_long;                 // lchain.rs:327-328
-    const int mdx = max(p.max_dist_x, bw), mdy = max(p.max_dist_y, bw);  // lchain.rs:63-66
-    const int mark_base = pass * n;                              // marks of the two passes never collide
-    // ---- parallel pre-pass ---------------------------------------------------------------------------------------
-    // The window start of lchain.rs:75-78 depends on the anchors only: they are sorted by x = (rev|rid, rpos), so
-    // "rid/strand differ or rpos(i) > rpos(st) + max_dist_x" is true on a prefix of [0, i) and `st` (which only ever
-    // advances) is the first index where it is false.  Every lane finds it for its own anchors by binary search.
-    // Anchors with an empty window (about half of them on ONT-like reads: random hits far from everything else) get
-    // their final DP state here (f = v = q_span, no predecessor, lchain.rs:77,89-90); the others go to a work list
-    // that the sequential DP below walks in index order.
-    int nwork = 0;
-    for (int i0 = 0; i0 < n; i0 += 32) {
-      const int i = i0 + lane;
-      bool work = false;
-      if (i < n) {
-        if (pass == 0) T[i] = -1;
-        const ulonglong2 ai = an[i];
-        const u32 hi_i = (u32)(ai.x >> 32);
-        const int ri = (int)(u32)ai.x, qi = (int)(u32)ai.y, spi = (int)((ai.y >> 32) & 0xff);
-        int lo = 0, hi = i;
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          const u64 xm = an[mid].x;
-          const bool adv = ((u32)(xm >> 32) != hi_i) || (ri > wadd((int)(u32)xm, mdx));
-          if (adv) lo = mid + 1; else hi = mid;
-        }
-        const int start_j = (wsub(i, p.max_chain_iter) > lo) ? wsub(i, p.max_chain_iter) : lo;  // lchain.rs:78
-        work = start_j < i;
-        int4 ob;
-        ob.x = wsub(qi, spi - 1); ob.y = wsub(ri, spi - 1); ob.z = i; ob.w = start_j;
-        B[i] = ob;
-        if (!work) A[i] = make_int4(spi, -1, spi, 1);
-      }
-      const u32 wm = __ballot_sync(0xFFFFFFFFu, work);
-      if (work) W[nwork + __popc(wm & ((1u << lane) - 1u))] = i;
-      nwork += __popc(wm);
-    }
-    __syncwarp();
-    for (int t = 0; t < nwork; ++t) {
-      const int i = W[t];
-      const ulonglong2 ai = an[i];
-      const u32 hi_i = (u32)(ai.x >> 32);
-      const int ri = (int)(u32)ai.x, qi = (int)(u32)ai.y, spi = (int)((ai.y >> 32) & 0xff);
-      const int start_j = B[i].w;
-      int max_f = spi, max_j = -1, n_skip = 0;
-      int mv = 0, mcnt = 0, mqs = 0, mts = 0, mfirst = 0;  // v/cnt/qs_min/ts_min/first of max_j
-      const int mark = mark_base + i;
-      for (int jb = i - 1; jb >= start_j; jb -= 32) {
-        const int j = jb - lane;
-        const bool act = j >= start_j;
-        bool valid = false;
-        int sc = NEG_INF;
-        int4 aj = make_int4(0, -1, 0, 0), bj = make_int4(0, 0, 0, 0);
-        if (act) {
-          const ulonglong2 v = an[j];
-          aj = A[j]; bj = B[j];
-          if ((u32)(v.x >> 32) == hi_i) {                         // lchain.rs:81
-            const int dq = wsub(qi, (int)(u32)v.y);               // lchain.rs:18
-            if (!(dq <= 0 || dq > mdx)) {
-              const int dr = wsub(ri, (int)(u32)v.x);
-              if (!(dr == 0 || dq > mdy)) {
-                int dd = wsub(dr, dq); if (dd < 0) dd = wsub(0, dd);   // i32::abs wraps on MIN in release
-                if (!(dd > bw || dd < 0)) {
-                  const int dg = min(dr, dq);
-                  const int q_span = (int)((v.y >> 32) & 0xff);
-                  int s0 = min(q_span, dg);
-                  if (dd != 0 || dg > q_span) {
-                    const float lin = __fadd_rn(__fmul_rn(p.chn_pen_gap, (float)dd), __fmul_rn(p.chn_pen_skip, (float)dg));
-                    s0 = wsub(s0, __float2int_rz(__fadd_rn(lin, G.half_log[dd])));
-                  }
-                  sc = wadd(s0, aj.x);
-                  valid = true;
-                }
-              }
-            }
-          }
-        }
-        if (valid && aj.y >= 0) T[aj.y] = mark;                   // lchain.rs:86 (all lanes first, see header)
-        __syncwarp();
-        const int tj = valid ? T[j] : -1;
-        // Fast path (most tiles of a long predecessor window): no lane beats the running maximum, so there is no new
-        // record in this tile and n_skip can only grow, by one per marked lane, until it crosses max_chain_skip.
-        if (__ballot_sync(0xFFFFFFFFu, valid && sc > max_f) == 0u) {
-          const u32 mm = __ballot_sync(0xFFFFFFFFu, valid && tj == mark);
-          const u32 am = __ballot_sync(0xFFFFFFFFu, act);
-          const int cnt = __popc(mm);
-          if (n_skip + cnt > p.max_chain_skip) {   // the (max_chain_skip + 1 - n_skip)-th marked lane is the `break`
-            u32 tm = mm;
-            for (int q = p.max_chain_skip - n_skip; q > 0; --q) tm &= tm - 1;   // drop the marked lanes that still fit
-            const int brk = __ffs(tm) - 1;
-            cells += (unsigned)(brk + 1);
-            break;
-          }
-          n_skip += cnt;
-          cells += (unsigned)__popc(am);
-          continue;
-        }
-        // exclusive prefix max of the scores, seeded with the running max_f
-        int incl = valid ? sc : NEG_INF * 4;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const int t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-          if (lane >= d) incl = max(incl, t);
-        }
-        int excl = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
-        if (lane == 0) excl = NEG_INF * 4;
-        excl = max(excl, max_f);
-        const bool rec = valid && sc > excl;                      // lchain.rs:84
-        const bool marked = valid && !rec && tj == mark;          // lchain.rs:85
-        // n_skip as a composition of x -> max(x + a, b)
-        int fa = rec ? -1 : (marked ? 1 : 0), fb = rec ? 0 : NEG_INF;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const int ta = __shfl_up_sync(0xFFFFFFFFu, fa, d), tb = __shfl_up_sync(0xFFFFFFFFu, fb, d);
-          if (lane >= d) { fb = max(tb + fa, fb); fa = ta + fa; }
-        }
-        const int x_after = max(n_skip + fa, fb);
-        const u32 bmask = __ballot_sync(0xFFFFFFFFu, marked && x_after > p.max_chain_skip);
-        const int first_brk = bmask ? (__ffs(bmask) - 1) : 32;
-        const u32 amask = __ballot_sync(0xFFFFFFFFu, act);
-        u32 rmask = __ballot_sync(0xFFFFFFFFu, rec);
-        if (first_brk < 32) rmask &= (1u << first_brk) - 1u;
-        if (rmask) {
-          const int last = 31 - __clz(rmask);
-          max_f = __shfl_sync(0xFFFFFFFFu, sc, last);
-          max_j = jb - last;
-          mv = __shfl_sync(0xFFFFFFFFu, aj.z, last);
-          mcnt = __shfl_sync(0xFFFFFFFFu, aj.w, last);
-          mqs = __shfl_sync(0xFFFFFFFFu, bj.x, last);
-          mts = __shfl_sync(0xFFFFFFFFu, bj.y, last);
-          mfirst = __shfl_sync(0xFFFFFFFFu, bj.z, last);
-        }
-        if (first_brk < 32) { cells += (unsigned)(first_brk + 1); break; }
-        cells += (unsigned)__popc(amask);
-        n_skip = __shfl_sync(0xFFFFFFFFu, x_after, 31);
-      }
-      // lchain.rs:89-90 (+ the chain reductions of paf.rs:136-147 carried along the best-predecessor links)
-      if (lane == 0) {
-        const int own_qs = wsub(qi, spi - 1), own_ts = wsub(ri, spi - 1);
-        int4 oa, ob;
-        oa.x = max_f; oa.y = max_j;
-        oa.z = (max_j >= 0 && mv > max_f) ? mv : max_f;
-        oa.w = max_j >= 0 ? mcnt + 1 : 1;
-        ob.x = max_j >= 0 ? min(mqs, own_qs) : own_qs;
-        ob.y = max_j >= 0 ? min(mts, own_ts) : own_ts;
-        ob.z = max_j >= 0 ? mfirst : i;
-        ob.w = start_j;
-        A[i] = oa; B[i] = ob;
-      }
-      __syncwarp();
-    }
-    // lchain.rs:163: Iterator::max_by_key returns the LAST maximum of f
-    int bf = NEG_INF * 4, bi = -1;
-    for (int j = lane; j < n; j += 32) {
-      const int f = A[j].x;
-      if (f >= bf) { bf = f; bi = j; }   // j ascending per lane
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      const int of = __shfl_xor_sync(0xFFFFFFFFu, bf, d), oi = __shfl_xor_sync(0xFFFFFFFFu, bi, d);
-      if (of > bf || (of == bf && oi > bi)) { bf = of; bi = oi; }
-    }
-    best = bi;
-    bestA = A[best]; bestB = B[best];
-    if (pass == 1 || !G.do_rescue) break;
-    // lchain.rs:321-330 rescue_long_join on the single (fallback) chain
-    const ulonglong2 ab = an[best];
-    const int qe = wadd((int)(u32)ab.y, 1);
-    const int qs = max(bestB.x, 0);
-    const int best_cov = max(wsub(qe, qs), 0);
-    const int uncovered = max(wsub(qlen, best_cov), 0);
-    const bool rescue = uncovered > p.rmq_rescue_size ||
-                        (float)best_cov < __fmul_rn((float)qlen, __fsub_rn(1.0f, p.rmq_rescue_ratio));
-    if (!rescue) break;
-    hit.flags |= 1u;
-    __syncwarp();
-  }
-
-  chain_finish(G, r, lane, an, A, a0, qlen, m0, m1, best, bestA, bestB, hit, cells);
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
 // chain_ring_kernel — the default.  One warp per read; the DP state of the 32 most recent anchors lives in REGISTERS:
 // lane l owns the ring slot of every anchor j with j % 32 == l (static x/y fields and f, pprev, v, cnt, qs_min, ts_min,
@@ -323,7 +114,7 @@ __global__ void __launch_bounds__(CH_WARPS * 32) chain_kernel(ChainArgs G) {
 //  * Only when the ring was visited without a break AND the slot that anchor i overwrites (j = i - 32) is still inside
 //    the window does the loop continue, 32 predecessors at a time, on A/T in global memory.  On ONT-like reads the loop
 //    breaks inside the ring for nearly every anchor (about 27 visited predecessors: max_chain_skip = 25).
-// Same arithmetic and same order of decisions as chain_kernel; tests/ compares both with the CPU restatement.
+// tests/ compares it (and the CTA-per-read variant below) with the CPU restatement, state by state.
 
 __device__ __forceinline__ u32 low_mask(int n) { return n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u); }
 // position of the n-th (1-based) set bit of m; popc(m) >= n
@@ -1035,10 +826,7 @@ int chain_batch(mm2_ctx* ctx, const ulonglong2* d_anchors, const u64* d_read_aof
   G.A = d_A; G.B = d_B; G.T = d_T; G.W = d_W; G.chain = d_chain; G.hits = d_hits; G.cells = d_cells;
   G.dense = nullptr; G.dense_min = 0x7fffffff; G.dense_ratio5 = 0;
   const int grid = (int)((nreads + CH_WARPS - 1) / CH_WARPS);
-  static const bool use_v1 = [] { const char* e = getenv("MM2_CHAIN"); return e && !strcmp(e, "v1"); }();   // comparison arm
-  if (use_v1) {
-    MM2_LAUNCH(ctx, chain_kernel, grid, CH_WARPS * 32, 0, G);
-  } else {
+  {
     MM2_TRY(ctx->read_class.ensure(((size_t)nreads + 4) * 4));
     G.dense = ctx->read_class.as<u32>();
     G.dense_min = ctx->chain_dense_min;

@@ -145,6 +145,7 @@ struct mm2_ctx {
   bool count_cells = false;  // diagnostics (mm2b200_diag.h): DP-cell counter of the chaining kernels
   u64 last_cells = 0;
   DevBuf diag;
+  DevBuf fine_tmp;               // index build: fine-bucket offsets (scratch of index_build_lookup)
   DevBuf mg_recv_k, mg_recv_v;   // sharded index build: records received from the other ranks
 };
 
@@ -175,14 +176,19 @@ struct IndexView {
   const u64* p;          // n_p
   const u32* seq_len;    // n_seq
   // Seed lookup: the keys are sorted by (bucket, minier>>b), so a FINE bucket = (bucket, top bits of a monotone
-  // equalising map of minier>>b) is a contiguous range of kv[]; fine_off[f] is its first entry (index_fine_id below).
-  const u32* fine_off;   // (1 << (b + fine_j)) + 1
+  // equalising map of minier>>b, index_fine_id below) is a contiguous run of kv[] of ~0.7 entries on average.  tab[] holds
+  // one 32-byte line per fine bucket: the run's first two records, or {first record, {TAB_MORE, (n-1)<<32 | index of the
+  // second record in kv}} when the run is longer; unused slots hold TAB_EMPTY.  Index::get is ONE 32-byte access for ~96 %
+  // of the keys, and the table is written by a streaming pass over the sorted records (no random claims).
+  const ulonglong2* tab; // 2 << (b + fine_j) records
   int fine_j, fine_pw, R;   // fine bits per bucket; squarings of the equalising map; R = bits of minier>>b (max(2k-b, 0))
   // blocked Bloom filter over the keys (one 16-byte block per key, 4 bits), small enough to live in L2: answers most
   // of the ~80 % of query minimizers that are absent from the index without touching HBM.  NULL = disabled.
   const uint4* bloom;
   u64 bloom_mask;
 };
+
+constexpr u64 TAB_EMPTY = ~0ULL, TAB_MORE = ~0ULL - 1;   // never a key: keys are (minier>>b)<<1|single < 2^57
 
 // Monotone map of hk = minier>>b (R bits) onto fine_j bits.  Minimizer hashes are window MINIMA, so hk is skewed towards 0
 // with density ~ w (1-x)^(w-1); u = 1 - (1-x)^(2^pw) (integer arithmetic: exactly monotone, identical wherever it is
@@ -211,7 +217,7 @@ struct mm2_index {
   u64 total_len = 0;
   u64 S_words_alloc = 0;       // kroundup64((total+7)/8) as allocated by build (native format writes all of it); 0 = no sequence array
   u64 n_keys = 0, n_p = 0, n_minimizers = 0;
-  DevBuf S, kv, bkt_koff, bkt_poff, p, seq_len, fine_off, bloom;
+  DevBuf S, kv, bkt_koff, bkt_poff, p, seq_len, tab, bloom;
   int fine_j = 0, fine_pw = 0;
   u64 bloom_mask = 0;
   bool has_bloom = false;
@@ -219,7 +225,7 @@ struct mm2_index {
   std::vector<u64> occ_hist;
   std::vector<u32> occ_big;     // counts >= 65536
   float build_ms[5] = {0, 0, 0, 0, 0};
-  mm2_index() { S.pooled = kv.pooled = bkt_koff.pooled = bkt_poff.pooled = p.pooled = seq_len.pooled = fine_off.pooled = bloom.pooled = true; }
+  mm2_index() { S.pooled = kv.pooled = bkt_koff.pooled = bkt_poff.pooled = p.pooled = seq_len.pooled = tab.pooled = bloom.pooled = true; }
   IndexView view() const;
 };
 

@@ -186,26 +186,30 @@ __device__ __forceinline__ void seed_hits_read(const SeedHitArgs& G, const u32 r
       for (int q = 0; q < 4; ++q) { const u32 b = (u32)(h >> (7 * q)) & 127u; maybe = maybe && ((wd[b >> 5] >> (b & 31)) & 1u); }
     }
     if (!maybe) continue;
-    // Index::get (index.rs:143-154): the key's fine bucket is a short contiguous run of kv[] (ascending keys)
+    // Index::get (index.rs:143-154): one 32-byte table line per fine bucket (see IndexView::tab)
     const u64 hk = minier >> G.V.b;
     const u64 f = ((minier & bmask) << G.V.fine_j) | (u64)index_fine_cdf(hk, G.V.R, G.V.fine_j, G.V.fine_pw);
-    const u32 e0 = __ldg(G.V.fine_off + f), e1 = __ldg(G.V.fine_off + f + 1);
+    const ulonglong2 e0 = ld_hint_v2(&G.V.tab[2 * f], pol_stream), e1 = ld_hint_v2(&G.V.tab[2 * f + 1], pol_stream);
+    ulonglong2 hit = make_ulonglong2(TAB_EMPTY, 0);
+    if ((e0.x >> 1) == hk) hit = e0;
+    else if ((e1.x >> 1) == hk) hit = e1;
+    else if (e1.x == TAB_MORE) {                                 // a longer run: the rest of it is in kv[], ascending
+      const u32 lo = (u32)e1.y, n = (u32)(e1.y >> 32);
+      for (u32 e = 0; e < n; ++e) {
+        const ulonglong2 kv = ld_hint_v2(&G.V.kv[lo + e], pol_stream);
+        if ((kv.x >> 1) >= hk) { if ((kv.x >> 1) == hk) hit = kv; break; }
+      }
+    }
     u32 cnt = 0; u64 loc = 0;
-    for (u32 e = e0; e < e1; ++e) {
-      const ulonglong2 kv = ld_hint_v2(&G.V.kv[e], pol_stream);
-      const u64 kk = kv.x >> 1;
-      if (kk < hk) continue;
-      if (kk == hk) {
-        if (kv.x & 1) { cnt = 1; loc = kv.y; }                   // Occurrences::Single (never skipped, seeds.rs:47)
-        else {
-          const u64 c = kv.y & 0xffffffffULL;
-          if (!((i32)(u32)c > G.mid_occ)) {                      // seeds.rs:51 `slice.len() as i32 > mid_occ`
-            cnt = (u32)c;
-            loc = G.V.bkt_poff[minier & bmask] + (kv.y >> 32);
-          }
+    if (hit.x != TAB_EMPTY) {
+      if (hit.x & 1) { cnt = 1; loc = hit.y; }                   // Occurrences::Single (never skipped, seeds.rs:47)
+      else {
+        const u64 c = hit.y & 0xffffffffULL;
+        if (!((i32)(u32)c > G.mid_occ)) {                        // seeds.rs:51 `slice.len() as i32 > mid_occ`
+          cnt = (u32)c;
+          loc = G.V.bkt_poff[minier & bmask] + (hit.y >> 32);
         }
       }
-      break;
     }
     if (cnt) {
       const u64 rps = __ldcs(G.mval + i);
@@ -629,8 +633,6 @@ __global__ void __launch_bounds__(NT) anchor_sort_gmem_kernel(ulonglong2* __rest
 int seeds_set_attrs() {
   cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FL_SLOTS * 12);
   cudaFuncSetAttribute(filter_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FL_SLOTS * 12);
-  cudaFuncSetAttribute(anchor_sort_smem_kernel<1024, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 16);
-  cudaFuncSetAttribute(anchor_sort_smem_kernel<4096, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16);
   cudaFuncSetAttribute(anchor_sort_smem_kernel<12288, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12288 * 16);
   CUDA_TRY(cudaFuncSetAttribute(anchor_msort_kernel<512, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4608 * 16));
   return MM2_OK;
@@ -710,18 +712,12 @@ int seeds_fill_and_sort(mm2_ctx* ctx, const IndexView& V, const u64* d_mini_off,
   u32* d_lists = d_ccnt + 4;
   CUDA_TRY(cudaMemsetAsync(d_ccnt, 0, 16, ctx->stream));
   MM2_LAUNCH(ctx, anchor_class_kernel, (nreads + 255) / 256, 256, 0, d_aoff, nreads, d_lists, d_ccnt);
-  static const bool use_bitonic = [] { const char* e = getenv("MM2_ANCHOR_SORT"); return e && !strcmp(e, "bitonic"); }();   // comparison arm
   const int lgrid = (int)std::min<u32>(nreads, (u32)ctx->n_sm * 4u);
   MM2_LAUNCH(ctx, anchor_fill_hits_kernel, nreads, AF_NT, 0, V, H.hit_loc, H.hit_q, H.hit_aux, d_mini_off, d_read_off, nreads, H.read_nhit,
-             d_aoff, d_anchors, (u64)(use_bitonic ? 0 : 4096));
+             d_aoff, d_anchors, (u64)4096);
   ctx->timer.mark(ctx->stream, "anchor_sort");
-  if (use_bitonic) {
-    MM2_LAUNCH(ctx, (anchor_sort_smem_kernel<1024, 128>), nreads, 128, 1024 * 16, d_anchors, d_aoff, nreads, 1u, 1024u, (const u32*)nullptr, (const u32*)nullptr);
-    MM2_LAUNCH(ctx, (anchor_sort_smem_kernel<4096, 256>), lgrid, 256, 4096 * 16, d_anchors, d_aoff, nreads, 1024u, 4096u, (const u32*)d_lists, (const u32*)d_ccnt);
-  } else {
-    MM2_LAUNCH(ctx, (anchor_msort_kernel<128, true, false>), nreads, 128, 1152 * 16, d_anchors, d_aoff, nreads, 0u, 1024u, H, (const u32*)nullptr, (const u32*)nullptr);
-    MM2_LAUNCH(ctx, (anchor_msort_kernel<512, true, true>), lgrid, 512, 4608 * 16, d_anchors, d_aoff, nreads, 1024u, 4096u, H, (const u32*)d_lists, (const u32*)d_ccnt);
-  }
+  MM2_LAUNCH(ctx, (anchor_msort_kernel<128, true, false>), nreads, 128, 1152 * 16, d_anchors, d_aoff, nreads, 0u, 1024u, H, (const u32*)nullptr, (const u32*)nullptr);
+  MM2_LAUNCH(ctx, (anchor_msort_kernel<512, true, true>), lgrid, 512, 4608 * 16, d_anchors, d_aoff, nreads, 1024u, 4096u, H, (const u32*)d_lists, (const u32*)d_ccnt);
   MM2_LAUNCH(ctx, (anchor_sort_smem_kernel<12288, 1024>), lgrid, 1024, 12288 * 16, d_anchors, d_aoff, nreads, 4096u, 12288u,
              (const u32*)(d_lists + nreads), (const u32*)(d_ccnt + 1));
   MM2_LAUNCH(ctx, (anchor_sort_gmem_kernel<1024>), lgrid, 1024, 0, d_anchors, d_aoff, nreads, 12288u, (const u32*)(d_lists + 2 * (u64)nreads),
