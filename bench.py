@@ -30,7 +30,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ.setdefault("NCCL_DEBUG", "WARN")  # keeps stdout to the one JSON line unless the caller asks for NCCL's own log
+# NCCL_DEBUG is left to the caller (the driver reads NCCL's own log); the JSON line is the LAST line of stdout
 
 INT_PEAK = 148 * 128 * 1.965e9   # 148 SMs x 128 INT32 lanes x 1.965 GHz = 37.2 Tint-op/s (nominal)
 OPS_PER_CELL = 20                # integer operations credited per DP cell (lchain.rs:80 iteration)

@@ -72,7 +72,11 @@ int mm2_index_build_fasta(mm2_ctx_t* ctx, const char* path, int w, int k, int b,
 int mm2_index_build_seqs(mm2_ctx_t* ctx, const uint8_t* cat, const uint64_t* offs, const char* const* names,
                          size_t nseq, int w, int k, int b, int flag, mm2_index_t** out);
 int mm2_index_save_mmi(const mm2_index_t* idx, const char* path);               /* index.rs:233 save_to_mmi */
-int mm2_index_load_mmi(mm2_ctx_t* ctx, const char* path, mm2_index_t** out);    /* index.rs:361 load_from_mmi */
+/* same layout, the hash entries of every bucket in the slot order of C minimap2's khash table (what `minimap2 -d` dumps)
+ * instead of ascending key order (index.rs:279-287 writes std HashMap iteration order, which is random per process) */
+int mm2_index_save_mmi_khash(const mm2_index_t* idx, const char* path);
+/* index.rs:361 load_from_mmi.  Entries may come in any order; an index flagged MM_I_NO_SEQ (2) has no sequence array */
+int mm2_index_load_mmi(mm2_ctx_t* ctx, const char* path, mm2_index_t** out);
 int mm2_index_save_native(const mm2_index_t* idx, const char* path);            /* index.rs:156 save_to_file */
 int mm2_index_load_native(mm2_ctx_t* ctx, const char* path, mm2_index_t** out); /* index.rs:309 load_from_file */
 /* main.rs:135-145 load_index_auto: ".mmi" suffix -> MMI; else native format; else build from FASTA */

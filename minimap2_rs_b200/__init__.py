@@ -61,7 +61,7 @@ class _MapResult(C.Structure):
 ABI_SYMBOLS = [
     "mm2_ctx_create", "mm2_ctx_destroy", "mm2_ctx_set_stream", "mm2_ctx_synchronize", "mm2_last_error", "mm2_free",
     "mm2_host_alloc", "mm2_host_free", "mm2_sketch", "mm2_sketch_batch",
-    "mm2_index_build_fasta", "mm2_index_build_seqs", "mm2_index_save_mmi", "mm2_index_load_mmi", "mm2_index_save_native",
+    "mm2_index_build_fasta", "mm2_index_build_seqs", "mm2_index_save_mmi", "mm2_index_save_mmi_khash", "mm2_index_load_mmi", "mm2_index_save_native",
     "mm2_index_load_native", "mm2_index_load_auto", "mm2_index_free", "mm2_index_get", "mm2_index_stats",
     "mm2_index_calc_mid_occ", "mm2_index_params", "mm2_index_seq", "mm2_index_get_ref_subseq", "mm2_index_build_timings",
     "mm2_filter_query_minimizers", "mm2_build_anchors_filtered", "mm2_chain_dp_all", "mm2_chains_free",
@@ -106,7 +106,7 @@ def lib():
     L.mm2_sketch_batch.argtypes = [vp, vp, vp, sz, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(vp), C.POINTER(vp)]
     L.mm2_index_build_fasta.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     L.mm2_index_build_seqs.argtypes = [vp, vp, vp, vp, sz, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
-    for nm in ("mm2_index_save_mmi", "mm2_index_save_native"):
+    for nm in ("mm2_index_save_mmi", "mm2_index_save_native", "mm2_index_save_mmi_khash"):
         getattr(L, nm).argtypes = [vp, C.c_char_p]
     for nm in ("mm2_index_load_mmi", "mm2_index_load_native"):
         getattr(L, nm).argtypes = [vp, C.c_char_p, C.POINTER(vp)]
@@ -536,6 +536,10 @@ class Index:
 
     def save_to_mmi(self, path):
         _check(lib().mm2_index_save_mmi(self.h, path.encode()))
+
+    def save_to_mmi_khash(self, path):
+        """.mmi with every bucket's entries in C minimap2's khash slot order (mm_idx_dump)"""
+        _check(lib().mm2_index_save_mmi_khash(self.h, path.encode()))
 
     def save_to_file(self, path):
         _check(lib().mm2_index_save_native(self.h, path.encode()))

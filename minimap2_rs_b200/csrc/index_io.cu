@@ -6,6 +6,8 @@
 #include "mm2_internal.cuh"
 
 #include <algorithm>
+#include <new>
+#include <stdexcept>
 
 #include "stages.cuh"
 
@@ -58,7 +60,6 @@ struct FileW {
 struct MemR {  // bounds-checked little-endian reader over a whole file in memory
   const u8* p; size_t n, o = 0; bool ok = true;
   bool need(size_t k) { if (k > n - o) { ok = false; return false; } return true; }   // o <= n always; no wrap-around
-  size_t left() const { return n - o; }
   // k records of `rec` bytes each, with the multiplication checked against what is left in the file
   const u8* take_recs(size_t k, size_t rec) { if (k > (n - o) / rec) { ok = false; return nullptr; } return take(k * rec); }
   u8 u8_() { if (!need(1)) return 0; return p[o++]; }
@@ -142,6 +143,69 @@ int upload(mm2_ctx* ctx, mm2_index* idx, HostIndex& h) {
   return MM2_OK;
 }
 
+// Slot order of C minimap2's per-bucket hash table (klib khash 0.2.8 as instantiated in minimap2's index.c:
+// KHASH_INIT(idx, uint64_t, uint64_t, 1, idx_hash, idx_eq) with idx_hash(a) = a >> 1, truncated to khint_t), filled the way
+// mm_idx_post's worker does: kh_resize(h, n_keys), then one kh_put per key in ascending key order.  mm_idx_dump walks the
+// slots 0 .. kh_end and writes the occupied ones, so this permutation is the entry order of an .mmi written by C minimap2.
+// `ent` comes in ascending key order and leaves in slot order.  (Restated from the published klib algorithm; no minimap2
+// binary exists in this image to compare with, so the order is "as specified", and any order loads.)
+struct KhashSim {
+  std::vector<u64> keys, vals;
+  std::vector<u8> st;   // 0 empty, 1 occupied, 2 deleted
+  u32 n_buckets = 0, size = 0, n_occupied = 0, upper_bound = 0;
+  static u32 roundup32(u32 x) { --x; x |= x >> 1; x |= x >> 2; x |= x >> 4; x |= x >> 8; x |= x >> 16; return ++x; }
+  static u32 hash(u64 key) { return (u32)(key >> 1); }
+  void resize(u32 want) {
+    u32 nn = roundup32(want);
+    if (nn < 4) nn = 4;
+    if (size >= (u32)(nn * 0.77 + 0.5)) return;   // requested size is too small
+    std::vector<u8> nst(nn, 0);
+    if (n_buckets < nn) { keys.resize(nn, 0); vals.resize(nn, 0); }
+    for (u32 j = 0; j != n_buckets; ++j) {
+      if (st[j] != 1) continue;
+      u64 key = keys[j], val = vals[j];
+      const u32 new_mask = nn - 1;
+      st[j] = 2;
+      for (;;) {   // kick-out process
+        u32 i = hash(key) & new_mask, step = 0;
+        while (nst[i] != 0) i = (i + (++step)) & new_mask;
+        nst[i] = 1;
+        if (i < n_buckets && st[i] == 1) { std::swap(keys[i], key); std::swap(vals[i], val); st[i] = 2; }
+        else { keys[i] = key; vals[i] = val; break; }
+      }
+    }
+    if (n_buckets > nn) { keys.resize(nn); vals.resize(nn); }
+    st.swap(nst);
+    n_buckets = nn; n_occupied = size; upper_bound = (u32)(n_buckets * 0.77 + 0.5);
+  }
+  void put(u64 key, u64 val) {   // the key is absent (distinct keys); its low bit does not take part in hash / equality
+    if (n_occupied >= upper_bound) { if (n_buckets > (size << 1)) resize(n_buckets - 1); else resize(n_buckets + 1); }
+    const u32 mask = n_buckets - 1;
+    u32 i = hash(key) & mask, step = 0, site = n_buckets, x = n_buckets;
+    if (st[i] == 0) x = i;
+    else {
+      const u32 last = i;
+      while (st[i] != 0 && (st[i] == 2 || (keys[i] >> 1) != (key >> 1))) {
+        if (st[i] == 2) site = i;
+        i = (i + (++step)) & mask;
+        if (i == last) { x = site; break; }
+      }
+      if (x == n_buckets) x = (st[i] == 0 && site != n_buckets) ? site : i;
+    }
+    if (st[x] == 0) { ++size; ++n_occupied; } else if (st[x] == 2) ++size;
+    keys[x] = key; vals[x] = val; st[x] = 1;
+  }
+};
+void khash_slot_order(u64* kv, size_t n) {   // kv: n (key, value) pairs in ascending key order -> khash slot order
+  if (n < 2) return;
+  KhashSim h;
+  h.resize((u32)n);
+  for (size_t i = 0; i < n; ++i) h.put(kv[2 * i], kv[2 * i + 1]);
+  size_t o = 0;
+  for (u32 sidx = 0; sidx < h.n_buckets; ++sidx)
+    if (h.st[sidx] == 1) { kv[2 * o] = h.keys[sidx]; kv[2 * o + 1] = h.vals[sidx]; ++o; }
+}
+
 bool ends_with(const char* s, const char* suf) {
   const size_t a = strlen(s), b = strlen(suf);
   return a >= b && memcmp(s + a - b, suf, b) == 0;
@@ -168,8 +232,18 @@ extern "C" int mm2_index_build_fasta(mm2_ctx_t* ctx, const char* path, int w, in
 }
 
 // ---- index.rs:233-307 ---------------------------------------------------------------------------------------------------
+static int save_mmi_impl(const mm2_index_t* idx, const char* path, bool khash_order);
 extern "C" int mm2_index_save_mmi(const mm2_index_t* idx, const char* path) {
   if (!idx || !path) { mm2_set_error("mm2_index_save_mmi: NULL argument"); return MM2_E_ARG; }
+  try { return save_mmi_impl(idx, path, false); }
+  catch (const std::bad_alloc&) { mm2_set_error("out of host memory"); return MM2_E_OOM; }
+}
+extern "C" int mm2_index_save_mmi_khash(const mm2_index_t* idx, const char* path) {
+  if (!idx || !path) { mm2_set_error("mm2_index_save_mmi_khash: NULL argument"); return MM2_E_ARG; }
+  try { return save_mmi_impl(idx, path, true); }
+  catch (const std::bad_alloc&) { mm2_set_error("out of host memory"); return MM2_E_OOM; }
+}
+static int save_mmi_impl(const mm2_index_t* idx, const char* path, bool khash_order) {
   HostIndex h;
   MM2_TRY(download(idx, h, true));
   FILE* fp = fopen(path, "wb");
@@ -197,11 +271,15 @@ extern "C" int mm2_index_save_mmi(const mm2_index_t* idx, const char* path) {
     wr.u32_((u32)(k1 - k0));
     kv.resize((size_t)(k1 - k0) * 2);
     for (u64 q = k0; q < k1; ++q) { kv[(size_t)(q - k0) * 2] = h.hkeys[q]; kv[(size_t)(q - k0) * 2 + 1] = h.hvals[q]; }
+    if (khash_order) khash_slot_order(kv.data(), (size_t)(k1 - k0));
     wr.bytes(kv.data(), kv.size() * 8);
   }
+  // index.rs:291 writes the packed sequence unconditionally ("C checks NO_SEQ bit itself"); an index that was LOADED from a
+  // file flagged MM_I_NO_SEQ (2) has none, and is written back the way C minimap2 dumps such an index: without it
   const size_t words = (size_t)((sum_len + 7) / 8);
-  if (words > h.S.size()) { fclose(fp); mm2_set_error("index has no sequence array to write"); return MM2_E_FORMAT; }
-  wr.bytes(h.S.data(), words * 4);
+  if (words > h.S.size()) {
+    if (!(idx->flag & 2)) { fclose(fp); mm2_set_error("index has no sequence array to write"); return MM2_E_FORMAT; }
+  } else wr.bytes(h.S.data(), words * 4);
   bool ok = wr.ok;
   if (fclose(fp) != 0) ok = false;
   if (!ok) { mm2_set_error("write error on %s", path); return MM2_E_IO; }
@@ -209,8 +287,14 @@ extern "C" int mm2_index_save_mmi(const mm2_index_t* idx, const char* path) {
 }
 
 // ---- index.rs:361-424 ---------------------------------------------------------------------------------------------------
+static int load_mmi_impl(mm2_ctx_t* ctx, const char* path, mm2_index_t** out);
 extern "C" int mm2_index_load_mmi(mm2_ctx_t* ctx, const char* path, mm2_index_t** out) {
   if (!ctx || !path || !out) { mm2_set_error("mm2_index_load_mmi: NULL argument"); return MM2_E_ARG; }
+  try { return load_mmi_impl(ctx, path, out); }   // nothing may throw across the C boundary
+  catch (const std::bad_alloc&) { mm2_set_error("out of host memory while loading %s", path); return MM2_E_OOM; }
+  catch (const std::exception& e) { mm2_set_error("invalid index file %s (%s)", path, e.what()); return MM2_E_FORMAT; }
+}
+static int load_mmi_impl(mm2_ctx_t* ctx, const char* path, mm2_index_t** out) {
   CUDA_TRY(cudaSetDevice(ctx->device));
   std::vector<u8> data;
   MM2_TRY(slurp(path, data));
@@ -256,11 +340,16 @@ extern "C" int mm2_index_load_mmi(mm2_ctx_t* ctx, const char* path, mm2_index_t*
   }
   if (!rd.ok) return fail(MM2_E_FORMAT, "truncated MMI bucket table");
   h.koff[nb] = h.hkeys.size(); h.poff[nb] = h.p.size();
-  const size_t words = (size_t)((sum_len + 7) / 8);
-  const u8* sp = rd.take_recs(words, 4);
-  if (!rd.ok) return fail(MM2_E_FORMAT, "truncated MMI sequence array");
-  h.S.resize(words);
-  if (words) memcpy(h.S.data(), sp, words * 4);
+  // MM_I_NO_SEQ (flag bit 1, value 2): C minimap2 dumps such an index without the packed sequence.  The reference's loader
+  // (index.rs:417-419) reads the array unconditionally and fails on these files; honouring the flag is what makes indexes
+  // written by `minimap2 -d` with --idx-no-seq usable.  Mapping never touches S.
+  if (!(idx->flag & 2)) {
+    const size_t words = (size_t)((sum_len + 7) / 8);
+    const u8* sp = rd.take_recs(words, 4);
+    if (!rd.ok) return fail(MM2_E_FORMAT, "truncated MMI sequence array");
+    h.S.resize(words);
+    if (words) memcpy(h.S.data(), sp, words * 4);
+  }
   const int rc = upload(ctx, idx, h);
   if (rc != MM2_OK) { mm2_index_free(idx); return rc; }
   *out = idx;
@@ -311,8 +400,14 @@ extern "C" int mm2_index_save_native(const mm2_index_t* idx, const char* path) {
 }
 
 // ---- index.rs:309-358 ---------------------------------------------------------------------------------------------------
+static int load_native_impl(mm2_ctx_t* ctx, const char* path, mm2_index_t** out);
 extern "C" int mm2_index_load_native(mm2_ctx_t* ctx, const char* path, mm2_index_t** out) {
   if (!ctx || !path || !out) { mm2_set_error("mm2_index_load_native: NULL argument"); return MM2_E_ARG; }
+  try { return load_native_impl(ctx, path, out); }
+  catch (const std::bad_alloc&) { mm2_set_error("out of host memory while loading %s", path); return MM2_E_OOM; }
+  catch (const std::exception& e) { mm2_set_error("invalid index file %s (%s)", path, e.what()); return MM2_E_FORMAT; }
+}
+static int load_native_impl(mm2_ctx_t* ctx, const char* path, mm2_index_t** out) {
   CUDA_TRY(cudaSetDevice(ctx->device));
   std::vector<u8> data;
   MM2_TRY(slurp(path, data));

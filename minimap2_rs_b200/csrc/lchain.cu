@@ -221,137 +221,8 @@ __global__ void chain_classify_kernel(ChainArgs G) {
   if (chain_is_dense(G, r)) G.dense[2 + atomicAdd(&G.dense[0], 1u)] = r;
 }
 
-// Shared state of a CTA that chains one dense read: warp 0 runs the ring algorithm; when a window goes on beyond the ring
-// it posts the anchor here and all NW warps evaluate the next 32 tiles (1024 predecessors) of the window in parallel.
-// Window ring of a dense read in shared memory: the static fields and the DP result (f, pprev) of the last DENSE_CAP
-// anchors that have left the register ring, slot = j % DENSE_CAP, plus one mark bit per slot (lchain.rs:86 `t[pprev] = i`,
-// see `tg`).  Every far predecessor of a window of at most max_chain_iter <= DENSE_CAP - 64 anchors is in
-// there, so a DP cell costs shared-memory loads instead of L2 round trips (the kernel was bound by those: 48 B per cell,
-// 2,800 cells per anchor on configs[4]).  Larger max_chain_iter values fall back to the arrays in global memory.
-#ifdef MM2_DENSE_PROF
-// build with -DMM2_DENSE_PROF: cycles of warp 0 per phase of the dense path, printed by chain_batch (diagnostic only)
-__device__ unsigned long long g_dense_prof[8];
-#define DPROF_T(v) const long long v = clock64()
-#define DPROF_ADD(k, a, b) do { if (NW > 1 && lane == 0) dprof[k] += (unsigned long long)((b) - (a)); } while (0)
-#define DPROF_INC(k) do { if (NW > 1 && lane == 0) dprof[k] += 1ull; } while (0)
-#else
-#define DPROF_T(v)
-#define DPROF_ADD(k, a, b)
-#define DPROF_INC(k)
-#endif
-constexpr int DENSE_CAP = 5120;
-struct DenseSh {
-  int op;                      // 0: evaluate a round, 1: the read is done
-  int ri, qi, jb, start_j, mark, bw, mdx, mdy;
-  u32 hi_i;
-  u32 next;                    // next dense read of this CTA
-  int use_sm;                  // the window ring below is in use (max_chain_iter fits)
-  int* sx; int* sq; int* sf; int* sp; u8* ss;   // DENSE_CAP entries each
-  u16* tg;                      // mark of lchain.rs:86 per slot: tag of the last anchor that marked it (0 = none); tag(i) = i % 65535 + 1
-                                // is unique among the anchors that can have marked a live slot, so nothing is cleared per anchor
-  int tag;                      // tag of the anchor being evaluated
-  u32 V[32], M[32], ACT[32];   // per tile: ballots of "has a score", "t[j] == i", "inside the window"
-  int tmax[32];                // per tile: best score
-  int sc[32][33];
-};
-
-template <int NW>
-__device__ __forceinline__ void dense_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory"); }
-
-// One round: tiles t = 0..31 cover j = jb - 32 t - lane; warp w takes tiles w, w + NW, ...  (all NW warps call this)
-template <int NW>
-__device__ __forceinline__ void dense_eval_round(const ChainArgs& G, DenseSh* sh, const ulonglong2* __restrict__ an, const int4* A, int* T,
-                                                 int wid, int lane) {
-  constexpr int TPW = 32 / NW;
-  const int ri = sh->ri, qi = sh->qi, jb = sh->jb, start_j = sh->start_j, mark = sh->mark, bw = sh->bw, mdx = sh->mdx, mdy = sh->mdy;
-  const u32 hi_i = sh->hi_i;
-  int sc2[TPW];
-  bool v2[TPW];
-  if (sh->use_sm) {
-    const int* __restrict__ sx = sh->sx; const int* __restrict__ sq = sh->sq; const int* __restrict__ sf = sh->sf;
-    const int* __restrict__ sp = sh->sp; const u8* __restrict__ ss = sh->ss;
-    u16* tg = sh->tg;
-    const u16 tag = (u16)sh->tag;
-    const float pen_gap = G.p.chn_pen_gap, pen_skip = G.p.chn_pen_skip;
-    const float* __restrict__ half_log = G.half_log;
-    int slot_b = jb % DENSE_CAP;                                    // slots go down with j and wrap at most once (window <= DENSE_CAP)
-    // The cells of one lane are written without branches (comput_sc's early returns become one predicate, lchain.rs:17-34), so
-    // that the loads and the arithmetic of the TPW cells overlap instead of running one after the other.
-#pragma unroll
-    for (int u = 0; u < TPW; ++u) {
-      const int back = 32 * (wid + NW * u) + lane;                  // j = jb - back
-      const int j = jb - back;
-      const bool act = j >= start_j;                                // same rid/strand as anchor i: start_j is inside its block
-      int slot = slot_b - back; if (slot < 0) slot += DENSE_CAP;
-      if (!act) slot = 0;
-      const int rj = sx[slot], qj = sq[slot], span_j = (int)ss[slot], fj = sf[slot], pp = sp[slot];
-      const int dq = wsub(qi, qj), dr = wsub(ri, rj);
-      int dd = wsub(dr, dq); if (dd < 0) dd = wsub(0, dd);
-      const bool ok = act && dq > 0 && dq <= mdx && dr != 0 && dq <= mdy && dd <= bw && dd >= 0;
-      const int dg = min(dr, dq);
-      int s0 = min(span_j, dg);
-      const int ddc = ok ? dd : 0;
-      const float lin = __fadd_rn(__fmul_rn(pen_gap, (float)ddc), __fmul_rn(pen_skip, (float)dg));
-      const int pen = __float2int_rz(__fadd_rn(lin, half_log[ddc]));
-      if (ddc != 0 || dg > span_j) s0 = wsub(s0, pen);
-      sc2[u] = ok ? wadd(s0, fj) : NEG_INF;
-      v2[u] = ok;
-      if (ok && pp >= start_j) {                                    // lchain.rs:86; marks below the window are never read
-        int ps = slot - (j - pp); if (ps < 0) ps += DENSE_CAP;
-        tg[ps] = tag;
-      }
-    }
-    dense_bar<NW>();                                                // every mark of this round is visible
-#pragma unroll
-    for (int u = 0; u < TPW; ++u) {
-      const int t = wid + NW * u;
-      const int j = jb - 32 * t - lane;
-      bool tm = false;
-      if (v2[u]) { int slot = slot_b - 32 * t - lane; if (slot < 0) slot += DENSE_CAP; tm = tg[slot] == tag; }
-      const u32 Vb = __ballot_sync(0xFFFFFFFFu, v2[u]), Mb = __ballot_sync(0xFFFFFFFFu, tm), Ab = __ballot_sync(0xFFFFFFFFu, j >= start_j);
-      const int tmx = __reduce_max_sync(0xFFFFFFFFu, sc2[u]);
-      sh->sc[t][lane] = sc2[u];
-      if (lane == 0) { sh->V[t] = Vb; sh->M[t] = Mb; sh->ACT[t] = Ab; sh->tmax[t] = tmx; }
-    }
-    dense_bar<NW>();                                                // the tile summaries are in shared memory
-    return;
-  }
-#pragma unroll
-  for (int u = 0; u < TPW; ++u) {
-    const int j = jb - 32 * (wid + NW * u) - lane;
-    sc2[u] = NEG_INF; v2[u] = false;
-    if (j >= start_j) {
-      const ulonglong2 v = an[j];
-      if ((u32)(v.x >> 32) == hi_i) {                             // lchain.rs:81
-        int s0;
-        if (chain_sc(ri, qi, (int)(u32)v.x, (int)(u32)v.y, (int)((v.y >> 32) & 0xff), mdx, mdy, bw, G.p.chn_pen_gap, G.p.chn_pen_skip,
-                     G.half_log, s0)) {
-          const int2 fj = *reinterpret_cast<const int2*>(A + j);
-          sc2[u] = wadd(s0, fj.x);
-          v2[u] = true;
-          if (fj.y >= 0) T[fj.y] = mark;                          // lchain.rs:86: marks by slots past the break are never read
-        }
-      }
-    }
-  }
-  dense_bar<NW>();                                                // every mark of this round is visible
-#pragma unroll
-  for (int u = 0; u < TPW; ++u) {
-    const int t = wid + NW * u;
-    const int j = jb - 32 * t - lane;
-    const bool tm = v2[u] ? (T[j] == mark) : false;
-    const u32 Vb = __ballot_sync(0xFFFFFFFFu, v2[u]), Mb = __ballot_sync(0xFFFFFFFFu, tm), Ab = __ballot_sync(0xFFFFFFFFu, j >= start_j);
-    const int tmx = __reduce_max_sync(0xFFFFFFFFu, sc2[u]);
-    sh->sc[t][lane] = sc2[u];
-    if (lane == 0) { sh->V[t] = Vb; sh->M[t] = Mb; sh->ACT[t] = Ab; sh->tmax[t] = tmx; }
-  }
-  dense_bar<NW>();                                                // the tile summaries are in shared memory
-}
-
-// NW = 1: one warp per read (chain_ring_kernel).  NW > 1: one CTA of NW warps per read (chain_dense_kernel); warps 1.. only
-// serve dense_eval_round.
-template <int NW>
-__device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, const int lane, const int wid, DenseSh* sh) {
+// one warp per read (chain_ring_kernel)
+__device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, const int lane) {
   const u64 a0 = G.read_aoff[r];
   const i64 n64 = (i64)(G.read_aoff[r + 1] - a0);
   const i32 qlen = (i32)(G.read_off[r + 1] - G.read_off[r]);
@@ -378,31 +249,6 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
   int best = 0;
   int4 bestA = make_int4(0, -1, 0, 0), bestB = make_int4(0, 0, 0, 0);
   bool t_init = false;
-#ifdef MM2_DENSE_PROF
-  unsigned long long dprof[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // 0 ring phase, 1 window search + marks, 2 eval rounds, 3 walk, 4 anchors, 5 rounds, 6 record tiles, 7 total
-  const long long dprof_t0 = clock64();
-#endif
-  bool use_sm = false;
-  int blk_start = 0;   // first anchor of the rid/strand block that holds the last anchor of the previous tile
-  if constexpr (NW > 1) {
-    use_sm = max_iter <= DENSE_CAP - 64;
-    if (wid == 0 && lane == 0) sh->use_sm = use_sm ? 1 : 0;
-    if (use_sm) {
-      for (int x = wid * 32 + lane; x < DENSE_CAP; x += NW * 32) sh->tg[x] = 0;
-    } else {
-      for (int x = wid * 32 + lane; x < n; x += NW * 32) T[x] = -1;
-    }
-    t_init = true;
-    dense_bar<NW>();
-    if (wid > 0) {
-      for (;;) {
-        dense_bar<NW>();                                          // a command is posted
-        if (sh->op != 0) return;
-        dense_eval_round<NW>(G, sh, an, A, T, wid, lane);
-      }
-    }
-  }
-
   for (int pass = 0; pass < 2; ++pass) {
     const int bw = pass == 0 ? p.bw : p.bw_long;                 // lchain.rs:327-328
     const int mdx = max(p.max_dist_x, bw), mdy = max(p.max_dist_y, bw);  // lchain.rs:63-66
@@ -423,7 +269,6 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
       const int own_qs = wsub(cq, csp - 1), own_ts = wsub(cx, csp - 1);
       // anchors whose window is not empty: the predicate of lchain.rs:75 is false for i - 1, and max_chain_iter >= 1
       u32 workmask;
-      u32 bnd = 0;   // lanes whose anchor starts a new rid/strand block (NW > 1 only)
       {
         int px = __shfl_up_sync(0xFFFFFFFFu, cx, 1);
         u32 phi = __shfl_up_sync(0xFFFFFFFFu, chi, 1);
@@ -433,15 +278,12 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
         const int i = i0 + lane;
         const bool work = lane < tile_n && i > 0 && (i - 1) >= wsub(i, max_iter) && phi == chi && !(cx > wadd(px, mdx));
         workmask = __ballot_sync(0xFFFFFFFFu, work);
-        if constexpr (NW > 1) bnd = __ballot_sync(0xFFFFFFFFu, lane < tile_n && (i == 0 || phi != chi));
       }
       int done = 0;   // lanes [0, done) of this tile are committed to the ring
       while (workmask) {
         const int c = __ffs(workmask) - 1;
         workmask &= workmask - 1;
         const int i = i0 + c;
-        DPROF_T(tp0);
-        DPROF_INC(4);
         if (done < c) {
           if (lane >= done && lane < c) {                        // anchors before i with an empty window (lchain.rs:77,89-90)
             rj = i0 + lane; rx = cx; rq = cq; rsp = csp; rhi = chi;
@@ -497,8 +339,6 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
           cells += (unsigned)__popc(inmask);
         }
         int mv = 0, mcnt = 0, mqs = 0, mts = 0, mfirst = 0;     // state of max_j
-        DPROF_T(tp1);
-        DPROF_ADD(0, tp0, tp1);
         if (more) {
           // ---- the window goes on beyond the ring: 32 predecessors at a time from global memory -------------------------
           if (!t_init) {
@@ -508,40 +348,7 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
           }
           const int mark = mark_base + i;
           const int hi_known = i - 32;                           // inside the window
-          bool sm_path = false;
-          if constexpr (NW > 1) sm_path = use_sm;
           int lo = st;
-          if (sm_path) {
-            // window start on the shared ring.  Inside the rid/strand block of anchor i (it starts at blk0) the predicate of
-            // lchain.rs:75 is `rpos(i) > rpos(j) + max_dist_x`; anchors below i - max_chain_iter are outside the window
-            // whatever the predicate says (lchain.rs:78) and may already be overwritten in the ring, so the search starts there.
-            const u32 bm = bnd & low_mask(c + 1);
-            const int blk0 = bm ? i0 + 31 - __clz(bm) : blk_start;
-            lo = max(max(st, blk0), max(low_iter, 0));
-            const int* __restrict__ sx = sh->sx;
-            int rounds = 0;
-            for (;;) {
-              const int j = lo + lane;
-              bool adv = false;
-              if (j < hi_known) adv = ri > wadd(sx[j % DENSE_CAP], mdx);
-              const u32 b = __ballot_sync(0xFFFFFFFFu, !adv);
-              if (b) { lo += __ffs(b) - 1; break; }
-              lo += 32;
-              if (++rounds == 2) {
-                int hi = hi_known;
-                while (lo < hi) {
-                  const int mid = (lo + hi) >> 1;
-                  if (ri > wadd(sx[mid % DENSE_CAP], mdx)) lo = mid + 1; else hi = mid;
-                }
-                break;
-              }
-            }
-            // the ring slots mark their in-window predecessors with this anchor's tag
-            const int sj = low_iter > lo ? low_iter : lo;
-            const int tag = i % 65535 + 1;
-            if (lane == 0) sh->tag = tag;
-            if (valid && rpp >= sj && rpp < hi_known) sh->tg[rpp % DENSE_CAP] = (u16)tag;
-          } else {
           if (valid && rpp >= 0 && rpp < hi_known) T[rpp] = mark;   // marks of the ring slots on older anchors
           // window start: first j in [st, i - 32] for which the predicate of lchain.rs:75 is false
           {
@@ -568,72 +375,9 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
               }
             }
           }
-          }
           st = lo;
           const int start_j = low_iter > lo ? low_iter : lo;
-          DPROF_T(tp2);
-          DPROF_ADD(1, tp1, tp2);
-          if constexpr (NW > 1) {
-            // 32 tiles per round, evaluated by all warps; this warp then walks the tile summaries: lane t holds tile t
-            bool brk = false;
-            for (int jb = i - 33; jb >= start_j && !brk; jb -= 32 * 32) {
-              if (lane == 0) {
-                sh->op = 0; sh->ri = ri; sh->qi = qi; sh->hi_i = hi_i; sh->jb = jb; sh->start_j = start_j; sh->mark = mark;
-                sh->bw = bw; sh->mdx = mdx; sh->mdy = mdy;
-              }
-              DPROF_T(tp3);
-              dense_bar<NW>();
-              dense_eval_round<NW>(G, sh, an, A, T, 0, lane);
-              DPROF_T(tp4);
-              DPROF_ADD(2, tp3, tp4);
-              DPROF_INC(5);
-              const int nround = min(32, (jb - start_j + 32) >> 5);   // tiles that reach into the window
-              const u32 tV = sh->V[lane], tM = sh->M[lane], tA = sh->ACT[lane];
-              const int tmx = lane < nround ? sh->tmax[lane] : NEG_INF;
-              int cur = 0;
-              while (cur < nround) {
-                // tiles [cur, tf) hold no score above max_f, i.e. no record (lchain.rs:84): n_skip only grows there
-                const u32 cand = __ballot_sync(0xFFFFFFFFu, lane >= cur && tmx > max_f);
-                const int tf = cand ? (__ffs(cand) - 1) : nround;
-                if (tf > cur) {
-                  const bool mine = lane >= cur && lane < tf;
-                  const int cnt = mine ? __popc(tM & tV) : 0;
-                  const int total = __reduce_add_sync(0xFFFFFFFFu, cnt);
-                  const int need = max(max_skip + 1 - n_skip, 1);
-                  if (total >= need) {                            // lchain.rs:85: the need-th marked slot breaks the loop
-                    if (count_cells) {
-                      int incl = cnt;
-#pragma unroll
-                      for (int d = 1; d < 32; d <<= 1) {
-                        const int o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                        if (lane >= d) incl += o;
-                      }
-                      const u32 hit_m = __ballot_sync(0xFFFFFFFFu, incl >= need);
-                      const int tb = __ffs(hit_m) - 1;
-                      const int before = __reduce_add_sync(0xFFFFFFFFu, (mine && lane < tb) ? __popc(tA) : 0);
-                      const int excl_tb = __shfl_sync(0xFFFFFFFFu, incl - cnt, tb);
-                      const u32 mtb = __shfl_sync(0xFFFFFFFFu, tM & tV, tb);
-                      cells += (unsigned)(before + nth_set_bit(mtb, need - excl_tb) + 1);
-                    }
-                    brk = true;
-                    break;
-                  }
-                  n_skip += total;
-                  if (count_cells) cells += (unsigned)__reduce_add_sync(0xFFFFFFFFu, mine ? __popc(tA) : 0);
-                }
-                if (tf >= nround) break;
-                DPROF_INC(6);
-                int rec_last;
-                const bool b = chain_tile_walk(lane, sh->V[tf], sh->M[tf], sh->ACT[tf], sh->sc[tf][lane], max_skip, max_f, n_skip, rec_last,
-                                               cells);
-                if (rec_last >= 0) { max_j = jb - 32 * tf - rec_last; from_ring = false; }
-                if (b) { brk = true; break; }
-                cur = tf + 1;
-              }
-              DPROF_T(tp5);
-              DPROF_ADD(3, tp4, tp5);
-            }
-          } else {
+          {
             for (int jb = i - 33; jb >= start_j; jb -= 32) {
               const int j = jb - lane;
               const bool act = j >= start_j;
@@ -691,14 +435,6 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
         A[i0 + lane] = make_int4(rf, rpp, rv, rcnt);
         B[i0 + lane] = make_int4(rqs, rts, rfirst, 0);
       }
-      if constexpr (NW > 1) {
-        if (use_sm && lane < tile_n) {                           // ... and they enter the shared window ring
-          const int slot = (i0 + lane) % DENSE_CAP;
-          sh->sx[slot] = rx; sh->sq[slot] = rq; sh->ss[slot] = (u8)rsp; sh->sf[slot] = rf; sh->sp[slot] = rpp;
-          sh->tg[slot] = 0;                                      // a new anchor lives here: nobody has marked it yet
-        }
-        if (bnd) blk_start = i0 + 31 - __clz(bnd);
-      }
       {  // lchain.rs:163: the LAST maximum of f
         const int fl = lane < tile_n ? rf : NEG_INF * 4;
         const int m = __reduce_max_sync(0xFFFFFFFFu, fl);
@@ -726,44 +462,460 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
     __syncwarp();
   }
   chain_finish(G, r, lane, an, A, a0, qlen, m0, m1, best, bestA, bestB, hit, cells);
-  if constexpr (NW > 1) {
-    if (lane == 0) sh->op = 1;
-    dense_bar<NW>();                                              // releases warps 1..
-#ifdef MM2_DENSE_PROF
-    if (lane == 0) {
-      dprof[7] = (unsigned long long)(clock64() - dprof_t0);
-      for (int x = 0; x < 8; ++x) atomicAdd(&g_dense_prof[x], dprof[x]);
-    }
-#endif
-  }
 }
 
 #ifndef MM2_CH_OCC
 #define MM2_CH_OCC 8   // CTAs per SM (64 registers; measured 7.5 / 6.8 / 8.0 ms per 100k reads at 6 / 8 / 10)
 #endif
+// ---------------------------------------------------------------------------------------------------------------------
+// chain_dense_kernel — one CTA of NW warps per dense read (repeat-rich ultra-long reads: predecessor windows of thousands of
+// anchors, lchain.rs:74-91 at its max_chain_iter bound).  The read is processed in tiles of 32 anchors, pipelined:
+//   * warp 0 runs the sequential part of tile T (the ring algorithm of chain_read for the last 32 anchors, then the rest of
+//     tile T-1, then the FAR part of the window through per-tile summaries);
+//   * warps 1.. meanwhile evaluate the far part of the windows of tile T+1: every predecessor j < i0(T) is final by then
+//     (tile T-1 was committed before the previous barrier), so the scores sc(i, j) = comput_sc + f[j] of ALL 32 anchors i of
+//     the tile against a 32-aligned tile of predecessors are computed by one warp with the predecessors' state held in
+//     registers (lane = predecessor), and reduced to {valid bits, best score} per (anchor, predecessor tile), plus the
+//     anchor's mark bitmask (lchain.rs:86: every valid predecessor marks ITS predecessor; marks do not depend on where the
+//     loop later breaks, because a mark is only ever read at a lower j than the one that set it).
+//   * the walk of a far tile needs its cells one by one only when the tile's best score beats the running maximum (a new
+//     record, lchain.rs:84); otherwise n_skip just grows by the number of marked valid cells (lchain.rs:85).
+// One barrier per 32 anchors instead of two per 1024 cells; the per-anchor latency chain (round 1: ~6,500 cycles per anchor,
+// profiles/r01_ncu_v11.md) shrinks to the ring step plus a few lane-parallel rounds over tile summaries.
+// tests/models.py:chain_dense_model is the CPU model of this pipeline (checked against the oracle, cell counts included).
+// State of the last DENSE_CAP anchors in shared memory (slot = j % DENSE_CAP): {x, q}, {f, pprev}, span.  A window reaches at
+// most max_chain_iter <= DENSE_CAP - 64 anchors back, and a slot is overwritten only by anchor j + DENSE_CAP.
+constexpr int DENSE_CAP = 5120;
+constexpr int DENSE_JT = 160;          // far predecessor tiles per window: ceil((max_chain_iter + 31) / 32) + 1 <= 160
+constexpr int DENSE_MKW = DENSE_JT + 2;   // mark words per anchor: [0] = tile T, [1] = tile T-1, [2 + r] = far tile r
+struct DenseBuf {                      // summaries of one tile of 32 anchors (double-buffered)
+  u32 V[32][DENSE_JT];                 // valid cells of (anchor, far tile r), bit p = p-th visited (j descending)
+  int TM[32][DENSE_JT];                // best score of the tile's valid cells (NEG_INF: none)
+  u32 MK[32][DENSE_MKW];               // marks, bit = j & 31 (ascending)
+  int far_lo[32];                      // first far predecessor of the anchor; >= far_hi: no far part
+};
+struct DenseSh {
+  int rescue_flag;                     // pass 0 -> pass 1 decision of warp 0 (lchain.rs:321-330)
+  int2* sxq; int2* sfp; u8* ss;        // DENSE_CAP entries each
+  DenseBuf* buf;                       // [2]
+  u32 next;                            // next dense read of this CTA
+  int cm_blk[2];                       // per tile parity: first anchor of the rid/strand block of the tile's last anchor
+  u32 cm_hi[2];                        // ... and that anchor's rev|rid
+};
+constexpr int DENSE_DYN = DENSE_CAP * (8 + 8 + 1) + 2 * (int)sizeof(DenseBuf) + 64;
+constexpr int DENSE_NW = 16;           // warps per dense read: warp 0 walks, 15 evaluate
+
+template <int NW>
+__device__ __forceinline__ void dense_bar_all() { asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory"); }
+template <int NW>
+__device__ __forceinline__ void dense_bar_helpers() { asm volatile("bar.sync 2, %0;" ::"n"((NW - 1) * 32) : "memory"); }
+
+// Phase A of tile `tile` (anchors i0 .. i0 + 31), run by warps 1 .. NW-1 while warp 0 walks tile - 1.
+template <int NW>
+__device__ __forceinline__ void dense_phase_a(const ChainArgs& G, DenseSh* sh, const ulonglong2* __restrict__ an, const int n, const int tile,
+                                              const int bw, const int mdx, const int mdy, const int max_iter, const int wid, const int lane) {
+  DenseBuf& B = sh->buf[tile & 1];
+  const int i0 = tile * 32;
+  const int far_hi = i0 - 32;                       // predecessors below it are final (tiles <= tile - 2 are committed)
+  const int hw = wid - 1, nh = NW - 1;              // helper index / count
+  // zero the mark words of this buffer; warp 1 finds the anchors' far window starts
+  for (int x = hw * 32 + lane; x < 32 * DENSE_MKW; x += nh * 32) (&B.MK[0][0])[x] = 0u;
+  int my_x = 0, my_q = 0;                            // anchor i0 + lane of the tile (every helper warp holds a copy)
+  if (i0 + lane < n) { const ulonglong2 a = an[i0 + lane]; my_x = (int)(u32)a.x; my_q = (int)(u32)a.y; }
+  if (hw == 0) {
+    int lo = far_hi;                                 // "no far part"
+    const int i = i0 + lane;
+    if (i < n && far_hi > 0) {
+      const u32 hi_i = (u32)(an[i].x >> 32);
+      // the far part is non-empty only if the anchor lies in the rid/strand block of the last committed anchor (far_hi - 1):
+      // windows never cross a block (lchain.rs:75), and blocks are contiguous because the anchors are sorted by x
+      if (hi_i == sh->cm_hi[tile & 1]) {
+        int a = max(max(sh->cm_blk[tile & 1], wsub(i, max_iter)), 0), b = far_hi;   // first j in [a, far_hi) with !(ri > x_j + mdx)
+        const int2* __restrict__ sxq = sh->sxq;
+        while (a < b) {
+          const int mid = (a + b) >> 1;
+          if (my_x > wadd(sxq[mid % DENSE_CAP].x, mdx)) a = mid + 1; else b = mid;
+        }
+        lo = a;
+      }
+    }
+    B.far_lo[lane] = lo;
+  }
+  dense_bar_helpers<NW>();
+  if (far_hi <= 0) return;
+  const int jt_top = (far_hi >> 5) - 1;              // far_hi is a multiple of 32: the first far tile visited
+  const int my_lo = B.far_lo[lane];                  // lane a: far_lo of anchor a
+  const int lo_min = __reduce_min_sync(0xFFFFFFFFu, my_lo);
+  if (lo_min >= far_hi) return;
+  const int nr = jt_top - (lo_min >> 5) + 1;         // far tiles that some anchor of the tile needs
+  const float pen_gap = G.p.chn_pen_gap, pen_skip = G.p.chn_pen_skip;
+  const float* __restrict__ half_log = G.half_log;
+  for (int r = hw; r < nr; r += nh) {
+    const int jt = jt_top - r;
+    const int j = jt * 32 + lane;                    // this lane's predecessor (ascending inside the tile)
+    const int slot = (jt * 32) % DENSE_CAP + lane;
+    const int2 xq = sh->sxq[slot], fp = sh->sfp[slot];
+    const int span_j = (int)sh->ss[slot];
+    // where this predecessor's mark goes: word 2 + (jt_top - (pprev >> 5)) of the anchor's mark array
+    const int tw = fp.y >= 0 ? 2 + jt_top - (fp.y >> 5) : DENSE_MKW;
+    const bool okw = tw < DENSE_MKW;
+    const u32 tb = 1u << (fp.y & 31);
+    const u32 peers = __match_any_sync(0xFFFFFFFFu, okw ? tw : DENSE_MKW + lane);
+    const u32 leaders = __ballot_sync(0xFFFFFFFFu, okw && lane == __ffs(peers) - 1);   // one lane per distinct mark word
+    for (int a = 0; a < 32; ++a) {
+      const int lo_a = __shfl_sync(0xFFFFFFFFu, my_lo, a);
+      if (lo_a >= far_hi || (lo_a >> 5) > jt) continue;            // warp-uniform: the anchor's window does not reach this tile
+      const int ri = __shfl_sync(0xFFFFFFFFu, my_x, a), qi = __shfl_sync(0xFFFFFFFFu, my_q, a);
+      const bool act = j >= lo_a;
+      const int dq = wsub(qi, xq.y), dr = wsub(ri, xq.x);
+      int dd = wsub(dr, dq); if (dd < 0) dd = wsub(0, dd);
+      const bool ok = act && dq > 0 && dq <= mdx && dr != 0 && dq <= mdy && dd <= bw && dd >= 0;
+      const int dg = min(dr, dq);
+      int s0 = min(span_j, dg);
+      const int ddc = ok ? dd : 0;
+      const float lin = __fadd_rn(__fmul_rn(pen_gap, (float)ddc), __fmul_rn(pen_skip, (float)dg));
+      const int pen = __float2int_rz(__fadd_rn(lin, half_log[ddc]));
+      if (ddc != 0 || dg > span_j) s0 = wsub(s0, pen);
+      const int sc = ok ? wadd(s0, fp.x) : NEG_INF;
+      const u32 Vb = __ballot_sync(0xFFFFFFFFu, ok);
+      const int tm = __reduce_max_sync(0xFFFFFFFFu, sc);
+      if (lane == 0) { B.V[a][r] = __brev(Vb); B.TM[a][r] = tm; }
+      u32 rem = leaders;
+      while (rem) {                                                // lchain.rs:86, one shared atomic per distinct word
+        const int L = __ffs(rem) - 1;
+        rem &= rem - 1;
+        const int W = __shfl_sync(0xFFFFFFFFu, tw, L);
+        const u32 bits = __reduce_or_sync(0xFFFFFFFFu, (ok && tw == W) ? tb : 0u);
+        if (lane == 0 && bits) atomicOr(&B.MK[a][W], bits);
+      }
+    }
+  }
+}
+
+// One CTA per dense read.  wid == 0: the sequential walk; wid >= 1: phase A of the next tile.
+template <int NW>
+__device__ __forceinline__ void chain_read_dense(const ChainArgs& G, const u32 r, const int lane, const int wid, DenseSh* sh) {
+  const u64 a0 = G.read_aoff[r];
+  const i64 n64 = (i64)(G.read_aoff[r + 1] - a0);
+  const i32 qlen = (i32)(G.read_off[r + 1] - G.read_off[r]);
+  const u64 m0 = G.mini_off[r], m1 = G.mini_off[r + 1];
+  ReadHit hit;
+  hit.rid_rev = 0xFFFFFFFFu; hit.qs = hit.qe = hit.ts = hit.te = 0; hit.cm = 0; hit.score = 0;
+  hit.n_anchors = (u32)n64; hit.n_mini = (u32)(m1 - m0); hit.sum_span = G.sum_span[r];
+  hit.st_rank = hit.en_rank = -1; hit.flags = 0; hit.best = -1; hit.pad0 = hit.pad1 = 0;
+  const int n = (int)n64;                                        // chain_is_dense: 0 < n <= 0x7fffffff
+  const ulonglong2* __restrict__ an = G.anchors + a0;
+  int4* A = G.A + a0;
+  int4* B = G.B + a0;
+  const mm2_chain_params_t& p = G.p;
+  const int max_skip = min(max(p.max_chain_skip, -1), 0x3fffffff);
+  const int max_iter = p.max_chain_iter;
+  const int ntile = (n + 31) >> 5;
+  unsigned long long cells = 0;
+  const bool count_cells = G.cells != nullptr;
+  int best = 0;
+  int4 bestA = make_int4(0, -1, 0, 0), bestB = make_int4(0, 0, 0, 0);
+  const int2* __restrict__ sxq = sh->sxq; const int2* __restrict__ sfp = sh->sfp; const u8* __restrict__ ss = sh->ss;
+
+  for (int pass = 0; pass < 2; ++pass) {
+    const int bw = pass == 0 ? p.bw : p.bw_long;                 // lchain.rs:327-328
+    const int mdx = max(p.max_dist_x, bw), mdy = max(p.max_dist_y, bw);  // lchain.rs:63-66
+    if (wid > 0) {
+      // ---- helpers: phase A of tile T + 1 while warp 0 walks tile T (tiles 0 and 1 have no far part) -----------------------
+      for (int T = 0; T < ntile; ++T) {
+        if (T + 1 < ntile) dense_phase_a<NW>(G, sh, an, n, T + 1, bw, mdx, mdy, max_iter, wid, lane);
+        dense_bar_all<NW>();
+      }
+      // the rescue decision (lchain.rs:321-330) is taken by warp 0 and published through shared memory
+      dense_bar_all<NW>();
+      if (pass == 1 || !sh->rescue_flag) break;
+      dense_bar_all<NW>();
+      continue;
+    }
+    // ---- warp 0: the sequential walk -----------------------------------------------------------------------------------------
+    int rj = -1, rx = 0, rq = 0, rsp = 0; u32 rhi = 0;           // ring slot of this lane (anchor j with j % 32 == lane)
+    int rf = 0, rpp = -1, rv = 0, rcnt = 0, rqs = 0, rts = 0, rfirst = 0;
+    int bf = NEG_INF * 4, bi = 0;
+    int blk_start = 0;   // first anchor of the rid/strand block that holds the last anchor of the previous tile
+    ulonglong2 nxt = make_ulonglong2(0, 0);
+    if (lane < n) nxt = an[lane];
+    for (int T = 0; T < ntile; ++T) {
+      const int i0 = T * 32;
+      const int tile_n = min(32, n - i0);
+      DenseBuf& SB = sh->buf[T & 1];
+      const int far_hi = i0 - 32;
+      const int jt_top = (far_hi >> 5) - 1;
+      const ulonglong2 cur = nxt;
+      if (i0 + 32 + lane < n) nxt = an[i0 + 32 + lane];
+      const int cx = (int)(u32)cur.x, cq = (int)(u32)cur.y, csp = (int)((cur.y >> 32) & 0xff);
+      const u32 chi = (u32)(cur.x >> 32);
+      const int own_qs = wsub(cq, csp - 1), own_ts = wsub(cx, csp - 1);
+      u32 workmask, bnd;
+      {
+        int px = __shfl_up_sync(0xFFFFFFFFu, cx, 1);
+        u32 phi = __shfl_up_sync(0xFFFFFFFFu, chi, 1);
+        const int rx31 = __shfl_sync(0xFFFFFFFFu, rx, 31);
+        const u32 rhi31 = __shfl_sync(0xFFFFFFFFu, rhi, 31);
+        if (lane == 0) { px = rx31; phi = rhi31; }
+        const int i = i0 + lane;
+        const bool work = lane < tile_n && i > 0 && (i - 1) >= wsub(i, max_iter) && phi == chi && !(cx > wadd(px, mdx));
+        workmask = __ballot_sync(0xFFFFFFFFu, work);
+        bnd = __ballot_sync(0xFFFFFFFFu, lane < tile_n && (i == 0 || phi != chi));   // anchors that start a rid/strand block
+      }
+      int done = 0;   // lanes [0, done) of this tile are committed to the ring
+      while (workmask) {
+        const int c = __ffs(workmask) - 1;
+        workmask &= workmask - 1;
+        const int i = i0 + c;
+        if (done < c) {
+          if (lane >= done && lane < c) {                        // anchors before i with an empty window (lchain.rs:77,89-90)
+            rj = i0 + lane; rx = cx; rq = cq; rsp = csp; rhi = chi;
+            rf = csp; rpp = -1; rv = csp; rcnt = 1; rqs = own_qs; rts = own_ts; rfirst = i0 + lane;
+          }
+        }
+        done = c + 1;
+        const int ri = __shfl_sync(0xFFFFFFFFu, cx, c), qi = __shfl_sync(0xFFFFFFFFu, cq, c), spi = __shfl_sync(0xFFFFFFFFu, csp, c);
+        const u32 hi_i = __shfl_sync(0xFFFFFFFFu, chi, c);
+        const int low_iter = wsub(i, max_iter);                  // lchain.rs:78
+        const bool inwin = rj >= max(low_iter, 0) && rhi == hi_i && !(ri > wadd(rx, mdx));   // empty slots hold rj = -1
+        int s0;
+        const bool valid = chain_sc_flat(inwin, ri, qi, rx, rq, rsp, mdx, mdy, bw, p.chn_pen_gap, p.chn_pen_skip, G.half_log, s0);
+        const int sc = valid ? wadd(s0, rf) : NEG_INF;
+        const u32 inmask = __ballot_sync(0xFFFFFFFFu, inwin);
+        const u32 vmask = __ballot_sync(0xFFFFFFFFu, valid);
+        int max_f = spi, max_j = -1, n_skip = 0;
+        bool from_ring = true;                                   // max_j's state is in the ring (else in A/B)
+        bool more = (inmask >> c) & 1u;                          // slot c holds j = i - 32: the window may go on beyond the ring
+        if (vmask) {
+          const int low_ring = max(i - 32, 0);
+          const u32 markbits = __reduce_or_sync(0xFFFFFFFFu, (valid && rpp >= low_ring) ? (1u << (rpp & 31)) : 0u) & vmask;
+          const u32 Mr = __funnelshift_r(markbits, markbits, c);
+          const int m = __reduce_max_sync(0xFFFFFFFFu, sc);
+          int hb = 32;
+          if (m > spi) {
+            const u32 eq = __ballot_sync(0xFFFFFFFFu, valid && sc == m);
+            hb = 31 - __clz(__funnelshift_r(eq, eq, c));
+          }
+          if (hb == 32 || (Mr & (0xFFFFFFFEu << hb)) == 0u) {
+            u32 after = Mr;
+            if (hb < 32) { max_f = m; max_j = i - 32 + hb; after = Mr & ((1u << hb) - 1u); }
+            const int cnt = __popc(after), need = max(max_skip + 1, 1);
+            if (cnt >= need) {
+              if (count_cells) cells += (unsigned)(nth_set_bit(__brev(after), need) + 1);
+              more = false;
+            } else {
+              n_skip = cnt;
+              if (count_cells) cells += (unsigned)__popc(inmask);
+            }
+          } else {
+            const int sc_s = __shfl_sync(0xFFFFFFFFu, sc, (c - 1 - lane) & 31);
+            const u32 Vs = __brev(__funnelshift_r(vmask, vmask, c)), As = __brev(__funnelshift_r(inmask, inmask, c));
+            int rec_last;
+            const bool brk = chain_tile_walk(lane, Vs, __brev(Mr), As, sc_s, max_skip, max_f, n_skip, rec_last, cells);
+            if (rec_last >= 0) max_j = i - 1 - rec_last;
+            if (brk) more = false;
+          }
+        } else if (count_cells) {
+          cells += (unsigned)__popc(inmask);
+        }
+        int mv = 0, mcnt = 0, mqs = 0, mts = 0, mfirst = 0;     // state of max_j
+        if (more) {
+          // ---- the window goes on beyond the ring --------------------------------------------------------------------------
+          // first anchor of the rid/strand block of i: the last block boundary at or before lane c, else the previous tile's
+          const u32 bm = bnd & low_mask(c + 1);
+          const int blk0 = bm ? i0 + 31 - __clz(bm) : blk_start;
+          const int fl = (far_hi > 0) ? SB.far_lo[c] : far_hi;   // first far predecessor (>= far_hi: none)
+          u32* MK = &SB.MK[c][0];
+          // (1) the ring slots mark their predecessors below the ring: tiles T (word 0), T-1 (word 1) and the far tiles
+          if (valid && rpp >= 0 && rpp < i - 32) {
+            const int wdx = (i0 >> 5) - (rpp >> 5);              // 0: tile T (cannot be: rpp < i - 32 < i0), 1: tile T-1, 2 + r: far
+            if (wdx < DENSE_MKW) atomicOr(&MK[wdx], 1u << (rpp & 31));
+          }
+          __syncwarp();
+          // (2) the rest of tile T-1: j = i - 33 - lane, down to the window start; its anchors are committed to shared memory
+          bool brk = false;
+          const int late_lo = max(max(far_hi, blk0), max(low_iter, 0));   // not below tile T-1, the block, the iteration bound
+          if (c > 0) {
+            const int j = i - 33 - lane;
+            const bool inr = j >= late_lo;                       // inside tile T-1 (and the block); the distance test is per cell
+            const int slot = ((j % DENSE_CAP) + DENSE_CAP) % DENSE_CAP;
+            const int2 xq = sxq[slot], fp = sfp[slot];
+            const bool act = inr && !(ri > wadd(xq.x, mdx));     // lchain.rs:75: monotone, so these are the cells down to start_j
+            int s1;
+            const bool v2 = chain_sc_flat(act, ri, qi, xq.x, xq.y, (int)ss[slot], mdx, mdy, bw, p.chn_pen_gap, p.chn_pen_skip, G.half_log, s1);
+            const int sc2 = v2 ? wadd(s1, fp.x) : NEG_INF;
+            if (v2 && fp.y >= 0) {                               // lchain.rs:86 (all lanes first, see the header of this file)
+              const int wdx = (i0 >> 5) - (fp.y >> 5);
+              if (wdx < DENSE_MKW) atomicOr(&MK[wdx], 1u << (fp.y & 31));
+            }
+            __syncwarp();
+            const bool tm = v2 && ((MK[1] >> (j & 31)) & 1u);    // tile T-1 is word 1
+            const u32 V2 = __ballot_sync(0xFFFFFFFFu, v2), M2 = __ballot_sync(0xFFFFFFFFu, tm), A2 = __ballot_sync(0xFFFFFFFFu, act);
+            int rec_last;
+            brk = chain_tile_walk(lane, V2, M2, A2, sc2, max_skip, max_f, n_skip, rec_last, cells);
+            if (rec_last >= 0) { max_j = i - 33 - rec_last; from_ring = false; }
+            // the window ends inside tile T-1 when some cell of it fails the distance test (or the bounds above cut it)
+            if (A2 != low_mask(c)) more = false;
+          }
+          // (3) the far tiles, through their summaries: lane t holds tile r = base + t
+          if (!brk && more && fl < far_hi) {
+            const int nr = jt_top - (fl >> 5) + 1;
+            for (int base = 0; base < nr && !brk; base += 32) {
+              const int rr = base + lane;
+              const bool have = rr < nr;
+              const u32 tV = have ? SB.V[c][rr] : 0u;
+              const u32 tMa = have ? SB.MK[c][2 + rr] : 0u;
+              const int tmx = have ? SB.TM[c][rr] : NEG_INF;
+              const u32 tM = __brev(tMa);                        // visiting order
+              // cells of the tile inside the window: all 32, except in the window's lowest tile
+              const int jt = jt_top - rr;
+              u32 tA = have ? 0xFFFFFFFFu : 0u;
+              if (have && jt * 32 < fl) tA = low_mask(jt * 32 + 32 - fl);
+              const int nround = min(32, nr - base);
+              int curt = 0;
+              while (curt < nround) {
+                // tiles [curt, tf) hold no score above max_f, i.e. no record (lchain.rs:84): n_skip only grows there
+                const u32 cand = __ballot_sync(0xFFFFFFFFu, lane >= curt && lane < nround && tmx > max_f);
+                const int tf = cand ? (__ffs(cand) - 1) : nround;
+                if (tf > curt) {
+                  const bool mine = lane >= curt && lane < tf;
+                  const int cnt = mine ? __popc(tM & tV) : 0;
+                  const int total = __reduce_add_sync(0xFFFFFFFFu, cnt);
+                  const int need = max(max_skip + 1 - n_skip, 1);
+                  if (total >= need) {                            // lchain.rs:85: the need-th marked slot breaks the loop
+                    if (count_cells) {
+                      int incl = cnt;
+#pragma unroll
+                      for (int d = 1; d < 32; d <<= 1) {
+                        const int o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                        if (lane >= d) incl += o;
+                      }
+                      const u32 hit_m = __ballot_sync(0xFFFFFFFFu, incl >= need);
+                      const int tb = __ffs(hit_m) - 1;
+                      const int before = __reduce_add_sync(0xFFFFFFFFu, (mine && lane < tb) ? __popc(tA) : 0);
+                      const int excl_tb = __shfl_sync(0xFFFFFFFFu, incl - cnt, tb);
+                      const u32 mtb = __shfl_sync(0xFFFFFFFFu, tM & tV, tb);
+                      cells += (unsigned)(before + nth_set_bit(mtb, need - excl_tb) + 1);
+                    }
+                    brk = true;
+                    break;
+                  }
+                  n_skip += total;
+                  if (count_cells) cells += (unsigned)__reduce_add_sync(0xFFFFFFFFu, mine ? __popc(tA) : 0);
+                }
+                if (tf >= nround) break;
+                // a record tile: its cells one by one (recomputed: the predecessors' state is in shared memory)
+                {
+                  const int jtf = jt_top - (base + tf);
+                  const int j = jtf * 32 + 31 - lane;            // visiting order
+                  const int slot = (jtf * 32) % DENSE_CAP + 31 - lane;
+                  const int2 xq = sxq[slot], fp = sfp[slot];
+                  const bool act = j >= fl;
+                  int s1;
+                  const bool v2 = chain_sc_flat(act, ri, qi, xq.x, xq.y, (int)ss[slot], mdx, mdy, bw, p.chn_pen_gap, p.chn_pen_skip, G.half_log, s1);
+                  const int sc2 = v2 ? wadd(s1, fp.x) : NEG_INF;
+                  const u32 Vt = __shfl_sync(0xFFFFFFFFu, tV, tf), Mt = __shfl_sync(0xFFFFFFFFu, tM, tf), At = __shfl_sync(0xFFFFFFFFu, tA, tf);
+                  int rec_last;
+                  const bool b2 = chain_tile_walk(lane, Vt, Mt, At, sc2, max_skip, max_f, n_skip, rec_last, cells);
+                  if (rec_last >= 0) { max_j = jtf * 32 + 31 - rec_last; from_ring = false; }
+                  if (b2) { brk = true; break; }
+                }
+                curt = tf + 1;
+              }
+            }
+          }
+          if (!from_ring) {
+            // the state of a predecessor outside the ring: v, cnt from A, the chain reductions from B (tile T-1 and older are in
+            // global memory: written at the end of their tile, before the barrier)
+            const int4 aj = A[max_j], bj = B[max_j];
+            mv = aj.z; mcnt = aj.w; mqs = bj.x; mts = bj.y; mfirst = bj.z;
+          }
+        }
+        // ---- lchain.rs:89-90 and the chain reductions of paf.rs:136-147 carried along the best-predecessor links -------
+        if (max_j >= 0 && from_ring) {
+          const int L = max_j & 31;
+          mv = __shfl_sync(0xFFFFFFFFu, rv, L); mcnt = __shfl_sync(0xFFFFFFFFu, rcnt, L); mqs = __shfl_sync(0xFFFFFFFFu, rqs, L);
+          mts = __shfl_sync(0xFFFFFFFFu, rts, L); mfirst = __shfl_sync(0xFFFFFFFFu, rfirst, L);
+        }
+        if (lane == c) {                                         // anchor i takes over its ring slot
+          rj = i; rx = cx; rq = cq; rsp = csp; rhi = chi;
+          rf = max_f; rpp = max_j;
+          rv = (max_j >= 0 && mv > max_f) ? mv : max_f;
+          rcnt = max_j >= 0 ? mcnt + 1 : 1;
+          rqs = max_j >= 0 ? min(mqs, own_qs) : own_qs;
+          rts = max_j >= 0 ? min(mts, own_ts) : own_ts;
+          rfirst = max_j >= 0 ? mfirst : i;
+        }
+      }
+      if (lane >= done && lane < tile_n) {
+        rj = i0 + lane; rx = cx; rq = cq; rsp = csp; rhi = chi;
+        rf = csp; rpp = -1; rv = csp; rcnt = 1; rqs = own_qs; rts = own_ts; rfirst = i0 + lane;
+      }
+      if (lane < tile_n) {                                       // every lane now holds its own anchor of this tile
+        A[i0 + lane] = make_int4(rf, rpp, rv, rcnt);
+        B[i0 + lane] = make_int4(rqs, rts, rfirst, 0);
+        const int slot = (i0 + lane) % DENSE_CAP;                // ... and they enter the shared window ring
+        sh->sxq[slot] = make_int2(rx, rq); sh->sfp[slot] = make_int2(rf, rpp); sh->ss[slot] = (u8)rsp;
+      }
+      if (bnd) blk_start = i0 + 31 - __clz(bnd);
+      if (lane == 0) {
+        // what phase A of tile T + 2 needs to know about the last committed anchor (i0 + tile_n - 1)
+        sh->cm_blk[T & 1] = blk_start;
+      }
+      if (lane == tile_n - 1) sh->cm_hi[T & 1] = chi;
+      {  // lchain.rs:163: the LAST maximum of f
+        const int fl2 = lane < tile_n ? rf : NEG_INF * 4;
+        const int m = __reduce_max_sync(0xFFFFFFFFu, fl2);
+        if (m >= bf) {
+          const u32 eq = __ballot_sync(0xFFFFFFFFu, fl2 == m);
+          bf = m;
+          bi = i0 + 31 - __clz(eq);
+        }
+      }
+      __threadfence_block();
+      dense_bar_all<NW>();                                       // tile T is committed; the summaries of tile T + 1 are complete
+    }
+    best = bi;
+    bestA = A[best]; bestB = B[best];
+    bool rescue = false;
+    if (pass == 0 && G.do_rescue) {
+      // lchain.rs:321-330 rescue_long_join on the single (fallback) chain
+      const ulonglong2 ab = an[best];
+      const int qe = wadd((int)(u32)ab.y, 1);
+      const int qs = max(bestB.x, 0);
+      const int best_cov = max(wsub(qe, qs), 0);
+      const int uncovered = max(wsub(qlen, best_cov), 0);
+      rescue = uncovered > p.rmq_rescue_size || (float)best_cov < __fmul_rn((float)qlen, __fsub_rn(1.0f, p.rmq_rescue_ratio));
+    }
+    if (lane == 0) sh->rescue_flag = rescue ? 1 : 0;
+    __threadfence_block();
+    dense_bar_all<NW>();                                         // the helpers read the decision
+    if (!rescue) break;
+    hit.flags |= 1u;
+    dense_bar_all<NW>();                                         // ... before the flag is rewritten
+  }
+  if (wid == 0) chain_finish(G, r, lane, an, A, a0, qlen, m0, m1, best, bestA, bestB, hit, cells);
+}
+
 __global__ void __launch_bounds__(CH_WARPS * 32, MM2_CH_OCC) chain_ring_kernel(ChainArgs G) {
   const u32 r = blockIdx.x * CH_WARPS + (threadIdx.x >> 5);
   if (r >= G.nreads) return;
   if (chain_is_dense(G, r)) return;                               // chain_dense_kernel's
-  chain_read<1>(G, r, threadIdx.x & 31, 0, nullptr);
+  chain_read(G, r, threadIdx.x & 31);
 }
 
-// NW warps per dense read, MINB resident CTAs per SM (register cap 65536 / (NW * 32 * MINB)).  A dense read is bound by the
-// latency of its anchor-after-anchor dependency, so the throughput of an SM is (reads resident on it) / (latency per anchor):
-// few dense reads want wide CTAs (short latency), many dense reads want many narrow CTAs.  The host launches the variants
-// whose [lo, hi) range of dense-read counts it wants; the CTAs of the others return at once.
-template <int NW, int MINB>
-__global__ void __launch_bounds__(NW * 32, MINB) chain_dense_kernel(ChainArgs G, u32 nd_lo, u32 nd_hi) {
+// NW warps per dense read, one resident CTA per SM (the window ring and the two summary buffers take ~210 KB of shared memory).
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, 1) chain_dense_kernel(ChainArgs G) {
   __shared__ DenseSh sh;
   extern __shared__ __align__(16) unsigned char dense_dyn[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const u32 ndense = G.dense[0];
-  if (ndense < nd_lo || ndense >= nd_hi) return;
   if (threadIdx.x == 0) {
-    int* base = reinterpret_cast<int*>(dense_dyn);
-    sh.sx = base; sh.sq = base + DENSE_CAP; sh.sf = base + 2 * DENSE_CAP; sh.sp = base + 3 * DENSE_CAP;
-    sh.tg = reinterpret_cast<u16*>(base + 4 * DENSE_CAP);
-    sh.ss = reinterpret_cast<u8*>(base + 4 * DENSE_CAP + DENSE_CAP / 2);
+    sh.sxq = reinterpret_cast<int2*>(dense_dyn);
+    sh.sfp = sh.sxq + DENSE_CAP;
+    sh.buf = reinterpret_cast<DenseBuf*>(dense_dyn + DENSE_CAP * 16);
+    sh.ss = reinterpret_cast<u8*>(dense_dyn + DENSE_CAP * 16 + 2 * sizeof(DenseBuf));
   }
   for (;;) {
     __syncthreads();
@@ -771,19 +923,17 @@ __global__ void __launch_bounds__(NW * 32, MINB) chain_dense_kernel(ChainArgs G,
     __syncthreads();
     const u32 k = sh.next;
     if (k >= ndense) return;
-    chain_read<NW>(G, G.dense[2 + k], lane, wid, &sh);
+    chain_read_dense<NW>(G, G.dense[2 + k], lane, wid, &sh);
   }
 }
 
-constexpr int DENSE_DYN = 4 * DENSE_CAP * 4 + DENSE_CAP * 2 + DENSE_CAP;   // window ring (see DenseSh)
+
 }  // namespace
 
 // Opt-in to more than 48 KB of dynamic shared memory.  The attribute is per device, so mm2_ctx_create calls this for
 // every context (after cudaSetDevice) instead of once per process.
 int lchain_init_device() {
-  CUDA_TRY(cudaFuncSetAttribute(chain_dense_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_DYN));
-  CUDA_TRY(cudaFuncSetAttribute(chain_dense_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_DYN));
-  CUDA_TRY(cudaFuncSetAttribute(chain_dense_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_DYN));
+  CUDA_TRY(cudaFuncSetAttribute(chain_dense_kernel<DENSE_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_DYN));
   return MM2_OK;
 }
 
@@ -829,30 +979,15 @@ int chain_batch(mm2_ctx* ctx, const ulonglong2* d_anchors, const u64* d_read_aof
   {
     MM2_TRY(ctx->read_class.ensure(((size_t)nreads + 4) * 4));
     G.dense = ctx->read_class.as<u32>();
-    G.dense_min = ctx->chain_dense_min;
+    // the CTA-per-read kernel keeps the window in shared memory: larger max_chain_iter values stay with the warp-per-read kernel
+    G.dense_min = p.max_chain_iter <= DENSE_CAP - 64 ? ctx->chain_dense_min : 0x7fffffff;
     G.dense_ratio5 = ctx->chain_dense_ratio5;
     CUDA_TRY(cudaMemsetAsync(G.dense, 0, 8, ctx->stream));
     MM2_LAUNCH(ctx, chain_classify_kernel, (int)((nreads + 255) / 256), 256, 0, G);
     MM2_LAUNCH(ctx, chain_ring_kernel, grid, CH_WARPS * 32, 0, G);
-    // persistent CTAs, one dense read at a time each; with no dense read they exit at once
-    const u32 sm = (u32)ctx->n_sm;
-    static const int force_nw = [] { const char* e = getenv("MM2_DENSE_NW"); return e ? atoi(e) : 0; }();   // experiment knob: warps per dense read
-    const int dgrid = (int)std::min<u64>(nreads, (u64)sm * 2);
-    if (force_nw == 16) MM2_LAUNCH(ctx, (chain_dense_kernel<16, 2>), dgrid, 16 * 32, DENSE_DYN, G, 1u, 0xFFFFFFFFu);
-    else if (force_nw == 4) MM2_LAUNCH(ctx, (chain_dense_kernel<4, 2>), dgrid, 4 * 32, DENSE_DYN, G, 1u, 0xFFFFFFFFu);
-    else MM2_LAUNCH(ctx, (chain_dense_kernel<8, 2>), dgrid, 8 * 32, DENSE_DYN, G, 1u, 0xFFFFFFFFu);
+    // persistent CTAs (one per SM), one dense read at a time each; with no dense read they exit at once
+    if (G.dense_min != 0x7fffffff) MM2_LAUNCH(ctx, chain_dense_kernel<DENSE_NW>, (int)std::min<u64>(nreads, (u64)ctx->n_sm), DENSE_NW * 32, DENSE_DYN, G);
   }
-#ifdef MM2_DENSE_PROF
-  {
-    cudaStreamSynchronize(ctx->stream);
-    unsigned long long h[8];
-    cudaMemcpyFromSymbol(h, g_dense_prof, sizeof h);
-    if (h[4]) fprintf(stderr, "[dense prof] anchors %llu rounds %llu record-tiles %llu | cycles per anchor: ring %.0f search+marks %.0f eval %.0f walk %.0f total %.0f\n",
-                      h[4], h[5], h[6], (double)h[0] / h[4], (double)h[1] / h[4], (double)h[2] / h[4], (double)h[3] / h[4], (double)h[7] / h[4]);
-    memset(h, 0, sizeof h);
-    cudaMemcpyToSymbol(g_dense_prof, h, sizeof h);
-  }
-#endif
   CUDA_TRY(cudaGetLastError());
   return MM2_OK;
 }

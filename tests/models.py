@@ -184,3 +184,139 @@ def chain_fwd_model(anchors, p, half_log_lut=None):
         pprev[i] = max_j
         v[i] = v[max_j] if (max_j >= 0 and v[max_j] > max_f) else max_f
     return f, pprev, v
+
+
+def chain_dense_model(anchors, p, lut=None):
+    """CPU model of chain_dense_kernel's tile pipeline (lchain.cu): anchors are processed in tiles of 32.  While the sequential
+    warp walks tile T-1, the helper warps evaluate, for every anchor of tile T, the FAR part of its predecessor window
+    (j < i0 - 32: final DP state) into per-(anchor, 32-aligned j-tile) summaries {valid bits, best score} and a per-anchor mark
+    bitmask (lchain.rs:86).  The sequential pass then visits, in the reference's order, the ring [i-32, i-1], the rest of the
+    previous tile [i0-32, i-33], and the far tiles through their summaries (a far tile is re-evaluated cell by cell only when
+    its best score beats the running maximum).  Returns f, pprev, v, cells."""
+    x = anchors["x"].astype(np.uint64)
+    y = anchors["y"].astype(np.uint64)
+    n = x.size
+    rpos = (x & np.uint64(0xffffffff)).astype(np.uint32).view(np.int32).astype(np.int64)
+    hi = (x >> np.uint64(32)).astype(np.int64)
+    qpos = (y & np.uint64(0xffffffff)).astype(np.uint32).view(np.int32).astype(np.int64)
+    qspan = ((y >> np.uint64(32)) & np.uint64(0xff)).astype(np.int64)
+    mdx = max(p.max_dist_x, p.bw)
+    mdy = max(p.max_dist_y, p.bw)
+    f32 = np.float32
+    f = np.zeros(n, dtype=np.int64)
+    v = np.zeros(n, dtype=np.int64)
+    pprev = np.full(n, -1, dtype=np.int64)
+    pen_cache = {}
+
+    def pen(dd, dg):
+        key = (dd, dg if p.chn_pen_skip != 0 else 0)
+        if key not in pen_cache:
+            lin = f32(f32(p.chn_pen_gap) * f32(dd)) + f32(f32(p.chn_pen_skip) * f32(dg))
+            lg = f32(0.0) if dd < 1 else np.log(f32(dd + 1), dtype=np.float32) / f32(0.6931472)
+            pen_cache[key] = int(f32(lin) + f32(0.5) * lg)
+        return pen_cache[key]
+
+    def score(i, j):
+        dq = qpos[i] - qpos[j]
+        if dq <= 0 or dq > mdx:
+            return None
+        dr = rpos[i] - rpos[j]
+        if dr == 0 or dq > mdy:
+            return None
+        dd = abs(dr - dq)
+        if dd > p.bw:
+            return None
+        dg = min(dr, dq)
+        s = min(int(qspan[j]), dg)
+        if dd != 0 or dg > qspan[j]:
+            s -= pen(int(dd), int(dg))
+        return int(s + f[j])
+
+    # window starts (static)
+    st_arr = np.zeros(n, dtype=np.int64)
+    st = 0
+    for i in range(n):
+        while st < i and (hi[st] != hi[i] or rpos[i] > rpos[st] + mdx):
+            st += 1
+        st_arr[i] = max(st, i - p.max_chain_iter)
+    cells = 0
+    for i0 in range(0, n, 32):
+        far_hi = i0 - 32
+        # ---- phase A: summaries of the far part, from DP state that is final when tile i0-32 is still being walked
+        summ = {}
+        for a in range(min(32, n - i0)):
+            i = i0 + a
+            lo = int(st_arr[i])
+            if far_hi <= 0 or lo >= far_hi:
+                continue
+            V, TM, MK = {}, {}, set()
+            for j in range(lo, far_hi):
+                s = score(i, j)
+                jt = j >> 5
+                if s is not None:
+                    V[jt] = V.get(jt, 0) | (1 << (j & 31))
+                    TM[jt] = max(TM.get(jt, -(1 << 40)), s)
+                    if pprev[j] >= lo:
+                        MK.add(int(pprev[j]))
+            summ[a] = (lo, V, TM, MK)
+        # ---- phase B: the sequential walk
+        for a in range(min(32, n - i0)):
+            i = i0 + a
+            lo = int(st_arr[i])
+            max_f = int(qspan[i])
+            max_j = -1
+            n_skip = 0
+            marks = set()
+            broke = False
+
+            def visit(j):
+                nonlocal max_f, max_j, n_skip, broke, cells
+                cells += 1
+                s = score(i, j)
+                if s is None:
+                    return
+                if s > max_f:
+                    max_f, max_j = s, j
+                    if n_skip > 0:
+                        n_skip -= 1
+                elif j in marks:
+                    n_skip += 1
+                    if n_skip > p.max_chain_skip:
+                        broke = True
+                        return
+                if pprev[j] >= 0:
+                    marks.add(int(pprev[j]))
+
+            # ring + rest of the previous tile: cell by cell
+            near_lo = max(lo, far_hi, 0)
+            j = i - 1
+            while j >= near_lo and not broke:
+                visit(j)
+                j -= 1
+            if not broke and a in summ:
+                flo, V, TM, MK = summ[a]
+                marks |= MK                      # far marks: every far valid j' marks its predecessor, whatever the break does later
+                jt = (far_hi - 1) >> 5
+                while jt >= (flo >> 5) and not broke:
+                    jlo, jhi = max(flo, jt << 5), min(far_hi, (jt + 1) << 5)
+                    if TM.get(jt, -(1 << 40)) > max_f:
+                        for j in range(jhi - 1, jlo - 1, -1):
+                            visit(j)
+                            if broke:
+                                break
+                    else:
+                        # no record in this tile: n_skip only grows, by one per marked valid cell, in visiting order
+                        vb = V.get(jt, 0)
+                        mk = [j for j in range(jhi - 1, jlo - 1, -1) if (vb >> (j & 31)) & 1 and j in marks]
+                        need = max(p.max_chain_skip + 1 - n_skip, 1)
+                        if len(mk) >= need:
+                            cells += jhi - mk[need - 1]
+                            broke = True
+                        else:
+                            n_skip += len(mk)
+                            cells += jhi - jlo
+                    jt -= 1
+            f[i] = max_f
+            pprev[i] = max_j
+            v[i] = v[max_j] if (max_j >= 0 and v[max_j] > max_f) else max_f
+    return f, pprev, v, cells

@@ -766,3 +766,83 @@ def test_config1_full_size_mmi_and_600bp_read(ctx, mm2, orc, gen, tmp_path):
     # a sample of BASELINE configs[1] reads on the same full-size index, every stage compared
     cat, roffs = gen.reads(0xB2001002, g, offs, 200, 10_000, 0.0333, 0.0333, 0.0333)
     _map_compare(ctx, mm2, orc, gi, oi, cat, roffs, ["r%06d" % i for i in range(200)])
+
+
+def test_mmi_foreign_layouts_no_seq_any_order_any_b(ctx, mm2, orc, gen, tmp_path):
+    """indexes written by other tools — entries of a bucket in any order (C minimap2 dumps khash slot
+    order, the reference writes random HashMap order), MM_I_NO_SEQ files without the packed sequence, b != 14."""
+    import mmi_util
+    g = gen.repeat_genome(141, 700_000, 0.3, 0.2)
+    seqs = [g[:400_000].tobytes(), b"N", g[400_000:].tobytes()]
+    cat, offs = cases.cat_offs(seqs)
+    names = ["ca", "pad", "cb"]
+    rc, ro = gen.reads(5, cat, offs, 40, 3000, 0.02, 0.02, 0.02)
+    qn = ["f%d" % i for i in range(40)]
+    rng = np.random.default_rng(3)
+    for b in (10, 14, 17):
+        oi = orc.Index.build(cat, offs, names, w=10, k=15, b=b, threads=8)
+        want, _ = oi.align_batch(rc, ro, qn, threads=8)
+        po = str(tmp_path / ("o%d.mmi" % b))
+        oi.save_mmi(po)
+        canon = open(po, "rb").read()
+        m = mmi_util.parse(canon)
+        assert mmi_util.serialise(m) == canon                       # the fixture writer reproduces the layout
+        # (1) every bucket's entries in random order
+        m["buckets"] = [(p, ent[rng.permutation(len(ent))]) for p, ent in m["buckets"]]
+        ps = str(tmp_path / ("s%d.mmi" % b))
+        open(ps, "wb").write(mmi_util.serialise(m))
+        gs = mm2.Index.load_from_mmi(ctx, ps)
+        assert gs.stats() == oi.stats() and gs.calc_mid_occ() == oi.calc_mid_occ() and gs.b == b
+        assert ctx.map_batch(gs, rc, ro).paf_lines(qn) == want
+        pb = str(tmp_path / ("b%d.mmi" % b))
+        gs.save_to_mmi(pb)
+        assert open(pb, "rb").read() == canon                       # order-independent: written back canonically
+        # (2) MM_I_NO_SEQ: flag bit 1 set, no packed sequence at the end of the file
+        m["flag"] |= 2
+        pn = str(tmp_path / ("n%d.mmi" % b))
+        open(pn, "wb").write(mmi_util.serialise(m, with_seq=False))
+        gn = mm2.Index.load_from_mmi(ctx, pn)
+        assert gn.stats() == oi.stats() and (gn.flag & 2)
+        assert ctx.map_batch(gn, rc, ro).paf_lines(qn) == want      # mapping never touches S
+        with pytest.raises(mm2.Mm2Error) as e:
+            gn.get_ref_subseq(0, 0, 10)
+        assert e.value.code == mm2.MM2_E_FORMAT
+        pn2 = str(tmp_path / ("n2_%d.mmi" % b))
+        gn.save_to_mmi(pn2)
+        m2 = mmi_util.parse(open(pn2, "rb").read())
+        assert m2["flag"] & 2 and len(m2["S"]) == 0
+        # a NO_SEQ flag on a file that is simply truncated elsewhere is still an error
+        with pytest.raises(mm2.Mm2Error):
+            open(pn, "wb").write(mmi_util.serialise(m, with_seq=False)[:-9])
+            mm2.Index.load_from_mmi(ctx, pn)
+        for x in (gs, gn):
+            x.close()
+
+
+def test_mmi_khash_slot_order_writer(ctx, mm2, orc, gen, tmp_path):
+    """.mmi with every bucket in the slot order of C minimap2's khash table.  Checked against an independent
+    Python model of klib's khash (tests/mmi_util.py), for bucket sizes below and above the 0.77 load factor of the initial
+    table (the latter force khash's in-place rehash with its kick-out chain)."""
+    import mmi_util
+    g = gen.repeat_genome(143, 600_000, 0.3, 0.2)
+    offs = np.array([0, g.size], dtype=np.uint64)
+    for b in (6, 12):     # b = 6: ~1500 keys per bucket; b = 12: ~25
+        gi = mm2.Index.build(ctx, g, offs, ["k"], w=10, k=15, b=b)
+        pc, pk = str(tmp_path / "c.mmi"), str(tmp_path / "k.mmi")
+        gi.save_to_mmi(pc)
+        gi.save_to_mmi_khash(pk)
+        mc, mk = mmi_util.parse(open(pc, "rb").read()), mmi_util.parse(open(pk, "rb").read())
+        assert mc["seqs"] == mk["seqs"] and mc["S"] == mk["S"]
+        n_resized = 0
+        for (p1, e1), (p2, e2) in zip(mc["buckets"], mk["buckets"]):
+            assert (p1 == p2).all() and len(e1) == len(e2)
+            want = mmi_util.khash_order([(int(a), int(c)) for a, c in e1])
+            assert [(int(a), int(c)) for a, c in e2] == want
+            nb0 = max(4, mmi_util.Khash._roundup32(len(e1))) if len(e1) else 0
+            n_resized += int(len(e1) > int(nb0 * 0.77 + 0.5))
+        assert n_resized > 0                                        # the rehash path was exercised
+        g2 = mm2.Index.load_from_mmi(ctx, pk)
+        pr = str(tmp_path / "r.mmi")
+        g2.save_to_mmi(pr)
+        assert open(pr, "rb").read() == open(pc, "rb").read()
+        gi.close(); g2.close()

@@ -180,3 +180,33 @@ def test_oracle_matches_golden_fixtures(orc, gen):
     assert (a["x"] == s["ax"]).all() and (a["y"] == s["ay"]).all()
     o = orc.chain_dp_all(a, orc.default_chain_params(15))
     assert (o["f"] == s["f"]).all() and (o["pprev"] == s["pprev"]).all() and (o["chains"][0] == s["chain0"]).all()
+
+
+@pytest.mark.parametrize("density,max_skip,max_iter,bw", [(300, 25, 5000, 500), (300, 3, 200, 500), (120, 25, 100, 100000), (600, 0, 5000, 500),
+                                                         (40, 25, 33, 500), (300, 1000, 700, 500)])
+def test_chain_dense_tile_model_matches_oracle(orc, density, max_skip, max_iter, bw):
+    """the tile pipeline of chain_dense_kernel (summaries of the far window + sequential walk) against the oracle:
+    f, pprev, v and the inner-loop cell count"""
+    rng = np.random.default_rng(density + max_skip + max_iter)
+    n = 1300
+    parts = []
+    for rid, rev, cnt in ((0, 0, n // 2), (0, 1, n // 4), (2, 0, n // 4)):
+        extent = max(cnt * 5000 // density, 50)
+        rpos = np.sort(rng.integers(20, 20 + extent, cnt)).astype(np.int64)
+        diag = rng.choice([0, 0, 0, 7, -13, 400, -2500], cnt).astype(np.int64)
+        run = rng.integers(0, 4, cnt) == 0
+        diag[1:][run[1:]] = diag[:-1][run[1:]]
+        qpos = np.clip(rpos + diag + rng.integers(-3, 4, cnt) * (rng.integers(0, 3, cnt) == 0), 14, None)
+        x = (np.uint64(rev) << np.uint64(63)) | (np.uint64(rid) << np.uint64(32)) | rpos.astype(np.uint64)
+        y = (np.uint64(15) << np.uint64(32)) | qpos.astype(np.uint64)
+        parts.append(np.stack([x, y], axis=1))
+    xy = np.concatenate(parts)
+    xy = xy[np.lexsort((xy[:, 1], xy[:, 0]))]
+    a = np.zeros(xy.shape[0], dtype=orc.ANCHOR_DT)
+    a["x"], a["y"] = xy[:, 0], xy[:, 1]
+    p = orc.default_chain_params(15)
+    p.max_chain_skip, p.max_chain_iter, p.bw = max_skip, max_iter, bw
+    o = orc.chain_dp_all(a, p)
+    f, pp, v, cells = models.chain_dense_model(a, p)
+    assert (f == o["f"]).all() and (pp == o["pprev"]).all() and (v == o["v"]).all()
+    assert cells == o["cells"]
