@@ -54,6 +54,7 @@ int mm2_ctx_synchronize(mm2_ctx_t* ctx);
 const char* mm2_last_error(void);
 void mm2_free(void* p);               /* releases any `**out` array */
 void* mm2_host_alloc(size_t bytes);   /* page-locked host buffer (fast H2D/D2H); NULL on failure */
+void* mm2_host_alloc_on(int device, size_t bytes);   /* the same, on the NUMA node next to that GPU (multi-rank uploads) */
 void mm2_host_free(void* p);
 /* (launch counters, stage timers and the DP-cell counter used by bench.py are diagnostics: see mm2b200_diag.h) */
 

@@ -60,7 +60,7 @@ class _MapResult(C.Structure):
 # every symbol include/mm2b200.h declares (tests check that the library exports all of them)
 ABI_SYMBOLS = [
     "mm2_ctx_create", "mm2_ctx_destroy", "mm2_ctx_set_stream", "mm2_ctx_synchronize", "mm2_last_error", "mm2_free",
-    "mm2_host_alloc", "mm2_host_free", "mm2_sketch", "mm2_sketch_batch",
+    "mm2_host_alloc", "mm2_host_alloc_on", "mm2_host_free", "mm2_sketch", "mm2_sketch_batch",
     "mm2_index_build_fasta", "mm2_index_build_seqs", "mm2_index_save_mmi", "mm2_index_save_mmi_khash", "mm2_index_load_mmi", "mm2_index_save_native",
     "mm2_index_load_native", "mm2_index_load_auto", "mm2_index_free", "mm2_index_get", "mm2_index_stats",
     "mm2_index_calc_mid_occ", "mm2_index_params", "mm2_index_seq", "mm2_index_get_ref_subseq", "mm2_index_build_timings",
@@ -90,6 +90,8 @@ def lib():
     L.mm2_last_error.restype = C.c_char_p
     L.mm2_host_alloc.restype = vp
     L.mm2_host_alloc.argtypes = [sz]
+    L.mm2_host_alloc_on.restype = vp
+    L.mm2_host_alloc_on.argtypes = [C.c_int, sz]
     L.mm2_host_free.argtypes = [vp]
     L.mm2_free.argtypes = [vp]
     L.mm2_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
@@ -176,7 +178,7 @@ class PinnedBuffer:
 
     def __init__(self, nbytes, device=None):
         self.nbytes = max(1, int(nbytes))
-        self.p = lib().mm2_host_alloc(self.nbytes)
+        self.p = lib().mm2_host_alloc(self.nbytes) if device is None else lib().mm2_host_alloc_on(int(device), self.nbytes)
         if not self.p:
             raise Mm2Error(MM2_E_OOM, lib().mm2_last_error().decode())
         self._raw = (C.c_char * self.nbytes).from_address(self.p)

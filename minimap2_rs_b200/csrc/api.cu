@@ -10,6 +10,9 @@
 #include <atomic>
 #include <chrono>
 #include <malloc.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+#include <cctype>
 #include <thread>
 
 #include "stages.cuh"
@@ -30,6 +33,36 @@ extern "C" void* mm2_host_alloc(size_t bytes) {
   return p;
 }
 extern "C" void mm2_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// Page-locked memory on the NUMA node the GPU hangs off.  With one process per GPU on a two-socket box, half of the ranks
+// otherwise stream their reads across the socket interconnect (round 1: 21 GB/s of upload per GPU with eight ranks copying
+// at once, against 55 GB/s for one).  The node comes from sysfs (PCI bus id of the device); the allocation runs under a
+// temporary MPOL_BIND policy (raw syscall: no libnuma in the image).  Any failure falls back to the default placement.
+static int gpu_numa_node(int device) {
+  char bus[32] = "";
+  if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return -1; }
+  for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+  char path[128];
+  snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+  FILE* f = fopen(path, "r");
+  if (!f) return -1;
+  int node = -1;
+  if (fscanf(f, "%d", &node) != 1) node = -1;
+  fclose(f);
+  return node;
+}
+extern "C" void* mm2_host_alloc_on(int device, size_t bytes) {
+  const int node = gpu_numa_node(device);
+  bool bound = false;
+  if (node >= 0 && node < 1024 && !getenv("MM2_NO_NUMA")) {
+    unsigned long mask[16] = {0};
+    mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+    bound = syscall(SYS_set_mempolicy, 2 /* MPOL_BIND */, mask, (unsigned long)(sizeof mask * 8)) == 0;
+  }
+  void* p = mm2_host_alloc(bytes);
+  if (bound) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul);
+  return p;
+}
 
 // ---- context ---------------------------------------------------------------------------------------------------------
 extern "C" int mm2_ctx_create(int device, mm2_ctx_t** out) {

@@ -485,16 +485,31 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
 // tests/models.py:chain_dense_model is the CPU model of this pipeline (checked against the oracle, cell counts included).
 // State of the last DENSE_CAP anchors in shared memory (slot = j % DENSE_CAP): {x, q}, {f, pprev}, span.  A window reaches at
 // most max_chain_iter <= DENSE_CAP - 64 anchors back, and a slot is overwritten only by anchor j + DENSE_CAP.
+#ifdef MM2_DENSE_PROF
+// build with -DMM2_DENSE_PROF: cycle counters of the dense pipeline, printed by chain_batch (diagnostic only)
+// 0 ring step, 1 rest of tile T-1, 2 far walk, 3 warp 0 waiting at the tile barrier, 4 anchors with a window, 5 far rounds,
+// 6 record tiles, 7 total (warp 0), 8 phase A (helper warp 1), 9 helper waiting at the tile barrier, 10 tiles, 11 far (anchor, tile) pairs
+__device__ unsigned long long g_dense_prof[12];
+#define DPROF_T(v) const long long v = clock64()
+#define DPROF_ADD(k, a, b) do { if (lane == 0) dprof[k] += (unsigned long long)((b) - (a)); } while (0)
+#define DPROF_INC(k, x) do { if (lane == 0) dprof[k] += (unsigned long long)(x); } while (0)
+#else
+#define DPROF_T(v)
+#define DPROF_ADD(k, a, b)
+#define DPROF_INC(k, x)
+#endif
 constexpr int DENSE_CAP = 5120;
 constexpr int DENSE_JT = 160;          // far predecessor tiles per window: ceil((max_chain_iter + 31) / 32) + 1 <= 160
 constexpr int DENSE_MKW = DENSE_JT + 2;   // mark words per anchor: [0] = tile T, [1] = tile T-1, [2 + r] = far tile r
-struct DenseBuf {                      // summaries of one tile of 32 anchors (double-buffered)
-  u32 V[32][DENSE_JT];                 // valid cells of (anchor, far tile r), bit p = p-th visited (j descending)
-  int TM[32][DENSE_JT];                // best score of the tile's valid cells (NEG_INF: none)
-  u32 MK[32][DENSE_MKW];               // marks, bit = j & 31 (ascending)
+struct DenseBuf {                      // summaries of one tile of 32 anchors (double-buffered); odd row strides: lane = anchor
+  u32 V[32][DENSE_JT + 1];             // valid cells of (anchor, far tile r), bit p = p-th visited (j descending)
+  int TM[32][DENSE_JT + 1];            // best score of the tile's valid cells (NEG_INF: none)
+  u32 MK[32][DENSE_MKW + 1];           // marks, bit = j & 31 (ascending)
   int far_lo[32];                      // first far predecessor of the anchor; >= far_hi: no far part
 };
+constexpr int DENSE_LUT = 2048;        // gap penalties (lchain.rs:28-32) of dd < DENSE_LUT as 16-bit integers in shared memory
 struct DenseSh {
+  u16* pen16;                          // (int)(chn_pen_gap * dd + 0.5 * log2(dd + 1)): a function of dd alone when chn_pen_skip == 0
   int rescue_flag;                     // pass 0 -> pass 1 decision of warp 0 (lchain.rs:321-330)
   int2* sxq; int2* sfp; u8* ss;        // DENSE_CAP entries each
   DenseBuf* buf;                       // [2]
@@ -502,34 +517,38 @@ struct DenseSh {
   int cm_blk[2];                       // per tile parity: first anchor of the rid/strand block of the tile's last anchor
   u32 cm_hi[2];                        // ... and that anchor's rev|rid
 };
-constexpr int DENSE_DYN = DENSE_CAP * (8 + 8 + 1) + 2 * (int)sizeof(DenseBuf) + 64;
-constexpr int DENSE_NW = 16;           // warps per dense read: warp 0 walks, 15 evaluate
+constexpr int DENSE_DYN = DENSE_CAP * (8 + 8 + 1) + 2 * (int)sizeof(DenseBuf) + DENSE_LUT * 2 + 64;
+constexpr int DENSE_NW = 16;           // warps per dense read: warp 0 walks alone on its scheduler, 12 evaluate, 3 only keep the barriers
 
 template <int NW>
 __device__ __forceinline__ void dense_bar_all() { asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory"); }
 template <int NW>
-__device__ __forceinline__ void dense_bar_helpers() { asm volatile("bar.sync 2, %0;" ::"n"((NW - 1) * 32) : "memory"); }
+__device__ __forceinline__ void dense_bar_helpers() { asm volatile("bar.sync 2, %0;" ::"n"((NW - NW / 4) * 32) : "memory"); }
 
-// Phase A of tile `tile` (anchors i0 .. i0 + 31), run by warps 1 .. NW-1 while warp 0 walks tile - 1.
+// Phase A of tile `tile` (anchors i0 .. i0 + 31), run by the helper warps while warp 0 walks tile - 1.  A helper warp takes
+// one 32-aligned tile of far predecessors at a time and evaluates it against all 32 anchors with LANE = ANCHOR: the
+// predecessor's state is a broadcast shared-memory load, the anchor's a register, so the valid bits and the best score of
+// (anchor, tile) accumulate in lane-private registers without a ballot or a reduction per cell, and the predecessor's mark
+// target (lchain.rs:86) is warp-uniform: every lane ORs into its own anchor's mark row (conflict-free, odd row stride).
 template <int NW>
 __device__ __forceinline__ void dense_phase_a(const ChainArgs& G, DenseSh* sh, const ulonglong2* __restrict__ an, const int n, const int tile,
                                               const int bw, const int mdx, const int mdy, const int max_iter, const int wid, const int lane) {
   DenseBuf& B = sh->buf[tile & 1];
   const int i0 = tile * 32;
   const int far_hi = i0 - 32;                       // predecessors below it are final (tiles <= tile - 2 are committed)
-  const int hw = wid - 1, nh = NW - 1;              // helper index / count
-  // zero the mark words of this buffer; warp 1 finds the anchors' far window starts
-  for (int x = hw * 32 + lane; x < 32 * DENSE_MKW; x += nh * 32) (&B.MK[0][0])[x] = 0u;
+  const int hw = wid - 1 - (wid >> 2), nh = NW - NW / 4;   // helper index / count (warps 4, 8, 12 leave warp 0's scheduler alone)
+  // zero the mark words of this buffer; helper 0 finds the anchors' far window starts
+  for (int x = hw * 32 + lane; x < 32 * (DENSE_MKW + 1); x += nh * 32) (&B.MK[0][0])[x] = 0u;
   int my_x = 0, my_q = 0;                            // anchor i0 + lane of the tile (every helper warp holds a copy)
-  if (i0 + lane < n) { const ulonglong2 a = an[i0 + lane]; my_x = (int)(u32)a.x; my_q = (int)(u32)a.y; }
+  u32 my_hi = 0;
+  if (i0 + lane < n) { const ulonglong2 a = an[i0 + lane]; my_x = (int)(u32)a.x; my_q = (int)(u32)a.y; my_hi = (u32)(a.x >> 32); }
   if (hw == 0) {
     int lo = far_hi;                                 // "no far part"
     const int i = i0 + lane;
     if (i < n && far_hi > 0) {
-      const u32 hi_i = (u32)(an[i].x >> 32);
       // the far part is non-empty only if the anchor lies in the rid/strand block of the last committed anchor (far_hi - 1):
       // windows never cross a block (lchain.rs:75), and blocks are contiguous because the anchors are sorted by x
-      if (hi_i == sh->cm_hi[tile & 1]) {
+      if (my_hi == sh->cm_hi[tile & 1]) {
         int a = max(max(sh->cm_blk[tile & 1], wsub(i, max_iter)), 0), b = far_hi;   // first j in [a, far_hi) with !(ri > x_j + mdx)
         const int2* __restrict__ sxq = sh->sxq;
         while (a < b) {
@@ -544,51 +563,112 @@ __device__ __forceinline__ void dense_phase_a(const ChainArgs& G, DenseSh* sh, c
   dense_bar_helpers<NW>();
   if (far_hi <= 0) return;
   const int jt_top = (far_hi >> 5) - 1;              // far_hi is a multiple of 32: the first far tile visited
-  const int my_lo = B.far_lo[lane];                  // lane a: far_lo of anchor a
+  const int my_lo = B.far_lo[lane];                  // far_lo of this lane's anchor
   const int lo_min = __reduce_min_sync(0xFFFFFFFFu, my_lo);
   if (lo_min >= far_hi) return;
   const int nr = jt_top - (lo_min >> 5) + 1;         // far tiles that some anchor of the tile needs
   const float pen_gap = G.p.chn_pen_gap, pen_skip = G.p.chn_pen_skip;
   const float* __restrict__ half_log = G.half_log;
+  const int2* __restrict__ sxq = sh->sxq; const int2* __restrict__ sfp = sh->sfp; const u8* __restrict__ ss = sh->ss;
+  const int ri = my_x, qi = my_q;
+  const bool use_lut = pen_skip == 0.0f;
+  const u16* __restrict__ pen16 = sh->pen16;
+  u32* mk_row = &B.MK[lane][0];
+  const int slot_top = (jt_top * 32) % DENSE_CAP;                 // slots go down by 32 per tile and wrap at most once
   for (int r = hw; r < nr; r += nh) {
     const int jt = jt_top - r;
-    const int j = jt * 32 + lane;                    // this lane's predecessor (ascending inside the tile)
-    const int slot = (jt * 32) % DENSE_CAP + lane;
-    const int2 xq = sh->sxq[slot], fp = sh->sfp[slot];
-    const int span_j = (int)sh->ss[slot];
-    // where this predecessor's mark goes: word 2 + (jt_top - (pprev >> 5)) of the anchor's mark array
-    const int tw = fp.y >= 0 ? 2 + jt_top - (fp.y >> 5) : DENSE_MKW;
-    const bool okw = tw < DENSE_MKW;
-    const u32 tb = 1u << (fp.y & 31);
-    const u32 peers = __match_any_sync(0xFFFFFFFFu, okw ? tw : DENSE_MKW + lane);
-    const u32 leaders = __ballot_sync(0xFFFFFFFFu, okw && lane == __ffs(peers) - 1);   // one lane per distinct mark word
-    for (int a = 0; a < 32; ++a) {
-      const int lo_a = __shfl_sync(0xFFFFFFFFu, my_lo, a);
-      if (lo_a >= far_hi || (lo_a >> 5) > jt) continue;            // warp-uniform: the anchor's window does not reach this tile
-      const int ri = __shfl_sync(0xFFFFFFFFu, my_x, a), qi = __shfl_sync(0xFFFFFFFFu, my_q, a);
-      const bool act = j >= lo_a;
+    int slot0 = slot_top - 32 * r; if (slot0 < 0) slot0 += DENSE_CAP;
+    const int j0 = jt * 32;
+    const bool a_on = my_lo < far_hi && (my_lo >> 5) <= jt;       // this anchor's window reaches the tile
+    const int t_min = a_on ? max(my_lo - j0, 0) : 32;             // cells t >= t_min of the tile are inside this anchor's window
+    // this lane's predecessor of the tile, for the marks below
+    const int pp_l = sfp[slot0 + lane].y;
+    const int tw_l = pp_l >= 0 ? 2 + jt_top - (pp_l >> 5) : DENSE_MKW;
+    const u32 tb_l = 1u << (pp_l & 31);
+    u32 Va = 0;
+    int TMa = NEG_INF;
+    // (1) the 32 cells of this lane's anchor: straight-line code, no branch, so that the iterations overlap
+#pragma unroll 8
+    for (int t = 31; t >= 0; --t) {                               // visiting order: j descending, bit p = 31 - t
+      const int2 xq = sxq[slot0 + t];                             // broadcast loads
+      const int fj = sfp[slot0 + t].x;
+      const int span_j = (int)ss[slot0 + t];
       const int dq = wsub(qi, xq.y), dr = wsub(ri, xq.x);
       int dd = wsub(dr, dq); if (dd < 0) dd = wsub(0, dd);
-      const bool ok = act && dq > 0 && dq <= mdx && dr != 0 && dq <= mdy && dd <= bw && dd >= 0;
+      const bool ok = t >= t_min && dq > 0 && dq <= mdx && dr != 0 && dq <= mdy && dd <= bw && dd >= 0;
       const int dg = min(dr, dq);
       int s0 = min(span_j, dg);
       const int ddc = ok ? dd : 0;
-      const float lin = __fadd_rn(__fmul_rn(pen_gap, (float)ddc), __fmul_rn(pen_skip, (float)dg));
-      const int pen = __float2int_rz(__fadd_rn(lin, half_log[ddc]));
-      if (ddc != 0 || dg > span_j) s0 = wsub(s0, pen);
-      const int sc = ok ? wadd(s0, fp.x) : NEG_INF;
-      const u32 Vb = __ballot_sync(0xFFFFFFFFu, ok);
-      const int tm = __reduce_max_sync(0xFFFFFFFFu, sc);
-      if (lane == 0) { B.V[a][r] = __brev(Vb); B.TM[a][r] = tm; }
-      u32 rem = leaders;
-      while (rem) {                                                // lchain.rs:86, one shared atomic per distinct word
-        const int L = __ffs(rem) - 1;
-        rem &= rem - 1;
-        const int W = __shfl_sync(0xFFFFFFFFu, tw, L);
-        const u32 bits = __reduce_or_sync(0xFFFFFFFFu, (ok && tw == W) ? tb : 0u);
-        if (lane == 0 && bits) atomicOr(&B.MK[a][W], bits);
+      int pen;
+      if (use_lut) {   // chn_pen_skip == 0: the penalty depends on dd only (same float operations, done once per dd)
+        pen = ddc < DENSE_LUT ? (int)pen16[ddc] : __float2int_rz(__fadd_rn(__fmul_rn(pen_gap, (float)ddc), half_log[ddc]));
+      } else {
+        const float lin = __fadd_rn(__fmul_rn(pen_gap, (float)ddc), __fmul_rn(pen_skip, (float)dg));
+        pen = __float2int_rz(__fadd_rn(lin, half_log[ddc]));
       }
+      if (ddc != 0 || dg > span_j) s0 = wsub(s0, pen);
+      const int sc = ok ? wadd(s0, fj) : NEG_INF;
+      Va |= (ok ? 1u : 0u) << (31 - t);
+      TMa = max(TMa, sc);
     }
+    B.V[lane][r] = Va;
+    B.TM[lane][r] = TMa;
+    // (2) lchain.rs:86: predecessor t marks pprev[t] for every anchor it scores with.  The target word is warp-uniform per t,
+    //     so each lane accumulates the bits of its own anchor and flushes when the word changes (lane-private rows: no conflict)
+    if (__ballot_sync(0xFFFFFFFFu, Va != 0u)) {
+      int mw = DENSE_MKW;                                         // word being accumulated; DENSE_MKW = none
+      u32 macc = 0;
+#pragma unroll 4
+      for (int t = 31; t >= 0; --t) {
+        const int tw = __shfl_sync(0xFFFFFFFFu, tw_l, t);
+        const u32 tb = __shfl_sync(0xFFFFFFFFu, tb_l, t);
+        if (tw != mw) {
+          if (mw < DENSE_MKW && macc) atomicOr(&mk_row[mw], macc);
+          mw = tw; macc = 0;
+        }
+        macc |= ((Va >> (31 - t)) & 1u) ? tb : 0u;
+      }
+      if (mw < DENSE_MKW && macc) atomicOr(&mk_row[mw], macc);
+    }
+#ifdef MM2_DENSE_PROF
+    if (lane == 0) atomicAdd(&g_dense_prof[11], 32ull);
+#endif
+  }
+}
+
+// lchain.rs:90 (v) and the chain reductions of paf.rs:136-147 (length, extents, first anchor) of one committed tile, carried
+// along the best-predecessor links.  None of them feeds the DP of later anchors, so they are taken off warp 0's critical path:
+// a helper warp derives them one tile behind (lane = anchor; a parent outside the tile is final in global memory, a parent
+// inside it sits in a lower lane and is resolved in lane order).
+__device__ __forceinline__ void dense_reduce_tile(const ulonglong2* __restrict__ an, int4* A, int4* B, const int n, const int tile, const int lane) {
+  const int i0 = tile * 32, i = i0 + lane;
+  const bool in = i < n;
+  int f = 0, pp = -1, own_qs = 0, own_ts = 0;
+  if (in) {
+    const int2 fp = *reinterpret_cast<const int2*>(&A[i]);
+    f = fp.x; pp = fp.y;
+    const ulonglong2 a = an[i];
+    const int sp = (int)((a.y >> 32) & 0xff);
+    own_qs = wsub((int)(u32)a.y, sp - 1); own_ts = wsub((int)(u32)a.x, sp - 1);
+  }
+  int v = f, cnt = 1, qs = own_qs, ts = own_ts, first = i;
+  if (in && pp >= 0 && pp < i0) {
+    const int4 pa = A[pp], pb = B[pp];
+    v = pa.z > f ? pa.z : f; cnt = pa.w + 1; qs = min(pb.x, own_qs); ts = min(pb.y, own_ts); first = pb.z;
+  }
+  const bool intile = in && pp >= i0;
+  const int pl = pp & 31;
+  u32 todo = __ballot_sync(0xFFFFFFFFu, intile);
+  while (todo) {                                                 // ascending lanes: a parent is always final before its children
+    const int c = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const int pv = __shfl_sync(0xFFFFFFFFu, v, pl), pc = __shfl_sync(0xFFFFFFFFu, cnt, pl), pq = __shfl_sync(0xFFFFFFFFu, qs, pl);
+    const int pt = __shfl_sync(0xFFFFFFFFu, ts, pl), pf = __shfl_sync(0xFFFFFFFFu, first, pl);
+    if (lane == c) { v = pv > f ? pv : f; cnt = pc + 1; qs = min(pq, own_qs); ts = min(pt, own_ts); first = pf; }
+  }
+  if (in) {
+    reinterpret_cast<int2*>(&A[i])[1] = make_int2(v, cnt);
+    B[i] = make_int4(qs, ts, first, 0);
   }
 }
 
@@ -616,16 +696,33 @@ __device__ __forceinline__ void chain_read_dense(const ChainArgs& G, const u32 r
   int best = 0;
   int4 bestA = make_int4(0, -1, 0, 0), bestB = make_int4(0, 0, 0, 0);
   const int2* __restrict__ sxq = sh->sxq; const int2* __restrict__ sfp = sh->sfp; const u8* __restrict__ ss = sh->ss;
+#ifdef MM2_DENSE_PROF
+  unsigned long long dprof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const long long dprof_t0 = clock64();
+#endif
 
   for (int pass = 0; pass < 2; ++pass) {
     const int bw = pass == 0 ? p.bw : p.bw_long;                 // lchain.rs:327-328
     const int mdx = max(p.max_dist_x, bw), mdy = max(p.max_dist_y, bw);  // lchain.rs:63-66
+    for (int x = wid * 32 + lane; x < DENSE_LUT; x += NW * 32)     // first read after the barrier of tile 0
+      sh->pen16[x] = (u16)__float2int_rz(__fadd_rn(__fmul_rn(p.chn_pen_gap, (float)x), G.half_log[min(x, max(bw, 0) + 1)]));
     if (wid > 0) {
       // ---- helpers: phase A of tile T + 1 while warp 0 walks tile T (tiles 0 and 1 have no far part) -----------------------
       for (int T = 0; T < ntile; ++T) {
-        if (T + 1 < ntile) dense_phase_a<NW>(G, sh, an, n, T + 1, bw, mdx, mdy, max_iter, wid, lane);
+        DPROF_T(ha0);
+        if (wid == 2 && T >= 1) dense_reduce_tile(an, A, B, n, T - 1, lane);   // tile T - 1 was committed before the last barrier
+        if (T + 1 < ntile && (wid & 3) != 0) dense_phase_a<NW>(G, sh, an, n, T + 1, bw, mdx, mdy, max_iter, wid, lane);
+        DPROF_T(ha1);
         dense_bar_all<NW>();
+        DPROF_T(ha2);
+        if (wid == 1) { DPROF_ADD(8, ha0, ha1); DPROF_ADD(9, ha1, ha2); }
       }
+#ifdef MM2_DENSE_PROF
+      if (wid == 1 && lane == 0 && (pass == 1 || true)) { atomicAdd(&g_dense_prof[8], dprof[8]); atomicAdd(&g_dense_prof[9], dprof[9]); dprof[8] = dprof[9] = 0; }
+#endif
+      if (wid == 2) dense_reduce_tile(an, A, B, n, ntile - 1, lane);
+      __threadfence_block();
+      dense_bar_all<NW>();                           // every anchor's v / chain length / extents are in global memory
       // the rescue decision (lchain.rs:321-330) is taken by warp 0 and published through shared memory
       dense_bar_all<NW>();
       if (pass == 1 || !sh->rescue_flag) break;
@@ -634,7 +731,7 @@ __device__ __forceinline__ void chain_read_dense(const ChainArgs& G, const u32 r
     }
     // ---- warp 0: the sequential walk -----------------------------------------------------------------------------------------
     int rj = -1, rx = 0, rq = 0, rsp = 0; u32 rhi = 0;           // ring slot of this lane (anchor j with j % 32 == lane)
-    int rf = 0, rpp = -1, rv = 0, rcnt = 0, rqs = 0, rts = 0, rfirst = 0;
+    int rf = 0, rpp = -1;   // DP result of the slot; v / chain length / chain extents are derived by a helper warp (dense_reduce_tile)
     int bf = NEG_INF * 4, bi = 0;
     int blk_start = 0;   // first anchor of the rid/strand block that holds the last anchor of the previous tile
     ulonglong2 nxt = make_ulonglong2(0, 0);
@@ -649,7 +746,6 @@ __device__ __forceinline__ void chain_read_dense(const ChainArgs& G, const u32 r
       if (i0 + 32 + lane < n) nxt = an[i0 + 32 + lane];
       const int cx = (int)(u32)cur.x, cq = (int)(u32)cur.y, csp = (int)((cur.y >> 32) & 0xff);
       const u32 chi = (u32)(cur.x >> 32);
-      const int own_qs = wsub(cq, csp - 1), own_ts = wsub(cx, csp - 1);
       u32 workmask, bnd;
       {
         int px = __shfl_up_sync(0xFFFFFFFFu, cx, 1);
@@ -667,10 +763,12 @@ __device__ __forceinline__ void chain_read_dense(const ChainArgs& G, const u32 r
         const int c = __ffs(workmask) - 1;
         workmask &= workmask - 1;
         const int i = i0 + c;
+        DPROF_T(tp0);
+        DPROF_INC(4, 1);
         if (done < c) {
           if (lane >= done && lane < c) {                        // anchors before i with an empty window (lchain.rs:77,89-90)
             rj = i0 + lane; rx = cx; rq = cq; rsp = csp; rhi = chi;
-            rf = csp; rpp = -1; rv = csp; rcnt = 1; rqs = own_qs; rts = own_ts; rfirst = i0 + lane;
+            rf = csp; rpp = -1;
           }
         }
         done = c + 1;
@@ -684,7 +782,6 @@ __device__ __forceinline__ void chain_read_dense(const ChainArgs& G, const u32 r
         const u32 inmask = __ballot_sync(0xFFFFFFFFu, inwin);
         const u32 vmask = __ballot_sync(0xFFFFFFFFu, valid);
         int max_f = spi, max_j = -1, n_skip = 0;
-        bool from_ring = true;                                   // max_j's state is in the ring (else in A/B)
         bool more = (inmask >> c) & 1u;                          // slot c holds j = i - 32: the window may go on beyond the ring
         if (vmask) {
           const int low_ring = max(i - 32, 0);
@@ -718,7 +815,8 @@ __device__ __forceinline__ void chain_read_dense(const ChainArgs& G, const u32 r
         } else if (count_cells) {
           cells += (unsigned)__popc(inmask);
         }
-        int mv = 0, mcnt = 0, mqs = 0, mts = 0, mfirst = 0;     // state of max_j
+        DPROF_T(tp1);
+        DPROF_ADD(0, tp0, tp1);
         if (more) {
           // ---- the window goes on beyond the ring --------------------------------------------------------------------------
           // first anchor of the rid/strand block of i: the last block boundary at or before lane c, else the previous tile's
@@ -726,16 +824,19 @@ __device__ __forceinline__ void chain_read_dense(const ChainArgs& G, const u32 r
           const int blk0 = bm ? i0 + 31 - __clz(bm) : blk_start;
           const int fl = (far_hi > 0) ? SB.far_lo[c] : far_hi;   // first far predecessor (>= far_hi: none)
           u32* MK = &SB.MK[c][0];
-          // (1) the ring slots mark their predecessors below the ring: tiles T (word 0), T-1 (word 1) and the far tiles
-          if (valid && rpp >= 0 && rpp < i - 32) {
-            const int wdx = (i0 >> 5) - (rpp >> 5);              // 0: tile T (cannot be: rpp < i - 32 < i0), 1: tile T-1, 2 + r: far
-            if (wdx < DENSE_MKW) atomicOr(&MK[wdx], 1u << (rpp & 31));
+          // (1) the ring slots mark their predecessors below the ring (lchain.rs:86): tile T-1's marks stay in a register
+          //     (they are only read by the cells of step 2), the far tiles' go to the anchor's mark row in shared memory
+          u32 m1;
+          {
+            const bool rm = valid && rpp >= 0 && rpp < i - 32;
+            const int wdx = (i0 >> 5) - (rpp >> 5);              // 1: tile T-1, 2 + r: far tile r (0 cannot be: rpp < i - 32 < i0)
+            m1 = __reduce_or_sync(0xFFFFFFFFu, (rm && wdx == 1) ? (1u << (rpp & 31)) : 0u);
+            if (rm && wdx >= 2 && wdx < DENSE_MKW) atomicOr(&MK[wdx], 1u << (rpp & 31));
           }
-          __syncwarp();
           // (2) the rest of tile T-1: j = i - 33 - lane, down to the window start; its anchors are committed to shared memory
           bool brk = false;
-          const int late_lo = max(max(far_hi, blk0), max(low_iter, 0));   // not below tile T-1, the block, the iteration bound
           if (c > 0) {
+            const int late_lo = max(max(far_hi, blk0), max(low_iter, 0));   // not below tile T-1, the block, the iteration bound
             const int j = i - 33 - lane;
             const bool inr = j >= late_lo;                       // inside tile T-1 (and the block); the distance test is per cell
             const int slot = ((j % DENSE_CAP) + DENSE_CAP) % DENSE_CAP;
@@ -744,23 +845,36 @@ __device__ __forceinline__ void chain_read_dense(const ChainArgs& G, const u32 r
             int s1;
             const bool v2 = chain_sc_flat(act, ri, qi, xq.x, xq.y, (int)ss[slot], mdx, mdy, bw, p.chn_pen_gap, p.chn_pen_skip, G.half_log, s1);
             const int sc2 = v2 ? wadd(s1, fp.x) : NEG_INF;
-            if (v2 && fp.y >= 0) {                               // lchain.rs:86 (all lanes first, see the header of this file)
+            {                                                    // lchain.rs:86 (all lanes first, see the header of this file)
+              const bool lm = v2 && fp.y >= 0;
               const int wdx = (i0 >> 5) - (fp.y >> 5);
-              if (wdx < DENSE_MKW) atomicOr(&MK[wdx], 1u << (fp.y & 31));
+              m1 |= __reduce_or_sync(0xFFFFFFFFu, (lm && wdx == 1) ? (1u << (fp.y & 31)) : 0u);
+              if (lm && wdx >= 2 && wdx < DENSE_MKW) atomicOr(&MK[wdx], 1u << (fp.y & 31));
             }
-            __syncwarp();
-            const bool tm = v2 && ((MK[1] >> (j & 31)) & 1u);    // tile T-1 is word 1
+            const bool tm = v2 && ((m1 >> (j & 31)) & 1u);
             const u32 V2 = __ballot_sync(0xFFFFFFFFu, v2), M2 = __ballot_sync(0xFFFFFFFFu, tm), A2 = __ballot_sync(0xFFFFFFFFu, act);
-            int rec_last;
-            brk = chain_tile_walk(lane, V2, M2, A2, sc2, max_skip, max_f, n_skip, rec_last, cells);
-            if (rec_last >= 0) { max_j = i - 33 - rec_last; from_ring = false; }
+            if (__ballot_sync(0xFFFFFFFFu, v2 && sc2 > max_f) == 0u) {
+              // no record among these cells (lchain.rs:84): n_skip only grows, by one per marked cell
+              const int cnt = __popc(M2), need = max(max_skip + 1 - n_skip, 1);
+              if (cnt >= need) { brk = true; if (count_cells) cells += (unsigned)(nth_set_bit(M2, need) + 1); }
+              else { n_skip += cnt; if (count_cells) cells += (unsigned)__popc(A2); }
+            } else {
+              int rec_last;
+              brk = chain_tile_walk(lane, V2, M2, A2, sc2, max_skip, max_f, n_skip, rec_last, cells);
+              if (rec_last >= 0) max_j = i - 33 - rec_last;
+            }
             // the window ends inside tile T-1 when some cell of it fails the distance test (or the bounds above cut it)
             if (A2 != low_mask(c)) more = false;
           }
+          __syncwarp();                                          // the far marks of steps 1 and 2 are in shared memory
+          DPROF_T(tp2);
+          DPROF_ADD(1, tp1, tp2);
           // (3) the far tiles, through their summaries: lane t holds tile r = base + t
           if (!brk && more && fl < far_hi) {
             const int nr = jt_top - (fl >> 5) + 1;
+            const int slot_top0 = (jt_top * 32) % DENSE_CAP;
             for (int base = 0; base < nr && !brk; base += 32) {
+              DPROF_INC(5, 1);
               const int rr = base + lane;
               const bool have = rr < nr;
               const u32 tV = have ? SB.V[c][rr] : 0u;
@@ -805,10 +919,12 @@ __device__ __forceinline__ void chain_read_dense(const ChainArgs& G, const u32 r
                 }
                 if (tf >= nround) break;
                 // a record tile: its cells one by one (recomputed: the predecessors' state is in shared memory)
+                DPROF_INC(6, 1);
                 {
                   const int jtf = jt_top - (base + tf);
                   const int j = jtf * 32 + 31 - lane;            // visiting order
-                  const int slot = (jtf * 32) % DENSE_CAP + 31 - lane;
+                  int slot = slot_top0 - 32 * (base + tf); if (slot < 0) slot += DENSE_CAP;
+                  slot += 31 - lane;
                   const int2 xq = sxq[slot], fp = sfp[slot];
                   const bool act = j >= fl;
                   int s1;
@@ -817,43 +933,27 @@ __device__ __forceinline__ void chain_read_dense(const ChainArgs& G, const u32 r
                   const u32 Vt = __shfl_sync(0xFFFFFFFFu, tV, tf), Mt = __shfl_sync(0xFFFFFFFFu, tM, tf), At = __shfl_sync(0xFFFFFFFFu, tA, tf);
                   int rec_last;
                   const bool b2 = chain_tile_walk(lane, Vt, Mt, At, sc2, max_skip, max_f, n_skip, rec_last, cells);
-                  if (rec_last >= 0) { max_j = jtf * 32 + 31 - rec_last; from_ring = false; }
+                  if (rec_last >= 0) max_j = jtf * 32 + 31 - rec_last;
                   if (b2) { brk = true; break; }
                 }
                 curt = tf + 1;
               }
             }
           }
-          if (!from_ring) {
-            // the state of a predecessor outside the ring: v, cnt from A, the chain reductions from B (tile T-1 and older are in
-            // global memory: written at the end of their tile, before the barrier)
-            const int4 aj = A[max_j], bj = B[max_j];
-            mv = aj.z; mcnt = aj.w; mqs = bj.x; mts = bj.y; mfirst = bj.z;
-          }
-        }
-        // ---- lchain.rs:89-90 and the chain reductions of paf.rs:136-147 carried along the best-predecessor links -------
-        if (max_j >= 0 && from_ring) {
-          const int L = max_j & 31;
-          mv = __shfl_sync(0xFFFFFFFFu, rv, L); mcnt = __shfl_sync(0xFFFFFFFFu, rcnt, L); mqs = __shfl_sync(0xFFFFFFFFu, rqs, L);
-          mts = __shfl_sync(0xFFFFFFFFu, rts, L); mfirst = __shfl_sync(0xFFFFFFFFu, rfirst, L);
+          DPROF_T(tp3);
+          DPROF_ADD(2, tp2, tp3);
         }
         if (lane == c) {                                         // anchor i takes over its ring slot
           rj = i; rx = cx; rq = cq; rsp = csp; rhi = chi;
-          rf = max_f; rpp = max_j;
-          rv = (max_j >= 0 && mv > max_f) ? mv : max_f;
-          rcnt = max_j >= 0 ? mcnt + 1 : 1;
-          rqs = max_j >= 0 ? min(mqs, own_qs) : own_qs;
-          rts = max_j >= 0 ? min(mts, own_ts) : own_ts;
-          rfirst = max_j >= 0 ? mfirst : i;
+          rf = max_f; rpp = max_j;                               // lchain.rs:89
         }
       }
       if (lane >= done && lane < tile_n) {
         rj = i0 + lane; rx = cx; rq = cq; rsp = csp; rhi = chi;
-        rf = csp; rpp = -1; rv = csp; rcnt = 1; rqs = own_qs; rts = own_ts; rfirst = i0 + lane;
+        rf = csp; rpp = -1;
       }
       if (lane < tile_n) {                                       // every lane now holds its own anchor of this tile
-        A[i0 + lane] = make_int4(rf, rpp, rv, rcnt);
-        B[i0 + lane] = make_int4(rqs, rts, rfirst, 0);
+        *reinterpret_cast<int2*>(&A[i0 + lane]) = make_int2(rf, rpp);   // {v, chain length} and B follow from dense_reduce_tile
         const int slot = (i0 + lane) % DENSE_CAP;                // ... and they enter the shared window ring
         sh->sxq[slot] = make_int2(rx, rq); sh->sfp[slot] = make_int2(rf, rpp); sh->ss[slot] = (u8)rsp;
       }
@@ -873,8 +973,13 @@ __device__ __forceinline__ void chain_read_dense(const ChainArgs& G, const u32 r
         }
       }
       __threadfence_block();
+      DPROF_T(tb0);
       dense_bar_all<NW>();                                       // tile T is committed; the summaries of tile T + 1 are complete
+      DPROF_T(tb1);
+      DPROF_ADD(3, tb0, tb1);
+      DPROF_INC(10, 1);
     }
+    dense_bar_all<NW>();                                         // dense_reduce_tile has finished the last tile
     best = bi;
     bestA = A[best]; bestB = B[best];
     bool rescue = false;
@@ -895,6 +1000,12 @@ __device__ __forceinline__ void chain_read_dense(const ChainArgs& G, const u32 r
     dense_bar_all<NW>();                                         // ... before the flag is rewritten
   }
   if (wid == 0) chain_finish(G, r, lane, an, A, a0, qlen, m0, m1, best, bestA, bestB, hit, cells);
+#ifdef MM2_DENSE_PROF
+  if (wid == 0 && lane == 0) {
+    dprof[7] = (unsigned long long)(clock64() - dprof_t0);
+    for (int x = 0; x < 12; ++x) if (x != 8 && x != 9) atomicAdd(&g_dense_prof[x], dprof[x]);
+  }
+#endif
 }
 
 __global__ void __launch_bounds__(CH_WARPS * 32, MM2_CH_OCC) chain_ring_kernel(ChainArgs G) {
@@ -915,7 +1026,8 @@ __global__ void __launch_bounds__(NW * 32, 1) chain_dense_kernel(ChainArgs G) {
     sh.sxq = reinterpret_cast<int2*>(dense_dyn);
     sh.sfp = sh.sxq + DENSE_CAP;
     sh.buf = reinterpret_cast<DenseBuf*>(dense_dyn + DENSE_CAP * 16);
-    sh.ss = reinterpret_cast<u8*>(dense_dyn + DENSE_CAP * 16 + 2 * sizeof(DenseBuf));
+    sh.pen16 = reinterpret_cast<u16*>(dense_dyn + DENSE_CAP * 16 + 2 * sizeof(DenseBuf));
+    sh.ss = reinterpret_cast<u8*>(dense_dyn + DENSE_CAP * 16 + 2 * sizeof(DenseBuf) + DENSE_LUT * 2);
   }
   for (;;) {
     __syncthreads();
@@ -988,6 +1100,18 @@ int chain_batch(mm2_ctx* ctx, const ulonglong2* d_anchors, const u64* d_read_aof
     // persistent CTAs (one per SM), one dense read at a time each; with no dense read they exit at once
     if (G.dense_min != 0x7fffffff) MM2_LAUNCH(ctx, chain_dense_kernel<DENSE_NW>, (int)std::min<u64>(nreads, (u64)ctx->n_sm), DENSE_NW * 32, DENSE_DYN, G);
   }
+#ifdef MM2_DENSE_PROF
+  {
+    cudaStreamSynchronize(ctx->stream);
+    unsigned long long h[12];
+    cudaMemcpyFromSymbol(h, g_dense_prof, sizeof h);
+    if (h[4]) fprintf(stderr, "[dense prof] anchors-with-window %llu tiles %llu far-rounds %llu record-tiles %llu far-pairs %llu | warp 0 cycles per anchor: ring %.0f late %.0f far %.0f barrier-wait %.0f total %.0f | helper warp: phase A %.0f wait %.0f cycles per tile\n",
+                      h[4], h[10], h[5], h[6], h[11], (double)h[0] / h[4], (double)h[1] / h[4], (double)h[2] / h[4], (double)h[3] / h[4], (double)h[7] / h[4],
+                      (double)h[8] / std::max(1ull, h[10]), (double)h[9] / std::max(1ull, h[10]));
+    memset(h, 0, sizeof h);
+    cudaMemcpyToSymbol(g_dense_prof, h, sizeof h);
+  }
+#endif
   CUDA_TRY(cudaGetLastError());
   return MM2_OK;
 }

@@ -5,7 +5,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "mm2b200.h"
@@ -27,88 +29,130 @@ struct Fasta {
   std::vector<uint8_t> cat;
   std::vector<uint64_t> offs;
 };
-// noodles-like record semantics (name = up to the first whitespace; sequence lines concatenated)
-// Extension (the reference reads FASTA only): a query file whose first byte is '@' is read as FASTQ --
-// '@name ...', sequence lines up to a line starting with '+', then as many quality characters as there were bases.
-bool read_fastq(FILE* fp, bool first_only, Fasta& fa) {
-  std::vector<char> buf(1 << 20);
-  enum { HEADER, SEQ, PLUS, QUAL } st = QUAL;
-  bool line_start = true, name_done = false;
-  size_t n, need_q = 0, nrec = 0;
-  while ((n = fread(buf.data(), 1, buf.size(), fp)) > 0) {
-    for (size_t i = 0; i < n; ++i) {
-      const char c = buf[i];
-      if (c == '\r') continue;
-      switch (st) {
-        case HEADER:
-          if (c == '\n') { st = SEQ; line_start = true; }
-          else if (!name_done) { if (c == ' ' || c == '\t') name_done = true; else fa.names.back().push_back(c); }
-          break;
-        case SEQ:
-          if (c == '\n') { line_start = true; break; }
-          if (line_start && c == '+') { st = PLUS; need_q = fa.cat.size() - fa.offs.back(); break; }
-          line_start = false;
-          fa.cat.push_back((uint8_t)c);
-          break;
-        case PLUS:
-          if (c == '\n') { st = QUAL; line_start = true; }
-          break;
-        case QUAL:
-          if (need_q) { if (c != '\n') --need_q; break; }
-          if (c == '\n') { line_start = true; break; }
-          if (c == '@') {   // quality strings may contain '@', but only inside their need_q characters
-            if (nrec && first_only) { fa.offs.push_back(fa.cat.size()); return true; }
-            ++nrec; st = HEADER; name_done = false;
-            fa.names.emplace_back(); fa.offs.push_back(fa.cat.size());
-          }
-          break;
-      }
-    }
-  }
-  fa.offs.push_back(fa.cat.size());
-  return true;
-}
 
-bool read_fasta(const std::string& path, bool first_only, Fasta& fa) {
-  FILE* fp = fopen(path.c_str(), "rb");
-  if (!fp) return false;
-  {
+// One batch of query records: the bases live in a page-locked buffer (mm2_host_alloc) so that mm2_map_batch uploads them
+// at full PCIe speed straight from where the parser wrote them.
+struct Batch {
+  std::vector<std::string> names;
+  std::vector<uint64_t> offs;   // nreads + 1
+  uint8_t* cat = nullptr;
+  size_t len = 0, cap = 0;
+  void clear() { names.clear(); offs.clear(); len = 0; }
+  void push(uint8_t c) {
+    if (len == cap) {
+      const size_t ncap = cap ? cap * 2 : (size_t)1 << 20;
+      uint8_t* nb = (uint8_t*)mm2_host_alloc(ncap);
+      if (!nb) die("out of page-locked host memory");
+      if (len) memcpy(nb, cat, len);
+      if (cat) mm2_host_free(cat);
+      cat = nb; cap = ncap;
+    }
+    cat[len++] = c;
+  }
+  ~Batch() { if (cat) mm2_host_free(cat); }
+};
+
+// Streaming FASTA / FASTQ reader.  noodles-like record semantics (name = up to the first whitespace;
+// sequence lines concatenated).  FASTQ is an extension (the reference reads FASTA only): a file whose first byte is '@' --
+// '@name ...', sequence lines up to a line starting with '+', then as many quality characters as there were bases.
+// fill() appends whole records to a batch until it holds max_bases bases (or max_reads records) and stops at the next record
+// boundary, so a file of any size is mapped in bounded memory.
+struct ReadStream {
+  FILE* fp = nullptr;
+  std::vector<char> buf;
+  size_t pos = 0, n = 0;
+  bool fastq = false, eof = false;
+  enum { FA_SEQ, FA_HEADER, FQ_HEADER, FQ_SEQ, FQ_PLUS, FQ_QUAL } st = FA_SEQ;
+  bool line_start = true, name_done = false, have = false;   // have: inside a record
+  size_t need_q = 0, rec_start = 0;
+  bool open(const std::string& path) {
+    fp = fopen(path.c_str(), "rb");
+    if (!fp) return false;
+    buf.resize(4 << 20);
     const int c0 = fgetc(fp);
     if (c0 != EOF) ungetc(c0, fp);
-    if (c0 == '@') { const bool ok = read_fastq(fp, first_only, fa); fclose(fp); return ok; }
+    fastq = c0 == '@';
+    st = fastq ? FQ_QUAL : FA_SEQ;
+    return true;
   }
-  std::vector<char> buf(1 << 20);
-  bool in_header = false, line_start = true, have = false, name_done = false, stop = false;
-  size_t n;
-  while (!stop && (n = fread(buf.data(), 1, buf.size(), fp)) > 0) {
-    for (size_t i = 0; i < n; ++i) {
-      const char c = buf[i];
-      if (in_header) {
-        if (c == '\n') { in_header = false; line_start = true; }
-        else if (!name_done) { if (c == ' ' || c == '\t' || c == '\r') name_done = true; else fa.names.back().push_back(c); }
-        continue;
-      }
-      if (line_start && c == '>') {
-        if (have && first_only) { stop = true; break; }
-        have = true; in_header = true; name_done = false; line_start = false;
-        fa.names.emplace_back(); fa.offs.push_back(fa.cat.size());
-        continue;
-      }
-      if (c == '\n') { line_start = true; continue; }
-      line_start = false;
-      if (c == '\r') continue;
-      if (have) fa.cat.push_back((uint8_t)c);
+  ~ReadStream() { if (fp) fclose(fp); }
+  // true: the batch holds at least one record
+  bool fill(Batch& b, size_t max_bases, size_t max_reads) {
+    b.clear();
+    if (have) {   // the previous batch stopped in front of this record's first character
+      have = false;
     }
+    for (;;) {
+      if (pos == n) {
+        if (eof) break;
+        n = fread(buf.data(), 1, buf.size(), fp);
+        pos = 0;
+        if (n == 0) { eof = true; break; }
+      }
+      const char c = buf[pos];
+      const bool starts_record = fastq ? (st == FQ_QUAL && need_q == 0 && c == '@') : (st == FA_SEQ && line_start && c == '>');
+      if (starts_record) {
+        if (!b.names.empty() && (b.len >= max_bases || b.names.size() >= max_reads)) {   // leave the character for the next batch
+          b.offs.push_back(b.len);
+          return true;
+        }
+        ++pos;
+        b.names.emplace_back(); b.offs.push_back(b.len);
+        name_done = false; line_start = false;
+        st = fastq ? FQ_HEADER : FA_HEADER;
+        continue;
+      }
+      ++pos;
+      switch (st) {
+        case FA_HEADER:
+        case FQ_HEADER:
+          if (c == '\n') { st = fastq ? FQ_SEQ : FA_SEQ; line_start = true; }
+          else if (!name_done) { if (c == ' ' || c == '\t' || c == '\r') name_done = true; else b.names.back().push_back(c); }
+          break;
+        case FA_SEQ:
+          if (c == '\n') { line_start = true; break; }
+          line_start = false;
+          if (c == '\r') break;
+          if (!b.names.empty()) b.push((uint8_t)c);
+          break;
+        case FQ_SEQ:
+          if (c == '\r') break;
+          if (c == '\n') { line_start = true; break; }
+          if (line_start && c == '+') { st = FQ_PLUS; need_q = b.len - (size_t)b.offs.back(); break; }
+          line_start = false;
+          b.push((uint8_t)c);
+          break;
+        case FQ_PLUS:
+          if (c == '\n') { st = FQ_QUAL; line_start = true; }
+          break;
+        case FQ_QUAL:   // quality strings may contain '@', but only inside their need_q characters
+          if (c == '\r') break;
+          if (need_q) { if (c != '\n') --need_q; break; }
+          break;
+      }
+    }
+    if (b.names.empty()) return false;
+    b.offs.push_back(b.len);
+    return true;
   }
-  fclose(fp);
-  fa.offs.push_back(fa.cat.size());
+};
+
+// the first record only (main.rs:92-103), or everything, into one in-memory Fasta (anchors / chain subcommands)
+bool read_fasta(const std::string& path, bool first_only, Fasta& fa) {
+  ReadStream rs;
+  if (!rs.open(path)) return false;
+  Batch b;
+  if (rs.fill(b, first_only ? 0 : ~(size_t)0, first_only ? 1 : ~(size_t)0)) {
+    fa.names = b.names; fa.offs = b.offs; fa.cat.assign(b.cat, b.cat + b.len);
+  } else fa.offs.push_back(0);
   return true;
 }
 
 struct Args {
   std::vector<std::string> pos;
   int w = 10, k = 15, b = 14, bw = 5000;
-  bool hpc = false, all_reads = false, has_r = false;
+  bool hpc = false, all_reads = false, has_r = false, khash = false;
+  int gpus = 1, batch_mb = 1024;
   std::string dump, r, preset, output;
   bool has_dump = false, has_output = false, has_preset = false;
   float f = 2e-4f, mask_level = 0.5f, pri_ratio = 0.8f;
@@ -139,11 +183,13 @@ float need_f32(const std::string& flag, const std::string& s) {
 void usage() {
   fprintf(stderr,
           "mm2rs (B200): Rust rewrite of minimap2 (WIP) — GPU hot path\n\nUsage: mm2rs <COMMAND>\n\nCommands:\n"
-          "  index    <fasta> [-w 10] [-k 15] [-b 14] [-H|--hpc] [-d|--dump FILE]\n"
+          "  index    <fasta> [-w 10] [-k 15] [-b 14] [-H|--hpc] [-d|--dump FILE] [--gpus N] [--khash-order]\n"
           "  anchors  <ref> <qry> [-w 10] [-k 15] [-H]\n"
           "  chain    <ref> <qry> [-w 10] [-k 15] [-r 5000] [-H]\n"
           "  align    <ref> <qry> [-w 10] [-k 15] [-H] [-f 2e-4] [-g 5000] [-r NUM[,NUM]] [-n 3] [-m 40] [-M 0.5] [-p 0.8]\n"
-          "           [-N 5] [-x PRESET] [-a] [-o FILE] [--all-reads]\n");
+          "           [-N 5] [-x PRESET] [-a] [-o FILE] [--all-reads] [--batch-mb 1024]\n"
+          "Extensions over the reference CLI: index --gpus N (bucket-sharded build on N GPUs), --khash-order (.mmi entries in C\n"
+          "minimap2's hash-slot order); align --all-reads (every record of the query, streamed in batches of --batch-mb), FASTQ queries.\n");
 }
 
 // clap-style parsing of one subcommand's arguments: `-w 10`, `-w10`, `-w=10`, `--long v`, `--long=v`
@@ -152,7 +198,7 @@ Args parse(const std::string& cmd, int argc, char** argv) {
   if (cmd == "chain") a.bw = 5000;
   auto takes_value = [&](const std::string& f) {
     static const char* v[] = {"-w", "-k", "-b", "-d", "--dump", "-r", "-f", "-g", "-n", "-m", "-M", "--mask-level", "-p", "--pri-ratio",
-                              "-N", "--best-n", "-x", "-o"};
+                              "-N", "--best-n", "-x", "-o", "--gpus", "--batch-mb"};
     for (const char* x : v) if (f == x) return true;
     return false;
   };
@@ -187,9 +233,12 @@ Args parse(const std::string& cmd, int argc, char** argv) {
       else if (flag == "-N" || flag == "--best-n") a.best_n = need_i32(flag, val);
       else if (flag == "-x") { a.preset = val; a.has_preset = true; }
       else if (flag == "-o") { a.output = val; a.has_output = true; }
+      else if (flag == "--gpus") a.gpus = need_i32(flag, val);
+      else if (flag == "--batch-mb") a.batch_mb = need_i32(flag, val);
     } else if (flag == "-H" || flag == "--hpc") a.hpc = true;
     else if (flag == "-a") { /* parsed and ignored (main.rs:85-86) */ }
     else if (flag == "--all-reads") a.all_reads = true;
+    else if (flag == "--khash-order") a.khash = true;
     else { fprintf(stderr, "error: unexpected argument '%s' found\n", t.c_str()); exit(2); }
   }
   return a;
@@ -236,7 +285,21 @@ int main(int argc, char** argv) {
 
   if (cmd == "index") {  // main.rs:150-159
     const int flag = a.hpc ? 1 : 0;
-    check(mm2_index_build_fasta(s.ctx, a.pos[0].c_str(), a.w, a.k, a.b, flag, &s.idx));
+    std::vector<mm2_ctx_t*> extra_ctx;
+    std::vector<mm2_index_t*> replicas;
+    if (a.gpus > 1) {
+      // extension: bucket-sharded build on N GPUs of this box (mm2_index_build_multi); the replica on the first GPU is dumped
+      Fasta ref;
+      if (!read_fasta(a.pos[0], false, ref)) die("cannot open " + a.pos[0]);
+      std::vector<mm2_ctx_t*> ctxs{s.ctx};
+      for (int d = 1; d < a.gpus; ++d) { mm2_ctx_t* c = nullptr; check(mm2_ctx_create((dev ? atoi(dev) : 0) + d, &c)); ctxs.push_back(c); extra_ctx.push_back(c); }
+      std::vector<const char*> np;
+      for (auto& nm : ref.names) np.push_back(nm.c_str());
+      replicas.assign(ctxs.size(), nullptr);
+      check(mm2_index_build_multi(ctxs.data(), (int)ctxs.size(), ref.cat.data(), ref.offs.data(), np.data(), ref.names.size(), a.w, a.k, a.b, flag,
+                                  replicas.data()));
+      s.idx = replicas[0];
+    } else check(mm2_index_build_fasta(s.ctx, a.pos[0].c_str(), a.w, a.k, a.b, flag, &s.idx));
     uint64_t n_keys = 0, total_len = 0;
     double avg_occ = 0, avg_spacing = 0;
     uint32_t n_seq = 0;
@@ -248,8 +311,10 @@ int main(int argc, char** argv) {
     if (a.has_dump) {
       const std::string& p = a.dump;
       const bool mmi = p.size() >= 4 && p.compare(p.size() - 4, 4, ".mmi") == 0;
-      check(mmi ? mm2_index_save_mmi(s.idx, p.c_str()) : mm2_index_save_native(s.idx, p.c_str()));
+      check(mmi ? (a.khash ? mm2_index_save_mmi_khash(s.idx, p.c_str()) : mm2_index_save_mmi(s.idx, p.c_str())) : mm2_index_save_native(s.idx, p.c_str()));
     }
+    for (size_t d = 1; d < replicas.size(); ++d) mm2_index_free(replicas[d]);
+    for (mm2_ctx_t* c : extra_ctx) mm2_ctx_destroy(c);
     return 0;
   }
 
@@ -257,8 +322,10 @@ int main(int argc, char** argv) {
   const int flag = a.hpc ? 1 : 0;
   check(mm2_index_load_auto(s.ctx, a.pos[0].c_str(), a.w, a.k, 14, flag, &s.idx));  // main.rs:135-145, b = 14
   Fasta q;
-  if (!read_fasta(a.pos[1], !(cmd == "align" && a.all_reads), q)) die("cannot open " + a.pos[1]);
-  if (q.names.empty()) { q.names.push_back("*"); q.offs.assign(2, 0); }  // main.rs:101: ("*", empty)
+  if (cmd != "align") {
+    if (!read_fasta(a.pos[1], true, q)) die("cannot open " + a.pos[1]);
+    if (q.names.empty()) { q.names.push_back("*"); q.offs.assign(2, 0); }  // main.rs:101: ("*", empty)
+  }
 
   if (cmd == "anchors") {  // main.rs:160-171
     mm2_anchor_t* an = nullptr; size_t n = 0;
@@ -303,29 +370,60 @@ int main(int argc, char** argv) {
       if (parse_i32(rest.substr(0, rest.find(',')), &v)) o.bw_long = v;
     }
   }
-  const size_t nreads = q.names.size();
-  for (size_t i = 0; i < nreads; ++i)
-    if (q.offs[i + 1] == q.offs[i]) die("empty query sequence (sketch.rs:30 asserts !seq.is_empty())", 101);
-  mm2_map_result_t res;
-  check(mm2_map_batch(s.ctx, s.idx, q.cat.data(), q.offs.data(), nreads, &o, &res));
-  if (res.n_panic) {
-    fprintf(stderr, "thread 'main' panicked: index out of bounds (anchor rid beyond the sequence table; read %u) — "
-                    "the reference mis-encodes odd target ids (seeds.rs:64-71)\n", res.panic_reads[0]);
-    mm2_map_result_free(&res);
-    return 101;
-  }
-  std::vector<const char*> qn;
-  for (auto& nm : q.names) qn.push_back(nm.c_str());
-  char* txt = nullptr; size_t tl = 0;
-  check(mm2_paf_format_batch(s.idx, &res, qn.data(), &txt, &tl));
+  // Streaming ingest: a reader thread parses batch i + 1 into page-locked memory while the GPU maps batch i; the PAF lines are
+  // written per batch, i.e. in input order, and memory stays bounded by two batches whatever the size of the file.
+  ReadStream rs;
+  if (!rs.open(a.pos[1])) die("cannot open " + a.pos[1]);
+  const size_t max_bases = a.all_reads ? (size_t)std::max(1, a.batch_mb) << 20 : 0, max_reads = a.all_reads ? ~(size_t)0 : 1;
+  Batch B[2];
+  bool have = rs.fill(B[0], max_bases, max_reads);
+  if (!have) { B[0].names.push_back("*"); B[0].offs.assign(2, 0); have = true; }  // main.rs:101: ("*", empty) -> the sketch asserts
   FILE* out = stdout;
   if (a.has_output && a.output != "-") {
     out = fopen(a.output.c_str(), "wb");
     if (!out) die("cannot create " + a.output);
   }
-  fwrite(txt, 1, tl, out);
+  size_t read_base = 0;
+  for (int cur = 0; have; cur ^= 1) {
+    Batch& b = B[cur];
+    bool next_have = false;
+    std::thread reader;
+    if (a.all_reads) reader = std::thread([&]() { next_have = rs.fill(B[cur ^ 1], max_bases, max_reads); });
+    const size_t nreads = b.names.size();
+    int rc_exit = 0;
+    std::string err;
+    for (size_t i = 0; i < nreads && !rc_exit; ++i)
+      if (b.offs[i + 1] == b.offs[i]) { rc_exit = 101; err = "empty query sequence (sketch.rs:30 asserts !seq.is_empty())"; }
+    mm2_map_result_t res;
+    memset(&res, 0, sizeof res);
+    if (!rc_exit) {
+      const int rc = mm2_map_batch(s.ctx, s.idx, b.cat, b.offs.data(), nreads, &o, &res);
+      if (rc != MM2_OK) { rc_exit = (rc == MM2_E_ARG || rc == MM2_E_REF_PANIC) ? 101 : 1; err = mm2_last_error(); }
+    }
+    if (!rc_exit && res.n_panic) {
+      char msg[256];
+      snprintf(msg, sizeof msg, "thread 'main' panicked: index out of bounds (anchor rid beyond the sequence table; read %zu) — "
+                                "the reference mis-encodes odd target ids (seeds.rs:64-71)", read_base + res.panic_reads[0]);
+      err = msg; rc_exit = 101;
+    }
+    if (!rc_exit) {
+      std::vector<const char*> qn;
+      for (auto& nm : b.names) qn.push_back(nm.c_str());
+      char* txt = nullptr; size_t tl = 0;
+      const int rc = mm2_paf_format_batch(s.idx, &res, qn.data(), &txt, &tl);
+      if (rc != MM2_OK) { rc_exit = 1; err = mm2_last_error(); }
+      else { fwrite(txt, 1, tl, out); mm2_free(txt); }
+    }
+    mm2_map_result_free(&res);
+    if (reader.joinable()) reader.join();
+    if (rc_exit) {
+      if (out != stdout) fclose(out);
+      if (rc_exit == 101 && err.rfind("thread", 0) == 0) { fprintf(stderr, "%s\n", err.c_str()); return 101; }
+      die(err, rc_exit);
+    }
+    read_base += nreads;
+    have = next_have;
+  }
   if (out != stdout) fclose(out);
-  mm2_free(txt);
-  mm2_map_result_free(&res);
   return 0;
 }

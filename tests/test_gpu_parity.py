@@ -846,3 +846,55 @@ def test_mmi_khash_slot_order_writer(ctx, mm2, orc, gen, tmp_path):
         g2.save_to_mmi(pr)
         assert open(pr, "rb").read() == open(pc, "rb").read()
         gi.close(); g2.close()
+
+
+def test_cli_streaming_ingest_bounded_batches(ctx, mm2, orc, gen, tmp_path):
+    """`align --all-reads` streams the query file in batches (a reader thread parses batch i + 1 into
+    page-locked memory while the GPU maps batch i); with --batch-mb 1 a 9 MB file goes through in ~9 batches and the PAF must
+    be the same lines in the same (input) order; FASTA with wrapped lines and FASTQ; reads without a hit leave no line."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(mm2.LIB_PATH), "mm2rs")
+    g = gen.genome(151, 1_500_000)
+    offs = np.array([0, g.size], dtype=np.uint64)
+    oi = orc.Index.build(g, offs, ["ref"], threads=8)
+    mmi = str(tmp_path / "ref.mmi")
+    oi.save_mmi(mmi)
+    n = 2300
+    rc, ro = gen.reads(9, g, offs, n, 4000, 0.02, 0.02, 0.02)
+    rc = rc.copy()
+    rng = np.random.default_rng(4)
+    for i in range(5, n, 11):                       # unrelated reads: no anchors, no PAF line
+        rc[int(ro[i]):int(ro[i + 1])] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, 4000)]
+    names = ["s%05d" % i for i in range(n)]
+    want, _ = oi.align_batch(rc, ro, names, threads=8)
+    fa, fq = str(tmp_path / "q.fa"), str(tmp_path / "q.fq")
+    with open(fa, "wb") as f, open(fq, "wb") as f2:
+        for i in range(n):
+            sq = rc[int(ro[i]):int(ro[i + 1])].tobytes()
+            f.write(b">" + names[i].encode() + b" desc\n")
+            for j in range(0, len(sq), 80):
+                f.write(sq[j:j + 80] + (b"\r\n" if i % 3 == 0 else b"\n"))
+            f2.write(b"@" + names[i].encode() + b"\n" + sq + b"\n+\n" + b"@" * len(sq) + b"\n")
+    for path in (fa, fq):
+        for mb in ("1", "3", "1024"):
+            out = subprocess.run([exe, "align", mmi, path, "--all-reads", "--batch-mb", mb], capture_output=True, text=True)
+            assert out.returncode == 0, out.stderr
+            assert out.stdout == "\n".join(want) + "\n", (path, mb)
+    # without --all-reads: the first record only (main.rs:92-103)
+    out = subprocess.run([exe, "align", mmi, fa], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout == want[0] + "\n"
+    # khash-order dump from the CLI loads back and maps the same
+    fref, mk = str(tmp_path / "ref.fa"), str(tmp_path / "k.mmi")
+    with open(fref, "wb") as f:
+        f.write(b">ref\n" + g.tobytes() + b"\n")
+    out = subprocess.run([exe, "index", "-d", mk, "--khash-order", fref], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert open(mk, "rb").read() != open(mmi, "rb").read() and os.path.getsize(mk) == os.path.getsize(mmi)
+    out = subprocess.run([exe, "align", mk, fa, "--all-reads"], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout == "\n".join(want) + "\n"
+    import torch
+    if torch.cuda.device_count() >= 2:              # extension: `index --gpus 2` = mm2_index_build_multi
+        m2 = str(tmp_path / "m2.mmi")
+        out = subprocess.run([exe, "index", "-d", m2, "--gpus", "2", fref], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        assert open(m2, "rb").read() == open(mmi, "rb").read()

@@ -173,12 +173,15 @@ def run_c3(a):
             e["one_gpu_device_ms"] = g1.build_timings()
             e["speedup_vs_one_gpu"] = e["one_gpu_build_s"] / e["sharded_build_s"]
             g1.close()
-            if not a.no_cpu:
-                from oracle import orc
+            if not a.no_sha:
                 pg = "/tmp/c3_gpu_k%d.mmi" % k
+                t0 = time.time()
                 gi.save_to_mmi(pg)
                 e["gpu_mmi_sha256"], e["mmi_bytes"] = sha_file(pg)
+                e["save_and_sha_s"] = time.time() - t0
                 os.remove(pg)
+            if not a.no_cpu:
+                from oracle import orc
                 t0 = time.time()
                 oi = orc.Index.build(g, goffs, gnames, w=10, k=k, threads=os.cpu_count() or 1)
                 e["oracle_build_s"] = time.time() - t0
@@ -199,18 +202,41 @@ def run_c3(a):
     return out if rank == 0 else None
 
 
+def run_c3cpu(a):
+    """the CPU side of configs[2]: the oracle builds the 3.1 Gbp index (k = 15, 19), writes the .mmi and hashes it; the sharded GPU
+    build of a `--which c3 --no-cpu` run on the same seeded genome must produce the same sha256"""
+    from oracle import orc
+    ncpu = os.cpu_count() or 1
+    g, goffs, gnames = wl.genome_c3() if not a.genome_mbp else wl.genome_c3(16, int(a.genome_mbp * 1e6 / 16))
+    out = {"config": "c3cpu", "genome_bp": int(g.size), "records": len(gnames), "threads": ncpu, "builds": []}
+    for k in [int(x) for x in a.k.split(",")]:
+        t0 = time.time()
+        oi = orc.Index.build(g, goffs, gnames, w=10, k=k, threads=ncpu)
+        e = {"k": k, "w": 10, "oracle_build_s": time.time() - t0, "gbp_per_s": g.size / (time.time() - t0) / 1e9, "stats": oi.stats(), "mid_occ": oi.calc_mid_occ()}
+        po = "/tmp/c3_cpu_k%d.mmi" % k
+        t0 = time.time()
+        oi.save_mmi(po)
+        e["cpu_mmi_sha256"], e["mmi_bytes"] = sha_file(po)
+        e["save_and_sha_s"] = time.time() - t0
+        os.remove(po)
+        oi.close()
+        out["builds"].append(e)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--which", required=True, choices=["c3", "c4", "c5"])
+    ap.add_argument("--which", required=True, choices=["c3", "c3cpu", "c4", "c5"])
     ap.add_argument("--reads", type=int, default=0)
     ap.add_argument("--sample", type=int, default=1000)
     ap.add_argument("--cell-reads", type=int, default=2000, help="reads of the DP-cell counting pass")
     ap.add_argument("--genome-mbp", type=float, default=0.0)
     ap.add_argument("--k", default="15,19")
-    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="c3: skip the CPU build (its sha256 comes from a `--which c3cpu` run on the same genome)")
+    ap.add_argument("--no-sha", action="store_true")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
-    out = run_c3(a) if a.which == "c3" else run_mapping(a.which, a)
+    out = run_c3(a) if a.which == "c3" else run_c3cpu(a) if a.which == "c3cpu" else run_mapping(a.which, a)
     if out is not None:
         path = a.out or os.path.join(ROOT, "gpurun_out", "config_%s.json" % a.which)
         os.makedirs(os.path.dirname(path), exist_ok=True)

@@ -1,18 +1,24 @@
-"""Small dense-anchor workload (repeat-rich genome, long reads) for profiling the chain kernel on configs[4]-like input."""
+"""Small dense-anchor workload (configs[4]-shaped: repeat-rich genome, 100 kb reads at 8 % error) for profiling the CTA-per-read
+chaining kernel.  With MM2_LIB_PATH=minimap2_rs_b200/libmm2b200_prof.so (make -C minimap2_rs_b200/csrc prof) the library prints
+the cycle counters of the dense pipeline on stderr."""
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import minimap2_rs_b200 as mm2
-from tools import gen
-g = gen.repeat_genome(0xB2000005, 10_000_000, 0.4, 0.2)
-offs = np.array([0, g.size], dtype=np.uint64)
+from tools import workloads as wl
+nreads = int(sys.argv[1]) if len(sys.argv) > 1 else 148
+rlen = int(sys.argv[2]) if len(sys.argv) > 2 else 100000
+glen = int(float(sys.argv[3]) * 1e6) if len(sys.argv) > 3 else wl.C1_LEN
+g, offs, names = wl.genome_c5(glen)
 ctx = mm2.Context(0)
-gi = mm2.Index.build(ctx, g, offs, ["rep"])
-nreads = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-rlen = int(sys.argv[2]) if len(sys.argv) > 2 else 30000
-rc, ro = gen.reads(0xB2001005, g, offs, nreads, rlen, 0.027, 0.027, 0.026)
-for _ in range(2):
+gi = mm2.Index.build(ctx, g, offs, names)
+rc, ro = wl.reads("c5", g, offs, nreads, rlen)
+for it in range(2):
+    ctx.count_cells(it == 1)
     t0 = time.perf_counter()
     res = ctx.map_batch(gi, rc, ro)
-    print("reads", nreads, "anchors", res.stats["n_anchors"], "wall %.2f s" % (time.perf_counter() - t0), {k: round(v, 1) for k, v in ctx.last_timings().items()}, flush=True)
+    dt = time.perf_counter() - t0
+    tm = ctx.last_timings()
+    print("reads", nreads, "anchors", res.stats["n_anchors"], "rescued", res.stats["n_rescued"], "wall %.2f s" % dt, {k: round(v, 1) for k, v in tm.items()},
+          ("cells %d = %.1f per anchor, %.1f Gcells/s" % (ctx.last_cells, ctx.last_cells / max(1, res.stats["n_anchors"]), ctx.last_cells / 1e9 / (tm.get("chain", 1) / 1e3))) if it else "", flush=True)
     res.close()
