@@ -103,6 +103,7 @@ struct StageTimer {  // CUDA-event stopwatch on the context stream
       names_blob += names[i]; names_blob.push_back('\0');
     }
     names_blob.push_back('\0');
+    names.resize(n_used ? n_used - 1 : 0);   // drop the terminator's name: names[i] <-> ms[i] from here on (add_host appends to both)
   }
   void add_host(const char* name, float t) {  // a host-side wall-clock entry appended after finish()
     if (!names_blob.empty()) names_blob.pop_back();
