@@ -299,6 +299,8 @@ int index_build_lookup(mm2_ctx* ctx, mm2_index* idx) {
 // (ckey, y) pairs sorted by ckey (stable: equal keys keep their input order).  The input arrays are scratch afterwards;
 // ctx->sorted_k / ctx->sorted_v point at the result.
 int radix_sort_pairs(mm2_ctx* ctx, u64* a_keys, u64* a_vals, u64* b_keys, u64* b_vals, u64 n, int end_bit, u64** res_keys, u64** res_vals);
+int radix_partition_by_owner(mm2_ctx* ctx, const u64* keys, const u64* vals, u64* out_keys, u64* out_vals, u64 n, int key_shift, int b, int nranks,
+                             u64* d_bounds);
 static int index_sort_pairs(mm2_ctx* ctx, u64* ckey_in, u64* y_in, u64 n, int end_bit) {
   MM2_TRY(ctx->sort_keys2.ensure(std::max<u64>(1, n) * 8));
   MM2_TRY(ctx->sort_vals2.ensure(std::max<u64>(1, n) * 8));
@@ -520,8 +522,8 @@ extern "C" int mm2_index_get(const mm2_index_t* idx, uint64_t minier, uint64_t**
 //   1. every rank sketches its share of the genome — a contiguous range of TILES of the global tile list, i.e. the split
 //      runs inside sequences (a tile depends only on its bases plus a 2w+k halo), so a single-chromosome genome is
 //      sketched by all ranks; even k / HPC (literal kernel) fall back to whole sequences — and uploads only those bytes;
-//   2. local radix sort, bucket-major; rank r owns buckets [ceil(r 2^b / R), ceil((r+1) 2^b / R)), so every destination's
-//      records are one contiguous slice;
+//   2. one stable partition pass by bucket owner: rank r owns buckets [ceil(r 2^b / R), ceil((r+1) 2^b / R)), so every
+//      destination's records become one contiguous slice, still in emission (= position) order;
 //   3. all-to-all (grouped ncclSend / ncclRecv over NVLink);
 //   4. stable re-sort + run-length grouping of the owned buckets (index.rs:74-109) — the receive buffer is in source-rank
 //      = position order, and p_fill repairs a run should it ever not be;
@@ -537,18 +539,6 @@ extern "C" int mm2_index_get(const mm2_index_t* idx, uint64_t minier, uint64_t**
 #include <thread>
 
 namespace {
-__global__ void owner_bounds_kernel(const u64* __restrict__ ckey, u64 n, int b, int R, int nranks, u64* __restrict__ bounds) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r > nranks) return;
-  const u64 nb = 1ULL << b;
-  const u64 first_bucket = ((u64)r * nb + (u64)nranks - 1) / (u64)nranks;  // ceil(r * 2^b / nranks)
-  u64 lo = 0, hi = n;
-  while (lo < hi) {
-    const u64 mid = (lo + hi) >> 1;
-    if ((ckey[mid] >> R) < first_bucket) lo = mid + 1; else hi = mid;
-  }
-  bounds[r] = lo;
-}
 __global__ void add_u64_kernel(u64* __restrict__ dst, const u64* __restrict__ src, u64 n) {
   for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) dst[i] += src[i];
 }
@@ -648,14 +638,17 @@ int shard_local(mm2_ctx* ctx, const ShardPlan& P, const u8* h_cat, const u64* of
   ctx->timer.mark(st, "sort");
   const u64 n = so.total;
   const int R = std::max(2 * k - b, 0);
-  const int end_bit = std::max(1, std::min(64, b + R));
+  MM2_TRY(ctx->sort_keys2.ensure(std::max<u64>(1, n) * 8));
+  MM2_TRY(ctx->sort_vals2.ensure(std::max<u64>(1, n) * 8));
+  MM2_TRY(ctx->misc.ensure(((size_t)P.nranks + 2) * 8));
   if (n) {
     MM2_TRY(ctx->sort_tmp2.ensure(n * 8));
     MM2_LAUNCH(ctx, rekey_kernel, grid_for(n), 256, 0, ctx->mkey.as<u64>(), ctx->sort_tmp2.as<u64>(), n, b, R);
   }
-  MM2_TRY(index_sort_pairs(ctx, ctx->sort_tmp2.as<u64>(), ctx->mval.as<u64>(), n, end_bit));
-  MM2_TRY(ctx->misc.ensure(((size_t)P.nranks + 2) * 8));
-  MM2_LAUNCH(ctx, owner_bounds_kernel, (P.nranks + 1 + 63) / 64, 64, 0, ctx->sorted_k, n, b, R, P.nranks, ctx->misc.as<u64>());
+  // one stable partition pass by bucket owner (the owner sorts what it receives; a full local sort would be thrown away)
+  MM2_TRY(radix_partition_by_owner(ctx, ctx->sort_tmp2.as<u64>(), ctx->mval.as<u64>(), ctx->sort_keys2.as<u64>(), ctx->sort_vals2.as<u64>(), n, R, b,
+                                   P.nranks, ctx->misc.as<u64>()));
+  ctx->sorted_k = ctx->sort_keys2.as<u64>(); ctx->sorted_v = ctx->sort_vals2.as<u64>();
   bounds.assign((size_t)P.nranks + 1, 0);
   MM2_TRY(ctx->pin_small.ensure(((size_t)P.nranks + 1) * 8));
   CUDA_TRY(cudaMemcpyAsync(ctx->pin_small.p, ctx->misc.p, ((size_t)P.nranks + 1) * 8, cudaMemcpyDeviceToHost, st));

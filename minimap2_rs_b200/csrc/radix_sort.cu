@@ -24,7 +24,14 @@ constexpr int RS_BITS = 10;            // digit width: 30 key bits (k = 15) take
 constexpr int RS_BINS = 1 << RS_BITS;
 constexpr int RS_DPT = RS_BINS / RS_NT;  // digits per thread in the per-digit loops
 
-__global__ void __launch_bounds__(RS_NT) rs_hist_kernel(const u64* __restrict__ keys, u64 n, int shift, u32 ntiles, u32* __restrict__ counts) {
+// digit of a key: a bit field (the sort passes), or the rank that owns the key's bucket in the sharded index build
+// (owner = floor(bucket * nranks / 2^b): rank r owns buckets [ceil(r 2^b / R), ceil((r + 1) 2^b / R)); the key is bucket << shift | ...)
+struct DigitFn { int shift, b, nranks; };   // nranks == 0: bit field
+__device__ __forceinline__ u32 digit_of(u64 key, const DigitFn f) {
+  return f.nranks == 0 ? ((u32)(key >> f.shift) & (RS_BINS - 1)) : (u32)(((key >> f.shift) * (u64)f.nranks) >> f.b);
+}
+
+__global__ void __launch_bounds__(RS_NT) rs_hist_kernel(const u64* __restrict__ keys, u64 n, const DigitFn fn, u32 ntiles, u32* __restrict__ counts) {
   __shared__ u32 s_h[RS_BINS];
   for (u32 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
 #pragma unroll
@@ -34,7 +41,7 @@ __global__ void __launch_bounds__(RS_NT) rs_hist_kernel(const u64* __restrict__ 
 #pragma unroll 4
     for (int r = 0; r < RS_TILE / RS_NT; ++r) {
       const u64 i = base + (u64)r * RS_NT + threadIdx.x;
-      if (i < n) atomicAdd(&s_h[(u32)(keys[i] >> shift) & (RS_BINS - 1)], 1u);
+      if (i < n) atomicAdd(&s_h[digit_of(keys[i], fn)], 1u);
     }
     __syncthreads();
     // digit-major so that one scan orders digits first, tiles second
@@ -44,7 +51,7 @@ __global__ void __launch_bounds__(RS_NT) rs_hist_kernel(const u64* __restrict__ 
   }
 }
 
-__global__ void __launch_bounds__(RS_NT) rs_scatter_kernel(const u64* __restrict__ keys, const u64* __restrict__ vals, u64 n, int shift,
+__global__ void __launch_bounds__(RS_NT) rs_scatter_kernel(const u64* __restrict__ keys, const u64* __restrict__ vals, u64 n, const DigitFn fn,
                                                            u32 ntiles, const u64* __restrict__ offs, u64* __restrict__ out_keys,
                                                            u64* __restrict__ out_vals) {
   extern __shared__ __align__(16) unsigned char rs_smem[];
@@ -75,7 +82,7 @@ __global__ void __launch_bounds__(RS_NT) rs_scatter_kernel(const u64* __restrict
       const u64 i = wbase + (u64)r * 32 + lane;
       const bool in = i < n;
       k[r] = in ? keys[i] : ~0ULL;
-      const u32 d = in ? ((u32)(k[r] >> shift) & (RS_BINS - 1)) : (u32)RS_BINS;   // out-of-range lanes form their own group
+      const u32 d = in ? digit_of(k[r], fn) : (u32)RS_BINS;   // out-of-range lanes form their own group
       const u32 peers = __match_any_sync(0xFFFFFFFFu, d);
       const int leader = __ffs(peers) - 1;
       u32 old = 0;
@@ -123,7 +130,7 @@ __global__ void __launch_bounds__(RS_NT) rs_scatter_kernel(const u64* __restrict
     __syncthreads();
     for (u32 i = threadIdx.x; i < tile_n; i += RS_NT) {   // consecutive staged slots of a digit go to consecutive addresses
       const u64 kk = sk[i];
-      const u32 d = (u32)(kk >> shift) & (RS_BINS - 1);
+      const u32 d = digit_of(kk, fn);
       const u64 o = s_base[d] + (u64)(i - s_toff[d]);
       out_keys[o] = kk;
       out_vals[o] = sv[i];
@@ -152,12 +159,41 @@ int radix_sort_pairs(mm2_ctx* ctx, u64* a_keys, u64* a_vals, u64* b_keys, u64* b
   const int grid = (int)std::min<u32>(ntiles, 148u * 3u);
   u64 *src_k = a_keys, *src_v = a_vals, *dst_k = b_keys, *dst_v = b_vals;
   for (int pass = 0; pass < npass; ++pass) {
-    MM2_LAUNCH(ctx, rs_hist_kernel, grid, RS_NT, 0, src_k, n, pass * RS_BITS, ntiles, ctx->rs_counts.as<u32>());
+    const DigitFn fn{pass * RS_BITS, 0, 0};
+    MM2_LAUNCH(ctx, rs_hist_kernel, grid, RS_NT, 0, src_k, n, fn, ntiles, ctx->rs_counts.as<u32>());
     MM2_TRY(scan_u32_to_u64(ctx, ctx->rs_counts.as<u32>(), ctx->rs_offs.as<u64>(), ncnt));
-    MM2_LAUNCH(ctx, rs_scatter_kernel, grid, RS_NT, RS_TILE * 16, src_k, src_v, n, pass * RS_BITS, ntiles, ctx->rs_offs.as<u64>(), dst_k, dst_v);
+    MM2_LAUNCH(ctx, rs_scatter_kernel, grid, RS_NT, RS_TILE * 16, src_k, src_v, n, fn, ntiles, ctx->rs_offs.as<u64>(), dst_k, dst_v);
     std::swap(src_k, dst_k); std::swap(src_v, dst_v);
   }
   CUDA_TRY(cudaGetLastError());
   *res_keys = src_k; *res_vals = src_v;
+  return MM2_OK;
+}
+
+namespace {
+__global__ void owner_starts_kernel(const u64* __restrict__ offs, u32 ntiles, int nranks, u64 n, u64* __restrict__ bounds) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > nranks) return;
+  bounds[r] = r == nranks ? n : offs[(u64)r * ntiles];   // first output slot of digit r = records owned by the ranks below r
+}
+}  // namespace
+
+// Sharded index build: ONE stable partition pass that groups the (bucket-major key, value) pairs by the rank that owns their
+// bucket (instead of a full local sort: the owner sorts what it receives anyway).  d_bounds (device, nranks + 1): first record
+// of every owner in the output.
+int radix_partition_by_owner(mm2_ctx* ctx, const u64* keys, const u64* vals, u64* out_keys, u64* out_vals, u64 n, int key_shift, int b, int nranks,
+                             u64* d_bounds) {
+  if (nranks < 1 || nranks > RS_BINS) { mm2_set_error("partition: 1 <= nranks <= %d", RS_BINS); return MM2_E_ARG; }
+  const u32 ntiles = (u32)std::max<u64>(1, (n + RS_TILE - 1) / RS_TILE);
+  const size_t ncnt = (size_t)ntiles * RS_BINS;
+  MM2_TRY(ctx->rs_counts.ensure(ncnt * 4 + 64));
+  MM2_TRY(ctx->rs_offs.ensure((ncnt + 1) * 8 + 64));
+  const int grid = (int)std::min<u32>(ntiles, 148u * 3u);
+  const DigitFn fn{key_shift, b, nranks};
+  MM2_LAUNCH(ctx, rs_hist_kernel, grid, RS_NT, 0, keys, n, fn, ntiles, ctx->rs_counts.as<u32>());
+  MM2_TRY(scan_u32_to_u64(ctx, ctx->rs_counts.as<u32>(), ctx->rs_offs.as<u64>(), ncnt));
+  if (n) MM2_LAUNCH(ctx, rs_scatter_kernel, grid, RS_NT, RS_TILE * 16, keys, vals, n, fn, ntiles, ctx->rs_offs.as<u64>(), out_keys, out_vals);
+  MM2_LAUNCH(ctx, owner_starts_kernel, (nranks + 1 + 63) / 64, 64, 0, ctx->rs_offs.as<u64>(), ntiles, nranks, n, d_bounds);
+  CUDA_TRY(cudaGetLastError());
   return MM2_OK;
 }
