@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -47,7 +48,7 @@ struct DevBuf {
   int ensure(size_t bytes) {
     if (bytes <= cap) return MM2_OK;
     release();
-    size_t want = bytes + bytes / 8 + 256;
+    size_t want = bytes + std::min<size_t>(bytes / 8, (size_t)64 << 20) + 256;   // growth slack, capped: index tables reach tens of GB
     cudaError_t e;
     if (pooled) {
       e = cudaMallocAsync(&p, want, (cudaStream_t)0);
