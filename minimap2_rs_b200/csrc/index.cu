@@ -553,11 +553,13 @@ struct ShardPlan {
   u64 up_lo = 0, up_hi = 0;            // bytes uploaded (union of the two)
 };
 
-// S words of rank r: the used words split evenly; the last rank also clears the zero tail up to the allocated power of two
+// S words of rank r: equal slots of ceil(used / R) words (so that the replication is one in-place ncclAllGather); the zero
+// tail up to the allocated power of two is a local memset on every rank
+u64 shard_slot_words(u64 total, int nranks) { const u64 used = (total + 7) / 8; return (used + (u64)nranks - 1) / (u64)nranks; }
 void shard_words(u64 total, u64 S_words_alloc, int nranks, int rank, u64* lo, u64* hi) {
-  const u64 used = (total + 7) / 8;
-  *lo = used * (u64)rank / (u64)nranks;
-  *hi = rank + 1 == nranks ? S_words_alloc : used * (u64)(rank + 1) / (u64)nranks;
+  (void)S_words_alloc;
+  const u64 slot = shard_slot_words(total, nranks);
+  *lo = slot * (u64)rank; *hi = slot * (u64)(rank + 1);
 }
 
 void make_plan(const u64* off0, size_t nseq, int w, int k, int flag, u64 S_words_alloc, int nranks, int rank, ShardPlan* P) {
@@ -724,7 +726,12 @@ extern "C" int mm2_index_build_sharded(mm2_ctx_t* ctx, mm2_comm_t* comm, const u
   std::vector<u64> bounds;
   SB_TRY(shard_local(ctx, P, h_cat, off0.data(), nseq, w, k, b, flag, bounds));
   // the packed-sequence words of this rank, while its bytes are resident
-  SB_TRY(idx->S.ensure(std::max<u64>(1, idx->S_words_alloc) * 4));
+  const u64 s_slot = shard_slot_words(idx->total_len, R);
+  SB_TRY(idx->S.ensure(std::max<u64>(1, std::max<u64>(idx->S_words_alloc, s_slot * (u64)R)) * 4));
+  {
+    const u64 used = (idx->total_len + 7) / 8;
+    if (idx->S_words_alloc > used) SB_CUDA(cudaMemsetAsync(idx->S.as<u32>() + used, 0, (idx->S_words_alloc - used) * 4, st));   // index.rs:454: zero-filled
+  }
   ctx->timer.mark(st, "pack");
   SB_TRY(shard_pack(ctx, idx, P));
   // ---- phase 3: counts matrix, then the records
@@ -795,22 +802,34 @@ extern "C" int mm2_index_build_sharded(mm2_ctx_t* ctx, mm2_comm_t* comm, const u
   SB_CUDA(cudaMemcpyAsync(d_hist, part->occ_hist.data(), 65536 * 8, cudaMemcpyHostToDevice, st));
   std::vector<u64> big64(part->occ_big.begin(), part->occ_big.end());
   if (!big64.empty()) SB_CUDA(cudaMemcpyAsync(d_big + bo[(size_t)me], big64.data(), big64.size() * 8, cudaMemcpyHostToDevice, st));
+  // kv and p: every rank's part goes into an equal-sized slot of a staging buffer, ONE in-place ncclAllGather each replicates
+  // the slots (ring / NVLS at full NVLink rate; a broadcast per owner ran at a quarter of it), device copies close the gaps.
+  // S: the slots are equal by construction, so the all-gather is in place in the index array itself.
+  u64 maxk = 0, maxp = 0;
+  for (int r = 0; r < R; ++r) { maxk = std::max(maxk, sz[(size_t)r * 4]); maxp = std::max(maxp, sz[(size_t)r * 4 + 1]); }
+  const u64 kslot = maxk * 2, pslot = maxp;                     // u64 words per slot
+  SB_TRY(ctx->mg_stage.ensure(std::max<u64>(1, (kslot + pslot) * (u64)R) * 8));
+  u64* st_k = ctx->mg_stage.as<u64>();
+  u64* st_p = st_k + kslot * (u64)R;
+  if (part->n_keys) SB_CUDA(cudaMemcpyAsync(st_k + kslot * (u64)me, part->kv.p, part->n_keys * 16, cudaMemcpyDeviceToDevice, st));
+  if (part->n_p) SB_CUDA(cudaMemcpyAsync(st_p + pslot * (u64)me, part->p.p, part->n_p * 8, cudaMemcpyDeviceToDevice, st));
   SB_NCCL(N->GroupStart());
+  if (kslot) SB_NCCL(N->AllGather(st_k + kslot * (u64)me, st_k, kslot, ncclUint64, comm->comm, st));
+  if (pslot) SB_NCCL(N->AllGather(st_p + pslot * (u64)me, st_p, pslot, ncclUint64, comm->comm, st));
+  if (s_slot) SB_NCCL(N->AllGather(idx->S.as<u32>() + s_slot * (u64)me, idx->S.p, s_slot, ncclUint32, comm->comm, st));
   for (int r = 0; r < R; ++r) {
-    const u64 nk = sz[(size_t)r * 4], np = sz[(size_t)r * 4 + 1], ng = sz[(size_t)r * 4 + 2];
-    u64* kdst = idx->kv.as<u64>() + 2 * ko[(size_t)r];
-    u64* pdst = idx->p.as<u64>() + po[(size_t)r];
-    if (nk) SB_NCCL(N->Broadcast(r == me ? part->kv.p : (void*)kdst, kdst, nk * 2, ncclUint64, r, comm->comm, st));
-    if (np) SB_NCCL(N->Broadcast(r == me ? part->p.p : (void*)pdst, pdst, np, ncclUint64, r, comm->comm, st));
+    const u64 ng = sz[(size_t)r * 4 + 2];
     if (ng) SB_NCCL(N->Broadcast(d_big + bo[(size_t)r], d_big + bo[(size_t)r], ng, ncclUint64, r, comm->comm, st));
-    u64 w0, w1;
-    shard_words(idx->total_len, idx->S_words_alloc, R, r, &w0, &w1);
-    if (w1 > w0) SB_NCCL(N->Broadcast(idx->S.as<u32>() + w0, idx->S.as<u32>() + w0, w1 - w0, ncclUint32, r, comm->comm, st));
   }
   SB_NCCL(N->AllReduce(part->bkt_koff.p, idx->bkt_koff.p, nb + 1, ncclUint64, ncclSum, comm->comm, st));
   SB_NCCL(N->AllReduce(part->bkt_poff.p, idx->bkt_poff.p, nb + 1, ncclUint64, ncclSum, comm->comm, st));
   SB_NCCL(N->AllReduce(d_hist, d_hist, 65536, ncclUint64, ncclSum, comm->comm, st));
   SB_NCCL(N->GroupEnd());
+  for (int r = 0; r < R; ++r) {
+    const u64 nk = sz[(size_t)r * 4], np = sz[(size_t)r * 4 + 1];
+    if (nk) SB_CUDA(cudaMemcpyAsync(idx->kv.as<u64>() + 2 * ko[(size_t)r], st_k + kslot * (u64)r, nk * 16, cudaMemcpyDeviceToDevice, st));
+    if (np) SB_CUDA(cudaMemcpyAsync(idx->p.as<u64>() + po[(size_t)r], st_p + pslot * (u64)r, np * 8, cudaMemcpyDeviceToDevice, st));
+  }
   idx->occ_hist.assign(65536, 0);
   SB_CUDA(cudaMemcpyAsync(idx->occ_hist.data(), d_hist, 65536 * 8, cudaMemcpyDeviceToHost, st));
   big64.assign((size_t)tbig, 0);
@@ -855,7 +874,11 @@ extern "C" int mm2_index_build_sharded_emulated(mm2_ctx_t* ctx, int nranks, cons
 #define SE_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { mm2_set_error("%s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); return fail(MM2_E_CUDA); } } while (0)
   ctx->timer.reset();
   ctx->timer.mark(st, "h2d");
-  SE_TRY(idx->S.ensure(std::max<u64>(1, idx->S_words_alloc) * 4));
+  SE_TRY(idx->S.ensure(std::max<u64>(1, std::max<u64>(idx->S_words_alloc, shard_slot_words(idx->total_len, R) * (u64)R)) * 4));
+  {
+    const u64 used = (idx->total_len + 7) / 8;
+    if (idx->S_words_alloc > used) SE_CUDA(cudaMemsetAsync(idx->S.as<u32>() + used, 0, (idx->S_words_alloc - used) * 4, st));
+  }
   std::vector<std::vector<u64>> bounds((size_t)R);
   for (int r = 0; r < R; ++r) {
     ShardPlan P;

@@ -221,7 +221,8 @@ __global__ void chain_classify_kernel(ChainArgs G) {
   if (chain_is_dense(G, r)) G.dense[2 + atomicAdd(&G.dense[0], 1u)] = r;
 }
 
-// one warp per read (chain_ring_kernel)
+// one warp per read (chain_ring_kernel).  COUNT: also count DP cells (diagnostic; a compile-time switch, the bookkeeping costs ~5 %)
+template <bool COUNT>
 __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, const int lane) {
   const u64 a0 = G.read_aoff[r];
   const i64 n64 = (i64)(G.read_aoff[r + 1] - a0);
@@ -245,7 +246,7 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
   const int max_skip = min(max(p.max_chain_skip, -1), 0x3fffffff);
   const int max_iter = p.max_chain_iter;
   unsigned long long cells = 0;
-  const bool count_cells = G.cells != nullptr;   // a statistic (lchain.rs:80 iterations), not part of the result
+  constexpr bool count_cells = COUNT;            // a statistic (lchain.rs:80 iterations), not part of the result
   int best = 0;
   int4 bestA = make_int4(0, -1, 0, 0), bestB = make_int4(0, 0, 0, 0);
   bool t_init = false;
@@ -461,7 +462,7 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
     hit.flags |= 1u;
     __syncwarp();
   }
-  chain_finish(G, r, lane, an, A, a0, qlen, m0, m1, best, bestA, bestB, hit, cells);
+  chain_finish(G, r, lane, an, A, a0, qlen, m0, m1, best, bestA, bestB, hit, COUNT ? cells : 0ull);
 }
 
 #ifndef MM2_CH_OCC
@@ -1008,11 +1009,12 @@ __device__ __forceinline__ void chain_read_dense(const ChainArgs& G, const u32 r
 #endif
 }
 
+template <bool COUNT>
 __global__ void __launch_bounds__(CH_WARPS * 32, MM2_CH_OCC) chain_ring_kernel(ChainArgs G) {
   const u32 r = blockIdx.x * CH_WARPS + (threadIdx.x >> 5);
   if (r >= G.nreads) return;
   if (chain_is_dense(G, r)) return;                               // chain_dense_kernel's
-  chain_read(G, r, threadIdx.x & 31);
+  chain_read<COUNT>(G, r, threadIdx.x & 31);
 }
 
 // NW warps per dense read, one resident CTA per SM (the window ring and the two summary buffers take ~210 KB of shared memory).
@@ -1096,7 +1098,8 @@ int chain_batch(mm2_ctx* ctx, const ulonglong2* d_anchors, const u64* d_read_aof
     G.dense_ratio5 = ctx->chain_dense_ratio5;
     CUDA_TRY(cudaMemsetAsync(G.dense, 0, 8, ctx->stream));
     MM2_LAUNCH(ctx, chain_classify_kernel, (int)((nreads + 255) / 256), 256, 0, G);
-    MM2_LAUNCH(ctx, chain_ring_kernel, grid, CH_WARPS * 32, 0, G);
+    if (d_cells) MM2_LAUNCH(ctx, chain_ring_kernel<true>, grid, CH_WARPS * 32, 0, G);
+    else MM2_LAUNCH(ctx, chain_ring_kernel<false>, grid, CH_WARPS * 32, 0, G);
     // persistent CTAs (one per SM), one dense read at a time each; with no dense read they exit at once
     if (G.dense_min != 0x7fffffff) MM2_LAUNCH(ctx, chain_dense_kernel<DENSE_NW>, (int)std::min<u64>(nreads, (u64)ctx->n_sm), DENSE_NW * 32, DENSE_DYN, G);
   }

@@ -148,7 +148,7 @@ struct mm2_ctx {
   u64 last_cells = 0;
   DevBuf diag;
   DevBuf fine_tmp;               // index build: fine-bucket offsets (scratch of index_build_lookup)
-  DevBuf mg_recv_k, mg_recv_v;   // sharded index build: records received from the other ranks
+  DevBuf mg_recv_k, mg_recv_v, mg_stage;   // sharded index build: records received from the other ranks; all-gather staging
 };
 
 // The waits of the mapping path (minimizer total, anchor total, end of the batch).  cudaStreamSynchronize spins a host core; with

@@ -90,9 +90,7 @@ def _plan_worker(rank, world, port, q):
     if rank == 0:
         ok = True
         total = int(offs[-1])
-        words = 1
-        while words < (total + 7) // 8:
-            words *= 2
+        used = (total + 7) // 8
         for (w, k, flag), plans in res.items():
             tile = (k % 2 == 1) and not flag
             ok &= all(p["tile_path"] == int(tile) for p in plans)
@@ -107,7 +105,7 @@ def _plan_worker(rank, world, port, q):
                     ok &= p["sketch_byte_lo"] % 16 == 0 and p["sketch_byte_hi"] <= total
             else:
                 ok &= plans[-1]["hi"] == len(lens)
-            ok &= plans[0]["word_lo"] == 0 and plans[-1]["word_hi"] == words
+            ok &= plans[0]["word_lo"] == 0 and used <= plans[-1]["word_hi"] < used + world     # equal slots of ceil(used / world) words
             ok &= all(plans[r]["word_hi"] == plans[r + 1]["word_lo"] for r in range(world - 1))
         q.put(bool(ok))
     dist.barrier()
