@@ -299,6 +299,7 @@ int index_build_lookup(mm2_ctx* ctx, mm2_index* idx) {
 // (ckey, y) pairs sorted by ckey (stable: equal keys keep their input order).  The input arrays are scratch afterwards;
 // ctx->sorted_k / ctx->sorted_v point at the result.
 int radix_sort_pairs(mm2_ctx* ctx, u64* a_keys, u64* a_vals, u64* b_keys, u64* b_vals, u64 n, int end_bit, u64** res_keys, u64** res_vals);
+int radix_onesweep_pairs(mm2_ctx* ctx, u64* a_keys, u64* a_vals, u64* b_keys, u64* b_vals, u64 n, int end_bit, u64** res_keys, u64** res_vals);
 int radix_partition_by_owner(mm2_ctx* ctx, const u64* keys, const u64* vals, u64* out_keys, u64* out_vals, u64 n, int key_shift, int b, int nranks,
                              u64* d_bounds);
 static int index_sort_pairs(mm2_ctx* ctx, u64* ckey_in, u64* y_in, u64 n, int end_bit) {
@@ -306,7 +307,9 @@ static int index_sort_pairs(mm2_ctx* ctx, u64* ckey_in, u64* y_in, u64 n, int en
   MM2_TRY(ctx->sort_vals2.ensure(std::max<u64>(1, n) * 8));
   ctx->sorted_k = ctx->sort_keys2.as<u64>(); ctx->sorted_v = ctx->sort_vals2.as<u64>();
   if (n == 0) return MM2_OK;
-  return radix_sort_pairs(ctx, ckey_in, y_in, ctx->sort_keys2.as<u64>(), ctx->sort_vals2.as<u64>(), n, end_bit, &ctx->sorted_k, &ctx->sorted_v);
+  static const bool three_kernel = [] { const char* e = getenv("MM2_SORT"); return e && !strcmp(e, "3k"); }();   // A/B timing of the two pass structures
+  if (three_kernel) return radix_sort_pairs(ctx, ckey_in, y_in, ctx->sort_keys2.as<u64>(), ctx->sort_vals2.as<u64>(), n, end_bit, &ctx->sorted_k, &ctx->sorted_v);
+  return radix_onesweep_pairs(ctx, ckey_in, y_in, ctx->sort_keys2.as<u64>(), ctx->sort_vals2.as<u64>(), n, end_bit, &ctx->sorted_k, &ctx->sorted_v);
 }
 
 static int index_finish_from_sorted(mm2_ctx* ctx, mm2_index* idx, const u64* ckey, const u64* y, u64 n, bool build_table);
@@ -689,7 +692,7 @@ void finish_build_ms(mm2_ctx* ctx, mm2_index* idx) {
     const float t = ctx->timer.ms[i];
     if (nm == "sketch" || nm == "h2d") idx->build_ms[0] += t;
     else if (nm == "sort" || nm == "exchange") idx->build_ms[1] += t;
-    else if (nm == "bucket_build" || nm == "lookup_table" || nm == "replicate") idx->build_ms[2] += t;
+    else if (nm == "bucket_build" || nm == "lookup_table" || nm == "replicate" || nm == "rep_gather" || nm == "rep_compact") idx->build_ms[2] += t;
     else if (nm == "pack") idx->build_ms[3] += t;
     tot += t;
   }
@@ -805,6 +808,7 @@ extern "C" int mm2_index_build_sharded(mm2_ctx_t* ctx, mm2_comm_t* comm, const u
   // kv and p: every rank's part goes into an equal-sized slot of a staging buffer, ONE in-place ncclAllGather each replicates
   // the slots (ring / NVLS at full NVLink rate; a broadcast per owner ran at a quarter of it), device copies close the gaps.
   // S: the slots are equal by construction, so the all-gather is in place in the index array itself.
+  ctx->timer.mark(st, "rep_gather");
   u64 maxk = 0, maxp = 0;
   for (int r = 0; r < R; ++r) { maxk = std::max(maxk, sz[(size_t)r * 4]); maxp = std::max(maxp, sz[(size_t)r * 4 + 1]); }
   const u64 kslot = maxk * 2, pslot = maxp;                     // u64 words per slot
@@ -825,6 +829,7 @@ extern "C" int mm2_index_build_sharded(mm2_ctx_t* ctx, mm2_comm_t* comm, const u
   SB_NCCL(N->AllReduce(part->bkt_poff.p, idx->bkt_poff.p, nb + 1, ncclUint64, ncclSum, comm->comm, st));
   SB_NCCL(N->AllReduce(d_hist, d_hist, 65536, ncclUint64, ncclSum, comm->comm, st));
   SB_NCCL(N->GroupEnd());
+  ctx->timer.mark(st, "rep_compact");
   for (int r = 0; r < R; ++r) {
     const u64 nk = sz[(size_t)r * 4], np = sz[(size_t)r * 4 + 1];
     if (nk) SB_CUDA(cudaMemcpyAsync(idx->kv.as<u64>() + 2 * ko[(size_t)r], st_k + kslot * (u64)r, nk * 16, cudaMemcpyDeviceToDevice, st));

@@ -217,12 +217,7 @@ extern "C" void mm2_index_free(mm2_index_t* idx) {
   if (!idx) return;
   cudaSetDevice(idx->device);
   idx->S.release(); idx->kv.release(); idx->bkt_koff.release(); idx->bkt_poff.release();
-  const bool big = idx->tab.cap > ((size_t)4 << 30);
   idx->p.release(); idx->seq_len.release(); idx->tab.release(); idx->bloom.release();
-  if (big) {   // the pool keeps freed pages for the next build (a rebuilt 145 Mbp index reuses them); do not hoard tens of GB
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, idx->device) == cudaSuccess) { cudaDeviceSynchronize(); cudaMemPoolTrimTo(pool, (size_t)48 << 30); }   // keep one large index worth of pages for the next build
-  }
   delete idx;
 }
 

@@ -37,7 +37,7 @@ struct ChainArgs {
   int4* A; int4* B; int* T; int* W; int* chain;
   ReadHit* hits;
   unsigned long long* cells;
-  u32* dense;        // [0] number of dense reads, [1] ticket, [2..] their read indices (chain_classify_kernel)
+  u32* dense;        // [0] number of dense reads, [1] ticket, [2..9] reads per size class, [16 + class * nreads ..] their indices
   int dense_min;     // a read is dense when it has >= dense_min anchors and more than dense_ratio5 / 5 anchors per base
   int dense_ratio5;
 };
@@ -215,10 +215,27 @@ __device__ __forceinline__ bool chain_is_dense(const ChainArgs& G, u32 r) {
 
 // Reads with a dense anchor set (repeat-rich ultra-long reads: predecessor windows of thousands of anchors) are chained by
 // one CTA each (chain_dense_kernel); this kernel only lists them.
+// The list is kept in 8 size classes (anchor count 2^12 .. >= 2^19) and handed out largest class first: a dense read occupies
+// one CTA for its whole length, so starting the long reads first keeps the batch from waiting for a straggler at the end.
+constexpr int DENSE_BINS = 8;
+__device__ __forceinline__ int dense_bin(i64 n) { return min(max(63 - __clzll((unsigned long long)max(n, (i64)1)) - 12, 0), DENSE_BINS - 1); }
 __global__ void chain_classify_kernel(ChainArgs G) {
   const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= G.nreads) return;
-  if (chain_is_dense(G, r)) G.dense[2 + atomicAdd(&G.dense[0], 1u)] = r;
+  if (chain_is_dense(G, r)) {
+    const int b = dense_bin((i64)(G.read_aoff[r + 1] - G.read_aoff[r]));
+    atomicAdd(&G.dense[0], 1u);
+    G.dense[16 + (u64)b * G.nreads + atomicAdd(&G.dense[2 + b], 1u)] = r;
+  }
+}
+// ticket k (0 .. ndense-1) -> read: classes from the largest down
+__device__ __forceinline__ u32 dense_read_of_ticket(const ChainArgs& G, u32 k) {
+  for (int b = DENSE_BINS - 1; b >= 0; --b) {
+    const u32 c = G.dense[2 + b];
+    if (k < c) return G.dense[16 + (u64)b * G.nreads + k];
+    k -= c;
+  }
+  return 0;
 }
 
 // one warp per read (chain_ring_kernel).  COUNT: also count DP cells (diagnostic; a compile-time switch, the bookkeeping costs ~5 %)
@@ -1037,7 +1054,7 @@ __global__ void __launch_bounds__(NW * 32, 1) chain_dense_kernel(ChainArgs G) {
     __syncthreads();
     const u32 k = sh.next;
     if (k >= ndense) return;
-    chain_read_dense<NW>(G, G.dense[2 + k], lane, wid, &sh);
+    chain_read_dense<NW>(G, dense_read_of_ticket(G, k), lane, wid, &sh);
   }
 }
 
@@ -1091,12 +1108,12 @@ int chain_batch(mm2_ctx* ctx, const ulonglong2* d_anchors, const u64* d_read_aof
   G.dense = nullptr; G.dense_min = 0x7fffffff; G.dense_ratio5 = 0;
   const int grid = (int)((nreads + CH_WARPS - 1) / CH_WARPS);
   {
-    MM2_TRY(ctx->read_class.ensure(((size_t)nreads + 4) * 4));
+    MM2_TRY(ctx->read_class.ensure(((size_t)nreads * DENSE_BINS + 16) * 4));
     G.dense = ctx->read_class.as<u32>();
     // the CTA-per-read kernel keeps the window in shared memory: larger max_chain_iter values stay with the warp-per-read kernel
     G.dense_min = p.max_chain_iter <= DENSE_CAP - 64 ? ctx->chain_dense_min : 0x7fffffff;
     G.dense_ratio5 = ctx->chain_dense_ratio5;
-    CUDA_TRY(cudaMemsetAsync(G.dense, 0, 8, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(G.dense, 0, 64, ctx->stream));
     MM2_LAUNCH(ctx, chain_classify_kernel, (int)((nreads + 255) / 256), 256, 0, G);
     if (d_cells) MM2_LAUNCH(ctx, chain_ring_kernel<true>, grid, CH_WARPS * 32, 0, G);
     else MM2_LAUNCH(ctx, chain_ring_kernel<false>, grid, CH_WARPS * 32, 0, G);

@@ -49,14 +49,31 @@ struct DevBuf {
     if (bytes <= cap) return MM2_OK;
     release();
     size_t want = bytes + std::min<size_t>(bytes / 8, (size_t)64 << 20) + 256;   // growth slack, capped: index tables reach tens of GB
+    cudaError_t e = alloc(want);
+    if (e == cudaErrorMemoryAllocation) {
+      // The default pool keeps the pages of freed indexes for the next build (release threshold: unlimited).  When an
+      // allocation of either kind fails, hand that cache back to the driver and try once more.
+      cudaGetLastError();
+      int dev = 0;
+      cudaMemPool_t pool;
+      if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        cudaDeviceSynchronize();
+        cudaMemPoolTrimTo(pool, 0);
+        e = alloc(want);
+      }
+    }
+    if (e != cudaSuccess) { mm2_set_error("device allocation of %zu bytes failed: %s", want, cudaGetErrorString(e)); p = nullptr; cudaGetLastError(); return MM2_E_OOM; }
+    cap = want;
+    return MM2_OK;
+  }
+  cudaError_t alloc(size_t want) {
     cudaError_t e;
     if (pooled) {
       e = cudaMallocAsync(&p, want, (cudaStream_t)0);
       if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)0);
     } else e = cudaMalloc(&p, want);
-    if (e != cudaSuccess) { mm2_set_error("device allocation of %zu bytes failed: %s", want, cudaGetErrorString(e)); p = nullptr; cudaGetLastError(); return MM2_E_OOM; }
-    cap = want;
-    return MM2_OK;
+    if (e != cudaSuccess) p = nullptr;
+    return e;
   }
   void release() {
     if (p) {

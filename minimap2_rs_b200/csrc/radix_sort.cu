@@ -197,3 +197,165 @@ int radix_partition_by_owner(mm2_ctx* ctx, const u64* keys, const u64* vals, u64
   CUDA_TRY(cudaGetLastError());
   return MM2_OK;
 }
+
+// =====================================================================================================================
+// One-sweep variant of the sort passes (8-bit digits): every pass reads each pair ONCE.  All per-digit totals of all passes
+// come from one histogram kernel up front; inside a pass a tile publishes its per-digit counts and obtains its global offsets
+// by a decoupled look-back over the tiles before it (thread d follows digit d), so there is no separate histogram + scan per
+// pass.  Small tiles (2048 pairs, 256 threads x 8, ~40 KB of shared memory, <= 64 registers) keep 4 CTAs = 32 warps per SM in
+// flight; the three-kernel passes above sat at 2 CTAs / SM and were latency-bound (19 % warps active, 10 % issue-active).
+// Stable like the passes above: rows are ranked in order inside a warp, warps in order inside a tile, tiles by the look-back.
+namespace {
+constexpr int OS_NT = 256, OS_WARPS = OS_NT / 32, OS_IPT = 8, OS_TILE = OS_NT * OS_IPT, OS_BINS = 256;
+constexpr u32 OS_FLAG_AGG = 1u << 30, OS_FLAG_INCL = 2u << 30, OS_VAL = (1u << 30) - 1u;
+
+__global__ void __launch_bounds__(256) os_hist_kernel(const u64* __restrict__ keys, u64 n, int npass, unsigned long long* __restrict__ ghist) {
+  __shared__ u32 s_h[8][OS_BINS];
+  for (int x = threadIdx.x; x < 8 * OS_BINS; x += 256) (&s_h[0][0])[x] = 0;
+  __syncthreads();
+  for (u64 i = blockIdx.x * 256ull + threadIdx.x; i < n; i += (u64)gridDim.x * 256ull) {
+    const u64 k = keys[i];
+    for (int p = 0; p < npass; ++p) atomicAdd(&s_h[p][(u32)(k >> (8 * p)) & 255u], 1u);
+  }
+  __syncthreads();
+  for (int x = threadIdx.x; x < npass * OS_BINS; x += 256) {
+    const u32 c = (&s_h[0][0])[x];
+    if (c) atomicAdd(&ghist[x], (unsigned long long)c);
+  }
+}
+// exclusive scan of every pass's 256 totals (one CTA of 256 threads per pass)
+__global__ void __launch_bounds__(256) os_scan_kernel(unsigned long long* __restrict__ ghist) {
+  __shared__ unsigned long long s_w[8];
+  unsigned long long* h = ghist + (u64)blockIdx.x * OS_BINS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned long long v = h[threadIdx.x];
+  unsigned long long inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += t; }
+  if (lane == 31) s_w[warp] = inc;
+  __syncthreads();
+  unsigned long long base = 0;
+  for (int w = 0; w < warp; ++w) base += s_w[w];
+  h[threadIdx.x] = base + inc - v;
+}
+
+__global__ void __launch_bounds__(OS_NT, 4) os_pass_kernel(const u64* __restrict__ keys, const u64* __restrict__ vals, u64 n, int shift, u32 ntiles,
+                                                           const unsigned long long* __restrict__ gbase, u32* __restrict__ status, u32* __restrict__ ticket,
+                                                           u64* __restrict__ out_keys, u64* __restrict__ out_vals) {
+  __shared__ __align__(16) u64 sk[OS_TILE];
+  __shared__ __align__(16) u64 sv[OS_TILE];
+  __shared__ u16 s_cnt[OS_WARPS][OS_BINS];
+  __shared__ u64 s_gbase[OS_BINS];
+  __shared__ u16 s_toff[OS_BINS];
+  __shared__ u32 s_wsum[OS_WARPS];
+  __shared__ u32 s_tile;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
+  const u32 lt = (1u << lane) - 1u;
+  for (;;) {
+    __syncthreads();                                   // the previous tile's shared state is no longer in use
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);      // tiles in order: the look-back needs every earlier tile running or done
+#pragma unroll
+    for (int w = 0; w < OS_WARPS; ++w) s_cnt[w][tid] = 0;
+    __syncthreads();
+    const u32 tile = s_tile;
+    if (tile >= ntiles) return;
+    const u64 tbase = (u64)tile * OS_TILE;
+    const u64 wbase = tbase + (u64)warp * (OS_IPT * 32);
+    const u32 tile_n = (u32)min((u64)OS_TILE, n - tbase);
+    u64 k[OS_IPT];
+    u32 rk[OS_IPT];   // digit << 16 | rank inside the warp's slice
+#pragma unroll
+    for (int r = 0; r < OS_IPT; ++r) {
+      const u64 i = wbase + (u64)r * 32 + lane;
+      k[r] = i < n ? keys[i] : ~0ULL;
+    }
+#pragma unroll
+    for (int r = 0; r < OS_IPT; ++r) {
+      const bool in = wbase + (u64)r * 32 + lane < n;
+      const u32 d = in ? ((u32)(k[r] >> shift) & 255u) : 256u;   // out-of-range lanes form their own group
+      const u32 peers = __match_any_sync(0xFFFFFFFFu, d);
+      const int leader = __ffs(peers) - 1;
+      u32 old = 0;
+      if (lane == leader && in) { old = s_cnt[warp][d]; s_cnt[warp][d] = (u16)(old + __popc(peers)); }
+      old = __shfl_sync(0xFFFFFFFFu, old, leader);
+      rk[r] = (d << 16) | (old + __popc(peers & lt));
+      __syncwarp();
+    }
+    __syncthreads();
+    // thread d owns digit d: exclusive prefix of the per-warp counts, the tile's total, its place in the staged tile
+    u32 tot = 0;
+#pragma unroll
+    for (int w = 0; w < OS_WARPS; ++w) { const u32 c = s_cnt[w][tid]; s_cnt[w][tid] = (u16)tot; tot += c; }
+    volatile u32* st = status;
+    st[(u64)tile * OS_BINS + tid] = (tile == 0 ? OS_FLAG_INCL : OS_FLAG_AGG) | tot;
+    u32 inc = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const u32 t = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += t; }
+    if (lane == 31) s_wsum[warp] = inc;
+    __syncthreads();
+    u32 wb = 0;
+#pragma unroll
+    for (int w = 0; w < OS_WARPS; ++w) if (w < warp) wb += s_wsum[w];
+    const u32 toff = wb + inc - tot;
+    s_toff[tid] = (u16)toff;
+    // decoupled look-back for digit `tid`
+    u32 excl = 0;
+    if (tile != 0) {
+      for (i64 t = (i64)tile - 1;; --t) {
+        u32 v;
+        do { v = st[(u64)t * OS_BINS + tid]; } while ((v >> 30) == 0u);
+        excl += v & OS_VAL;
+        if ((v >> 30) == 2u) break;
+      }
+      st[(u64)tile * OS_BINS + tid] = OS_FLAG_INCL | (excl + tot);
+    }
+    s_gbase[tid] = (u64)gbase[tid] + (u64)excl - (u64)toff;   // output slot of staged slot i of digit d: s_gbase[d] + i
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < OS_IPT; ++r) {
+      const u64 i = wbase + (u64)r * 32 + lane;
+      if (i < n) {
+        const u32 d = rk[r] >> 16;
+        const u32 lp = s_toff[d] + s_cnt[warp][d] + (rk[r] & 0xFFFFu);
+        sk[lp] = k[r];
+        sv[lp] = vals[i];
+      }
+    }
+    __syncthreads();
+    for (u32 i = tid; i < tile_n; i += OS_NT) {   // consecutive staged slots of a digit go to consecutive addresses
+      const u64 kk = sk[i];
+      const u64 o = s_gbase[(u32)(kk >> shift) & 255u] + (u64)i;
+      out_keys[o] = kk;
+      out_vals[o] = sv[i];
+    }
+  }
+}
+}  // namespace
+
+// same contract as radix_sort_pairs; n < 2^30 (the 30-bit look-back counters), otherwise the caller uses radix_sort_pairs
+int radix_onesweep_pairs(mm2_ctx* ctx, u64* a_keys, u64* a_vals, u64* b_keys, u64* b_vals, u64 n, int end_bit, u64** res_keys, u64** res_vals) {
+  *res_keys = a_keys; *res_vals = a_vals;
+  if (n == 0) return MM2_OK;
+  const int npass = std::max(1, (end_bit + 7) / 8);
+  if (npass > 8 || n >= (1ull << 30)) return radix_sort_pairs(ctx, a_keys, a_vals, b_keys, b_vals, n, end_bit, res_keys, res_vals);
+  const u32 ntiles = (u32)((n + OS_TILE - 1) / OS_TILE);
+  const size_t status_bytes = (size_t)ntiles * OS_BINS * 4;
+  MM2_TRY(ctx->rs_counts.ensure(status_bytes + 64));                 // look-back status of one pass
+  MM2_TRY(ctx->rs_offs.ensure((size_t)8 * OS_BINS * 8 + 64 + 64));  // per-pass digit bases + tickets
+  unsigned long long* d_hist = ctx->rs_offs.as<unsigned long long>();
+  u32* d_ticket = reinterpret_cast<u32*>(d_hist + 8 * OS_BINS);
+  CUDA_TRY(cudaMemsetAsync(d_hist, 0, (size_t)8 * OS_BINS * 8 + 64, ctx->stream));
+  MM2_LAUNCH(ctx, os_hist_kernel, (int)std::min<u64>((n + 255) / 256, 148ull * 8), 256, 0, a_keys, n, npass, d_hist);
+  MM2_LAUNCH(ctx, os_scan_kernel, npass, 256, 0, d_hist);
+  const int grid = (int)std::min<u32>(ntiles, 148u * 4u);
+  u64 *src_k = a_keys, *src_v = a_vals, *dst_k = b_keys, *dst_v = b_vals;
+  for (int pass = 0; pass < npass; ++pass) {
+    CUDA_TRY(cudaMemsetAsync(ctx->rs_counts.p, 0, status_bytes, ctx->stream));
+    MM2_LAUNCH(ctx, os_pass_kernel, grid, OS_NT, 0, src_k, src_v, n, pass * 8, ntiles, d_hist + (size_t)pass * OS_BINS, ctx->rs_counts.as<u32>(),
+               d_ticket + pass, dst_k, dst_v);
+    std::swap(src_k, dst_k); std::swap(src_v, dst_v);
+  }
+  CUDA_TRY(cudaGetLastError());
+  *res_keys = src_k; *res_vals = src_v;
+  return MM2_OK;
+}

@@ -164,6 +164,7 @@ def run_c3(a):
         e["sharded_build_s"] = float(t[0])
         e["gbp_per_s"] = g.size / float(t[0]) / 1e9
         e["device_ms_rank0"] = gi.build_timings()
+        e["stages_ms_rank0"] = {kk: round(v, 2) for kk, v in ctx.last_timings().items()}
         e["stats"] = gi.stats()
         if rank == 0:
             t0 = time.perf_counter()
