@@ -320,3 +320,122 @@ def chain_dense_model(anchors, p, lut=None):
             pprev[i] = max_j
             v[i] = v[max_j] if (max_j >= 0 and v[max_j] > max_f) else max_f
     return f, pprev, v, cells
+
+
+def sketch_model_v4(seq, w, k, rid=0, region=2048, ch=8):
+    """Model of sketch_tile_kernel_v4 (csrc/sketch.cu): every tile owns T = region - 2w POSITIONS of one sequence.
+
+    * clean chunk (no N / sequence START in bases [c-w-k+1, c+ch-1+w]): position x is a minimizer iff its key equals the
+      minimum of some full window that holds it, i.e. the morphological opening (window minimum, then window maximum
+      of the minima over the next w windows) returns the key itself;
+    * dirty chunk: its positions are marked by a literal simulation of the steps of this chunk and the next
+      ceil((w + ch - 1) / ch) chunks (the by-step rules of sketch_model), each step seeded from the keys of its window.
+    The reference emits positions in ascending order and never twice, so the marked set IS the output."""
+    assert k % 2 == 1 and w >= ch + 1
+    c = _NT4[np.frombuffer(bytes(seq), dtype=np.uint8)].astype(np.int64)
+    L = c.size
+    valid = c < 4
+    idx = np.arange(L)
+    lastN = np.maximum.accumulate(np.where(valid, -1, idx)) if L else idx
+    l = idx - lastN
+    c2 = (c & 3).astype(np.uint64)
+    fwd = np.zeros(L, dtype=np.uint64)
+    rev = np.zeros(L, dtype=np.uint64)
+    for t in range(min(k, L)):
+        sh = np.zeros(L, dtype=np.uint64)
+        sh[t:] = c2[:L - t]
+        fwd |= sh << np.uint64(2 * t)
+        shc = np.zeros(L, dtype=np.uint64)
+        shc[t:] = np.uint64(3) - c2[:L - t]
+        rev |= shc << np.uint64(2 * (k - 1 - t))
+    mask = (1 << (2 * k)) - 1
+    z = (fwd >= rev).astype(np.uint64)
+    km = np.where(z == 0, fwd, rev)
+    gkey = np.where(l >= k, hash64(km, mask), U64MAX) if L else np.zeros(0, dtype=np.uint64)
+    T = region - 2 * w
+    D = (w + ch - 1) // ch
+    ntiles = max(1, (L + T - 1) // T)
+    marked = np.zeros(L, dtype=bool)
+
+    def K(p):  # key at sequence position p (outside: invalid)
+        return gkey[p] if 0 <= p < L else U64MAX
+
+    def isN(b):   # only real N: neither end of the sequence needs the by-step rules (see start_tie below)
+        return 0 <= b < L and not valid[b]
+
+    # The first w keys of a sequence: sketch.rs:80-86 treats ties among them specially (duplicates of the first partial
+    # minimum are emitted at l == w+k-1, and a minimum replaced before l reaches w+k is not).  With an equal pair there, the
+    # chunks that see the sequence start fall back to the by-step rules.
+    first = gkey[k - 1:k - 1 + w]
+    start_tie = first.size < w or np.unique(first).size < first.size or bool((first == U64MAX).any())
+    garbage = np.random.default_rng(L * 131 + w).integers(0, 1 << 40, size=region, dtype=np.uint64)
+
+    for tile in range(ntiles):
+        s = tile * T
+        P0 = s - w
+        nown = min(T, L - s)
+        nch = region // ch
+        # past the end of the sequence the kernel computes keys from whatever follows in the buffer: nothing may depend on them
+        key = np.array([K(P0 + u) if P0 + u < L else garbage[u] for u in range(region)], dtype=np.uint64)   # no k-mer before position k-1: KMAX
+        u_first = (k - 1) + (w - 1) - P0              # region index of the first full window
+        u_last = min(region - 1, L - 1 - P0)
+        has_end = (L - 1 - P0) <= region - 1
+        dirty = np.zeros(nch, dtype=bool)
+        for t in range(nch):
+            c0 = t * ch
+            lo, hi = P0 + c0 - w - k + 1, P0 + min(c0 + ch - 1 + w, region - 1)
+            dirty[t] = any(isN(b) for b in range(lo, hi + 1)) or (start_tie and lo < 0)
+        emit = np.zeros(region, dtype=bool)
+        # by-position, clean chunks
+        # windows that would run past the last k-mer of the sequence do not exist: M = 0 (below every key) for them
+        M = np.array([key[max(0, u - w + 1):u + 1].min() if u_first <= u <= u_last else 0 for u in range(region)], dtype=np.uint64)
+        for t in range(nch):
+            if dirty[t]:
+                continue
+            for x in range(t * ch, t * ch + ch):
+                if x + w - 1 < region and x - w + 1 >= 0 and P0 + x >= k - 1:
+                    if M[x:x + w].max() == key[x] and key[x] != U64MAX:
+                        emit[x] = True
+        # by-step, chunks within D of a dirty chunk
+        for t in range(nch):
+            if not dirty[max(0, t - D):t + 1].any():
+                continue
+            for u in range(t * ch, t * ch + ch):
+                if u < w or u > u_last:
+                    continue
+                i = P0 + u
+                li = l[i] if valid[i] else 0
+                win = key[u - w:u]                      # window of step u-1: [u-w, u-1]
+                mk = win.min()
+                prev = u - w + int(np.nonzero(win == mk)[0][-1])
+                kp = key[prev]
+                ki = key[u]
+                win2 = key[u - w + 1:u + 1]
+                mk2 = win2.min()
+                eq2 = np.nonzero(win2 == mk2)[0]
+                cur = u - w + 1 + int(eq2[-1])
+                if kp != U64MAX:
+                    if li == w + k - 1:
+                        for j in range(u - w + 1, u):
+                            if key[j] == kp and j != prev:
+                                emit[j] = True
+                    if ki <= kp:
+                        if li >= w + k:
+                            emit[prev] = True
+                    elif prev == u - w:
+                        if li >= w + k - 1:
+                            emit[prev] = True
+                            if key[cur] != U64MAX and eq2.size > 1:
+                                for j in range(u - w + 1, u + 1):
+                                    if key[j] == key[cur] and j != cur:
+                                        emit[j] = True
+                if has_end and u == u_last and key[cur] != U64MAX:
+                    emit[cur] = True
+        for x in range(w, w + max(nown, 0)):
+            if emit[x]:
+                marked[P0 + x] = True
+    pos = np.nonzero(marked)[0]
+    res = np.zeros(pos.size, dtype=[("key_span", "<u8"), ("rid_pos_strand", "<u8")])
+    res["key_span"] = (gkey[pos] << np.uint64(8)) | np.uint64(k)
+    res["rid_pos_strand"] = (np.uint64(rid) << np.uint64(32)) | (pos.astype(np.uint64) << np.uint64(1)) | z[pos]
+    return res

@@ -19,6 +19,26 @@ def test_sketch_model_matches_oracle(orc):
             assert a.size == m.size and (a == m).all(), (name, w, k)
 
 
+def test_sketch_model_v4_matches_oracle(orc):
+    """the by-position restatement of sketch_tile_kernel_v4 (opening of the key sequence + by-step marking of dirty
+    chunks) on small regions, so that tile boundaries, N runs, sequence ends and tie-rich windows all meet"""
+    for w, k in [(10, 15), (9, 5), (19, 7), (12, 3)]:
+        for name, s in cases.sketch_cases():
+            if len(s) > 3100:
+                continue
+            a = orc.sketch(s, w, k, rid=2)
+            m = models.sketch_model_v4(s, w, k, rid=2, region=256 if w < 20 else 512)
+            assert a.size == m.size and (a == m).all(), (name, w, k)
+    rng = np.random.default_rng(12)
+    for it in range(400):
+        w = int(rng.integers(9, 24))
+        k = int(rng.choice([3, 5, 7, 9, 15]))
+        s = cases.rnd_seq(rng, int(rng.integers(1, 700)), ["AC", "ACGT", "A", "ACGTN", "AT", "ACGTNNN"][int(rng.integers(0, 6))])
+        a = orc.sketch(s, w, k, rid=1)
+        m = models.sketch_model_v4(s, w, k, rid=1, region=int(rng.choice([128, 256])))
+        assert a.size == m.size and (a == m).all(), (it, w, k, len(s))
+
+
 def test_sketch_properties(orc):
     rng = np.random.default_rng(5)
     s = cases.rnd_seq(rng, 50_000)

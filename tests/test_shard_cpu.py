@@ -96,7 +96,7 @@ def _plan_worker(rank, world, port, q):
             ok &= all(p["tile_path"] == int(tile) for p in plans)
             ok &= plans[0]["lo"] == 0 and all(plans[r]["hi"] == plans[r + 1]["lo"] for r in range(world - 1))   # shares tile the list
             if tile:
-                T = 2048 - w
+                T = 2048 - 2 * w if w >= 9 else 2048 - w   # positions (w >= 9) or steps per sketch tile
                 ntiles = sum(max(1, (l + T - 1) // T) for l in lens)
                 ok &= plans[-1]["hi"] == ntiles
                 # a rank uploads about 1 / world of the genome although sequences are far from balanced
