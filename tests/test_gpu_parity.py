@@ -43,6 +43,33 @@ def test_sketch_batch_many_sequences(ctx, orc):
     _eq(mv0, want, "rid 0 batch")
 
 
+def test_sketch_concurrent_contexts(mm2, orc, gen):
+    """four contexts sketch the same batch at the same time (what the pipelined mapping path does): the kernels of different
+    launches share the SMs, so that a CTA runs with fewer resident neighbours and other timings than alone"""
+    import threading
+    g = gen.genome(52, 1_000_000)
+    offs = np.array([0, g.size], dtype=np.uint64)
+    cat, roffs = gen.reads(9, g, offs, 1500, 4000, 0.03, 0.03, 0.03)
+    ctxs = [mm2.Context(0) for _ in range(4)]
+    want, wo = ctxs[0].sketch_batch(cat, roffs, 10, 15)
+    for i in (0, 7, 1499):
+        _eq(want[int(wo[i]):int(wo[i + 1])], orc.sketch(bytes(cat[int(roffs[i]):int(roffs[i + 1])]), 10, 15, rid=0), "read %d" % i)
+    bad = []
+
+    def work(c):
+        for rep in range(6):
+            mv, mo = c.sketch_batch(cat, roffs, 10, 15)
+            if mv.size != want.size or not (mv == want).all() or not (mo == wo).all():
+                bad.append(rep)
+
+    th = [threading.Thread(target=work, args=(c,)) for c in ctxs]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not bad
+
+
 def test_sketch_rejects_what_the_reference_asserts_on(ctx, mm2):
     for args in ((b"", 10, 15), (b"ACGT", 0, 15), (b"ACGT", 256, 15), (b"ACGT", 10, 0), (b"ACGT", 10, 29)):
         with pytest.raises(mm2.Mm2Error) as e:
