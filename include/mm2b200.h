@@ -198,6 +198,17 @@ int mm2_map_batch(mm2_ctx_t* ctx, const mm2_index_t* idx, const uint8_t* cat, co
  * host copy of the offsets).  Only the records travel D2H. */
 int mm2_map_batch_device(mm2_ctx_t* ctx, const mm2_index_t* idx, const void* d_cat, const void* d_offs,
                          const uint64_t* h_offs, size_t nreads, const mm2_map_opts_t* opts, mm2_map_result_t* out);
+/* The same with the reads as 2-bit codes: a quarter of the H2D bytes (the link, not the kernels, bounds mm2_map_batch from
+ * host memory, and eight GPUs behind one host share it).  packed: base i of the concatenation in bits 2*(i%4) of byte
+ * i/4, codes A0 C1 G2 T3 (nt4.rs:2-10); n_pos: ascending positions of the bases that are not ACGTacgt (nt4 code 4; they
+ * are restored as 'N', which sketch.rs cannot tell from the original letter).  offs as in mm2_map_batch, in bases;
+ * offs[0] must be a multiple of 16.  Results are identical to mm2_map_batch on the ASCII reads. */
+int mm2_map_batch_packed(mm2_ctx_t* ctx, const mm2_index_t* idx, const uint8_t* packed, const uint64_t* n_pos, size_t n_n,
+                         const uint64_t* offs, size_t nreads, const mm2_map_opts_t* opts, mm2_map_result_t* out);
+/* host helper: ASCII -> the two arrays above.  packed holds (n_bases + 3) / 4 bytes (round the allocation up to a multiple
+ * of 4 bytes plus 64: the upload moves whole 16-base words); *n_n is the number of non-ACGT bases, of which the first
+ * n_cap positions were written. */
+int mm2_pack_reads(const uint8_t* cat, uint64_t n_bases, uint8_t* packed, uint64_t* n_pos, size_t n_cap, size_t* n_n);
 void mm2_map_result_free(mm2_map_result_t* r);
 
 /* paf.rs:224 write_paf: formats one record; returns the number of bytes written (no NUL counted), < 0 on error */

@@ -65,7 +65,8 @@ ABI_SYMBOLS = [
     "mm2_index_load_native", "mm2_index_load_auto", "mm2_index_free", "mm2_index_get", "mm2_index_stats",
     "mm2_index_calc_mid_occ", "mm2_index_params", "mm2_index_seq", "mm2_index_get_ref_subseq", "mm2_index_build_timings",
     "mm2_filter_query_minimizers", "mm2_build_anchors_filtered", "mm2_chain_dp_all", "mm2_chains_free",
-    "mm2_default_chain_params", "mm2_default_map_opts", "mm2_map_batch", "mm2_map_batch_device", "mm2_map_result_free",
+    "mm2_default_chain_params", "mm2_default_map_opts", "mm2_map_batch", "mm2_map_batch_device", "mm2_map_batch_packed", "mm2_pack_reads",
+    "mm2_map_result_free",
     "mm2_paf_format", "mm2_paf_format_batch", "mm2_comm_get_unique_id", "mm2_comm_create", "mm2_comm_destroy", "mm2_comm_rank",
     "mm2_comm_barrier", "mm2_index_build_sharded", "mm2_index_build_sharded_emulated", "mm2_index_build_multi",
 ]
@@ -131,6 +132,8 @@ def lib():
     L.mm2_default_map_opts.restype = None
     L.mm2_map_batch.argtypes = [vp, vp, vp, vp, sz, C.POINTER(MapOpts), C.POINTER(_MapResult)]
     L.mm2_map_batch_device.argtypes = [vp, vp, vp, vp, vp, sz, C.POINTER(MapOpts), C.POINTER(_MapResult)]
+    L.mm2_map_batch_packed.argtypes = [vp, vp, vp, vp, sz, vp, sz, C.POINTER(MapOpts), C.POINTER(_MapResult)]
+    L.mm2_pack_reads.argtypes = [vp, C.c_uint64, vp, vp, sz, C.POINTER(sz)]
     L.mm2_map_result_free.argtypes = [C.POINTER(_MapResult)]
     L.mm2_paf_format.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p, sz]
     L.mm2_paf_format_batch.argtypes = [vp, C.POINTER(_MapResult), vp, C.POINTER(vp), C.POINTER(sz)]
@@ -342,6 +345,17 @@ class Context:
                                               offs.ctypes.data, offs.size - 1, C.byref(opts), C.byref(res)))
         return MapResult(idx, res, offs.size - 1)
 
+    def map_batch_packed(self, idx, packed, n_pos, offs, opts=None):
+        """reads as 2-bit codes + positions of the non-ACGT bases (pack_reads): a quarter of the H2D bytes of map_batch"""
+        opts = opts or default_map_opts(idx.w, idx.k)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        n_pos = np.ascontiguousarray(n_pos, dtype=np.uint64)
+        assert isinstance(packed, np.ndarray) and packed.dtype == np.uint8 and packed.flags.c_contiguous
+        res = _MapResult()
+        _check(lib().mm2_map_batch_packed(self.h, idx.h, packed.ctypes.data, n_pos.ctypes.data if n_pos.size else None, n_pos.size,
+                                          offs.ctypes.data, offs.size - 1, C.byref(opts), C.byref(res)))
+        return MapResult(idx, res, offs.size - 1)
+
     def close(self):
         if getattr(self, "h", None):
             lib().mm2_ctx_destroy(self.h)
@@ -352,6 +366,24 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+def pack_reads(cat, out=None):
+    """mm2_pack_reads: ASCII bases -> (packed 2-bit codes, positions of the bases that are not ACGTacgt).
+    out: optional uint8 buffer of at least (n + 3) // 4 + 64 bytes (e.g. page-locked)"""
+    cat = cat if isinstance(cat, np.ndarray) and cat.dtype == np.uint8 and cat.flags.c_contiguous else as_u8(cat)
+    n = cat.size
+    need = (n + 3) // 4 + 64
+    packed = out if out is not None else np.zeros(need, dtype=np.uint8)
+    assert packed.size >= need
+    cap = 1024
+    while True:
+        n_pos = np.zeros(cap, dtype=np.uint64)
+        nn = C.c_size_t()
+        _check(lib().mm2_pack_reads(cat.ctypes.data, n, packed.ctypes.data, n_pos.ctypes.data, cap, C.byref(nn)))
+        if nn.value <= cap:
+            return packed, n_pos[:nn.value].copy()
+        cap = nn.value
 
 
 class Comm:

@@ -737,8 +737,71 @@ extern "C" int mm2_map_batch_device(mm2_ctx_t* ctx, const mm2_index_t* idx, cons
 }
 
 // one sub-batch from host memory on `ctx`: H2D of the reads, the device pipeline, D2H of the hits
+// ---- reads as 2-bit codes (mm2_map_batch_packed): a quarter of the H2D bytes; unpacked to the ASCII layout on the device ----
+namespace {
+struct PackedSrc { const u8* packed; const u64* n_pos; size_t n_n; u64* d_npos; };   // d_npos: the positions, resident
+// 16 bases per thread: one packed word -> 16 letters (a 16-byte store).  first: 16-base group of the first thread.
+// first_valid: bases below it (in the first group) belong to an earlier upload whose N stamps must survive.
+__global__ void unpack_reads_kernel(const u32* __restrict__ packed, u64 group_lo, u64 ngroups, u64 group_base, u64 first_valid, uint4* __restrict__ out) {
+  const u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ngroups) return;
+  const u32 wd = packed[group_lo - group_base + g];
+  u32 o[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    u32 x = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const u32 c = (wd >> (8 * q + 2 * j)) & 3u;
+      x |= ((0x54474341u >> (8 * c)) & 0xFFu) << (8 * j);     // "ACGT"[c]
+    }
+    o[q] = x;
+  }
+  const u64 b16 = 16 * (group_lo + g);
+  if (b16 >= first_valid) out[group_lo - group_base + g] = make_uint4(o[0], o[1], o[2], o[3]);
+  else {
+    u8* ob = reinterpret_cast<u8*>(out + (group_lo - group_base + g));
+    for (int j = 0; j < 16; ++j) if (b16 + j >= first_valid) ob[j] = (u8)(o[j >> 2] >> (8 * (j & 3)));
+  }
+}
+__global__ void stamp_n_kernel(const u64* __restrict__ pos, u64 n, u64 base, u8* __restrict__ seq) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) seq[pos[i] - base] = (u8)'N';
+}
+}  // namespace
+// bases [b0, b1) of the batch (relative to `base`) -> ctx->seq, on stream st: a plain copy, or packed copy + unpack + N stamps
+static cudaError_t upload_reads(mm2_ctx* ctx, cudaStream_t st, const u8* cat, const PackedSrc* pk, u64 base, u64 b0, u64 b1) {
+  if (b1 <= b0) return cudaSuccess;
+  if (!pk) return cudaMemcpyAsync(ctx->seq.as<u8>() + b0, cat + base + b0, b1 - b0, cudaMemcpyHostToDevice, st);
+  const u64 gb = base / 16, g0 = (base + b0) / 16, g1 = (base + b1 + 15) / 16;   // base is a multiple of 16 (checked by the caller)
+  cudaError_t e = cudaMemcpyAsync(ctx->packed.as<u8>() + 4 * (g0 - gb), pk->packed + 4 * g0, 4 * (g1 - g0), cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return e;
+  unpack_reads_kernel<<<(unsigned)((g1 - g0 + 255) / 256), 256, 0, st>>>(ctx->packed.as<u32>(), g0, g1 - g0, gb, base + b0, ctx->seq.as<uint4>());
+  ctx->launches += 1;
+  if (pk->n_n) {
+    const u64* lo = std::lower_bound(pk->n_pos, pk->n_pos + pk->n_n, base + b0);
+    const u64* hi = std::lower_bound(pk->n_pos, pk->n_pos + pk->n_n, base + b1);
+    if (hi > lo) {
+      stamp_n_kernel<<<(unsigned)((hi - lo + 255) / 256), 256, 0, st>>>(pk->d_npos + (lo - pk->n_pos), (u64)(hi - lo), base, ctx->seq.as<u8>());
+      ctx->launches += 1;
+    }
+  }
+  return cudaGetLastError();
+}
+// device buffers of a packed batch (+ the N positions, uploaded once, on stream st)
+static int packed_prepare(mm2_ctx* ctx, cudaStream_t st, PackedSrc* pk, u64 total) {
+  MM2_TRY(ctx->packed.ensure(total / 4 + 64));
+  pk->d_npos = nullptr;
+  if (pk->n_n) {
+    MM2_TRY(ctx->packed_n.ensure(pk->n_n * 8));
+    pk->d_npos = ctx->packed_n.as<u64>();
+    CUDA_TRY(cudaMemcpyAsync(pk->d_npos, pk->n_pos, pk->n_n * 8, cudaMemcpyHostToDevice, st));
+  }
+  return MM2_OK;
+}
+
 static int map_host_single(mm2_ctx* ctx, const mm2_index* idx, const u8* cat, const u64* offs, size_t nreads, const mm2_map_opts_t* opts,
-                           mm2_map_result_t* out) {
+                           mm2_map_result_t* out, PackedSrc* pk = nullptr) {
   CUDA_TRY(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const u64 base = nreads ? offs[0] : 0, total = nreads ? offs[nreads] - base : 0;
@@ -755,7 +818,8 @@ static int map_host_single(mm2_ctx* ctx, const mm2_index* idx, const u8* cat, co
     static std::mutex h2d_mutex;
     std::lock_guard<std::mutex> lk(h2d_mutex);
     mm2_trace(ctx, "h2d start");
-    if (total) CUDA_TRY(cudaMemcpyAsync(ctx->seq.p, cat + base, total, cudaMemcpyHostToDevice, st));
+    if (pk) MM2_TRY(packed_prepare(ctx, st, pk, total));
+    CUDA_TRY(upload_reads(ctx, st, cat, pk, base, 0, total));
     memcpy(ctx->pin_in.p, off0.data(), (nreads + 1) * 8);  // pinned bounce: pageable sources serialise the streams
     CUDA_TRY(cudaMemcpyAsync(ctx->seq_off.p, ctx->pin_in.p, (nreads + 1) * 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -768,7 +832,7 @@ static int map_host_single(mm2_ctx* ctx, const mm2_index* idx, const u8* cat, co
 // host thread), so the H2D copy and the host-side record assembly of one sub-batch overlap the kernels of the other.
 // Reads are independent (main.rs:193-219), so the records are simply concatenated in input order.
 static int map_host_pipelined(mm2_ctx* ctx, const mm2_index* idx, const u8* cat, const u64* offs, size_t nreads,
-                              const mm2_map_opts_t* opts, mm2_map_result_t* out, size_t nsub) {
+                              const mm2_map_opts_t* opts, mm2_map_result_t* out, size_t nsub, PackedSrc* pk = nullptr) {
   const int NW = ctx->n_workers;
   for (int w = 0; w < NW; ++w)
     if (!ctx->worker[w]) MM2_TRY(mm2_ctx_create(ctx->device, &ctx->worker[w]));
@@ -788,6 +852,7 @@ static int map_host_pipelined(mm2_ctx* ctx, const mm2_index* idx, const u8* cat,
   MM2_TRY(ctx->seq.ensure(total + 64));
   MM2_TRY(ctx->seq_off.ensure((nreads + 1) * 8));
   MM2_TRY(ctx->pin_in.ensure((nreads + 1) * 8));
+  if (pk) MM2_TRY(packed_prepare(ctx, ctx->copy_stream, pk, total));
   u64* h_off0 = ctx->pin_in.as<u64>();
   for (size_t i = 0; i <= nreads; ++i) h_off0[i] = offs[i] - base;
   // sub-batch boundaries balanced by bases; the first sub-batch is split 1/4 + 3/4 so that the kernels start after a quarter
@@ -838,7 +903,7 @@ static int map_host_pipelined(mm2_ctx* ctx, const mm2_index* idx, const u8* cat,
     cudaError_t e = cudaMemcpyAsync(ctx->seq_off.p, h_off0, (nreads + 1) * 8, cudaMemcpyHostToDevice, cs);
     for (size_t sidx = 0; sidx < nsub && e == cudaSuccess; ++sidx) {
       const u64 b0 = h_off0[cut[sidx]], b1 = h_off0[cut[sidx + 1]];
-      if (b1 > b0) e = cudaMemcpyAsync(ctx->seq.as<u8>() + b0, cat + base + b0, b1 - b0, cudaMemcpyHostToDevice, cs);
+      e = upload_reads(ctx, cs, cat, pk, base, b0, b1);
       if (e == cudaSuccess) e = cudaEventRecord(ctx->copy_events[sidx], cs);
       if (e == cudaSuccess) n_issued.store(sidx + 1, std::memory_order_release);
     }
@@ -870,19 +935,20 @@ static int map_host_pipelined(mm2_ctx* ctx, const mm2_index* idx, const u8* cat,
   return MM2_OK;
 }
 
-extern "C" int mm2_map_batch(mm2_ctx_t* ctx, const mm2_index_t* idx, const uint8_t* cat, const uint64_t* offs, size_t nreads,
-                             const mm2_map_opts_t* opts, mm2_map_result_t* out) {
-  if (!ctx || !idx || !offs || !opts || !out || (nreads && !cat)) { mm2_set_error("mm2_map_batch: NULL argument"); return MM2_E_ARG; }
+static int map_host_any(mm2_ctx_t* ctx, const mm2_index_t* idx, const uint8_t* cat, PackedSrc* pk, const uint64_t* offs, size_t nreads,
+                        const mm2_map_opts_t* opts, mm2_map_result_t* out) {
   if (idx->device != ctx->device) { mm2_set_error("index lives on device %d, context on %d", idx->device, ctx->device); return MM2_E_ARG; }
   const u64 total = nreads ? offs[nreads] - offs[0] : 0;
   // sub-batches of ~64 Mbase (MM2_SUBBATCH_MB) over 4 worker contexts (MM2_WORKERS): measured best on configs[1]; small batches and stage dumps take the single-context path
-  size_t nsub = (size_t)std::min<u64>(64, total / ctx->subbatch_bytes);
+  // (packed reads: the upload of a sub-batch is four times shorter, twice the sub-batch size was measured best: 18.9 vs 19.8 ms)
+  const u64 sub_bytes = ctx->subbatch_bytes * (pk ? 2 : 1);
+  size_t nsub = (size_t)std::min<u64>(64, total / sub_bytes);
   if (nsub > nreads) nsub = nreads;
   if (nsub >= 2 && !opts->want_stage_dump && ctx->pipeline) {
     // the pipelined path keeps the whole batch resident: batches above MM2_RESIDENT_MB (default 4096) go through it in pieces
     const char* e_res = getenv("MM2_RESIDENT_MB");
     const u64 resident = (u64)(e_res && atoll(e_res) > 0 ? atoll(e_res) : 4096) << 20;
-    if (total <= resident) return map_host_pipelined(ctx, idx, cat, offs, nreads, opts, out, nsub);
+    if (total <= resident) return map_host_pipelined(ctx, idx, cat, offs, nreads, opts, out, nsub, pk);
     std::vector<size_t> first;
     std::vector<mm2_map_result_t> part;
     size_t lo = 0;
@@ -890,12 +956,13 @@ extern "C" int mm2_map_batch(mm2_ctx_t* ctx, const mm2_index_t* idx, const uint8
       size_t hi = (size_t)(std::upper_bound(offs + lo, offs + nreads + 1, offs[lo] + resident) - offs) - 1;
       if (hi <= lo) hi = lo + 1;
       if (hi > nreads) hi = nreads;
+      if (pk) while (hi < nreads && (offs[hi] & 15)) ++hi;   // packed pieces start on a 16-base boundary
       const u64 piece = offs[hi] - offs[lo];
-      size_t ns = (size_t)std::min<u64>(64, piece / ctx->subbatch_bytes);
+      size_t ns = (size_t)std::min<u64>(64, piece / sub_bytes);
       if (ns > hi - lo) ns = hi - lo;
       mm2_map_result_t r;
       memset(&r, 0, sizeof r);
-      const int rc = ns >= 2 ? map_host_pipelined(ctx, idx, cat, offs + lo, hi - lo, opts, &r, ns) : map_host_single(ctx, idx, cat, offs + lo, hi - lo, opts, &r);
+      const int rc = ns >= 2 ? map_host_pipelined(ctx, idx, cat, offs + lo, hi - lo, opts, &r, ns, pk) : map_host_single(ctx, idx, cat, offs + lo, hi - lo, opts, &r, pk);
       if (rc != MM2_OK) { for (auto& p : part) mm2_map_result_free(&p); return rc; }
       part.push_back(r); first.push_back(lo);
       lo = hi;
@@ -904,7 +971,39 @@ extern "C" int mm2_map_batch(mm2_ctx_t* ctx, const mm2_index_t* idx, const uint8
     merge_map_results(part.data(), first.data(), part.size(), out);
     return MM2_OK;
   }
-  return map_host_single(ctx, idx, cat, offs, nreads, opts, out);
+  return map_host_single(ctx, idx, cat, offs, nreads, opts, out, pk);
+}
+
+extern "C" int mm2_map_batch(mm2_ctx_t* ctx, const mm2_index_t* idx, const uint8_t* cat, const uint64_t* offs, size_t nreads,
+                             const mm2_map_opts_t* opts, mm2_map_result_t* out) {
+  if (!ctx || !idx || !offs || !opts || !out || (nreads && !cat)) { mm2_set_error("mm2_map_batch: NULL argument"); return MM2_E_ARG; }
+  return map_host_any(ctx, idx, cat, nullptr, offs, nreads, opts, out);
+}
+
+extern "C" int mm2_map_batch_packed(mm2_ctx_t* ctx, const mm2_index_t* idx, const uint8_t* packed, const uint64_t* n_pos, size_t n_n,
+                                    const uint64_t* offs, size_t nreads, const mm2_map_opts_t* opts, mm2_map_result_t* out) {
+  if (!ctx || !idx || !offs || !opts || !out || (nreads && !packed) || (n_n && !n_pos)) { mm2_set_error("mm2_map_batch_packed: NULL argument"); return MM2_E_ARG; }
+  if (nreads && (offs[0] & 15)) { mm2_set_error("mm2_map_batch_packed: offs[0] must be a multiple of 16 bases"); return MM2_E_ARG; }
+  PackedSrc pk{packed, n_pos, n_n, nullptr};
+  return map_host_any(ctx, idx, nullptr, &pk, offs, nreads, opts, out);
+}
+
+// nt4.rs:2-10 on the host: ASCII -> 2-bit codes + the positions of everything that is not ACGTacgt
+extern "C" int mm2_pack_reads(const uint8_t* cat, uint64_t n_bases, uint8_t* packed, uint64_t* n_pos, size_t n_cap, size_t* n_n) {
+  if ((n_bases && (!cat || !packed)) || !n_n) { mm2_set_error("mm2_pack_reads: NULL argument"); return MM2_E_ARG; }
+  static const struct Tab { u8 t[256]; Tab() { memset(t, 4, 256); t['A'] = t['a'] = 0; t['C'] = t['c'] = 1; t['G'] = t['g'] = 2; t['T'] = t['t'] = 3; } } tab;
+  size_t nn = 0;
+  for (u64 i = 0; i < n_bases; i += 4) {
+    u8 b = 0;
+    for (u64 j = i; j < i + 4 && j < n_bases; ++j) {
+      const u8 c = tab.t[cat[j]];
+      if (c > 3) { if (nn < n_cap && n_pos) n_pos[nn] = j; ++nn; }
+      b |= (u8)((c & 3) << (2 * (j - i)));
+    }
+    packed[i / 4] = b;
+  }
+  *n_n = nn;   // > n_cap: call again with a larger n_pos
+  return MM2_OK;
 }
 
 extern "C" void mm2_map_result_free(mm2_map_result_t* r) {

@@ -140,6 +140,7 @@ struct mm2_ctx {
   StageTimer timer;
   // scratch arenas (named by first use; all only ever grow)
   DevBuf seq, seq_off, tile_seq, tile_first, tile_status, misc;      // sketch inputs / bookkeeping
+  DevBuf packed, packed_n;                                           // mm2_map_batch_packed: 2-bit reads, N positions
   DevBuf mkey, mval, mini_off;                                       // minimizers (SoA) + per-sequence offsets
   DevBuf keep, occ_cnt, occ_loc, anchor_off_m, scan_status;          // filter / lookup
   DevBuf anchors, read_aoff, read_class;                             // anchors

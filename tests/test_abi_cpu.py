@@ -48,3 +48,21 @@ def test_default_params_match_reference_values(mm2):
     assert mm2.apply_preset("map-hifi", 10, 15) == (10, 19) and mm2.apply_preset("sr", 10, 15) == (11, 21)
     o = mm2.default_map_opts()
     assert (o.w, o.k, o.max_gap, o.min_cnt, o.min_chain_score, o.best_n) == (10, 15, 5000, 3, 40, 5)
+
+
+def test_pack_reads_host_helper(mm2):
+    """mm2_pack_reads (host only): nt4.rs:2-10 codes, 4 per byte, + the positions of everything else"""
+    import numpy as np
+    rng = np.random.default_rng(3)
+    cat = rng.choice(np.frombuffer(b"ACGTacgtNnRY", dtype=np.uint8), 10_003).astype(np.uint8)
+    packed, n_pos = mm2.pack_reads(cat)
+    nt4 = np.full(256, 4, dtype=np.uint8)
+    for i, ch in enumerate(b"ACGT"):
+        nt4[ch] = i
+        nt4[ch + 32] = i
+    codes = nt4[cat]
+    assert (n_pos == np.nonzero(codes == 4)[0]).all()
+    got = (packed[np.arange(cat.size) // 4] >> (2 * (np.arange(cat.size) % 4)).astype(np.uint8)) & 3
+    assert (got[codes < 4] == codes[codes < 4]).all() and (got[codes == 4] == 0).all()
+    p2, n2 = mm2.pack_reads(np.frombuffer(b"N" * 5000, dtype=np.uint8))     # more positions than the first capacity guess
+    assert n2.size == 5000

@@ -494,6 +494,35 @@ def test_cli_index_align_anchors_chain(ctx, mm2, orc, gen, tmp_path):
     assert out.returncode == 1 and out.stderr.startswith("Error:")
 
 
+def test_map_batch_packed_equals_ascii(mm2, orc, gen):
+    """mm2_map_batch_packed (2-bit reads + positions of the non-ACGT bases) == mm2_map_batch on the ASCII reads, on the single
+    path and on the pipelined path (sub-batch boundaries inside 16-base words, N and IUPAC letters next to them)"""
+    g = gen.genome(53, 1_500_000)
+    offs = np.array([0, g.size], dtype=np.uint64)
+    cat, roffs = gen.reads(10, g, offs, 2500, 3001, 0.03, 0.03, 0.03)      # odd read length: reads start inside 16-base words
+    cat = cat.copy()
+    rng = np.random.default_rng(6)
+    for p in rng.integers(0, cat.size, 4000):
+        cat[p] = rng.choice(np.frombuffer(b"NnRYacgt", dtype=np.uint8))
+    for lo in rng.integers(0, cat.size - 200, 30):
+        cat[lo:lo + int(rng.integers(1, 120))] = ord("N")
+    packed, n_pos = mm2.pack_reads(cat)
+    assert n_pos.size > 3000 and (np.diff(n_pos.astype(np.int64)) > 0).all()
+    for sub in (None, "1"):
+        if sub:
+            os.environ["MM2_SUBBATCH_MB"] = sub
+        c = mm2.Context(0)
+        os.environ.pop("MM2_SUBBATCH_MB", None)
+        gi = mm2.Index.build(c, g, offs, ["p"])
+        r1 = c.map_batch(gi, cat, roffs)
+        r2 = c.map_batch_packed(gi, packed, n_pos, roffs)
+        assert r1.recs.size == r2.recs.size and r1.recs.size > 2000 and (r1.recs == r2.recs).all(), sub
+        assert r1.stats == r2.stats
+    with pytest.raises(mm2.Mm2Error) as e:
+        c.map_batch_packed(gi, packed, n_pos, roffs[1:])                    # offs[0] = 3001: not on a 16-base boundary
+    assert e.value.code == mm2.MM2_E_ARG
+
+
 def test_map_batch_pipelined_equals_single(mm2, orc, gen):
     """large host batches are split into sub-batches over two worker contexts; records must not change"""
     g = gen.genome(51, 2_000_000)
