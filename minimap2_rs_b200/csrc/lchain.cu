@@ -273,7 +273,7 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
     const int mark_base = pass * n;
     // ring slot of this lane
     int rj = -1, rx = 0, rq = 0, rsp = 0; u32 rhi = 0;
-    int rf = 0, rpp = -1, rv = 0, rcnt = 0, rqs = 0, rts = 0, rfirst = 0;
+    int rf = 0, rpp = -1;
     int bf = NEG_INF * 4, bi = 0;
     int st = 0;   // lower bound of the window start, used only by windows longer than the ring
     ulonglong2 nxt = make_ulonglong2(0, 0);
@@ -305,7 +305,7 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
         if (done < c) {
           if (lane >= done && lane < c) {                        // anchors before i with an empty window (lchain.rs:77,89-90)
             rj = i0 + lane; rx = cx; rq = cq; rsp = csp; rhi = chi;
-            rf = csp; rpp = -1; rv = csp; rcnt = 1; rqs = own_qs; rts = own_ts; rfirst = i0 + lane;
+            rf = csp; rpp = -1;
           }
         }
         done = c + 1;
@@ -319,7 +319,6 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
         const u32 inmask = __ballot_sync(0xFFFFFFFFu, inwin);
         const u32 vmask = __ballot_sync(0xFFFFFFFFu, valid);
         int max_f = spi, max_j = -1, n_skip = 0;
-        bool from_ring = true;                                   // max_j's state is in the ring (else in A/B)
         bool more = (inmask >> c) & 1u;                          // slot c holds j = i - 32: the window may go on beyond the ring
         if (vmask) {
           const int low_ring = max(i - 32, 0);
@@ -356,7 +355,6 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
         } else if (count_cells) {
           cells += (unsigned)__popc(inmask);
         }
-        int mv = 0, mcnt = 0, mqs = 0, mts = 0, mfirst = 0;     // state of max_j
         if (more) {
           // ---- the window goes on beyond the ring: 32 predecessors at a time from global memory -------------------------
           if (!t_init) {
@@ -420,38 +418,47 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
               const u32 V2 = __ballot_sync(0xFFFFFFFFu, v2), M2 = __ballot_sync(0xFFFFFFFFu, tm), A2 = __ballot_sync(0xFFFFFFFFu, act);
               int rec_last;
               const bool brk = chain_tile_walk(lane, V2, M2, A2, sc2, max_skip, max_f, n_skip, rec_last, cells);
-              if (rec_last >= 0) { max_j = jb - rec_last; from_ring = false; }
+              if (rec_last >= 0) max_j = jb - rec_last;
               if (brk) break;
             }
           }
-          if (!from_ring) {
-            const int4 aj = A[max_j], bj = B[max_j];
-            mv = aj.z; mcnt = aj.w; mqs = bj.x; mts = bj.y; mfirst = bj.z;
-          }
         }
-        // ---- lchain.rs:89-90 and the chain reductions of paf.rs:136-147 carried along the best-predecessor links -------
-        if (max_j >= 0 && from_ring) {
-          const int L = max_j & 31;
-          mv = __shfl_sync(0xFFFFFFFFu, rv, L); mcnt = __shfl_sync(0xFFFFFFFFu, rcnt, L); mqs = __shfl_sync(0xFFFFFFFFu, rqs, L);
-          mts = __shfl_sync(0xFFFFFFFFu, rts, L); mfirst = __shfl_sync(0xFFFFFFFFu, rfirst, L);
-        }
+        // ---- lchain.rs:89-90.  v, the chain length and the chain extents (paf.rs:136-147) feed no DP decision: they are derived
+        //      for the whole tile at once below, by pointer jumping over the best-predecessor links ------------------------------
         if (lane == c) {                                         // anchor i takes over its ring slot
           rj = i; rx = cx; rq = cq; rsp = csp; rhi = chi;
           rf = max_f; rpp = max_j;
-          rv = (max_j >= 0 && mv > max_f) ? mv : max_f;
-          rcnt = max_j >= 0 ? mcnt + 1 : 1;
-          rqs = max_j >= 0 ? min(mqs, own_qs) : own_qs;
-          rts = max_j >= 0 ? min(mts, own_ts) : own_ts;
-          rfirst = max_j >= 0 ? mfirst : i;
         }
       }
       if (lane >= done && lane < tile_n) {
         rj = i0 + lane; rx = cx; rq = cq; rsp = csp; rhi = chi;
-        rf = csp; rpp = -1; rv = csp; rcnt = 1; rqs = own_qs; rts = own_ts; rfirst = i0 + lane;
+        rf = csp; rpp = -1;
       }
-      if (lane < tile_n) {                                       // every lane now holds its own anchor of this tile
-        A[i0 + lane] = make_int4(rf, rpp, rv, rcnt);
-        B[i0 + lane] = make_int4(rqs, rts, rfirst, 0);
+      {
+        // Every lane now holds its own anchor of this tile (f, best predecessor).  v = the maximum of f along the chain
+        // (lchain.rs:90), its length, the minima of the anchor starts and its first anchor (paf.rs:136-147) are aggregates
+        // over the predecessor path: a predecessor in an earlier tile contributes its finished values from A / B, and the
+        // links inside the tile are followed by pointer jumping (5 rounds for 32 anchors) instead of 5 shuffles per anchor.
+        int pv = rf, pcnt = 1, pqs = own_qs, pts = own_ts, pfirst = i0 + lane, ptr = -1;
+        if (lane < tile_n && rpp >= 0) {
+          if (rpp >= i0) ptr = rpp - i0;
+          else {
+            const int4 aj = A[rpp], bj = B[rpp];
+            pv = max(pv, aj.z); pcnt = aj.w + 1; pqs = min(pqs, bj.x); pts = min(pts, bj.y); pfirst = bj.z;
+          }
+        }
+#pragma unroll
+        for (int round = 0; round < 5; ++round) {
+          const int src = ptr >= 0 ? ptr : lane;
+          const int qv = __shfl_sync(0xFFFFFFFFu, pv, src), qcnt = __shfl_sync(0xFFFFFFFFu, pcnt, src);
+          const int qqs = __shfl_sync(0xFFFFFFFFu, pqs, src), qts = __shfl_sync(0xFFFFFFFFu, pts, src);
+          const int qfirst = __shfl_sync(0xFFFFFFFFu, pfirst, src), qptr = __shfl_sync(0xFFFFFFFFu, ptr, src);
+          if (ptr >= 0) { pv = max(pv, qv); pcnt += qcnt; pqs = min(pqs, qqs); pts = min(pts, qts); pfirst = qfirst; ptr = qptr; }
+        }
+        if (lane < tile_n) {
+          A[i0 + lane] = make_int4(rf, rpp, pv, pcnt);
+          B[i0 + lane] = make_int4(pqs, pts, pfirst, 0);
+        }
       }
       {  // lchain.rs:163: the LAST maximum of f
         const int fl = lane < tile_n ? rf : NEG_INF * 4;
