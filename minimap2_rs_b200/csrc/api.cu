@@ -112,7 +112,7 @@ extern "C" void mm2_ctx_destroy(mm2_ctx_t* c) {
   DevBuf* bufs[] = {&c->seq, &c->seq_off, &c->tile_seq, &c->tile_first, &c->tile_status, &c->misc, &c->mkey, &c->mval,
                     &c->mini_off, &c->keep, &c->occ_cnt, &c->occ_loc, &c->anchor_off_m, &c->scan_status, &c->anchors,
                     &c->read_aoff, &c->read_class, &c->read_flag, &c->read_nhit, &c->read_na, &c->flag_list, &c->dpA, &c->dpB, &c->dpT, &c->dpW, &c->hits, &c->chain_idx, &c->lut, &c->sort_tmp,
-                    &c->sort_tmp2, &c->sort_keys2, &c->sort_vals2, &c->runidx, &c->run_start, &c->run_gp, &c->rs_counts, &c->rs_offs, &c->diag, &c->mg_recv_k, &c->mg_recv_v, &c->mg_stage, &c->fine_tmp};
+                    &c->sort_tmp2, &c->sort_keys2, &c->sort_vals2, &c->runidx, &c->run_start, &c->run_gp, &c->rs_counts, &c->rs_offs, &c->diag, &c->mg_recv_k, &c->mg_recv_v, &c->mg_stage, &c->fine_tmp, &c->packed, &c->packed_n};
   for (DevBuf* b : bufs) b->release();
   c->pin_in.release(); c->pin_out.release(); c->pin_small.release(); c->pin_scalar.release();
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
