@@ -568,11 +568,11 @@ void shard_words(u64 total, u64 S_words_alloc, int nranks, int rank, u64* lo, u6
 void make_plan(const u64* off0, size_t nseq, int w, int k, int flag, u64 S_words_alloc, int nranks, int rank, ShardPlan* P) {
   const u64 total = nseq ? off0[nseq] : 0;
   P->nranks = nranks; P->rank = rank;
-  P->tile_path = (k & 1) && !(flag & 1);
+  P->tile_path = sketch_uses_tiles(w, k, flag & 1);
   if (P->tile_path) {
     const u64 nt = sketch_tile_count(off0, nseq, w);
     P->tile_lo = nt * (u64)rank / (u64)nranks; P->tile_hi = nt * (u64)(rank + 1) / (u64)nranks;
-    sketch_tile_bytes(off0, nseq, w, k, P->tile_lo, P->tile_hi, &P->sk_lo, &P->sk_hi);
+    sketch_tile_bytes(off0, nseq, w, k, flag & 1, P->tile_lo, P->tile_hi, &P->sk_lo, &P->sk_hi);
   } else {
     // contiguous sequence ranges balanced by bases
     auto cut = [&](int r) -> size_t {
@@ -635,7 +635,7 @@ int shard_local(mm2_ctx* ctx, const ShardPlan& P, const u8* h_cat, const u64* of
   so.total = 0;
   if (P.tile_path) {
     const SketchShard sh{P.tile_lo, P.tile_hi};
-    if (nseq) MM2_TRY(sketch_device(ctx, ctx->seq.as<u8>(), ctx->seq_off.as<u64>(), off0, nseq, w, k, 0, 1, 0, &so, nullptr, &sh));
+    if (nseq) MM2_TRY(sketch_device(ctx, ctx->seq.as<u8>(), ctx->seq_off.as<u64>(), off0, nseq, w, k, 0, 1, flag & 1, &so, nullptr, &sh));
   } else if (P.seq_hi > P.seq_lo) {
     MM2_TRY(sketch_device(ctx, ctx->seq.as<u8>(), ctx->seq_off.as<u64>() + P.seq_lo, off0 + P.seq_lo, P.seq_hi - P.seq_lo, w, k, (u32)P.seq_lo, 1,
                           flag & 1, &so));

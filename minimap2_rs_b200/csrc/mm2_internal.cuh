@@ -269,7 +269,8 @@ struct SketchFeed { int nchunks; const u64* chunk_end; cudaEvent_t* ev; };
 // sketch_tile_bytes() names need to be resident; out->total = minimizers of the shard, in global emission order.
 struct SketchShard { u64 tile_lo, tile_hi; };
 u64 sketch_tile_count(const u64* h_off, size_t nseq, int w);
-void sketch_tile_bytes(const u64* h_off, size_t nseq, int w, int k, u64 tile_lo, u64 tile_hi, u64* byte_lo, u64* byte_hi);
+void sketch_tile_bytes(const u64* h_off, size_t nseq, int w, int k, int is_hpc, u64 tile_lo, u64 tile_hi, u64* byte_lo, u64* byte_hi);
+bool sketch_uses_tiles(int w, int k, int is_hpc);
 int sketch_device(mm2_ctx* ctx, const u8* d_cat, const u64* d_off, const u64* h_off, size_t nseq, int w, int k,
                   u32 rid_base, u32 rid_step, int is_hpc, SketchOut* out, const SketchFeed* feed = nullptr,
                   const SketchShard* shard = nullptr);

@@ -455,9 +455,41 @@ __device__ __forceinline__ void sk4_convert16(const u32 (&wd)[4], u32& packed, u
     for (int j = 0; j < 4; ++j) nmask |= nbits4(__vcmpeq4(bad[j], 0u)) << (4 * j);
   }
 }
-// keys of a dirty chunk: the literal l counter (sketch.rs:63-76); returns zbits | ge_cap << 8 | eq_capm1 << 16
+__device__ __forceinline__ u32 sk4_nt4(u8 b) {   // nt4.rs:2-10
+  const u32 u = b & 0xDFu;
+  return u == 0x41u ? 0u : u == 0x43u ? 1u : u == 0x47u ? 2u : u == 0x54u ? 3u : 4u;
+}
+// key_span of the output (sketch.rs:74): 32-bit keys carry the hash only (the span is k); 64-bit keys carry the span in the
+// 8 bits below the hash, so that (hash, span) compares like the reference's key_span (HPC: sketch.rs:51-61,72-74)
 template <class KT>
-__device__ __noinline__ u32 sk4_keys_slow(const u32* s_pack, const u32* s_nm, KT* s_K, int tid, int r0, int k, int cap, int sla) {
+__device__ __forceinline__ u64 sk4_out_key(KT key, int sla, int k) {
+  if constexpr (sizeof(KT) == 8) return (u64)key >> (sla - 8);
+  else return ((u64)(key >> sla) << 8) | (u64)k;
+}
+// HPC mode of THIS reference (sketch.rs:51-61): the base index is not advanced over a homopolymer run, so the k-mers are
+// those of the plain sequence; only kmer_span changes: the sum, over the last k bases, of the length of the run that
+// REMAINS from each base on.  s_same: bit t = "base t + 1 is the same letter" (raw indices).  Returns min(run, 256).
+__device__ __forceinline__ u32 sk4_run_from(const u32* s_same, int t) {
+  int wd = t >> 5;
+  const int bit = t & 31;
+  u32 x = __funnelshift_r(s_same[wd], s_same[wd + 1], bit);
+  u32 ones = 0;
+  while (x == 0xFFFFFFFFu && ones < 256u) { ones += 32u; ++wd; x = __funnelshift_r(s_same[wd], s_same[wd + 1], bit); }
+  if (x != 0xFFFFFFFFu) ones += (u32)(__ffs(~x) - 1);
+  return min(ones + 1u, 256u);
+}
+// spans of the 8 positions of a chunk: sliding sums of k run lengths (s_skip[32 + region index])
+__device__ __forceinline__ void sk4_spans(const u16* s_skip, int c0, int k, int (&span)[SK_CH]) {
+  const u16* sk = s_skip + 32 + c0;
+  int sp = 0;
+  for (int t = -(k - 1); t <= 0; ++t) sp += sk[t];
+  span[0] = sp;
+#pragma unroll
+  for (int j = 1; j < SK_CH; ++j) { sp += (int)sk[j] - (int)sk[j - k]; span[j] = sp; }
+}
+// keys of a dirty chunk: the literal l counter (sketch.rs:63-76); returns zbits | ge_cap << 8 | eq_capm1 << 16
+template <class KT, bool HPC>
+__device__ __noinline__ u32 sk4_keys_slow(const u32* s_pack, const u32* s_nm, const u16* s_skip, KT* s_K, int tid, int r0, int k, int cap, int sla) {
   constexpr KT KMAX = (KT)~(KT)0;
   const KT mask = (KT)((((u64)1) << (2 * k)) - 1);
   const int shift1 = 2 * (k - 1);
@@ -474,6 +506,11 @@ __device__ __noinline__ u32 sk4_keys_slow(const u32* s_pack, const u32* s_nm, KT
   const u32 cw = __funnelshift_r(s_pack[r0 >> 4], s_pack[(r0 >> 4) + 1], 2 * (r0 & 15));
   const u32 nb = __funnelshift_r(s_nm[r0 >> 5], s_nm[(r0 >> 5) + 1], r0 & 31);
   u32 zbits = 0, ge_cap = 0, eq_capm1 = 0;
+  int span[SK_CH];
+#pragma unroll
+  for (int j = 0; j < SK_CH; ++j) span[j] = k;
+  if constexpr (HPC) sk4_spans(s_skip, SK_CH * tid, k, span);
+#pragma unroll
   for (int j = 0; j < SK_CH; ++j) {
     const u32 c = (cw >> (2 * j)) & 3u;
     l = ((nb >> j) & 1u) ? 0 : min(l + 1, cap);
@@ -481,7 +518,10 @@ __device__ __noinline__ u32 sk4_keys_slow(const u32* s_pack, const u32* s_nm, KT
     rev = (KT)((rev >> 2) | ((KT)(3u ^ c) << shift1));
     const bool z = !(fwd < rev);
     KT key = KMAX;
-    if (l >= k) key = sk4_hash<KT>((KT)((z ? rev : fwd) << sla), sla);
+    if (l >= k && span[j] < 256) {
+      key = sk4_hash<KT>((KT)((z ? rev : fwd) << sla), sla);
+      if constexpr (sizeof(KT) == 8) key |= (KT)((u64)span[j] << (sla - 8));
+    }
     s_K[sk4_idx<KT>(tid, j)] = key;
     zbits |= (u32)z << j;
     ge_cap |= (u32)(l >= cap) << j;
@@ -579,8 +619,9 @@ struct Sk4Meta { u32 tile, count, q, pad; u64 tfirst; };
 //    order) and the ticket + sequence-table reads of the tile three iterations ahead, so that no compute warp ever waits for a
 //    dependent global load at the top of a tile.  scanner -> compute: a sequence number in shared memory (s_done[b]);
 //    compute -> scanner: named barrier FULL[b].
-template <class KT, int W>
+template <class KT, int W, bool HPC>
 __global__ void __launch_bounds__(SK_NT + 32, sizeof(KT) == 4 ? MM2_SK4_OCC : MM2_SK4_OCC64) sketch_tile_kernel_v4(SketchParams P) {
+  static_assert(!HPC || sizeof(KT) == 8, "the span lives in the 8 bits below a 64-bit key");
   constexpr KT KMAX = (KT)~(KT)0;
   constexpr int PLN = 16 / (int)sizeof(KT), NPL = 8 / PLN;
   constexpr int KB = 8 * (int)sizeof(KT);
@@ -594,6 +635,8 @@ __global__ void __launch_bounds__(SK_NT + 32, sizeof(KT) == 4 ? MM2_SK4_OCC : MM
   __shared__ __align__(16) u32 s_pack[SK_MAXCHUNK + 4];
   __shared__ __align__(16) u32 s_nm[SK_MAXCHUNK / 2 + 4];
   __shared__ __align__(16) u32 s_nc[SK_NT / 32 + 4];            // per 16-base chunk: a real N inside the sequence
+  __shared__ __align__(16) u32 s_same[HPC ? SK_MAXCHUNK / 2 + 12 : 1];   // HPC: bit t = base t + 1 is the same letter as base t
+  __shared__ __align__(16) u16 s_skip[HPC ? SK_REGION + 32 : 8];         // HPC: min(remaining run, 256) of region index u at [32 + u]
   __shared__ __align__(16) u32 s_emit[SK_REGION / 32];
   __shared__ __align__(16) u32 s_dirty[SK_NT / 32 + 4];         // [0] = 0: "the warp before warp 0"; [1 + warp]
   __shared__ u32 s_wsum[SK_NT / 32];
@@ -629,7 +672,7 @@ __global__ void __launch_bounds__(SK_NT + 32, sizeof(KT) == 4 ? MM2_SK4_OCC : MM
         inf.g0 = (gidx >> 4) << 4;
         inf.delta = (int)(gidx - inf.g0);
         inf.ps0 = a - inf.delta;
-        inf.nchunks = (inf.delta + SK_REGION + cap + 15) >> 4;
+        inf.nchunks = (inf.delta + SK_REGION + cap + 15 + (HPC ? 256 : 0)) >> 4;   // HPC: a run may go on for 255 bases past the region
         inf.nown = (int)max((i64)0, min((i64)T, inf.len - s));
         inf.u_last = (int)max((i64)-1, min((i64)(SK_REGION - 1), inf.len - 1 - P0));
         inf.p0lo = (u32)P0;
@@ -704,13 +747,13 @@ __global__ void __launch_bounds__(SK_NT + 32, sizeof(KT) == 4 ? MM2_SK4_OCC : MM
       u64* dk = P.out_key + base;
       u64* dv = P.out_val + base;
       for (u32 e2 = (u32)tid; e2 < cnt; e2 += SK_NT) {
-        dk[e2] = ((u64)(ok[e2] >> sla) << 8) | (u64)k;
+        dk[e2] = sk4_out_key<KT>(ok[e2], sla, k);
         dv[e2] = rid_hi | (u64)op[e2];
       }
     } else {
       for (u32 e2 = (u32)tid; e2 < cnt; e2 += SK_NT) {
         const u64 o = base + e2;
-        if (o < P.out_cap) { P.out_key[o] = ((u64)(ok[e2] >> sla) << 8) | (u64)k; P.out_val[o] = rid_hi | (u64)op[e2]; }
+        if (o < P.out_cap) { P.out_key[o] = sk4_out_key<KT>(ok[e2], sla, k); P.out_val[o] = rid_hi | (u64)op[e2]; }
       }
     }
   };
@@ -758,10 +801,36 @@ __global__ void __launch_bounds__(SK_NT + 32, sizeof(KT) == 4 ? MM2_SK4_OCC : MM
         }
       }
       if (c < SK_MAXCHUNK + 4) { s_pack[c] = packed; reinterpret_cast<u16*>(s_nm)[c] = (u16)nmask; }
+      if constexpr (HPC) {
+        // "the next base is the same letter" for the 16 bases of this chunk; the 17th base comes from the next chunk's first byte
+        u32 same = 0;
+        if (c < inf.nchunks) {
+          const i64 gn = g0 + 16 * (i64)c + 16;
+          const u32 nx = (gn >= 0 && gn < (i64)P.buf_len && (ps0 + 16 * (i64)c + 16) < len && (ps0 + 16 * (i64)c + 16) >= 0) ? sk4_nt4(P.seq[gn]) : 4u;
+          const u32 x = packed ^ ((packed >> 2) | ((nx & 3u) << 30));       // 2-bit field t is zero iff code t == code t + 1
+          u32 y = ~(x | (x >> 1)) & 0x55555555u;
+          y = (y | (y >> 1)) & 0x33333333u; y = (y | (y >> 2)) & 0x0F0F0F0Fu; y = (y | (y >> 4)) & 0x00FF00FFu; y = (y | (y >> 8)) & 0x0000FFFFu;
+          const u32 nnext = (nmask >> 1) | ((nx > 3u ? 1u : 0u) << 15);     // N mask of the bases t + 1
+          same = y & ~nmask & ~nnext & 0xFFFFu;
+        }
+        if (c < SK_MAXCHUNK + 24) reinterpret_cast<u16*>(s_same)[c] = (u16)same;
+      }
       const u32 nb = __ballot_sync(0xFFFFFFFFu, nreal != 0u);
       if ((tid & 31) == 0) s_nc[tid >> 5] = nb;
     }
     sk3_bar_compute();
+    if constexpr (HPC) {
+      // remaining run length of every base of the region (and of the k - 1 bases in front of it)
+      const int rr = cap + inf.delta;                         // raw index of region index 0
+      {
+        u16 sk8[SK_CH];
+#pragma unroll
+        for (int j = 0; j < SK_CH; ++j) sk8[j] = (u16)sk4_run_from(s_same, rr + c0 + j);
+        *reinterpret_cast<uint4*>(&s_skip[32 + c0]) = *reinterpret_cast<const uint4*>(sk8);
+      }
+      if (tid < 32) { const int t = rr - 32 + tid; s_skip[tid] = (u16)(t >= 0 ? sk4_run_from(s_same, t) : 1u); }
+      sk3_bar_compute();
+    }
 
     // ---- phase 2: keys of this thread's 8 positions ----------------------------------------------------------------------
     KT K[SK_CH];
@@ -809,11 +878,20 @@ __global__ void __launch_bounds__(SK_NT + 32, sizeof(KT) == 4 ? MM2_SK4_OCC : MM
 #pragma unroll
         for (int j = 0; j < SK_CH; ++j) {
           const u32 vl = __funnelshift_r(n0, n1, 2 * j), vh = __funnelshift_r(n1, n2, 2 * j);
-          const u64 rv = ((u64)__funnelshift_l(vl, vh, sla) << 32) | (u64)(vl << sla);           // sla in [8, 30]
+          const u64 rv = (((u64)vh << 32) | (u64)vl) << sla;                                      // sla in [8, 62] (HPC uses 64-bit keys for every k)
           const u64 fw = (((u64)__funnelshift_l(g1, g2, 2 * j) << 32) | (u64)__funnelshift_l(g0b, g1, 2 * j)) & (u64)hm;
           const bool z = fw > rv;
           K[j] = sk4_hash<KT>((KT)(z ? rv : fw), sla);
           zbits |= (u32)z << j;
+        }
+        if constexpr (HPC) {
+          int span[SK_CH];
+          sk4_spans(s_skip, c0, k, span);
+#pragma unroll
+          for (int j = 0; j < SK_CH; ++j) K[j] = span[j] < 256 ? (KT)(K[j] | ((u64)span[j] << (sla - 8))) : KMAX;
+        } else {
+#pragma unroll
+          for (int j = 0; j < SK_CH; ++j) K[j] |= (KT)((u64)k << (sla - 8));
         }
       }
       if (first_tile && c0 < w + k - 1) {                     // no k-mer ends before position k - 1 (region index w + k - 1)
@@ -823,7 +901,7 @@ __global__ void __launch_bounds__(SK_NT + 32, sizeof(KT) == 4 ? MM2_SK4_OCC : MM
 #pragma unroll
       for (int v = 0; v < NPL; ++v) sk4_stvec<KT>(s_K, tid, v, &K[v * PLN]);
     } else {
-      const u32 g = sk4_keys_slow<KT>(s_pack, s_nm, s_K, tid, r0, k, cap, sla);
+      const u32 g = sk4_keys_slow<KT, HPC>(s_pack, s_nm, s_skip, s_K, tid, r0, k, cap, sla);
       zbits = g & 0xFFu; gates = g >> 8;
 #pragma unroll
       for (int v = 0; v < NPL; ++v) sk4_ldvec<KT>(s_K, tid, v, &K[v * PLN]);
@@ -932,7 +1010,7 @@ __global__ void __launch_bounds__(SK_NT + 32, sizeof(KT) == 4 ? MM2_SK4_OCC : MM
         KT d = sk_max(GM[j], h[j + r8]);
         if (q8 > 1) d = sk_max(d, common);
         if (j + r8 >= 8) d = sk_max(d, h[7]);
-        flags |= (u32)(d == K[j]) << j;
+        flags |= (u32)(d == K[j] && (!HPC || K[j] != KMAX)) << j;   // HPC: a k-mer whose span reaches 256 is no k-mer, with l unchanged
       }
     } else {
 #pragma unroll
@@ -941,7 +1019,7 @@ __global__ void __launch_bounds__(SK_NT + 32, sizeof(KT) == 4 ? MM2_SK4_OCC : MM
         const int ch = p >> 3;
         KT d = sk_max(GM[j], s_P[sk4_idx<KT>(ch, p & 7)]);
         for (int c = tid + 1; c < ch; ++c) d = sk_max(d, s_P[sk4_idx<KT>(c, 7)]);
-        flags |= (u32)(d == K[j]) << j;
+        flags |= (u32)(d == K[j] && (!HPC || K[j] != KMAX)) << j;   // HPC: a k-mer whose span reaches 256 is no k-mer, with l unchanged
       }
     }
     {
@@ -1039,7 +1117,7 @@ __global__ void __launch_bounds__(SK_NT + 32, sizeof(KT) == 4 ? MM2_SK4_OCC : MM
       for (int j = 0; j < SK_CH; ++j) {
         if ((flags >> j) & 1u) {
           if (o < P.out_cap) {
-            P.out_key[o] = ((u64)(K[j] >> sla) << 8) | (u64)k;
+            P.out_key[o] = sk4_out_key<KT>(K[j], sla, k);
             P.out_val[o] = rid_hi | (u64)(((pbase + (u32)j) << 1) | ((zbits >> j) & 1u));
           }
           ++o;
@@ -1201,6 +1279,9 @@ static int num_sms(int device) {
 // Tiles of the odd-k / non-HPC kernels, at least one per sequence: T = SK_REGION - 2w positions each (v4, w >= 9) or
 // SK_REGION - w steps (small windows).
 static inline int sk_tile_T(int w) { return w >= 9 ? SK_REGION - 2 * w : SK_REGION - w; }
+// which sequences go through the tile kernels: odd k (even k has palindromic k-mers that stall l); HPC only in the w >= 9 kernel
+// and while the 255-base run look-ahead fits the chunk table
+bool sketch_uses_tiles(int w, int k, int is_hpc) { return (k & 1) && (!is_hpc || (w >= 9 && w <= 64)); }
 u64 sketch_tile_count(const u64* h_off, size_t nseq, int w) {
   const u64 T = (u64)sk_tile_T(w);
   u64 nt = 0;
@@ -1208,7 +1289,7 @@ u64 sketch_tile_count(const u64* h_off, size_t nseq, int w) {
   return nt;
 }
 // bytes of the concatenated sequences (relative to h_off[0]) that the tiles [tile_lo, tile_hi) read, halo included
-void sketch_tile_bytes(const u64* h_off, size_t nseq, int w, int k, u64 tile_lo, u64 tile_hi, u64* byte_lo, u64* byte_hi) {
+void sketch_tile_bytes(const u64* h_off, size_t nseq, int w, int k, int is_hpc, u64 tile_lo, u64 tile_hi, u64* byte_lo, u64* byte_hi) {
   const u64 T = (u64)sk_tile_T(w), total = h_off[nseq] - h_off[0];
   *byte_lo = *byte_hi = 0;
   if (tile_hi <= tile_lo) return;
@@ -1221,7 +1302,7 @@ void sketch_tile_bytes(const u64* h_off, size_t nseq, int w, int k, u64 tile_lo,
       const u64 s = so + (a - t0) * T, e = so + std::min(len, (b - t0) * T);
       const u64 halo = (u64)(2 * w + k) + 32;
       lo = std::min(lo, s > halo ? s - halo : 0);
-      hi = std::max(hi, std::min(total, e + (u64)w + 32));   // a v4 region extends w positions above the owned range
+      hi = std::max(hi, std::min(total, e + (u64)w + 32 + (is_hpc ? 272 : 0)));   // a v4 region extends w positions above the owned range (HPC: + the run look-ahead)
     }
     t0 += ntq;
     if (t0 >= tile_hi) break;
@@ -1237,20 +1318,21 @@ __global__ void sketch_seed_prefix_kernel(u64* st, u32 t_lo) { if (threadIdx.x <
 }
 
 // w >= 9: the window sizes of the usual presets get their own instantiation (every shared-memory offset an immediate)
-template <class KT, int W>
+template <class KT, int W, bool HPC>
 static int launch_sketch_v4_t(mm2_ctx* ctx, int grid, const SketchParams& P) {
   const int smem = (int)(3 * SK_REGION * sizeof(KT) + 2 * SK_LIST * (sizeof(KT) + 4));
   // the opt-in is per device and cheap: set it on every launch (a context may live on any GPU of the process)
-  CUDA_TRY(cudaFuncSetAttribute(sketch_tile_kernel_v4<KT, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  CUDA_TRY(cudaFuncSetAttribute(sketch_tile_kernel_v4<KT, W>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  MM2_LAUNCH(ctx, (sketch_tile_kernel_v4<KT, W>), grid, SK_NT + 32, smem, P);
+  CUDA_TRY(cudaFuncSetAttribute(sketch_tile_kernel_v4<KT, W, HPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CUDA_TRY(cudaFuncSetAttribute(sketch_tile_kernel_v4<KT, W, HPC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  MM2_LAUNCH(ctx, (sketch_tile_kernel_v4<KT, W, HPC>), grid, SK_NT + 32, smem, P);
   return MM2_OK;
 }
-static int launch_sketch_v4(mm2_ctx* ctx, int grid, const SketchParams& P) {
+static int launch_sketch_v4(mm2_ctx* ctx, int grid, const SketchParams& P, int is_hpc) {
   const bool k32 = P.k <= 15;
-  if (P.w == 10) return k32 ? launch_sketch_v4_t<u32, 10>(ctx, grid, P) : launch_sketch_v4_t<u64, 10>(ctx, grid, P);
-  if (P.w == 19) return k32 ? launch_sketch_v4_t<u32, 19>(ctx, grid, P) : launch_sketch_v4_t<u64, 19>(ctx, grid, P);
-  return k32 ? launch_sketch_v4_t<u32, 0>(ctx, grid, P) : launch_sketch_v4_t<u64, 0>(ctx, grid, P);
+  if (is_hpc) return P.w == 10 ? launch_sketch_v4_t<u64, 10, true>(ctx, grid, P) : launch_sketch_v4_t<u64, 0, true>(ctx, grid, P);
+  if (P.w == 10) return k32 ? launch_sketch_v4_t<u32, 10, false>(ctx, grid, P) : launch_sketch_v4_t<u64, 10, false>(ctx, grid, P);
+  if (P.w == 19) return k32 ? launch_sketch_v4_t<u32, 19, false>(ctx, grid, P) : launch_sketch_v4_t<u64, 19, false>(ctx, grid, P);
+  return k32 ? launch_sketch_v4_t<u32, 0, false>(ctx, grid, P) : launch_sketch_v4_t<u64, 0, false>(ctx, grid, P);
 }
 
 int sketch_device(mm2_ctx* ctx, const u8* d_cat, const u64* d_off, const u64* h_off, size_t nseq, int w, int k,
@@ -1261,8 +1343,8 @@ int sketch_device(mm2_ctx* ctx, const u8* d_cat, const u64* d_off, const u64* h_
   const u64 total_len = h_off[nseq] - h_off[0];
   cudaStream_t st = ctx->stream;
   MM2_TRY(ctx->mini_off.ensure((nseq + 1) * 8));
-  const bool tile_path = (k & 1) && !is_hpc;
-  if (shard && !tile_path) { mm2_set_error("sketch: tile shards need the tile kernels (odd k, no HPC)"); return MM2_E_ARG; }
+  const bool tile_path = sketch_uses_tiles(w, k, is_hpc);
+  if (shard && !tile_path) { mm2_set_error("sketch: tile shards need the tile kernels (odd k; HPC: 9 <= w <= 64)"); return MM2_E_ARG; }
   if (tile_path) {
     const int T = sk_tile_T(w);
     const u64 nt = sketch_tile_count(h_off, nseq, w);
@@ -1318,8 +1400,9 @@ int sketch_device(mm2_ctx* ctx, const u8* d_cat, const u64* d_off, const u64* h_
             for (size_t q = 0; q < nseq; ++q) {
               const u64 so = h_off[q] - h_off[0], len = h_off[q + 1] - h_off[q];
               const u64 ntq = std::max<u64>(1, (len + T - 1) / T);
-              if (so + len + 16 <= B) { t_end += ntq; continue; }
-              if (B > so + 16 + (u64)w) t_end += std::min<u64>(ntq - 1, (B - so - 16 - (u64)w) / (u64)T);   // tiles whose region ends (with a 16-byte margin) below B
+              const u64 mg = 16 + (u64)w + (is_hpc ? 272 : 0);                      // region end + alignment (+ the run look-ahead of HPC)
+              if (so + len + mg <= B) { t_end += ntq; continue; }
+              if (B > so + mg) t_end += std::min<u64>(ntq - 1, (B - so - mg) / (u64)T);   // tiles whose region ends (with the margin) below B
               break;                                                                   // later sequences lie above B
             }
           }
@@ -1328,14 +1411,14 @@ int sketch_device(mm2_ctx* ctx, const u8* d_cat, const u64* d_off, const u64* h_
             P.tile_base = t_prev; P.ntiles = (u32)t_end;
             P.ticket = (u32*)((u8*)ctx->tile_status.p + (size_t)ntiles * 8 + 16) + c;
             const int g = (int)std::min<u64>(t_end - t_prev, (u64)num_sms(ctx->device) * (MM2_SK4_OCC + 2));
-            MM2_TRY(launch_sketch_v4(ctx, g, P));
+            MM2_TRY(launch_sketch_v4(ctx, g, P, is_hpc));
             t_prev = (u32)t_end;
           }
         }
       } else {
         if (feed && attempt == 0) for (int c = 0; c < feed->nchunks; ++c) CUDA_TRY(cudaStreamWaitEvent(st, feed->ev[c], 0));
         if (w >= 9) {   // per-thread prefix/suffix window minima + scanner warp
-          MM2_TRY(launch_sketch_v4(ctx, grid, P));
+          MM2_TRY(launch_sketch_v4(ctx, grid, P, is_hpc));
         } else {        // small windows: the O(w) window scan
           if (k <= 15) MM2_LAUNCH(ctx, sketch_tile_kernel<u32>, grid, SK_NT, 0, P);
           else MM2_LAUNCH(ctx, sketch_tile_kernel<u64>, grid, SK_NT, 0, P);

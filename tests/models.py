@@ -322,7 +322,7 @@ def chain_dense_model(anchors, p, lut=None):
     return f, pprev, v, cells
 
 
-def sketch_model_v4(seq, w, k, rid=0, region=2048, ch=8):
+def sketch_model_v4(seq, w, k, rid=0, region=2048, ch=8, is_hpc=False):
     """Model of sketch_tile_kernel_v4 (csrc/sketch.cu): every tile owns T = region - 2w POSITIONS of one sequence.
 
     * clean chunk (no N / sequence START in bases [c-w-k+1, c+ch-1+w]): position x is a minimizer iff its key equals the
@@ -351,7 +351,18 @@ def sketch_model_v4(seq, w, k, rid=0, region=2048, ch=8):
     mask = (1 << (2 * k)) - 1
     z = (fwd >= rev).astype(np.uint64)
     km = np.where(z == 0, fwd, rev)
-    gkey = np.where(l >= k, hash64(km, mask), U64MAX) if L else np.zeros(0, dtype=np.uint64)
+    # key_span as the reference compares it (sketch.rs:74): hash << 8 | kmer_span.  -H (sketch.rs:51-61, where the loop index
+    # is NOT advanced over a run): the k-mers stay those of the plain sequence, kmer_span is the sum over the last k bases of
+    # the homopolymer run that remains from each base on, and a k-mer whose span reaches 256 is dropped WITHOUT resetting l
+    span = np.full(L, k, dtype=np.int64)
+    if is_hpc and L:
+        skip = np.ones(L, dtype=np.int64)
+        for i in range(L - 2, -1, -1):
+            if valid[i] and valid[i + 1] and c[i] == c[i + 1]:
+                skip[i] = skip[i + 1] + 1
+        cs = np.concatenate([[0], np.cumsum(skip)])
+        span = cs[1:] - cs[np.maximum(idx + 1 - k, 0)]
+    gkey = np.where((l >= k) & (span < 256), (hash64(km, mask) << np.uint64(8)) | span.astype(np.uint64), U64MAX) if L else np.zeros(0, dtype=np.uint64)
     T = region - 2 * w
     D = (w + ch - 1) // ch
     ntiles = max(1, (L + T - 1) // T)
@@ -436,6 +447,6 @@ def sketch_model_v4(seq, w, k, rid=0, region=2048, ch=8):
                 marked[P0 + x] = True
     pos = np.nonzero(marked)[0]
     res = np.zeros(pos.size, dtype=[("key_span", "<u8"), ("rid_pos_strand", "<u8")])
-    res["key_span"] = (gkey[pos] << np.uint64(8)) | np.uint64(k)
+    res["key_span"] = gkey[pos]
     res["rid_pos_strand"] = (np.uint64(rid) << np.uint64(32)) | (pos.astype(np.uint64) << np.uint64(1)) | z[pos]
     return res

@@ -31,6 +31,23 @@ def test_sketch_literal_kernel(ctx, orc, w, k, hpc):
         _eq(ctx.sketch_sequence(s, w, k, rid=1, is_hpc=hpc), orc.sketch(s, w, k, rid=1, is_hpc=hpc), "literal %d" % i)
 
 
+@pytest.mark.parametrize("w,k", [(10, 15), (10, 19), (11, 21), (19, 17), (9, 5), (64, 27)])
+def test_sketch_hpc_tile_kernel(ctx, orc, w, k):
+    """-H on the tile kernel (odd k, 9 <= w <= 64): same k-mers as the plain sketch, kmer_span = sum over the last k bases of
+    the homopolymer run that remains from each base on (sketch.rs:51-61: the loop index is not advanced), k-mers with a span
+    of 256 or more dropped; runs across tile and sequence boundaries, runs next to N, runs longer than 256"""
+    rng = np.random.default_rng(14)
+    seqs = [s for _, s in cases.sketch_cases()]
+    seqs += [b"A" * 5000, cases.rnd_seq(rng, 2000) + b"C" * 300 + cases.rnd_seq(rng, 1800) + b"G" * 40 + b"N" + b"G" * 40 + cases.rnd_seq(rng, 500),
+             cases.rnd_seq(rng, 6000, "AAAC"), cases.rnd_seq(rng, 4096, "AACCGGTTN"), b"T" * 255 + b"A" + b"T" * 256 + cases.rnd_seq(rng, 100)]
+    for i, s in enumerate(seqs):
+        _eq(ctx.sketch_sequence(s, w, k, rid=2, is_hpc=True), orc.sketch(s, w, k, rid=2, is_hpc=True), "hpc tile %d w=%d k=%d" % (i, w, k))
+    cat, offs = cases.cat_offs(seqs)
+    mv, mo = ctx.sketch_batch(cat, offs, w, k, rid_base=0, rid_step=1, is_hpc=True)
+    for i, s in enumerate(seqs):
+        _eq(mv[int(mo[i]):int(mo[i + 1])], orc.sketch(s, w, k, rid=i, is_hpc=True), "hpc batch seq %d" % i)
+
+
 def test_sketch_batch_many_sequences(ctx, orc):
     rng = np.random.default_rng(8)
     seqs = [cases.rnd_seq(rng, int(n)) for n in rng.integers(1, 9000, 300)] + [b"N" * 100, b"A"]

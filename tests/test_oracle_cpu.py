@@ -37,6 +37,17 @@ def test_sketch_model_v4_matches_oracle(orc):
         a = orc.sketch(s, w, k, rid=1)
         m = models.sketch_model_v4(s, w, k, rid=1, region=int(rng.choice([128, 256])))
         assert a.size == m.size and (a == m).all(), (it, w, k, len(s))
+    # -H: the span (sum of the remaining homopolymer runs of the last k bases) is part of the key; k-mers whose span reaches 256
+    # drop out without resetting l
+    for it in range(300):
+        w = int(rng.integers(9, 24))
+        k = int(rng.choice([3, 5, 9, 15, 19]))
+        s = cases.rnd_seq(rng, int(rng.integers(1, 900)), ["AC", "ACGT", "AAAAC", "AACCGGTTN", "A" * 40 + "C"][int(rng.integers(0, 5))])
+        if it % 5 == 0:
+            s = s[:len(s) // 3] + b"G" * int(rng.integers(200, 400)) + s[len(s) // 3:]
+        a = orc.sketch(s, w, k, rid=1, is_hpc=True)
+        m = models.sketch_model_v4(s, w, k, rid=1, region=int(rng.choice([128, 256])), is_hpc=True)
+        assert a.size == m.size and (a == m).all(), ("hpc", it, w, k, len(s))
 
 
 def test_sketch_properties(orc):

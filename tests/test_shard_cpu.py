@@ -92,7 +92,7 @@ def _plan_worker(rank, world, port, q):
         total = int(offs[-1])
         used = (total + 7) // 8
         for (w, k, flag), plans in res.items():
-            tile = (k % 2 == 1) and not flag
+            tile = (k % 2 == 1) and (not flag or 9 <= w <= 64)   # even k -> whole sequences; HPC rides the w >= 9 tile kernel
             ok &= all(p["tile_path"] == int(tile) for p in plans)
             ok &= plans[0]["lo"] == 0 and all(plans[r]["hi"] == plans[r + 1]["lo"] for r in range(world - 1))   # shares tile the list
             if tile:
