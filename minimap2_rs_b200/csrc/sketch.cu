@@ -2,17 +2,16 @@
 // sequences (a genome's chromosomes, or the reads of a mapping batch) in one launch.
 //
 // Three kernels:
-//  * sketch_tile_kernel_v4 — odd k, non-HPC, w >= 9 (every BASELINE config).  Minimizers by POSITION: a position is
-//    emitted iff its key is the minimum of some window that holds it (morphological opening of the key sequence); the
+//  * sketch_tile_kernel_v4 — odd k, w >= 9, with or without -H (every BASELINE config).  Minimizers by POSITION: a position
+//    is emitted iff its key is the minimum of some window that holds it (morphological opening of the key sequence); the
 //    literal per-step rules of sketch.rs:80-96 run only around N bases and tie-rich sequence starts.  A CTA owns a tile
 //    of 2048-2w consecutive positions of one sequence; per-tile output counts are turned into global offsets by a
 //    single-pass decoupled look-back, so the minimizers land in exactly the reference's order.
 //    tests/models.py:sketch_model_v4 is the CPU model of this restatement (checked against the oracle).
 //  * sketch_tile_kernel — the same path for w < 9: the window state after step i as a pure function of the last w keys,
 //    by an O(w) scan per step (tests/models.py:sketch_model).
-//  * sketch_literal_kernel — any k (even k has palindromic k-mers that stall `l`, sketch.rs:67-69) and HPC mode
-//    (sketch.rs:51-61): one thread per sequence runs the reference state machine literally.  Correct for every
-//    parameter set, slow for long sequences; used only where the tile kernels do not apply.
+//  * sketch_literal_kernel — even k (palindromic k-mers stall `l`, sketch.rs:67-69) and -H outside 9 <= w <= 64: one thread
+//    per sequence runs the reference state machine literally.  Correct for every parameter set, slow for long sequences.
 #include "mm2_internal.cuh"
 
 #include <algorithm>
