@@ -743,11 +743,17 @@ __global__ void __launch_bounds__(SK_NT + 32, sizeof(KT) == 4 ? MM2_SK4_OCC : MM
     const KT* ok = s_okey[pb];
     const u32* op = s_opos[pb];
     if (base + cnt <= P.out_cap) {
-      u64* dk = P.out_key + base;
-      u64* dv = P.out_val + base;
-      for (u32 e2 = (u32)tid; e2 < cnt; e2 += SK_NT) {
-        dk[e2] = sk4_out_key<KT>(ok[e2], sla, k);
-        dv[e2] = rid_hi | (u64)op[e2];
+      // one pointer per array and thread, the (at most SK_LIST / SK_NT) records of a thread at immediate offsets
+      u64* dk = P.out_key + base + tid;
+      u64* dv = P.out_val + base + tid;
+      const KT* okt = ok + tid;
+      const u32* opt = op + tid;
+#pragma unroll
+      for (int r = 0; r < SK_LIST / SK_NT; ++r) {
+        if ((u32)tid + (u32)(SK_NT * r) < cnt) {
+          dk[SK_NT * r] = sk4_out_key<KT>(okt[SK_NT * r], sla, k);
+          dv[SK_NT * r] = rid_hi | (u64)opt[SK_NT * r];
+        }
       }
     } else {
       for (u32 e2 = (u32)tid; e2 < cnt; e2 += SK_NT) {
@@ -1069,14 +1075,15 @@ __global__ void __launch_bounds__(SK_NT + 32, sizeof(KT) == 4 ? MM2_SK4_OCC : MM
     }
     if ((tid & 31) == 31) s_wsum[tid >> 5] = inc;
     sk3_bar_compute();
-    u32 wbase = 0, tile_count = 0;
+    u32 wv = (tid & 31) < SK_NT / 32 ? s_wsum[tid & 31] : 0u;    // inclusive scan of the warp sums, in every warp
 #pragma unroll
-    for (int x = 0; x < SK_NT / 32; ++x) {
-      const u32 ws = s_wsum[x];
-      if (x < (tid >> 5)) wbase += ws;
-      tile_count += ws;
+    for (int d = 1; d < SK_NT / 32; d <<= 1) {
+      const u32 tt = __shfl_up_sync(0xFFFFFFFFu, wv, d);
+      if ((tid & 31) >= d) wv += tt;
     }
-    const u32 my_off = wbase + inc - tot;
+    const u32 tile_count = __shfl_sync(0xFFFFFFFFu, wv, SK_NT / 32 - 1);
+    const u32 wprev = __shfl_sync(0xFFFFFFFFu, wv, ((tid >> 5) + 31) & 31);
+    const u32 my_off = ((tid >> 5) ? wprev : 0u) + inc - tot;
     const bool staged = tile_count <= (u32)SK_LIST;
     const u32 q = inf.q;
     if (tid == 0) {
@@ -1087,16 +1094,15 @@ __global__ void __launch_bounds__(SK_NT + 32, sizeof(KT) == 4 ? MM2_SK4_OCC : MM
 
     // ---- records of this thread's flagged positions, in position order, into buffer b ------------------------------------------
     const u32 pbase = inf.p0lo + (u32)c0;
-    if (staged) {
-      KT* okey = s_okey[b];
-      u32* opos = s_opos[b];
-      u32 o = my_off;
+    if (staged && flags) {
+      KT* pk = s_okey[b] + my_off;
+      u32* pp = s_opos[b] + my_off;
+      const u32 pb2 = pbase << 1;
 #pragma unroll
       for (int j = 0; j < SK_CH; ++j) {
         if ((flags >> j) & 1u) {
-          okey[o] = K[j];
-          opos[o] = ((pbase + (u32)j) << 1) | ((zbits >> j) & 1u);
-          ++o;
+          *pk++ = K[j];
+          *pp++ = (pb2 + 2u * (u32)j) | ((zbits >> j) & 1u);
         }
       }
     }
