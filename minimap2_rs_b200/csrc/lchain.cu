@@ -34,6 +34,7 @@ struct ChainArgs {
   mm2_chain_params_t p;
   int do_rescue;
   const float* half_log;  // 0.5 * mg_log2(dd + 1), dd = 0 .. max(bw, bw_long)
+  const int* pen_int;     // chn_pen_skip == 0: the whole gap penalty of lchain.rs:28-32 as a function of dd (same float operations, done once per dd on the host)
   int4* A; int4* B; int* T; int* W; int* chain;
   ReadHit* hits;
   unsigned long long* cells;
@@ -173,8 +174,9 @@ __device__ __forceinline__ bool chain_tile_walk(int lane, u32 V, u32 M, u32 ACT,
 }
 
 // comput_sc (lchain.rs:17-34) of anchor i = (ri, qi) against a predecessor (rj, qj, span_j) of the same rid/strand
+template <bool LUT>
 __device__ __forceinline__ bool chain_sc(int ri, int qi, int rj, int qj, int span_j, int mdx, int mdy, int bw, float pen_gap,
-                                         float pen_skip, const float* __restrict__ half_log, int& s0) {
+                                         float pen_skip, const float* __restrict__ half_log, const int* __restrict__ pen_int, int& s0) {
   const int dq = wsub(qi, qj);
   if (dq <= 0 || dq > mdx) return false;
   const int dr = wsub(ri, rj);
@@ -184,8 +186,11 @@ __device__ __forceinline__ bool chain_sc(int ri, int qi, int rj, int qj, int spa
   const int dg = min(dr, dq);
   s0 = min(span_j, dg);
   if (dd != 0 || dg > span_j) {
-    const float lin = __fadd_rn(__fmul_rn(pen_gap, (float)dd), __fmul_rn(pen_skip, (float)dg));
-    s0 = wsub(s0, __float2int_rz(__fadd_rn(lin, half_log[dd])));
+    if constexpr (LUT) s0 = wsub(s0, pen_int[dd]);
+    else {
+      const float lin = __fadd_rn(__fmul_rn(pen_gap, (float)dd), __fmul_rn(pen_skip, (float)dg));
+      s0 = wsub(s0, __float2int_rz(__fadd_rn(lin, half_log[dd])));
+    }
   }
   return true;
 }
@@ -193,16 +198,21 @@ __device__ __forceinline__ bool chain_sc(int ri, int qi, int rj, int qj, int spa
 // The same without branches (one predicate instead of the early returns): used where every lane of the warp evaluates a cell,
 // so the warp executes the whole body anyway and the branch / reconvergence instructions are pure overhead.  `act` = the lane
 // has a cell at all; the table index is clamped for the lanes that do not.
+template <bool LUT = false>
 __device__ __forceinline__ bool chain_sc_flat(bool act, int ri, int qi, int rj, int qj, int span_j, int mdx, int mdy, int bw, float pen_gap,
-                                              float pen_skip, const float* __restrict__ half_log, int& s0) {
+                                              float pen_skip, const float* __restrict__ half_log, int& s0, const int* __restrict__ pen_int = nullptr) {
   const int dq = wsub(qi, qj), dr = wsub(ri, rj);
   int dd = wsub(dr, dq); if (dd < 0) dd = wsub(0, dd);
   const bool ok = act && dq > 0 && dq <= mdx && dr != 0 && dq <= mdy && dd <= bw && dd >= 0;
   const int dg = min(dr, dq);
   s0 = min(span_j, dg);
   const int ddc = ok ? dd : 0;
-  const float lin = __fadd_rn(__fmul_rn(pen_gap, (float)ddc), __fmul_rn(pen_skip, (float)dg));
-  const int pen = __float2int_rz(__fadd_rn(lin, half_log[ddc]));
+  int pen;
+  if constexpr (LUT) pen = pen_int[ddc];   // chn_pen_skip == 0: pen_gap * dd + 0 * dg == pen_gap * dd exactly (both products are >= +0)
+  else {
+    const float lin = __fadd_rn(__fmul_rn(pen_gap, (float)ddc), __fmul_rn(pen_skip, (float)dg));
+    pen = __float2int_rz(__fadd_rn(lin, half_log[ddc]));
+  }
   if (ddc != 0 || dg > span_j) s0 = wsub(s0, pen);
   return ok;
 }
@@ -239,7 +249,7 @@ __device__ __forceinline__ u32 dense_read_of_ticket(const ChainArgs& G, u32 k) {
 }
 
 // one warp per read (chain_ring_kernel).  COUNT: also count DP cells (diagnostic; a compile-time switch, the bookkeeping costs ~5 %)
-template <bool COUNT>
+template <bool COUNT, bool LUT>
 __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, const int lane) {
   const u64 a0 = G.read_aoff[r];
   const i64 n64 = (i64)(G.read_aoff[r + 1] - a0);
@@ -314,7 +324,7 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
         const int low_iter = wsub(i, max_iter);                  // lchain.rs:78
         const bool inwin = rj >= max(low_iter, 0) && rhi == hi_i && !(ri > wadd(rx, mdx));   // empty slots hold rj = -1
         int s0;
-        const bool valid = chain_sc_flat(inwin, ri, qi, rx, rq, rsp, mdx, mdy, bw, p.chn_pen_gap, p.chn_pen_skip, G.half_log, s0);
+        const bool valid = chain_sc_flat<LUT>(inwin, ri, qi, rx, rq, rsp, mdx, mdy, bw, p.chn_pen_gap, p.chn_pen_skip, G.half_log, s0, G.pen_int);
         const int sc = valid ? wadd(s0, rf) : NEG_INF;
         const u32 inmask = __ballot_sync(0xFFFFFFFFu, inwin);
         const u32 vmask = __ballot_sync(0xFFFFFFFFu, valid);
@@ -403,8 +413,8 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
                 const ulonglong2 v = an[j];
                 if ((u32)(v.x >> 32) == hi_i) {                     // lchain.rs:81
                   int s0;
-                  if (chain_sc(ri, qi, (int)(u32)v.x, (int)(u32)v.y, (int)((v.y >> 32) & 0xff), mdx, mdy, bw, p.chn_pen_gap,
-                               p.chn_pen_skip, G.half_log, s0)) {
+                  if (chain_sc<LUT>(ri, qi, (int)(u32)v.x, (int)(u32)v.y, (int)((v.y >> 32) & 0xff), mdx, mdy, bw, p.chn_pen_gap,
+                                    p.chn_pen_skip, G.half_log, G.pen_int, s0)) {
                     const int2 fj = *reinterpret_cast<const int2*>(A + j);
                     sc2 = wadd(s0, fj.x);
                     ppj = fj.y;
@@ -1033,12 +1043,12 @@ __device__ __forceinline__ void chain_read_dense(const ChainArgs& G, const u32 r
 #endif
 }
 
-template <bool COUNT>
+template <bool COUNT, bool LUT>
 __global__ void __launch_bounds__(CH_WARPS * 32, MM2_CH_OCC) chain_ring_kernel(ChainArgs G) {
   const u32 r = blockIdx.x * CH_WARPS + (threadIdx.x >> 5);
   if (r >= G.nreads) return;
   if (chain_is_dense(G, r)) return;                               // chain_dense_kernel's
-  chain_read<COUNT>(G, r, threadIdx.x & 31);
+  chain_read<COUNT, LUT>(G, r, threadIdx.x & 31);
 }
 
 // NW warps per dense read, one resident CTA per SM (the window ring and the two summary buffers take ~210 KB of shared memory).
@@ -1099,18 +1109,32 @@ int chain_batch(mm2_ctx* ctx, const ulonglong2* d_anchors, const u64* d_read_aof
   const int max_bw = std::max(p.bw, do_rescue ? p.bw_long : p.bw);
   if (max_bw < 0 || max_bw > (1 << 26)) { mm2_set_error("chain: bandwidth out of range"); return MM2_E_ARG; }
   const int nl = max_bw + 2;
-  if (ctx->lut_n < nl) {  // the table depends on dd only: upload once per context and keep it (no per-batch H2D)
-    std::vector<float> hl = build_half_log(nl);
-    MM2_TRY(ctx->lut.ensure((size_t)nl * 4));
-    MM2_TRY(ctx->pin_small.ensure((size_t)nl * 4));
-    memcpy(ctx->pin_small.p, hl.data(), (size_t)nl * 4);
-    CUDA_TRY(cudaMemcpyAsync(ctx->lut.p, ctx->pin_small.p, (size_t)nl * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (ctx->lut_n < nl || ctx->lut_gap != p.chn_pen_gap) {
+    // the tables depend on dd (and the second one on chn_pen_gap) only: upload once per context and keep them (no per-batch
+    // H2D).  [0, n2): 0.5 * mg_log2(dd + 1); [n2, 2 n2): the integer penalty int(chn_pen_gap * dd + 0.5 * mg_log2(dd + 1)) of
+    // lchain.rs:28-32 for chn_pen_skip == 0, with the reference's float operations in the reference's order
+    const int n2 = std::max(nl, ctx->lut_n);
+    std::vector<float> hl = build_half_log(n2);
+    std::vector<int> pi((size_t)n2);
+    for (int dd = 0; dd < n2; ++dd) {
+      volatile float lin = p.chn_pen_gap * (float)dd;
+      volatile float sum = lin + hl[(size_t)dd];
+      pi[(size_t)dd] = (int)sum;
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));   // earlier launches of this context may still read the old tables
+    MM2_TRY(ctx->lut.ensure((size_t)n2 * 8));
+    MM2_TRY(ctx->pin_small.ensure((size_t)n2 * 8));
+    memcpy(ctx->pin_small.p, hl.data(), (size_t)n2 * 4);
+    memcpy((u8*)ctx->pin_small.p + (size_t)n2 * 4, pi.data(), (size_t)n2 * 4);
+    CUDA_TRY(cudaMemcpyAsync(ctx->lut.p, ctx->pin_small.p, (size_t)n2 * 8, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    ctx->lut_n = nl;
+    ctx->lut_n = n2; ctx->lut_gap = p.chn_pen_gap;
   }
   ChainArgs G;
   G.anchors = d_anchors; G.read_aoff = d_read_aoff; G.read_off = d_read_off; G.mini_off = d_mini_off; G.mval = d_mval;
   G.sum_span = d_sum_span; G.nreads = nreads; G.p = p; G.do_rescue = do_rescue; G.half_log = ctx->lut.as<float>();
+  G.pen_int = reinterpret_cast<const int*>(ctx->lut.as<float>() + ctx->lut_n);
+  const bool lut = p.chn_pen_skip == 0.0f;
   G.A = d_A; G.B = d_B; G.T = d_T; G.W = d_W; G.chain = d_chain; G.hits = d_hits; G.cells = d_cells;
   G.dense = nullptr; G.dense_min = 0x7fffffff; G.dense_ratio5 = 0;
   const int grid = (int)((nreads + CH_WARPS - 1) / CH_WARPS);
@@ -1122,8 +1146,8 @@ int chain_batch(mm2_ctx* ctx, const ulonglong2* d_anchors, const u64* d_read_aof
     G.dense_ratio5 = ctx->chain_dense_ratio5;
     CUDA_TRY(cudaMemsetAsync(G.dense, 0, 64, ctx->stream));
     MM2_LAUNCH(ctx, chain_classify_kernel, (int)((nreads + 255) / 256), 256, 0, G);
-    if (d_cells) MM2_LAUNCH(ctx, chain_ring_kernel<true>, grid, CH_WARPS * 32, 0, G);
-    else MM2_LAUNCH(ctx, chain_ring_kernel<false>, grid, CH_WARPS * 32, 0, G);
+    if (d_cells) { if (lut) MM2_LAUNCH(ctx, (chain_ring_kernel<true, true>), grid, CH_WARPS * 32, 0, G); else MM2_LAUNCH(ctx, (chain_ring_kernel<true, false>), grid, CH_WARPS * 32, 0, G); }
+    else { if (lut) MM2_LAUNCH(ctx, (chain_ring_kernel<false, true>), grid, CH_WARPS * 32, 0, G); else MM2_LAUNCH(ctx, (chain_ring_kernel<false, false>), grid, CH_WARPS * 32, 0, G); }
     // persistent CTAs (one per SM), one dense read at a time each; with no dense read they exit at once
     if (G.dense_min != 0x7fffffff) MM2_LAUNCH(ctx, chain_dense_kernel<DENSE_NW>, (int)std::min<u64>(nreads, (u64)ctx->n_sm), DENSE_NW * 32, DENSE_DYN, G);
   }

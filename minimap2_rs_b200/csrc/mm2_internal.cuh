@@ -158,6 +158,7 @@ struct mm2_ctx {
   bool pipeline = true;
   u64 subbatch_bytes = 64ull << 20;
   int lut_n = 0;        // entries of the chaining log table resident in `lut`
+  float lut_gap = -1.0f;   // chn_pen_gap of the integer penalty table behind it
   int n_sm = 148;
   // chaining: reads with >= chain_dense_min anchors and more than chain_dense_ratio5 / 5 anchors per base get a CTA each
   int chain_dense_min = 4096, chain_dense_ratio5 = 2;
