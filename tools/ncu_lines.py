@@ -42,9 +42,15 @@ tmpls = re.findall(r"<([^<>]*)>", kname.split("(")[0])
 tmpl = tmpls[-1] if tmpls else None
 start = None
 cands = [i for i, l in enumerate(dis) if l.startswith("_Z") and core in l and l.rstrip().endswith(":")]
-if tmpl and len(cands) > 1:
+mint = re.search(r"<\(int\)(\d+)>\(", kname)
+if mint and len(cands) > 1:
+    cands = [i for i in cands if "%sILi%sE" % (core, mint.group(1)) in dis[i]] or cands
+elif tmpl and len(cands) > 1:
     t = tmpl
     key = {"unsigned int": "Ij", "unsigned long": "Im", "unsigned long long": "Iy"}.get(t)
+    mi = re.fullmatch(r"\(int\)(\d+)", t.strip())
+    if mi:
+        key = "ILi%sE" % mi.group(1)
     if key:
         cands = [i for i in cands if core + key in dis[i]] or cands
 start = cands[0]
