@@ -189,7 +189,9 @@ __device__ __forceinline__ void seed_hits_read(const SeedHitArgs& G, const u32 r
     // Index::get (index.rs:143-154): one 32-byte table line per fine bucket (see IndexView::tab)
     const u64 hk = minier >> G.V.b;
     const u64 f = ((minier & bmask) << G.V.fine_j) | (u64)index_fine_cdf(hk, G.V.R, G.V.fine_j, G.V.fine_pw);
-    const ulonglong2 e0 = ld_hint_v2(&G.V.tab[2 * f], pol_stream), e1 = ld_hint_v2(&G.V.tab[2 * f + 1], pol_stream);
+    const ulonglong2* line = &G.V.tab[2 * f];
+    ulonglong2 e0, e1;   // ONE 256-bit access for the line (two 128-bit loads cost 4 % more kernel time)
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u64 {%0, %1, %2, %3}, [%4], %5;" : "=l"(e0.x), "=l"(e0.y), "=l"(e1.x), "=l"(e1.y) : "l"(line), "l"(pol_stream));
     ulonglong2 hit = make_ulonglong2(TAB_EMPTY, 0);
     if ((e0.x >> 1) == hk) hit = e0;
     else if ((e1.x >> 1) == hk) hit = e1;
