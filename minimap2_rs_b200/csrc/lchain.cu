@@ -198,12 +198,16 @@ __device__ __forceinline__ bool chain_sc(int ri, int qi, int rj, int qj, int spa
 // The same without branches (one predicate instead of the early returns): used where every lane of the warp evaluates a cell,
 // so the warp executes the whole body anyway and the branch / reconvergence instructions are pure overhead.  `act` = the lane
 // has a cell at all; the table index is clamped for the lanes that do not.
-template <bool LUT = false>
+template <bool LUT = false, bool TRIM = false>
 __device__ __forceinline__ bool chain_sc_flat(bool act, int ri, int qi, int rj, int qj, int span_j, int mdx, int mdy, int bw, float pen_gap,
                                               float pen_skip, const float* __restrict__ half_log, int& s0, const int* __restrict__ pen_int = nullptr) {
   const int dq = wsub(qi, qj), dr = wsub(ri, rj);
   int dd = wsub(dr, dq); if (dd < 0) dd = wsub(0, dd);
-  const bool ok = act && dq > 0 && dq <= mdx && dr != 0 && dq <= mdy && dd <= bw && dd >= 0;
+  bool ok;
+  // TRIM (the caller has checked bw >= 0, hence mdx, mdy >= bw >= 0): 1 <= dq <= min(mdx, mdy) and 0 <= dd <= bw as one unsigned
+  // compare each
+  if constexpr (TRIM) ok = act && (u32)wsub(dq, 1) < (u32)min(mdx, mdy) && dr != 0 && (u32)dd <= (u32)bw;
+  else ok = act && dq > 0 && dq <= mdx && dr != 0 && dq <= mdy && dd <= bw && dd >= 0;
   const int dg = min(dr, dq);
   s0 = min(span_j, dg);
   const int ddc = ok ? dd : 0;
@@ -249,7 +253,10 @@ __device__ __forceinline__ u32 dense_read_of_ticket(const ChainArgs& G, u32 k) {
 }
 
 // one warp per read (chain_ring_kernel).  COUNT: also count DP cells (diagnostic; a compile-time switch, the bookkeeping costs ~5 %)
-template <bool COUNT, bool LUT>
+// FAST (chosen by chain_batch): chn_pen_skip == 0 (integer penalty table), max_chain_iter >= 32 (every filled ring slot
+// j >= i - 32 passes the max_chain_iter bound of lchain.rs:78) and bw, bw_long >= 0 (unsigned range compares).  Same results,
+// ~5 instructions fewer per anchor with a window.
+template <bool COUNT, bool FAST>
 __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, const int lane) {
   const u64 a0 = G.read_aoff[r];
   const i64 n64 = (i64)(G.read_aoff[r + 1] - a0);
@@ -322,9 +329,9 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
         const int ri = __shfl_sync(0xFFFFFFFFu, cx, c), qi = __shfl_sync(0xFFFFFFFFu, cq, c), spi = __shfl_sync(0xFFFFFFFFu, csp, c);
         const u32 hi_i = __shfl_sync(0xFFFFFFFFu, chi, c);
         const int low_iter = wsub(i, max_iter);                  // lchain.rs:78
-        const bool inwin = rj >= max(low_iter, 0) && rhi == hi_i && !(ri > wadd(rx, mdx));   // empty slots hold rj = -1
+        const bool inwin = (FAST ? rj >= 0 : rj >= max(low_iter, 0)) && rhi == hi_i && !(ri > wadd(rx, mdx));   // empty slots hold rj = -1
         int s0;
-        const bool valid = chain_sc_flat<LUT>(inwin, ri, qi, rx, rq, rsp, mdx, mdy, bw, p.chn_pen_gap, p.chn_pen_skip, G.half_log, s0, G.pen_int);
+        const bool valid = chain_sc_flat<FAST, FAST>(inwin, ri, qi, rx, rq, rsp, mdx, mdy, bw, p.chn_pen_gap, p.chn_pen_skip, G.half_log, s0, G.pen_int);
         const int sc = valid ? wadd(s0, rf) : NEG_INF;
         const u32 inmask = __ballot_sync(0xFFFFFFFFu, inwin);
         const u32 vmask = __ballot_sync(0xFFFFFFFFu, valid);
@@ -413,7 +420,7 @@ __device__ __forceinline__ void chain_read(const ChainArgs& G, const u32 r, cons
                 const ulonglong2 v = an[j];
                 if ((u32)(v.x >> 32) == hi_i) {                     // lchain.rs:81
                   int s0;
-                  if (chain_sc<LUT>(ri, qi, (int)(u32)v.x, (int)(u32)v.y, (int)((v.y >> 32) & 0xff), mdx, mdy, bw, p.chn_pen_gap,
+                  if (chain_sc<FAST>(ri, qi, (int)(u32)v.x, (int)(u32)v.y, (int)((v.y >> 32) & 0xff), mdx, mdy, bw, p.chn_pen_gap,
                                     p.chn_pen_skip, G.half_log, G.pen_int, s0)) {
                     const int2 fj = *reinterpret_cast<const int2*>(A + j);
                     sc2 = wadd(s0, fj.x);
@@ -1043,12 +1050,12 @@ __device__ __forceinline__ void chain_read_dense(const ChainArgs& G, const u32 r
 #endif
 }
 
-template <bool COUNT, bool LUT>
+template <bool COUNT, bool FAST>
 __global__ void __launch_bounds__(CH_WARPS * 32, MM2_CH_OCC) chain_ring_kernel(ChainArgs G) {
   const u32 r = blockIdx.x * CH_WARPS + (threadIdx.x >> 5);
   if (r >= G.nreads) return;
   if (chain_is_dense(G, r)) return;                               // chain_dense_kernel's
-  chain_read<COUNT, LUT>(G, r, threadIdx.x & 31);
+  chain_read<COUNT, FAST>(G, r, threadIdx.x & 31);
 }
 
 // NW warps per dense read, one resident CTA per SM (the window ring and the two summary buffers take ~210 KB of shared memory).
@@ -1134,7 +1141,7 @@ int chain_batch(mm2_ctx* ctx, const ulonglong2* d_anchors, const u64* d_read_aof
   G.anchors = d_anchors; G.read_aoff = d_read_aoff; G.read_off = d_read_off; G.mini_off = d_mini_off; G.mval = d_mval;
   G.sum_span = d_sum_span; G.nreads = nreads; G.p = p; G.do_rescue = do_rescue; G.half_log = ctx->lut.as<float>();
   G.pen_int = reinterpret_cast<const int*>(ctx->lut.as<float>() + ctx->lut_n);
-  const bool lut = p.chn_pen_skip == 0.0f;
+  const bool lut = p.chn_pen_skip == 0.0f && p.max_chain_iter >= 32 && p.bw >= 0 && p.bw_long >= 0;   // chain_read<.., FAST>
   G.A = d_A; G.B = d_B; G.T = d_T; G.W = d_W; G.chain = d_chain; G.hits = d_hits; G.cells = d_cells;
   G.dense = nullptr; G.dense_min = 0x7fffffff; G.dense_ratio5 = 0;
   const int grid = (int)((nreads + CH_WARPS - 1) / CH_WARPS);

@@ -218,7 +218,11 @@ __host__ __device__ __forceinline__ u32 index_fine_cdf(u64 hk, int R, int j, int
   if (j <= 0) return 0u;
   const u64 t = (R >= 64 ? ~0ULL : ((1ULL << R) - 1)) - hk;
   u32 t32 = R >= 32 ? (u32)(t >> (R - 32)) : (u32)(t << (32 - R));
-  for (int s = 0; s < pw; ++s) t32 = (u32)(((u64)t32 * (u64)t32) >> 32);
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int s = 0; s < 5; ++s)   // pw <= 5 (index.cu); predicated instead of a loop
+    if (s < pw) t32 = (u32)(((u64)t32 * (u64)t32) >> 32);
   return (~t32) >> (32 - j);
 }
 __host__ __device__ __forceinline__ u64 index_fine_id(const IndexView& V, u64 minier) {
